@@ -1,0 +1,135 @@
+"""CPU tests: the oracle (oracle/abd_oracle.py) against the fixtures produced by executing the
+reference's own code (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import abd_oracle as ora
+
+
+def test_reference_tests_ran_under_standin(kats):
+    info = kats["_reference_tests_under_standin"]
+    assert info["ran"] == 45 and info["passed"] == 41
+    assert all("TestModel" in s for s in info["skipped_need_pymc"])
+
+
+def test_mask_multiple_infections(kats):
+    for k in kats["mask_multiple"]:
+        out = ora.mask_multiple_infections_chunks(np.array(k["arr"]), k["splits"])
+        assert np.array_equal(out, np.array(k["out"]))
+
+
+def test_incorporate_pcrpos(kats):
+    for k in kats["incorporate_pcrpos"]:
+        assert np.array_equal(ora.incorporate_pcrpos(k["i_raw"], k["pcrpos"]), np.array(k["out"]))
+
+
+def test_mask_three_gaps(kats):
+    for k in kats["mask_three_gaps"]:
+        assert np.array_equal(ora.mask_three_gaps(k["arr"]), np.array(k["out"]))
+
+
+def test_mask_future_infection_truth_table():
+    # reference test_abd.py:14-63 (i0 = 10 passes through, :30)
+    assert ora.mask_future_infection(10, 0, 0, 0) == 10
+    for i0 in (0, 1):
+        for taps in range(8):
+            im3, im2, im1 = taps >> 2 & 1, taps >> 1 & 1, taps & 1
+            assert ora.mask_future_infection(i0, im3, im2, im1) == (0 if taps else i0)
+
+
+def test_constrain_infections(kats):
+    for k in kats["constrain"]:
+        out = ora.constrain_infections(np.array(k["i_raw"]), np.array(k["pcrpos"]), tuple(k["splits"]))
+        assert np.array_equal(out, np.array(k["out"])), k["splits"]
+
+
+def test_temp_response(kats):
+    for k in kats["temp_response"]:
+        expo = np.array(k["exposure"])
+        rho = np.array(k["rho"])
+        dense = ora.temp_response_dense(expo, rho)
+        scan = ora.temp_response_scan(expo, rho)
+        scale = k["temp"] if k["kind"] == "scalar" else 1.0  # the vector version ignores temp (abd.py:263-274)
+        np.testing.assert_allclose(dense * scale, np.array(k["out"]), rtol=1e-14, atol=1e-15)
+        np.testing.assert_allclose(scan * scale, np.array(k["out"]), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_joint_logp_and_grad_match_reference(goldens, cohorts, dense):
+    z, cases = goldens
+    for c in cases:
+        if not dense and c["cohort"] == "cohort" and not c["key"].endswith("/0"):
+            continue
+        o = ora.Oracle(cohorts[c["cohort"]], splits=c["splits"], ignore_pcrpos=c["ignore_pcrpos"], dense=dense)
+        k = c["key"]
+        logp, grad = o.logp_dlogp(z[f"{k}/q"], z[f"{k}/i_raw"], z[f"{k}/w"])
+        ref = float(z[f"{k}/logp"])
+        assert abs(logp - ref) <= 1e-11 * abs(ref), (k, logp, ref)
+        gref = z[f"{k}/grad"]
+        tol = 1e-10 * np.maximum(np.abs(gref), 1e-3 * np.abs(gref).max())
+        assert np.all(np.abs(grad - gref) <= tol), (k, grad - gref)
+
+
+def test_deterministics_match_reference(goldens, cohorts):
+    z, cases = goldens
+    for c in cases:
+        k = c["key"]
+        o = ora.Oracle(cohorts[c["cohort"]], splits=c["splits"], ignore_pcrpos=c["ignore_pcrpos"])
+        vals = ora.backward(z[f"{k}/q"])[0]
+        th = np.array([vals[n] for n in ora.THETA13])
+        i, mu_n, mu_s = o.deterministics(th, z[f"{k}/i_raw"], z[f"{k}/w"])
+        assert int(i.sum()) == int(z[f"{k}/i_sum"])
+        np.testing.assert_allclose(mu_n.sum(), float(z[f"{k}/mu_n_sum"]), rtol=1e-12)
+        np.testing.assert_allclose(mu_s.sum(), float(z[f"{k}/mu_s_sum"]), rtol=1e-12)
+        if f"{k}/i" in z:
+            assert np.array_equal(i, z[f"{k}/i"])
+            np.testing.assert_allclose(mu_n, z[f"{k}/mu_n"], rtol=1e-13, atol=1e-13)
+            np.testing.assert_allclose(mu_s, z[f"{k}/mu_s"], rtol=1e-13, atol=1e-13)
+
+
+def test_cond_logodds_match_reference(goldens, cohorts):
+    z, cases = goldens
+    n = 0
+    for c in cases:
+        k = c["key"]
+        if f"{k}/cond" not in z:
+            continue
+        o = ora.Oracle(cohorts[c["cohort"]], splits=c["splits"], ignore_pcrpos=c["ignore_pcrpos"])
+        vals = ora.backward(z[f"{k}/q"])[0]
+        th = np.array([vals[m] for m in ora.THETA13])
+        lo, lo_w = o.cond_logodds(th, vals["p"], vals["ab_s_p_waner"], z[f"{k}/i_raw"], z[f"{k}/w"])
+        # the reference differences two ~1e3-magnitude joint logps: absolute tolerance
+        np.testing.assert_allclose(lo, z[f"{k}/cond"], rtol=1e-9, atol=2e-9)
+        np.testing.assert_allclose(lo_w, z[f"{k}/cond_w"], rtol=1e-9, atol=2e-9)
+        n += 1
+    assert n >= 8
+
+
+def test_gradient_finite_difference(cohorts):
+    rng = np.random.default_rng(3)
+    co = cohorts["test_cohort"]
+    o = ora.Oracle(co, splits=(14, 20))
+    q = ora.forward(ora.sample_prior(rng, o.G))
+    i_raw = (rng.random((o.G, o.N)) < 0.06).astype(np.int8)
+    w = (rng.random(o.N) < 0.5).astype(np.int8)
+    _, g = o.logp_dlogp(q, i_raw, w)
+    for k in range(17):
+        h = 1e-6
+        qp, qm = q.copy(), q.copy()
+        qp[k] += h
+        qm[k] -= h
+        fd = (o.logp(qp, i_raw, w) - o.logp(qm, i_raw, w)) / (2 * h)
+        assert abs(fd - g[k]) <= 1e-5 * max(1.0, abs(g[k])), (k, fd, g[k])
+
+
+def test_gibbs_sweep_restatement_keeps_shapes(cohorts):
+    rng = np.random.default_rng(0)
+    co = cohorts["test_cohort"]
+    o = ora.Oracle(co, splits=(14, 20), dense=False)
+    vals = ora.sample_prior(rng, o.G)
+    th = np.array([vals[m] for m in ora.THETA13])
+    i_raw = np.zeros((o.G, o.N), np.int8)
+    w = np.zeros(o.N, np.int8)
+    i2, w2 = ora.binary_gibbs_metropolis_sweep(o, th, 0.04, 0.5, i_raw, w, rng)
+    assert i2.shape == (o.G, o.N) and w2.shape == (o.N,)
+    assert set(np.unique(i2)) <= {0, 1} and set(np.unique(w2)) <= {0, 1}
