@@ -1,0 +1,1167 @@
+// libabd_b200.so -- kernels (sm_100a) and the C ABI declared in include/abd_b200.h.
+//
+// HBM layout (all built once in abd_create):
+//   pcr[N], vac[N]              one bit mask over gaps per individual (uint32 if G <= 31)
+//   per antigen a in {N, S}:    CSR by individual -- rp_a[N+1] (int32), and row arrays sorted by
+//                               (individual, gap): od_a[R_a] f64, x_a[R_a] f64,
+//                               meta_a[R_a] u32 = individual << 6 | gap
+//   per chain (resident state): i_raw[C][G][N] int8, waner[C][N] int8  (the reference layout)
+//
+// Kernels
+//   k_sums      one CTA per (tile of individuals, chain): int8 columns -> bit masks ->
+//               constrained infections in shared memory; one thread per OD row evaluates the
+//               titer in closed form from the masks (power tables in shared memory), the
+//               logistic curve and the 13 gradient accumulators; warp-shuffle + block
+//               reduction; the last CTA of each chain (atomic ticket) reduces the tiles in a
+//               fixed order and applies priors / transforms (single launch, deterministic).
+//   k_finalize  the same finalisation as a separate launch (after an all-reduce when
+//               individuals are sharded across GPUs).
+//   k_gibbs     one warp per (individual, chain), lanes over that individual's OD rows; G+1
+//               sequential single-bit updates, both states evaluated, Philox4x32-10.
+//   k_determ    one thread per (individual, chain): i, ab_n_mu, ab_s_mu for a recorded draw.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/abd_b200.h"
+#include "abd_device.cuh"
+
+using namespace abd;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ABD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device-side view of the cohort
+// ------------------------------------------------------------------------------------------
+struct DevCohort {
+  int G, N;
+  unsigned ind_offset;       // global index of this shard's first individual (RNG streams)
+  const void* pcr;
+  const void* vac;
+  const int* rp[2];          // [0] = N antigen, [1] = S antigen
+  const double* od[2];
+  const double* x[2];
+  const uint32_t* meta[2];
+  Chunks ch;
+};
+
+constexpr int kSumsBlock = 256;
+constexpr int kTileMaxInds = 128;
+constexpr int kGibbsWarps = 8;
+constexpr int kGibbsTile = 32;  // individuals per Gibbs CTA
+
+template <int NV>
+__device__ __forceinline__ void warp_reduce(double (&v)[NV]) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+  }
+}
+
+__device__ __forceinline__ void load_theta(const double* theta, int theta_is_q, int c, int tid,
+                                           double* s_th) {
+  if (tid < 13) {
+    if (theta_is_q) {
+      const int j = kQOfTheta[tid];
+      s_th[tid] = backward(theta[(size_t)c * 17 + j], kQTransform[j]);
+    } else {
+      s_th[tid] = theta[(size_t)c * 13 + tid];
+    }
+  }
+}
+
+// pw[k] = rho^k, dpw[k] = k rho^(k-1), k < G
+__device__ __forceinline__ void fill_pow(double rho, int G, int lane, double* pw, double* dpw) {
+  for (int k = lane; k < G; k += 32) {
+    const double pkm1 = ipow(rho, k > 0 ? k - 1 : 0);
+    pw[k] = k > 0 ? pkm1 * rho : 1.0;
+    if (dpw) dpw[k] = k > 0 ? (double)k * pkm1 : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_sums
+// ------------------------------------------------------------------------------------------
+struct FinalizeCfg {
+  int mode;        // 0: write raw sums only; 1: loglik + grad13; 2: joint logp + dlogp17
+  Totals tot;
+  double* out_val;   // [C]
+  double* out_grad;  // [C][13] or [C][17] (may be null)
+};
+
+template <typename M>
+__global__ void __launch_bounds__(kSumsBlock)
+k_sums(const DevCohort dc, const int* __restrict__ tile_ind, const int ntiles,
+       const double* __restrict__ theta, const int theta_is_q,
+       const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
+       double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ sums,
+       const FinalizeCfg fin, const Priors* __restrict__ priors) {
+  const int tile = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int G = dc.G, N = dc.N;
+  const int i0 = tile_ind[tile], i1 = tile_ind[tile + 1];
+  const int ni = i1 - i0;
+
+  __shared__ double s_th[16];
+  __shared__ double s_pw[4][kMaxGaps];  // rho_n^k, d/drho; rho_s^k, d/drho
+  __shared__ M s_inf[kTileMaxInds];
+  __shared__ M s_vac[kTileMaxInds];
+  __shared__ unsigned char s_w[kTileMaxInds];
+  __shared__ double s_red[kSumsBlock / 32][kNSums];
+  __shared__ int s_last;
+
+  load_theta(theta, theta_is_q, c, tid, s_th);
+
+  // ---- phase 0: int8 columns -> bit masks (coalesced over individuals for every gap) ----
+  M raw = 0;
+  int w = 0;
+  if (tid < ni) {
+    const int8_t* col = i_raw + (size_t)c * G * N + (i0 + tid);
+#pragma unroll 8
+    for (int t = 0; t < G; ++t) raw |= (M)(col[(size_t)t * N] != 0) << t;
+    w = waner[(size_t)c * N + i0 + tid] != 0;
+  }
+  __syncthreads();
+  if (warp == 0) fill_pow(s_th[N_RHO], G, lane, s_pw[0], s_pw[1]);
+  if (warp == 1) fill_pow(s_th[S_RHO], G, lane, s_pw[2], s_pw[3]);
+  double acc[kNSums];
+#pragma unroll
+  for (int k = 0; k < kNSums; ++k) acc[k] = 0.0;
+  if (tid < ni) {
+    const M pcr = reinterpret_cast<const M*>(dc.pcr)[i0 + tid];
+    s_inf[tid] = constrain<M>(raw, pcr, dc.ch);
+    s_vac[tid] = reinterpret_cast<const M*>(dc.vac)[i0 + tid];
+    s_w[tid] = (unsigned char)w;
+    acc[S_KI] = (double)popc(raw);
+    acc[S_KW] = (double)w;
+  }
+  __syncthreads();
+
+  // ---- phase 1: one thread per OD row ----
+  {
+    const double init = s_th[N_INIT], perm = s_th[N_PERM], temp = s_th[N_TEMP];
+    const double b = s_th[N_B], d = s_th[N_D];
+    const int r0 = dc.rp[0][i0], r1 = dc.rp[0][i1];
+    const double* __restrict__ od = dc.od[0];
+    const double* __restrict__ xs = dc.x[0];
+    const uint32_t* __restrict__ meta = dc.meta[0];
+#pragma unroll 2
+    for (int r = r0 + tid; r < r1; r += kSumsBlock) {
+      const uint32_t mt = meta[r];
+      const int t = mt & 63, li = (int)(mt >> 6) - i0;
+      double P, T, dT, s, res, q, xm;
+      traj_n<M>(s_inf[li], t, s_pw[0], s_pw[1], P, T, dT);
+      row_eval(xs[r], od[r], init + perm * P + temp * T, b, d, s, res, q, xm);
+      acc[SN_0] += res * res;
+      acc[SN_1] += res * s;
+      acc[SN_2] += q * xm;
+      acc[SN_QINIT] += q;
+      acc[SN_QPERM] += q * P;
+      acc[SN_QTEMP] += q * T;
+      acc[SN_QRHO] += q * dT;
+    }
+  }
+  {
+    const double init = s_th[S_INIT], perm = s_th[S_PERM];
+    const double b = s_th[S_B], d = s_th[S_D];
+    const int r0 = dc.rp[1][i0], r1 = dc.rp[1][i1];
+    const double* __restrict__ od = dc.od[1];
+    const double* __restrict__ xs = dc.x[1];
+    const uint32_t* __restrict__ meta = dc.meta[1];
+#pragma unroll 2
+    for (int r = r0 + tid; r < r1; r += kSumsBlock) {
+      const uint32_t mt = meta[r];
+      const int t = mt & 63, li = (int)(mt >> 6) - i0;
+      double P, U, dU, s, res, q, xm;
+      traj_s<M>(s_inf[li], s_vac[li], s_w[li], t, s_pw[2], s_pw[3], P, U, dU);
+      row_eval(xs[r], od[r], init + perm * P + U, b, d, s, res, q, xm);
+      acc[SS_0] += res * res;
+      acc[SS_1] += res * s;
+      acc[SS_2] += q * xm;
+      acc[SS_QINIT] += q;
+      acc[SS_QPERM] += q * P;
+      acc[SS_QRHO] += q * dU;
+    }
+  }
+
+  // ---- block reduction: shuffles inside a warp, shared memory across warps ----
+  warp_reduce<kNSums>(acc);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kNSums; ++k) s_red[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (tid < kNSums) {
+    double v = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kSumsBlock / 32; ++wv) v += s_red[wv][tid];
+    partial[((size_t)c * ntiles + tile) * kNSums + tid] = v;
+  }
+
+  // ---- last CTA of this chain: ordered reduction over tiles, then finalise ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&ticket[c], 1u) == (unsigned)(ntiles - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    const int k = tid & 15, g = tid >> 4;  // 16 groups of 16 values
+    double v = 0.0;
+    for (int tl = g; tl < ntiles; tl += kSumsBlock / 16)
+      v += __ldcg(&partial[((size_t)c * ntiles + tl) * kNSums + k]);
+    __shared__ double s_fin[kSumsBlock / 16][kNSums];
+    s_fin[g][k] = v;
+    __syncthreads();
+    if (tid < kNSums) {
+      double tot = 0.0;
+#pragma unroll
+      for (int gg = 0; gg < kSumsBlock / 16; ++gg) tot += s_fin[gg][tid];
+      s_red[0][tid] = tot;
+      if (sums) sums[(size_t)c * kNSums + tid] = tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ticket[c] = 0;  // re-arm for the next launch
+    if (fin.mode == 1) {
+      finalize_loglik(s_th, s_red[0], fin.tot, &fin.out_val[c],
+                      fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
+    } else if (fin.mode == 2) {
+      finalize_logp(&theta[(size_t)c * 17], s_red[0], fin.tot, *priors, &fin.out_val[c],
+                    fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
+    }
+  }
+}
+
+__global__ void k_finalize(const int C, const double* __restrict__ theta,
+                           const double* __restrict__ sums, const FinalizeCfg fin,
+                           const Priors* __restrict__ priors) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (fin.mode == 1) {
+    finalize_loglik(&theta[(size_t)c * 13], &sums[(size_t)c * kNSums], fin.tot, &fin.out_val[c],
+                    fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
+  } else {
+    finalize_logp(&theta[(size_t)c * 17], &sums[(size_t)c * kNSums], fin.tot, *priors,
+                  &fin.out_val[c], fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_gibbs
+// ------------------------------------------------------------------------------------------
+struct GibbsCfg {
+  uint64_t seed, sweep;
+  int mode;          // ABD_GIBBS_*; -1 = conditional log-odds only (no update, no RNG)
+  double transit_p;
+  double* out_i;     // [C][G][N] (mode -1)
+  double* out_w;     // [C][N]
+  unsigned long long* stats;  // [C][2] proposals, accepted flips (may be null)
+};
+
+// log-likelihood of one individual's rows (up to the additive constant), all lanes return it
+template <typename M>
+__device__ __forceinline__ double indiv_ll(const DevCohort& dc, int n, M inf, M vac, int w,
+                                           const double* s_th, const double (*s_pw)[kMaxGaps],
+                                           int lane, int rn0, int rn1, int rs0, int rs1) {
+  double a = 0.0;
+  {
+    const double init = s_th[N_INIT], perm = s_th[N_PERM], temp = s_th[N_TEMP];
+    const double b = s_th[N_B], d = s_th[N_D];
+    double sub = 0.0;
+    for (int r = rn0 + lane; r < rn1; r += 32) {
+      const int t = dc.meta[0][r] & 63;
+      sub += row_resid2(dc.x[0][r], dc.od[0][r], mu_n_at<M>(inf, t, s_pw[0], init, perm, temp), b, d);
+    }
+    a += sub * s_th[13];  // -1 / (2 sigma_n^2)
+  }
+  {
+    const double init = s_th[S_INIT], perm = s_th[S_PERM];
+    const double b = s_th[S_B], d = s_th[S_D];
+    double sub = 0.0;
+    for (int r = rs0 + lane; r < rs1; r += 32) {
+      const int t = dc.meta[1][r] & 63;
+      sub += row_resid2(dc.x[1][r], dc.od[1][r], mu_s_at<M>(inf, vac, w, t, s_pw[1], init, perm), b, d);
+    }
+    a += sub * s_th[14];  // -1 / (2 sigma_s^2)
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+  return a;
+}
+
+template <typename M>
+__global__ void __launch_bounds__(kGibbsWarps * 32)
+k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is_q,
+        const double* __restrict__ p_arr, const double* __restrict__ pw_arr,
+        int8_t* __restrict__ i_raw, int8_t* __restrict__ waner, const GibbsCfg cfg) {
+  constexpr int NSLOT = sizeof(M) / 4;  // proposals owned per lane
+  const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = dc.G, N = dc.N;
+  const int i0 = blockIdx.x * kGibbsTile;
+  const int ni = min(kGibbsTile, N - i0);
+
+  __shared__ double s_th[16];
+  __shared__ double s_pw[2][kMaxGaps];
+  __shared__ double s_lo[2];  // logit(p), logit(p_w)
+  __shared__ unsigned char s_bytes[kMaxGaps][kGibbsTile];
+  __shared__ unsigned s_stat[2];
+
+  load_theta(theta, theta_is_q, c, tid, s_th);
+  if (tid == 32) {
+    if (theta_is_q) {  // logit of a logodds-transformed value is the value itself
+      s_lo[0] = theta[(size_t)c * 17 + kQ_P];
+      s_lo[1] = theta[(size_t)c * 17 + kQ_PW];
+    } else {
+      const double p = p_arr[c], pw = pw_arr[c];
+      s_lo[0] = log(p) - log1p(-p);
+      s_lo[1] = log(pw) - log1p(-pw);
+    }
+  }
+  if (tid < 2) s_stat[tid] = 0;
+  for (int idx = tid; idx < G * kGibbsTile; idx += kGibbsWarps * 32) {
+    const int t = idx / kGibbsTile, j = idx % kGibbsTile;
+    s_bytes[t][j] = (j < ni) ? (unsigned char)(i_raw[((size_t)c * G + t) * N + i0 + j] != 0) : 0;
+  }
+  __syncthreads();
+  if (warp == 0) fill_pow(s_th[N_RHO], G, lane, s_pw[0], nullptr);
+  if (warp == 1) fill_pow(s_th[S_RHO], G, lane, s_pw[1], nullptr);
+  if (tid == 64) {
+    s_th[13] = -0.5 / (s_th[N_SIGMA] * s_th[N_SIGMA]);
+    s_th[14] = -0.5 / (s_th[S_SIGMA] * s_th[S_SIGMA]);
+  }
+  __syncthreads();
+
+  const int nprop = G + 1;  // proposal j < G flips i_raw[j, n]; j == G flips waner[n]
+  unsigned n_prop = 0, n_acc = 0;
+
+  for (int j = warp; j < ni; j += kGibbsWarps) {
+    const int n = i0 + j;
+    // column -> mask
+    M raw = 0;
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; ++sl) {
+      const int t = lane + 32 * sl;
+      const unsigned bal = __ballot_sync(0xffffffffu, t < G && s_bytes[t][j]);
+      raw |= (M)bal << (32 * sl);
+    }
+    int w = waner[(size_t)c * N + n] != 0;
+    const M pcr = reinterpret_cast<const M*>(dc.pcr)[n];
+    const M vac = reinterpret_cast<const M*>(dc.vac)[n];
+    const int rn0 = dc.rp[0][n], rn1 = dc.rp[0][n + 1], rs0 = dc.rp[1][n], rs1 = dc.rp[1][n + 1];
+
+    M inf = constrain<M>(raw, pcr, dc.ch);
+    double ll = indiv_ll<M>(dc, n, inf, vac, w, s_th, s_pw, lane, rn0, rn1, rs0, rs1);
+
+    // random visiting order: rank of a 32-bit Philox key per proposal (ties by index)
+    uint32_t rnd_t[NSLOT], rnd_a[NSLOT];
+    int rank[NSLOT];
+    if (cfg.mode >= 0) {
+      uint32_t key[NSLOT];
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const uint4 r = philox4x32_10(
+            make_uint4((uint32_t)(lane + 32 * sl), (uint32_t)n + dc.ind_offset, (uint32_t)c, (uint32_t)cfg.sweep),
+            make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32) ^ (uint32_t)(cfg.sweep >> 32)));
+        key[sl] = r.x;
+        rnd_t[sl] = r.y;
+        rnd_a[sl] = r.z;
+        rank[sl] = 0;
+      }
+      for (int jj = 0; jj < nprop; ++jj) {
+        const uint32_t kj = __shfl_sync(0xffffffffu, key[jj >> 5], jj & 31);
+#pragma unroll
+        for (int sl = 0; sl < NSLOT; ++sl) {
+          const int me = lane + 32 * sl;
+          rank[sl] += (kj < key[sl]) || (kj == key[sl] && jj < me);
+        }
+      }
+    }
+
+    for (int step = 0; step < nprop; ++step) {
+      int jp;  // proposal visited at this step
+      double u_t = 0.0, u_a = 1.0;
+      if (cfg.mode >= 0) {
+        jp = 0;
+#pragma unroll
+        for (int sl = 0; sl < NSLOT; ++sl) {
+          const int me = lane + 32 * sl;
+          const unsigned bal = __ballot_sync(0xffffffffu, me < nprop && rank[sl] == step);
+          if (bal) {
+            const int src = __ffs(bal) - 1;
+            jp = src + 32 * sl;
+            u_t = u01(__shfl_sync(0xffffffffu, rnd_t[sl], src));
+            u_a = u01(__shfl_sync(0xffffffffu, rnd_a[sl], src));
+          }
+        }
+        if (cfg.mode == ABD_GIBBS_METROPOLIS && !(u_t <= cfg.transit_p)) continue;
+      } else {
+        jp = step;
+      }
+      const bool is_w = (jp == G);
+      const M raw2 = is_w ? raw : (raw ^ ((M)1 << jp));
+      const int w2 = is_w ? (w ^ 1) : w;
+      const M inf2 = is_w ? inf : constrain<M>(raw2, pcr, dc.ch);
+      const int cur_bit = is_w ? w : (int)((raw >> jp) & 1);
+      double ll2 = ll;
+      if (inf2 != inf || is_w)
+        ll2 = indiv_ll<M>(dc, n, inf2, vac, w2, s_th, s_pw, lane, rn0, rn1, rs0, rs1);
+      const double lo = s_lo[is_w ? 1 : 0];
+      // log-odds of bit = 1 versus bit = 0
+      const double d10 = cur_bit ? (ll - ll2 + lo) : (ll2 - ll + lo);
+      if (cfg.mode < 0) {
+        if (lane == 0) {
+          if (is_w) cfg.out_w[(size_t)c * N + n] = d10;
+          else cfg.out_i[((size_t)c * G + jp) * N + n] = d10;
+        }
+        continue;
+      }
+      bool flip;
+      if (cfg.mode == ABD_GIBBS_METROPOLIS) {
+        const double delta = cur_bit ? -d10 : d10;  // logp(proposed) - logp(current)
+        flip = isfinite(delta) && (log(u_a) < delta);
+      } else {
+        const double p1 = 1.0 / (1.0 + exp(-d10));
+        const int nb = u_a <= p1;
+        flip = (nb != cur_bit);
+      }
+      ++n_prop;
+      if (flip) {
+        ++n_acc;
+        raw = raw2;
+        w = w2;
+        inf = inf2;
+        ll = ll2;
+      }
+    }
+
+    if (cfg.mode >= 0) {
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const int t = lane + 32 * sl;
+        if (t < G) s_bytes[t][j] = (unsigned char)((raw >> t) & 1);
+      }
+      if (lane == 0) waner[(size_t)c * N + n] = (int8_t)w;
+    }
+  }
+  if (cfg.mode < 0) return;
+  if (lane == 0 && cfg.stats) {
+    atomicAdd(&s_stat[0], n_prop);
+    atomicAdd(&s_stat[1], n_acc);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < G * kGibbsTile; idx += kGibbsWarps * 32) {
+    const int t = idx / kGibbsTile, j = idx % kGibbsTile;
+    if (j < ni) i_raw[((size_t)c * G + t) * N + i0 + j] = (int8_t)s_bytes[t][j];
+  }
+  if (cfg.stats && tid < 2) atomicAdd(&cfg.stats[(size_t)c * 2 + tid], (unsigned long long)s_stat[tid]);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_determ
+// ------------------------------------------------------------------------------------------
+template <typename M>
+__global__ void __launch_bounds__(128)
+k_determ(const DevCohort dc, const double* __restrict__ theta13, const int8_t* __restrict__ i_raw,
+         const int8_t* __restrict__ waner, int8_t* __restrict__ out_i, double* __restrict__ out_mu_n,
+         double* __restrict__ out_mu_s) {
+  const int c = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = dc.G, N = dc.N;
+  __shared__ double s_th[16];
+  load_theta(theta13, 0, c, threadIdx.x, s_th);
+  __syncthreads();
+  if (n >= N) return;
+  M raw = 0;
+  const int8_t* col = i_raw + (size_t)c * G * N + n;
+  for (int t = 0; t < G; ++t) raw |= (M)(col[(size_t)t * N] != 0) << t;
+  const int w = waner[(size_t)c * N + n] != 0;
+  const M inf = constrain<M>(raw, reinterpret_cast<const M*>(dc.pcr)[n], dc.ch);
+  const M vac = reinterpret_cast<const M*>(dc.vac)[n];
+  const double rho_n = s_th[N_RHO], rho_s = w ? s_th[S_RHO] : 1.0;
+  double T = 0.0, U = 0.0, Pn = 0.0, Ps = 0.0;
+  for (int t = 0; t < G; ++t) {  // the recurrence of abd.py:277-293
+    const int it = (int)((inf >> t) & 1), vt = (int)((vac >> t) & 1);
+    T = T * rho_n + it;
+    U = U * rho_s + (it + vt);
+    if (it) Pn = 1.0;
+    if (it | vt) Ps = 1.0;
+    const size_t o = ((size_t)c * G + t) * N + n;
+    if (out_i) out_i[o] = (int8_t)it;
+    if (out_mu_n) out_mu_n[o] = s_th[N_PERM] * Pn + s_th[N_TEMP] * T + s_th[N_INIT];
+    if (out_mu_s) out_mu_s[o] = s_th[S_PERM] * Ps + U + s_th[S_INIT];
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct abd_handle {
+  int device = 0;
+  int G = 0, N = 0;
+  bool wide = false;  // uint64 masks
+  int64_t R[2] = {0, 0};
+  Totals tot{};
+  DevCohort dc{};
+  std::vector<void*> owned;   // device allocations freed in abd_destroy
+  std::vector<int> h_rp[2];   // host copy of the CSR pointers (for tilings)
+  cudaStream_t stream = nullptr;
+  Priors* d_priors = nullptr;
+  int64_t launches = 0;
+
+  struct Tiling {
+    int ntiles = 0;
+    int* d_tile_ind = nullptr;
+  };
+  std::map<int, Tiling> tilings;  // keyed by rows per tile
+  int tile_rows_override = 0;
+
+  // per-chain scratch
+  int cap_chains = 0;
+  int8_t* d_iraw = nullptr;
+  int8_t* d_waner = nullptr;
+  double* d_theta = nullptr;   // [C][17]
+  double* d_p = nullptr;       // [C][2]
+  double* d_sums = nullptr;    // [C][16]
+  double* d_out = nullptr;     // [C][18]
+  unsigned* d_ticket = nullptr;
+  unsigned long long* d_stats = nullptr;
+  double* d_partial = nullptr;
+  size_t cap_partial = 0;
+  double* h_pin = nullptr;     // pinned staging [C][24]
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(abd_handle* h, T** p, size_t n, bool owned = true) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail(ABD_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  *p = (T*)q;
+  if (owned) h->owned.push_back(q);
+  return ABD_OK;
+}
+
+template <typename T>
+int upload(abd_handle* h, T** dptr, const std::vector<T>& v) {
+  int rc = dev_alloc(h, dptr, v.size());
+  if (rc) return rc;
+  if (!v.empty()) CU(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return ABD_OK;
+}
+
+Priors default_priors(int G) {
+  // abd.py:424 p ~ Beta(1, G-1); :329-340 N response; :367-388 S response; :464-467 sigmoids
+  auto normal = [](double mu, double sd) { return PriorSpec{0, mu, sd, -kHalfLog2Pi - std::log(sd)}; };
+  auto gamma = [](double mu, double sd) {
+    const double a = mu * mu / (sd * sd), b = mu / (sd * sd);
+    return PriorSpec{1, a, b, -std::lgamma(a) + a * std::log(b)};
+  };
+  auto beta = [](double a, double b) {
+    return PriorSpec{2, a, b, -(std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b))};
+  };
+  auto expo = [](double lam) { return PriorSpec{3, lam, 0.0, std::log(lam)}; };
+  Priors p;
+  p.v[0] = beta(1.0, (double)(G - 1));
+  p.v[1] = gamma(2.0, 0.5);
+  p.v[2] = gamma(1.0, 0.5);
+  p.v[3] = beta(10.0, 1.0);
+  p.v[4] = normal(-2.0, 1.0);
+  p.v[5] = gamma(2.0, 0.5);
+  p.v[6] = beta(10.0, 1.0);
+  p.v[7] = beta(1.0, 1.0);
+  p.v[8] = gamma(1.0, 0.5);
+  p.v[9] = gamma(1.0, 0.5);
+  p.v[10] = normal(-2.0, 1.0);
+  p.v[11] = normal(-1.0, 0.5);
+  p.v[12] = normal(2.0, 0.5);
+  p.v[13] = expo(1.0);
+  p.v[14] = normal(-1.0, 0.5);
+  p.v[15] = normal(2.0, 0.5);
+  p.v[16] = expo(1.0);
+  return p;
+}
+
+// CSR by individual for one antigen (counting sort by individual, then by gap inside)
+int build_rows(abd_handle* h, int a, int64_t R, const double* x, const double* od, const int32_t* gap,
+               const int32_t* ind) {
+  const int N = h->N, G = h->G;
+  if (R > 0 && (!x || !od || !gap || !ind)) return fail(ABD_ERR_INVALID, "NULL row array");
+  if (R >= (int64_t)1 << 31) return fail(ABD_ERR_INVALID, "too many OD rows for int32 CSR");
+  std::vector<int>& rp = h->h_rp[a];
+  rp.assign((size_t)N + 1, 0);
+  for (int64_t r = 0; r < R; ++r) {
+    if (ind[r] < 0 || ind[r] >= N) return fail(ABD_ERR_INVALID, "individual index out of range");
+    if (gap[r] < 0 || gap[r] >= G) return fail(ABD_ERR_INVALID, "gap index out of range");
+    rp[(size_t)ind[r] + 1]++;
+  }
+  for (int n = 0; n < N; ++n) rp[n + 1] += rp[n];
+  std::vector<int64_t> order((size_t)R);
+  {
+    std::vector<int> cur(rp.begin(), rp.end() - 1);
+    for (int64_t r = 0; r < R; ++r) order[(size_t)cur[ind[r]]++] = r;
+  }
+  for (int n = 0; n < N; ++n)
+    std::stable_sort(order.begin() + rp[n], order.begin() + rp[n + 1],
+                     [&](int64_t p, int64_t q) { return gap[p] < gap[q]; });
+  std::vector<double> xs((size_t)R), ods((size_t)R);
+  std::vector<uint32_t> meta((size_t)R);
+  for (int64_t k = 0; k < R; ++k) {
+    const int64_t r = order[(size_t)k];
+    xs[(size_t)k] = x[r];
+    ods[(size_t)k] = od[r];
+    meta[(size_t)k] = ((uint32_t)ind[r] << 6) | (uint32_t)gap[r];
+  }
+  int rc;
+  int* d_rp;
+  double *d_x, *d_od;
+  uint32_t* d_meta;
+  if ((rc = upload(h, &d_rp, rp))) return rc;
+  if ((rc = upload(h, &d_x, xs))) return rc;
+  if ((rc = upload(h, &d_od, ods))) return rc;
+  if ((rc = upload(h, &d_meta, meta))) return rc;
+  h->dc.rp[a] = d_rp;
+  h->dc.x[a] = d_x;
+  h->dc.od[a] = d_od;
+  h->dc.meta[a] = d_meta;
+  h->R[a] = R;
+  return ABD_OK;
+}
+
+int get_tiling(abd_handle* h, int rows_per_tile, abd_handle::Tiling** out) {
+  auto it = h->tilings.find(rows_per_tile);
+  if (it == h->tilings.end()) {
+    std::vector<int> ti{0};
+    int rows = 0, inds = 0;
+    for (int n = 0; n < h->N; ++n) {
+      const int rn = (h->h_rp[0][n + 1] - h->h_rp[0][n]) + (h->h_rp[1][n + 1] - h->h_rp[1][n]);
+      if (inds > 0 && (inds == kTileMaxInds || rows + rn > rows_per_tile)) {
+        ti.push_back(n);
+        rows = 0;
+        inds = 0;
+      }
+      rows += rn;
+      ++inds;
+    }
+    ti.push_back(h->N);
+    abd_handle::Tiling t;
+    t.ntiles = (int)ti.size() - 1;
+    int rc = upload(h, &t.d_tile_ind, ti);
+    if (rc) return rc;
+    it = h->tilings.emplace(rows_per_tile, t).first;
+  }
+  *out = &it->second;
+  return ABD_OK;
+}
+
+int ensure_chains(abd_handle* h, int C) {
+  if (C <= 0) return fail(ABD_ERR_INVALID, "n_chains must be positive");
+  if (C > 65535) return fail(ABD_ERR_INVALID, "n_chains must be <= 65535");
+  if (C <= h->cap_chains) return ABD_OK;
+  CU(cudaStreamSynchronize(h->stream));
+  int8_t *old_i = h->d_iraw, *old_w = h->d_waner;
+  const int oldC = h->cap_chains;
+  const size_t gn = (size_t)h->G * h->N;
+  int rc;
+  int8_t *ni, *nw;
+  if ((rc = dev_alloc(h, &ni, (size_t)C * gn, false))) return rc;
+  if ((rc = dev_alloc(h, &nw, (size_t)C * h->N, false))) return rc;
+  CU(cudaMemset(ni, 0, (size_t)C * gn));
+  CU(cudaMemset(nw, 0, (size_t)C * h->N));
+  if (oldC) {
+    CU(cudaMemcpy(ni, old_i, (size_t)oldC * gn, cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(nw, old_w, (size_t)oldC * h->N, cudaMemcpyDeviceToDevice));
+  }
+  for (void* p : {(void*)old_i, (void*)old_w, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
+                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats})
+    if (p) cudaFree(p);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  h->d_iraw = ni;
+  h->d_waner = nw;
+  if ((rc = dev_alloc(h, &h->d_theta, (size_t)C * 17, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_p, (size_t)C * 2, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_sums, (size_t)C * kNSums, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_out, (size_t)C * 18, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_ticket, (size_t)C, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_stats, (size_t)C * 2, false))) return rc;
+  CU(cudaMemset(h->d_ticket, 0, (size_t)C * sizeof(unsigned)));
+  CU(cudaMallocHost((void**)&h->h_pin, (size_t)C * 40 * sizeof(double)));
+  h->cap_chains = C;
+  return ABD_OK;
+}
+
+int auto_tile_rows(const abd_handle* h, int C) {
+  if (h->tile_rows_override > 0) return h->tile_rows_override;
+  const double row_evals = (double)(h->R[0] + h->R[1]) * C;
+  // aim for >= ~4 CTAs per SM while keeping >= 4 rows per thread
+  if (row_evals < 148.0 * 4 * 1024) return 1024;
+  if (row_evals < 148.0 * 16 * 2048) return 2048;
+  return 4096;
+}
+
+int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const int8_t* i_raw,
+                const int8_t* waner, double* sums, const FinalizeCfg& fin, cudaStream_t st) {
+  abd_handle::Tiling* tl;
+  int rc = get_tiling(h, auto_tile_rows(h, C), &tl);
+  if (rc) return rc;
+  const size_t need = (size_t)C * tl->ntiles * kNSums;
+  if (need > h->cap_partial) {
+    CU(cudaStreamSynchronize(st));
+    if (h->d_partial) cudaFree(h->d_partial);
+    if ((rc = dev_alloc(h, &h->d_partial, need, false))) return rc;
+    h->cap_partial = need;
+  }
+  dim3 grid(tl->ntiles, C);
+  if (h->wide)
+    k_sums<uint64_t><<<grid, kSumsBlock, 0, st>>>(h->dc, tl->d_tile_ind, tl->ntiles, theta, theta_is_q,
+                                                  i_raw, waner, h->d_partial, h->d_ticket, sums, fin,
+                                                  h->d_priors);
+  else
+    k_sums<uint32_t><<<grid, kSumsBlock, 0, st>>>(h->dc, tl->d_tile_ind, tl->ntiles, theta, theta_is_q,
+                                                  i_raw, waner, h->d_partial, h->d_ticket, sums, fin,
+                                                  h->d_priors);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
+int launch_gibbs(abd_handle* h, int C, const double* theta, int theta_is_q, const double* p,
+                 const double* pw, int8_t* i_raw, int8_t* waner, const GibbsCfg& cfg, cudaStream_t st) {
+  dim3 grid((h->N + kGibbsTile - 1) / kGibbsTile, C);
+  if (h->wide)
+    k_gibbs<uint64_t><<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, theta, theta_is_q, p, pw, i_raw, waner, cfg);
+  else
+    k_gibbs<uint32_t><<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, theta, theta_is_q, p, pw, i_raw, waner, cfg);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
+int set_device(const abd_handle* h) {
+  CU(cudaSetDevice(h->device));
+  return ABD_OK;
+}
+
+// copy optional host state into the resident buffers
+int stage_state(abd_handle* h, int C, const int8_t* i_raw, const int8_t* waner) {
+  const size_t gn = (size_t)h->G * h->N;
+  if (i_raw) CU(cudaMemcpyAsync(h->d_iraw, i_raw, (size_t)C * gn, cudaMemcpyHostToDevice, h->stream));
+  if (waner) CU(cudaMemcpyAsync(h->d_waner, waner, (size_t)C * h->N, cudaMemcpyHostToDevice, h->stream));
+  return ABD_OK;
+}
+
+#define PROLOGUE(h, C)                                         \
+  if (!(h)) return fail(ABD_ERR_INVALID, "NULL handle");       \
+  {                                                            \
+    int rc_ = set_device(h);                                   \
+    if (rc_) return rc_;                                       \
+    rc_ = ensure_chains(h, C);                                 \
+    if (rc_) return rc_;                                       \
+  }
+
+}  // namespace
+
+extern "C" {
+
+const char* abd_last_error(void) { return g_err.c_str(); }
+int abd_version(void) { return 100; }
+
+int abd_create(abd_handle** out, const abd_cohort* co, int device) {
+  if (!out || !co) return fail(ABD_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  const int G = co->n_gaps, N = co->n_inds;
+  if (G < 1 || G > ABD_MAX_GAPS) return fail(ABD_ERR_INVALID, "n_gaps must be in [1, 63]");
+  if (N < 1 || N >= (1 << 26)) return fail(ABD_ERR_INVALID, "n_inds must be in [1, 2^26)");
+  if (!co->vacs) return fail(ABD_ERR_INVALID, "vacs is NULL");
+  // check_splits, abd.py:604-622
+  if (co->n_splits < 0 || co->n_splits > 2)
+    return fail(ABD_ERR_INVALID, "only implemented 1-3 time chunks (0-2 splits)");  // abd.py:882
+  for (int k = 0; k < co->n_splits; ++k) {
+    if (co->splits[k] < 0) return fail(ABD_ERR_INVALID, "split indexes must be positive");
+    if (co->splits[k] > G) return fail(ABD_ERR_INVALID, "largest split must be less than n_gaps - 1");
+  }
+  if (co->n_splits == 2 && co->splits[0] == co->splits[1]) return fail(ABD_ERR_INVALID, "splits not unique");
+  if (co->n_splits == 2 && co->splits[0] > co->splits[1])
+    return fail(ABD_ERR_INVALID, "splits must be in ascending order");
+
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(ABD_ERR_CUDA, "no such CUDA device");
+  CU(cudaSetDevice(device));
+
+  abd_handle* h = new abd_handle();
+  h->device = device;
+  h->G = G;
+  h->N = N;
+  h->wide = G > 31;
+  auto bail = [&](int rc) {
+    abd_destroy(h);
+    return rc;
+  };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    return bail(fail(ABD_ERR_CUDA, "cudaStreamCreate failed"));
+
+  // bit masks per individual
+  std::vector<uint64_t> pcr((size_t)N, 0), vac((size_t)N, 0);
+  for (int t = 0; t < G; ++t)
+    for (int n = 0; n < N; ++n) {
+      if (co->pcrpos && co->pcrpos[(size_t)t * N + n]) pcr[n] |= 1ull << t;
+      if (co->vacs[(size_t)t * N + n]) vac[n] |= 1ull << t;
+    }
+  int rc;
+  if (h->wide) {
+    uint64_t *dp, *dv;
+    if ((rc = upload(h, &dp, pcr)) || (rc = upload(h, &dv, vac))) return bail(rc);
+    h->dc.pcr = dp;
+    h->dc.vac = dv;
+  } else {
+    std::vector<uint32_t> p32(pcr.begin(), pcr.end()), v32(vac.begin(), vac.end());
+    uint32_t *dp, *dv;
+    if ((rc = upload(h, &dp, p32)) || (rc = upload(h, &dv, v32))) return bail(rc);
+    h->dc.pcr = dp;
+    h->dc.vac = dv;
+  }
+  h->dc.G = G;
+  h->dc.N = N;
+  h->dc.ind_offset = (unsigned)co->ind_offset;
+  // time chunks, abd.py:865-882
+  h->dc.ch.n = co->n_splits + 1;
+  {
+    int edges[4] = {0, 0, 0, 0};
+    for (int k = 0; k < co->n_splits; ++k) edges[k + 1] = co->splits[k];
+    edges[co->n_splits + 1] = G;
+    for (int k = 0; k < 3; ++k) h->dc.ch.mask[k] = 0;
+    for (int k = 0; k <= co->n_splits; ++k)
+      for (int t = edges[k]; t < edges[k + 1]; ++t) h->dc.ch.mask[k] |= 1ull << t;
+  }
+  if ((rc = build_rows(h, 0, co->n_rows_n, co->x_n, co->od_n, co->gap_n, co->ind_n))) return bail(rc);
+  if ((rc = build_rows(h, 1, co->n_rows_s, co->x_s, co->od_s, co->gap_s, co->ind_s))) return bail(rc);
+
+  const double tn = co->total_inds > 0 ? (double)co->total_inds : (double)N;
+  h->tot.rows_n = co->total_rows_n > 0 ? (double)co->total_rows_n : (double)co->n_rows_n;
+  h->tot.rows_s = co->total_rows_s > 0 ? (double)co->total_rows_s : (double)co->n_rows_s;
+  h->tot.bits_i = tn * G;
+  h->tot.bits_w = tn;
+
+  Priors pr = default_priors(G);
+  if ((rc = dev_alloc(h, &h->d_priors, 1))) return bail(rc);
+  if (cudaMemcpy(h->d_priors, &pr, sizeof(pr), cudaMemcpyHostToDevice) != cudaSuccess)
+    return bail(fail(ABD_ERR_CUDA, "cudaMemcpy(priors) failed"));
+  *out = h;
+  return ABD_OK;
+}
+
+int abd_destroy(abd_handle* h) {
+  if (!h) return ABD_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->owned) cudaFree(p);
+  for (void* p : {(void*)h->d_iraw, (void*)h->d_waner, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
+                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_partial})
+    if (p) cudaFree(p);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return ABD_OK;
+}
+
+int abd_sizes(const abd_handle* h, int32_t* g, int32_t* n, int64_t* rs, int64_t* rn) {
+  if (!h) return fail(ABD_ERR_INVALID, "NULL handle");
+  if (g) *g = h->G;
+  if (n) *n = h->N;
+  if (rs) *rs = h->R[1];
+  if (rn) *rn = h->R[0];
+  return ABD_OK;
+}
+
+// B_const = 2 G N + 20 R + 8 (N + 1); B_chain = G N + N + 13*8 + 14*8
+int64_t abd_algorithmic_bytes_logp(const abd_handle* h, int C) {
+  if (!h) return 0;
+  const int64_t G = h->G, N = h->N, R = h->R[0] + h->R[1];
+  return (int64_t)C * (G * N + N + 216) + 2 * G * N + 20 * R + 8 * (N + 1);
+}
+int64_t abd_algorithmic_bytes_gibbs(const abd_handle* h, int C) {
+  if (!h) return 0;
+  const int64_t G = h->G, N = h->N, R = h->R[0] + h->R[1];
+  return (int64_t)C * (2 * (G * N + N) + 120) + 2 * G * N + 20 * R + 8 * (N + 1);
+}
+int64_t abd_launch_count(const abd_handle* h) { return h ? h->launches : 0; }
+
+int abd_set_tile_rows(abd_handle* h, int rows) {
+  if (!h) return fail(ABD_ERR_INVALID, "NULL handle");
+  if (rows < 0) return fail(ABD_ERR_INVALID, "rows_per_tile must be >= 0");
+  h->tile_rows_override = rows;
+  return ABD_OK;
+}
+
+int abd_upload_state(abd_handle* h, int C, const int8_t* i_raw, const int8_t* waner) {
+  PROLOGUE(h, C);
+  if (!i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL state");
+  int rc = stage_state(h, C, i_raw, waner);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return ABD_OK;
+}
+
+int abd_download_state(abd_handle* h, int C, int8_t* i_raw, int8_t* waner) {
+  PROLOGUE(h, C);
+  const size_t gn = (size_t)h->G * h->N;
+  if (i_raw) CU(cudaMemcpyAsync(i_raw, h->d_iraw, (size_t)C * gn, cudaMemcpyDeviceToHost, h->stream));
+  if (waner) CU(cudaMemcpyAsync(waner, h->d_waner, (size_t)C * h->N, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return ABD_OK;
+}
+
+int abd_state_dev(abd_handle* h, int C, int8_t** i_raw, int8_t** waner) {
+  PROLOGUE(h, C);
+  if (i_raw) *i_raw = h->d_iraw;
+  if (waner) *waner = h->d_waner;
+  return ABD_OK;
+}
+
+int abd_loglik_grad(abd_handle* h, int C, const double* theta13, const int8_t* i_raw, const int8_t* waner,
+                    double* out_loglik, double* out_grad, int64_t* out_counts) {
+  PROLOGUE(h, C);
+  if (!theta13 || !out_loglik) return fail(ABD_ERR_INVALID, "NULL argument");
+  int rc = stage_state(h, C, i_raw, waner);
+  if (rc) return rc;
+  std::memcpy(h->h_pin, theta13, (size_t)C * 13 * sizeof(double));
+  CU(cudaMemcpyAsync(h->d_theta, h->h_pin, (size_t)C * 13 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  FinalizeCfg fin{1, h->tot, h->d_out, h->d_out + C};
+  if ((rc = launch_sums(h, C, h->d_theta, 0, h->d_iraw, h->d_waner, h->d_sums, fin, h->stream))) return rc;
+  double* hp = h->h_pin;
+  CU(cudaMemcpyAsync(hp, h->d_out, (size_t)C * 14 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (out_counts)
+    CU(cudaMemcpyAsync(hp + (size_t)C * 14, h->d_sums, (size_t)C * kNSums * sizeof(double),
+                       cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::memcpy(out_loglik, hp, (size_t)C * sizeof(double));
+  if (out_grad) std::memcpy(out_grad, hp + C, (size_t)C * 13 * sizeof(double));
+  if (out_counts)
+    for (int c = 0; c < C; ++c) {
+      out_counts[2 * c] = (int64_t)hp[(size_t)C * 14 + (size_t)c * kNSums + S_KI];
+      out_counts[2 * c + 1] = (int64_t)hp[(size_t)C * 14 + (size_t)c * kNSums + S_KW];
+    }
+  return ABD_OK;
+}
+
+int abd_logp_dlogp(abd_handle* h, int C, const double* q17, const int8_t* i_raw, const int8_t* waner,
+                   double* out_logp, double* out_dlogp) {
+  PROLOGUE(h, C);
+  if (!q17 || !out_logp) return fail(ABD_ERR_INVALID, "NULL argument");
+  int rc = stage_state(h, C, i_raw, waner);
+  if (rc) return rc;
+  std::memcpy(h->h_pin, q17, (size_t)C * 17 * sizeof(double));
+  CU(cudaMemcpyAsync(h->d_theta, h->h_pin, (size_t)C * 17 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  FinalizeCfg fin{2, h->tot, h->d_out, h->d_out + C};
+  if ((rc = launch_sums(h, C, h->d_theta, 1, h->d_iraw, h->d_waner, h->d_sums, fin, h->stream))) return rc;
+  CU(cudaMemcpyAsync(h->h_pin, h->d_out, (size_t)C * 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  std::memcpy(out_logp, h->h_pin, (size_t)C * sizeof(double));
+  if (out_dlogp) std::memcpy(out_dlogp, h->h_pin + C, (size_t)C * 17 * sizeof(double));
+  return ABD_OK;
+}
+
+static int stage_gibbs_params(abd_handle* h, int C, const double* theta13, const double* p, const double* pw) {
+  double* hp = h->h_pin;
+  std::memcpy(hp, theta13, (size_t)C * 13 * sizeof(double));
+  for (int c = 0; c < C; ++c) {
+    hp[(size_t)C * 13 + c] = p[c];
+    hp[(size_t)C * 14 + c] = pw[c];
+  }
+  CU(cudaMemcpyAsync(h->d_theta, hp, (size_t)C * 13 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_p, hp + (size_t)C * 13, (size_t)C * 2 * sizeof(double), cudaMemcpyHostToDevice,
+                     h->stream));
+  return ABD_OK;
+}
+
+int abd_cond_logodds(abd_handle* h, int C, const double* theta13, const double* p, const double* p_w,
+                     const int8_t* i_raw, const int8_t* waner, double* out_i, double* out_w) {
+  PROLOGUE(h, C);
+  if (!theta13 || !p || !p_w || !out_i || !out_w) return fail(ABD_ERR_INVALID, "NULL argument");
+  int rc = stage_state(h, C, i_raw, waner);
+  if (rc) return rc;
+  if ((rc = stage_gibbs_params(h, C, theta13, p, p_w))) return rc;
+  const size_t gn = (size_t)h->G * h->N;
+  double *d_oi = nullptr, *d_ow = nullptr;
+  if ((rc = dev_alloc(h, &d_oi, (size_t)C * gn, false))) return rc;
+  if ((rc = dev_alloc(h, &d_ow, (size_t)C * h->N, false))) {
+    cudaFree(d_oi);
+    return rc;
+  }
+  GibbsCfg cfg{0, 0, -1, 1.0, d_oi, d_ow, nullptr};
+  rc = launch_gibbs(h, C, h->d_theta, 0, h->d_p, h->d_p + C, h->d_iraw, h->d_waner, cfg, h->stream);
+  cudaError_t e1 = cudaMemcpyAsync(out_i, d_oi, (size_t)C * gn * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e2 = cudaMemcpyAsync(out_w, d_ow, (size_t)C * h->N * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e3 = cudaStreamSynchronize(h->stream);
+  cudaFree(d_oi);
+  cudaFree(d_ow);
+  if (rc) return rc;
+  CU(e1);
+  CU(e2);
+  CU(e3);
+  return ABD_OK;
+}
+
+int abd_gibbs_sweep(abd_handle* h, int C, const double* theta13, const double* p, const double* p_w,
+                    int8_t* i_raw, int8_t* waner, uint64_t seed, uint64_t sweep_idx, int mode,
+                    double transit_p, int64_t* out_stats) {
+  PROLOGUE(h, C);
+  if (!theta13 || !p || !p_w) return fail(ABD_ERR_INVALID, "NULL argument");
+  if (mode != ABD_GIBBS_METROPOLIS && mode != ABD_GIBBS_HEATBATH) return fail(ABD_ERR_INVALID, "bad mode");
+  if (!(transit_p >= 0.0 && transit_p <= 1.0)) return fail(ABD_ERR_INVALID, "transit_p must be in [0, 1]");
+  int rc = stage_state(h, C, i_raw, waner);
+  if (rc) return rc;
+  if ((rc = stage_gibbs_params(h, C, theta13, p, p_w))) return rc;
+  CU(cudaMemsetAsync(h->d_stats, 0, (size_t)C * 2 * sizeof(unsigned long long), h->stream));
+  GibbsCfg cfg{seed, sweep_idx, mode, transit_p, nullptr, nullptr, h->d_stats};
+  if ((rc = launch_gibbs(h, C, h->d_theta, 0, h->d_p, h->d_p + C, h->d_iraw, h->d_waner, cfg, h->stream)))
+    return rc;
+  const size_t gn = (size_t)h->G * h->N;
+  if (i_raw) CU(cudaMemcpyAsync(i_raw, h->d_iraw, (size_t)C * gn, cudaMemcpyDeviceToHost, h->stream));
+  if (waner) CU(cudaMemcpyAsync(waner, h->d_waner, (size_t)C * h->N, cudaMemcpyDeviceToHost, h->stream));
+  if (out_stats)
+    CU(cudaMemcpyAsync(h->h_pin, h->d_stats, (size_t)C * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (out_stats) std::memcpy(out_stats, h->h_pin, (size_t)C * 2 * sizeof(int64_t));
+  return ABD_OK;
+}
+
+int abd_deterministics(abd_handle* h, int C, const double* theta13, const int8_t* i_raw, const int8_t* waner,
+                       int8_t* out_i, double* out_mu_n, double* out_mu_s) {
+  PROLOGUE(h, C);
+  if (!theta13) return fail(ABD_ERR_INVALID, "NULL argument");
+  int rc = stage_state(h, C, i_raw, waner);
+  if (rc) return rc;
+  std::memcpy(h->h_pin, theta13, (size_t)C * 13 * sizeof(double));
+  CU(cudaMemcpyAsync(h->d_theta, h->h_pin, (size_t)C * 13 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const size_t gn = (size_t)h->G * h->N * C;
+  int8_t* d_i = nullptr;
+  double *d_n = nullptr, *d_s = nullptr;
+  auto cleanup = [&]() {
+    if (d_i) cudaFree(d_i);
+    if (d_n) cudaFree(d_n);
+    if (d_s) cudaFree(d_s);
+  };
+  if (out_i && (rc = dev_alloc(h, &d_i, gn, false))) return rc;
+  if (out_mu_n && (rc = dev_alloc(h, &d_n, gn, false))) {
+    cleanup();
+    return rc;
+  }
+  if (out_mu_s && (rc = dev_alloc(h, &d_s, gn, false))) {
+    cleanup();
+    return rc;
+  }
+  rc = abd_deterministics_dev(h, C, h->d_theta, h->d_iraw, h->d_waner, d_i, d_n, d_s, h->stream);
+  cudaError_t e = cudaSuccess;
+  if (!rc && out_i) e = cudaMemcpyAsync(out_i, d_i, gn, cudaMemcpyDeviceToHost, h->stream);
+  if (!rc && e == cudaSuccess && out_mu_n)
+    e = cudaMemcpyAsync(out_mu_n, d_n, gn * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (!rc && e == cudaSuccess && out_mu_s)
+    e = cudaMemcpyAsync(out_mu_s, d_s, gn * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e2 = cudaStreamSynchronize(h->stream);
+  cleanup();
+  if (rc) return rc;
+  CU(e);
+  CU(e2);
+  return ABD_OK;
+}
+
+// ---- device-pointer variants ----------------------------------------------------------------
+int abd_sums_dev(abd_handle* h, int C, const double* theta, int theta_is_q17, const int8_t* i_raw,
+                 const int8_t* waner, double* sums, void* stream) {
+  PROLOGUE(h, C);
+  if (!theta || !i_raw || !waner || !sums) return fail(ABD_ERR_INVALID, "NULL argument");
+  FinalizeCfg fin{0, h->tot, nullptr, nullptr};
+  return launch_sums(h, C, theta, theta_is_q17, i_raw, waner, sums, fin, (cudaStream_t)stream);
+}
+
+int abd_finalize_loglik_dev(abd_handle* h, int C, const double* theta13, const double* sums, double* out_loglik,
+                            double* out_grad, void* stream) {
+  PROLOGUE(h, C);
+  if (!theta13 || !sums || !out_loglik) return fail(ABD_ERR_INVALID, "NULL argument");
+  FinalizeCfg fin{1, h->tot, out_loglik, out_grad};
+  k_finalize<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(C, theta13, sums, fin, h->d_priors);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
+int abd_finalize_logp_dev(abd_handle* h, int C, const double* q17, const double* sums, double* out_logp,
+                          double* out_dlogp, void* stream) {
+  PROLOGUE(h, C);
+  if (!q17 || !sums || !out_logp) return fail(ABD_ERR_INVALID, "NULL argument");
+  FinalizeCfg fin{2, h->tot, out_logp, out_dlogp};
+  k_finalize<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(C, q17, sums, fin, h->d_priors);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
+int abd_loglik_grad_dev(abd_handle* h, int C, const double* theta13, const int8_t* i_raw, const int8_t* waner,
+                        double* out_loglik, double* out_grad, void* stream) {
+  PROLOGUE(h, C);
+  if (!theta13 || !i_raw || !waner || !out_loglik) return fail(ABD_ERR_INVALID, "NULL argument");
+  FinalizeCfg fin{1, h->tot, out_loglik, out_grad};
+  return launch_sums(h, C, theta13, 0, i_raw, waner, h->d_sums, fin, (cudaStream_t)stream);
+}
+
+int abd_logp_dlogp_dev(abd_handle* h, int C, const double* q17, const int8_t* i_raw, const int8_t* waner,
+                       double* out_logp, double* out_dlogp, void* stream) {
+  PROLOGUE(h, C);
+  if (!q17 || !i_raw || !waner || !out_logp) return fail(ABD_ERR_INVALID, "NULL argument");
+  FinalizeCfg fin{2, h->tot, out_logp, out_dlogp};
+  return launch_sums(h, C, q17, 1, i_raw, waner, h->d_sums, fin, (cudaStream_t)stream);
+}
+
+int abd_gibbs_sweep_dev(abd_handle* h, int C, const double* theta, int theta_is_q17, const double* p,
+                        const double* p_w, int8_t* i_raw, int8_t* waner, uint64_t seed, uint64_t sweep_idx,
+                        int mode, double transit_p, unsigned long long* stats, void* stream) {
+  PROLOGUE(h, C);
+  if (!theta || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
+  if (!theta_is_q17 && (!p || !p_w)) return fail(ABD_ERR_INVALID, "p / p_w required with theta13");
+  if (mode != ABD_GIBBS_METROPOLIS && mode != ABD_GIBBS_HEATBATH) return fail(ABD_ERR_INVALID, "bad mode");
+  GibbsCfg cfg{seed, sweep_idx, mode, transit_p, nullptr, nullptr, stats};
+  return launch_gibbs(h, C, theta, theta_is_q17, p, p_w, i_raw, waner, cfg, (cudaStream_t)stream);
+}
+
+int abd_deterministics_dev(abd_handle* h, int C, const double* theta13, const int8_t* i_raw, const int8_t* waner,
+                           int8_t* out_i, double* out_mu_n, double* out_mu_s, void* stream) {
+  PROLOGUE(h, C);
+  if (!theta13 || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
+  dim3 grid((h->N + 127) / 128, C);
+  if (h->wide)
+    k_determ<uint64_t><<<grid, 128, 0, (cudaStream_t)stream>>>(h->dc, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s);
+  else
+    k_determ<uint32_t><<<grid, 128, 0, (cudaStream_t)stream>>>(h->dc, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+// Device-side building blocks shared by the kernels in abd_b200.cu.
+//
+// Everything here restates, per individual and in closed form, what the reference graph
+// computes with dense (G,G,N) tensors:
+//   constrain()        abd.py:640-667 (+ :560-601, :732-771, :774-862)    integer prologue
+//   traj_*()           abd.py:242-274, :296-306, :329-341, :367-391       titer trajectories
+//   row_eval()         abd.py:445-469, :556-557                           OD-row likelihood
+//   finalize_*()       PyMC priors / transforms / Bernoulli terms invoked at abd.py:329-340,
+//                      :367-388, :424-427, :464-467
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace abd {
+
+constexpr int kMaxGaps = 64;   // mask width; usable gaps <= 63 (one lane slot is the waner bit)
+constexpr int kNSums = 16;
+constexpr double kHalfLog2Pi = 0.918938533204672741780329736406;  // log(sqrt(2 pi))
+
+// ---- indexes into theta13 -------------------------------------------------------------
+enum Theta {
+  N_PERM = 0, N_TEMP, N_RHO, N_INIT, S_PERM, S_RHO, S_INIT,
+  N_B, N_D, N_SIGMA, S_B, S_D, S_SIGMA
+};
+// ---- indexes into the per-chain raw sums ------------------------------------------------
+enum Sums {
+  SN_0 = 0, SN_1, SN_2, SN_QINIT, SN_QPERM, SN_QTEMP, SN_QRHO,
+  SS_0, SS_1, SS_2, SS_QINIT, SS_QPERM, SS_QRHO,
+  S_KI, S_KW, S_PAD
+};
+
+// position of each theta13 entry inside q17
+__constant__ const int kQOfTheta[13] = {1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14, 15, 16};
+// transform of each q17 entry: 0 none, 1 log, 2 logodds
+__constant__ const int kQTransform[17] = {2, 1, 1, 2, 0, 1, 2, 2, 1, 1, 0, 0, 0, 1, 0, 0, 1};
+constexpr int kQ_P = 0, kQ_PW = 7;
+
+struct Chunks {
+  int n;               // number of time chunks (1 => OneTimeChunk rule)
+  uint64_t mask[3];    // bit t set <=> gap t belongs to the chunk
+};
+
+struct Totals {        // sizes over ALL shards (Bernoulli terms and likelihood constants)
+  double rows_n, rows_s, bits_i, bits_w;
+};
+
+// prior of one continuous RV, in the form the finaliser needs
+struct PriorSpec {
+  int kind;      // 0 Normal(mu,sigma)  1 Gamma(alpha,beta)  2 Beta(a,b)  3 Exponential(lam)
+  double a, b;   // (mu, sigma) | (alpha, beta) | (a, b) | (lam, -)
+  double c;      // additive normalising constant
+};
+struct Priors {
+  PriorSpec v[17];
+};
+
+// ---- bit helpers -------------------------------------------------------------------------
+__device__ __forceinline__ int ctz(uint32_t v) { return __ffs((int)v) - 1; }
+__device__ __forceinline__ int ctz(uint64_t v) { return __ffsll((long long)v) - 1; }
+__device__ __forceinline__ int popc(uint32_t v) { return __popc(v); }
+__device__ __forceinline__ int popc(uint64_t v) { return __popcll(v); }
+template <typename M>
+__device__ __forceinline__ M low_mask(int t) {  // bits 0..t inclusive
+  return (M)(~(M)0) >> (sizeof(M) * 8 - 1 - t);
+}
+
+// i_raw column (as a bit mask over gaps) -> constrained infection mask.
+//   one chunk : i = mask3(i_raw | pcrpos)                                   abd.py:640-649
+//   k chunks  : per chunk, PCR+ bits replace the column if any, else keep only the first
+//               raw infection of the chunk (abd.py:658-667, :691-697, :722-729, :792-818);
+//   then no infection within 3 gaps after an accepted one, scanning from t = 0 on the OUTPUT
+//   (abd.py:560-601).
+template <typename M>
+__device__ __forceinline__ M constrain(M raw, M pcr, const Chunks& ch) {
+  M m;
+  if (ch.n == 1) {
+    m = raw | pcr;
+  } else {
+    m = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < ch.n) {
+        const M cm = (M)ch.mask[k];
+        const M p = pcr & cm, r = raw & cm;
+        m |= p ? p : (r & (~r + 1));
+      }
+    }
+  }
+  M out = 0;
+  while (m) {
+    const M b = m & (~m + 1);
+    out |= b;
+    m &= ~(b | (b << 1) | (b << 2) | (b << 3));
+  }
+  return out;
+}
+
+__device__ __forceinline__ double ipow(double r, int k) {
+  double acc = 1.0, b = r;
+  while (k) {
+    if (k & 1) acc *= b;
+    b *= b;
+    k >>= 1;
+  }
+  return acc;
+}
+
+// N antigen at gap t: P = 1[any infection <= t], T = sum_{s in inf, s<=t} rho^(t-s),
+// dT = dT/drho.  pw[k] = rho^k, dpw[k] = k rho^(k-1).
+template <typename M>
+__device__ __forceinline__ void traj_n(M inf, int t, const double* pw, const double* dpw,
+                                       double& P, double& T, double& dT) {
+  M e = inf & low_mask<M>(t);
+  P = e ? 1.0 : 0.0;
+  T = 0.0;
+  dT = 0.0;
+  while (e) {
+    const int k = t - ctz(e);
+    e &= e - 1;
+    T += pw[k];
+    dT += dpw[k];
+  }
+}
+
+// S antigen: exposure = i + v (a month with both counts twice, abd.py:378-386).
+// w == 0 => rho_ind = 1 (abd.py:374): U = number of exposures so far, dU/drho_s = 0.
+template <typename M>
+__device__ __forceinline__ void traj_s(M inf, M vac, int w, int t, const double* pw,
+                                       const double* dpw, double& P, double& U, double& dU) {
+  const M lm = low_mask<M>(t);
+  M e = inf & lm, v = vac & lm;
+  P = (e | v) ? 1.0 : 0.0;
+  U = 0.0;
+  dU = 0.0;
+  if (w) {
+    while (e) {
+      const int k = t - ctz(e);
+      e &= e - 1;
+      U += pw[k];
+      dU += dpw[k];
+    }
+    while (v) {
+      const int k = t - ctz(v);
+      v &= v - 1;
+      U += pw[k];
+      dU += dpw[k];
+    }
+  } else {
+    U = (double)(popc(e) + popc(v));
+  }
+}
+
+// value-only versions for the Gibbs kernel
+template <typename M>
+__device__ __forceinline__ double mu_n_at(M inf, int t, const double* pw, double init, double perm,
+                                          double temp) {
+  M e = inf & low_mask<M>(t);
+  double T = 0.0;
+  const double P = e ? perm : 0.0;
+  while (e) {
+    T += pw[t - ctz(e)];
+    e &= e - 1;
+  }
+  return init + P + temp * T;
+}
+template <typename M>
+__device__ __forceinline__ double mu_s_at(M inf, M vac, int w, int t, const double* pw, double init,
+                                          double perm) {
+  const M lm = low_mask<M>(t);
+  M e = inf & lm, v = vac & lm;
+  const double P = (e | v) ? perm : 0.0;
+  double U = 0.0;
+  if (w) {
+    while (e) {
+      U += pw[t - ctz(e)];
+      e &= e - 1;
+    }
+    while (v) {
+      U += pw[t - ctz(v)];
+      v &= v - 1;
+    }
+  } else {
+    U = (double)(popc(e) + popc(v));
+  }
+  return init + P + U;
+}
+
+// One OD row: s = 1/(1+E), E = exp(-b (x - m));  r = od - d s;  q = r s (1 - s).
+// 1 - s is formed as E s (no cancellation); E is capped so that E s stays finite.
+__device__ __forceinline__ void row_eval(double x, double od, double m, double b, double d,
+                                         double& s, double& r, double& q, double& xm) {
+  xm = x - m;
+  double z = -b * xm;
+  z = (z > 700.0) ? 700.0 : z;  // NaN stays NaN
+  const double E = exp(z);
+  s = 1.0 / (1.0 + E);
+  r = fma(-d, s, od);
+  q = r * s * (E * s);
+}
+__device__ __forceinline__ double row_resid2(double x, double od, double m, double b, double d) {
+  double z = -b * (x - m);
+  z = (z > 700.0) ? 700.0 : z;
+  const double s = 1.0 / (1.0 + exp(z));
+  const double r = fma(-d, s, od);
+  return r * r;
+}
+
+__device__ __forceinline__ double softplus(double y) {  // log(1 + e^y)
+  return log1p(exp(-fabs(y))) + fmax(y, 0.0);
+}
+
+// q17 entry -> constrained value
+__device__ __forceinline__ double backward(double y, int transform) {
+  if (transform == 1) return exp(y);
+  if (transform == 2) return 1.0 / (1.0 + exp(-y));
+  return y;
+}
+
+// Data log-likelihood and gradient w.r.t. theta13 from the raw sums.
+__device__ inline void finalize_loglik(const double* th, const double* S, const Totals& tot,
+                                       double* loglik, double* g) {
+  const double sn = th[N_SIGMA], ss = th[S_SIGMA];
+  const double ivn = 1.0 / (sn * sn), ivs = 1.0 / (ss * ss);
+  *loglik = -0.5 * S[SN_0] * ivn - tot.rows_n * (kHalfLog2Pi + log(sn)) +
+            -0.5 * S[SS_0] * ivs - tot.rows_s * (kHalfLog2Pi + log(ss));
+  if (!g) return;
+  g[N_D] = S[SN_1] * ivn;
+  g[N_B] = th[N_D] * S[SN_2] * ivn;
+  g[N_SIGMA] = S[SN_0] * ivn / sn - tot.rows_n / sn;
+  const double cn = -th[N_D] * th[N_B] * ivn;
+  g[N_INIT] = cn * S[SN_QINIT];
+  g[N_PERM] = cn * S[SN_QPERM];
+  g[N_TEMP] = cn * S[SN_QTEMP];
+  g[N_RHO] = cn * th[N_TEMP] * S[SN_QRHO];
+  g[S_D] = S[SS_1] * ivs;
+  g[S_B] = th[S_D] * S[SS_2] * ivs;
+  g[S_SIGMA] = S[SS_0] * ivs / ss - tot.rows_s / ss;
+  const double cs = -th[S_D] * th[S_B] * ivs;
+  g[S_INIT] = cs * S[SS_QINIT];
+  g[S_PERM] = cs * S[SS_QPERM];
+  g[S_RHO] = cs * S[SS_QRHO];
+}
+
+// Joint logp over (q17, i_raw, waner) in PyMC's unconstrained space and d logp / d q17.
+__device__ inline void finalize_logp(const double* q, const double* S, const Totals& tot,
+                                     const Priors& pr, double* logp, double* dlogp) {
+  double th[13], g13[13], ll;
+  for (int k = 0; k < 13; ++k) th[k] = backward(q[kQOfTheta[k]], kQTransform[kQOfTheta[k]]);
+  finalize_loglik(th, S, tot, &ll, g13);
+  double gl[17];  // d loglik / d (constrained value) scattered to the 17 slots
+  for (int k = 0; k < 17; ++k) gl[k] = 0.0;
+  for (int k = 0; k < 13; ++k) gl[kQOfTheta[k]] = g13[k];
+
+  double total = ll;
+  for (int k = 0; k < 17; ++k) {
+    const double y = q[k];
+    const PriorSpec ps = pr.v[k];
+    const int tr = kQTransform[k];
+    double lp = 0.0, d = 0.0;
+    if (tr == 0) {  // Normal, no transform
+      const double z = (y - ps.a) / ps.b;
+      lp = -0.5 * z * z + ps.c;
+      d = -z / ps.b + gl[k];
+    } else if (tr == 1) {  // log transform: x = e^y, log|J| = y
+      const double x = exp(y);
+      if (ps.kind == 1) {  // Gamma(alpha, beta)
+        lp = ps.c - ps.b * x + (ps.a - 1.0) * y;
+        d = -ps.b * x + (ps.a - 1.0);
+      } else {  // Exponential(lam)
+        lp = ps.c - ps.a * x;
+        d = -ps.a * x;
+      }
+      lp += y;
+      d += 1.0 + gl[k] * x;
+    } else {  // logodds transform: x = sigmoid(y), log|J| = log x + log(1 - x)
+      const double lx = -softplus(-y), l1mx = -softplus(y);
+      const double x = exp(lx), omx = exp(l1mx);
+      double ca = ps.a - 1.0, cb = ps.b - 1.0;  // Beta(a, b)
+      if (k == kQ_P) {  // + Bernoulli(i_raw | p)      abd.py:427
+        ca += S[S_KI];
+        cb += tot.bits_i - S[S_KI];
+      } else if (k == kQ_PW) {  // + Bernoulli(ab_s_waner | p_waner)   abd.py:373
+        ca += S[S_KW];
+        cb += tot.bits_w - S[S_KW];
+      }
+      // (ca + 1) lx + (cb + 1) l1mx: prior, Bernoulli counts and the Jacobian share one form
+      lp = ps.c + (ca == 0.0 ? 0.0 : ca * lx) + (cb == 0.0 ? 0.0 : cb * l1mx) + lx + l1mx;
+      d = (ca + 1.0) * omx - (cb + 1.0) * x + gl[k] * x * omx;
+    }
+    total += lp;
+    if (dlogp) dlogp[k] = d;
+  }
+  *logp = total;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: one call yields 4 x 32 random bits.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// (0, 1] uniform from 32 bits
+__device__ __forceinline__ double u01(uint32_t r) { return ((double)r + 1.0) * 2.3283064365386963e-10; }
+
+}  // namespace abd

@@ -1,0 +1,197 @@
+/* abd_b200.h -- C ABI of libabd_b200.so: the B200 (sm_100a) implementation of the abdpymc
+ * inference hot path (joint log-density + gradient of the antibody-dynamics model and the
+ * Gibbs sweep over its binary infection / waner indicators).
+ *
+ * The reference (davipatti/abdpymc, pure Python) has no FFI: its hot path is the PyTensor graph
+ * built by abd.model() (abd.py:396-442) and evaluated by PyMC's two step methods inside
+ * pm.sample() (abd.py:922).  Each entry point below replaces one evaluation of that graph; the
+ * "replaces" note names the reference code whose result it reproduces.  INTEGRATION.md shows
+ * the ctypes / PyTensor-Op / PyMC-step binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - Every function returns ABD_OK (0) or a negative ABD_ERR_* code; abd_last_error() returns a
+ *    thread-local message for the last failure.  No exception crosses the boundary.
+ *  - Matrices over (gap, individual) are row-major (G, N): element (t, n) at [t*N + n], the
+ *    layout of the reference graph (abd.py:413-418, dims ("gap","ind") abd.py:18).  A batch of
+ *    C chains is the outermost axis: i_raw[c][t][n], waner[c][n], theta[c][k].
+ *  - Binary variables are int8 0/1 (any non-zero byte counts as 1).
+ *  - theta13 (constrained, the 13 scalars that reach the likelihood), in this order:
+ *      ab_n_perm, ab_n_temp, ab_n_rho, ab_n_init, ab_s_perm, ab_s_rho, ab_s_init,
+ *      it_n_b, it_n_d, it_n_sigma, it_s_b, it_s_d, it_s_sigma
+ *  - q17 (PyMC's unconstrained value variables, declaration order abd.py:424,329-340,367-388,
+ *    464-467):  p_logodds__, ab_n_perm_log__, ab_n_temp_log__, ab_n_rho_logodds__, ab_n_init,
+ *      ab_s_perm_log__, ab_s_rho_logodds__, ab_s_p_waner_logodds__, ab_s_tempinf_log__,
+ *      ab_s_tempvac_log__, ab_s_init, it_n_b, it_n_d, it_n_sigma_log__, it_s_b, it_s_d,
+ *      it_s_sigma_log__
+ *  - Host-pointer functions copy inputs to the device, run, copy results back and return when
+ *    the results are in the caller's buffers.  The `_dev` variants take device pointers and a
+ *    cudaStream_t (as void*), enqueue work and return immediately.
+ *  - i_raw / waner may be NULL in the host-pointer compute calls: the chain state already
+ *    resident on the device (abd_upload_state, or left by the last abd_gibbs_sweep) is used.
+ *  - Ownership: the caller owns every buffer it passes; the library owns all device memory it
+ *    allocates (uploaded once in abd_create).  A handle is not re-entrant: serialise calls on
+ *    it.  The CUDA context is created lazily in the calling process (fork-safe as long as the
+ *    parent has not called into the library).
+ *  - There is NO CPU fallback: without a CUDA device every call fails with ABD_ERR_CUDA.
+ */
+#ifndef ABD_B200_H
+#define ABD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABD_OK 0
+#define ABD_ERR_INVALID (-1) /* bad argument (shape, split, NULL pointer ...) */
+#define ABD_ERR_CUDA (-2)    /* CUDA runtime error / no device */
+#define ABD_ERR_ALLOC (-3)
+
+#define ABD_N_THETA 13
+#define ABD_N_Q 17
+#define ABD_N_SUMS 16
+#define ABD_MAX_GAPS 63
+
+/* abd_gibbs_sweep modes */
+#define ABD_GIBBS_METROPOLIS 0 /* PyMC BinaryGibbsMetropolis semantics: propose the flip w.p.
+                                  transit_p, accept w.p. min(1, exp(delta)); random order   */
+#define ABD_GIBBS_HEATBATH 1   /* draw every bit from its exact full conditional            */
+
+typedef struct abd_handle abd_handle;
+
+/* The cohort, as TiterData holds it (abd.py:46-126), flattened.  Per antigen a in {s, n}:
+ * x = df_a["log_dilution"], od = df_a["od"] (abd.py:462,468), gap = idx_gap, ind = idx_ind
+ * (abd.py:35-36).  Rows may be in any order.  pcrpos / vacs are (G, N) 0/1 bytes, i.e.
+ * data.pcrpos.T / data.vacs.T (abd.py:413-418); pcrpos == NULL means ignore_pcrpos=True.
+ * splits: 0, 1 or 2 ascending gap indexes (abd.py:604-622, 865-882).                       */
+typedef struct abd_cohort {
+  int32_t n_gaps, n_inds;
+  int32_t n_splits;
+  int32_t splits[2];
+  const uint8_t* pcrpos;
+  const uint8_t* vacs;
+  int64_t n_rows_s;
+  const double* x_s;
+  const double* od_s;
+  const int32_t* gap_s;
+  const int32_t* ind_s;
+  int64_t n_rows_n;
+  const double* x_n;
+  const double* od_n;
+  const int32_t* gap_n;
+  const int32_t* ind_n;
+  /* Totals over ALL shards when individuals are sharded across GPUs (0 = this shard is the
+   * whole cohort).  Only the joint-logp finalisation uses them.                              */
+  int64_t total_inds, total_rows_s, total_rows_n;
+  /* Global index of this shard's first individual (0 if not sharded): keeps the Gibbs RNG
+   * stream of an individual independent of how the cohort is sharded.                       */
+  int64_t ind_offset;
+} abd_cohort;
+
+const char* abd_last_error(void);
+int abd_version(void);
+
+/* Builds the device-resident cohort on CUDA device `device`.  Replaces the data side of
+ * abd.model(): as_tensor(data.vacs.T), pcrpos (abd.py:413-418), make_time_chunks
+ * (abd.py:865-882), the gather indices (abd.py:343,393) and check_splits (abd.py:604-622).  */
+int abd_create(abd_handle** out, const abd_cohort* cohort, int device);
+int abd_destroy(abd_handle* h);
+
+/* Sizes and algorithmic-byte accounting.  Any pointer may be NULL.   */
+int abd_sizes(const abd_handle* h, int32_t* n_gaps, int32_t* n_inds, int64_t* n_rows_s,
+              int64_t* n_rows_n);
+int64_t abd_algorithmic_bytes_logp(const abd_handle* h, int n_chains);
+int64_t abd_algorithmic_bytes_gibbs(const abd_handle* h, int n_chains);
+/* Kernels launched by this handle so far (for bench.py's gpu_launches).                      */
+int64_t abd_launch_count(const abd_handle* h);
+
+/* Chain state resident on the device: i_raw[C][G][N], waner[C][N].                          */
+int abd_upload_state(abd_handle* h, int n_chains, const int8_t* i_raw, const int8_t* waner);
+int abd_download_state(abd_handle* h, int n_chains, int8_t* i_raw, int8_t* waner);
+
+/* Data log-likelihood and its gradient w.r.t. the 13 constrained parameters, for C chains.
+ * Replaces: the value and gradient of it_n_lik + it_s_lik (abd.py:445-469) as a function of
+ * the RVs of model_n_response / model_s_response (abd.py:309-393) given i_raw, ab_s_waner --
+ * i.e. constrain_infections (abd.py:640-667), perm_response (:296-306),
+ * _temp_response_scalar_rho / _vector_rho (:242-274), the gather mu[idx_gap, idx_ind]
+ * (:343,393) and logistic (:556-557).
+ * out_counts[c] = { sum(i_raw[c]), sum(waner[c]) } (for the Bernoulli terms abd.py:373,427);
+ * out_grad / out_counts may be NULL.                                                        */
+int abd_loglik_grad(abd_handle* h, int n_chains, const double* theta13, const int8_t* i_raw,
+                    const int8_t* waner, double* out_loglik, double* out_grad,
+                    int64_t* out_counts);
+
+/* Joint model log-density in PyMC's unconstrained space and d logp / d q17: what
+ * model.logp_dlogp_function() hands NUTS on every leapfrog (abd.py:921-922).  Adds to
+ * abd_loglik_grad the 17 priors (abd.py:329-340,367-388,424,464-467), the log / logodds
+ * transforms with their Jacobians, and the Bernoulli terms of i_raw and ab_s_waner.          */
+int abd_logp_dlogp(abd_handle* h, int n_chains, const double* q17, const int8_t* i_raw,
+                   const int8_t* waner, double* out_logp, double* out_dlogp);
+
+/* Conditional log-odds of every binary variable given all others (test hook; what "Gibbs
+ * parity" means):  out_i[c][t][n] = logp(i_raw[t,n]=1 | rest) -
+ * logp(i_raw[t,n]=0 | rest), out_w[c][n] likewise for ab_s_waner[n].  p, p_w: per-chain
+ * constrained Bernoulli probabilities ("p", "ab_s_p_waner").                                */
+int abd_cond_logodds(abd_handle* h, int n_chains, const double* theta13, const double* p,
+                     const double* p_w, const int8_t* i_raw, const int8_t* waner,
+                     double* out_i, double* out_w);
+
+/* One sweep over all G*N + N binary variables of each chain.  Replaces one
+ * BinaryGibbsMetropolis.astep (PyMC; assigned to i_raw and ab_s_waner by pm.sample,
+ * abd.py:922).  Individuals are updated in parallel (they are conditionally independent given
+ * theta, p, p_w); within an individual its G+1 bits are visited in a uniformly random order
+ * drawn from a counter-based Philox4x32-10 stream keyed by (seed; sweep_idx, chain, individual).
+ * i_raw / waner: in/out host buffers, or NULL to update the resident state only.
+ * out_stats[c] = { proposals, accepted flips } (may be NULL).                                */
+int abd_gibbs_sweep(abd_handle* h, int n_chains, const double* theta13, const double* p,
+                    const double* p_w, int8_t* i_raw, int8_t* waner, uint64_t seed,
+                    uint64_t sweep_idx, int mode, double transit_p, int64_t* out_stats);
+
+/* The three Deterministics PyMC records per draw: "i" (abd.py:649,667), "ab_n_mu" (:341),
+ * "ab_s_mu" (:389-391), each (C, G, N).  Any output may be NULL.                            */
+int abd_deterministics(abd_handle* h, int n_chains, const double* theta13, const int8_t* i_raw,
+                       const int8_t* waner, int8_t* out_i, double* out_mu_n, double* out_mu_s);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-pointer variants: every pointer is a device pointer, `stream` is a cudaStream_t.
+ * Work is enqueued on `stream`; nothing is synchronised.
+ * ------------------------------------------------------------------------------------- */
+
+/* Raw per-chain sums of this shard's individuals: sums[c][ABD_N_SUMS] =
+ *   { S0,S1,S2,Qinit,Qperm,Qtemp,Qrho (N antigen), S0,S1,S2,Qinit,Qperm,Qrho (S antigen),
+ *     sum(i_raw), sum(waner), 0 }  -- every entry is additive over shards, so individual-
+ * sharded ranks all-reduce this (C x 16 doubles) and then call abd_finalize_*_dev.
+ * theta_is_q17 != 0: `theta` holds q17 (C x 17) and is back-transformed on the device.       */
+int abd_sums_dev(abd_handle* h, int n_chains, const double* theta, int theta_is_q17,
+                 const int8_t* i_raw, const int8_t* waner, double* sums, void* stream);
+int abd_finalize_loglik_dev(abd_handle* h, int n_chains, const double* theta13,
+                            const double* sums, double* out_loglik, double* out_grad,
+                            void* stream);
+int abd_finalize_logp_dev(abd_handle* h, int n_chains, const double* q17, const double* sums,
+                          double* out_logp, double* out_dlogp, void* stream);
+/* Single-launch fused versions (sums + ordered cross-tile reduction + finalisation).        */
+int abd_loglik_grad_dev(abd_handle* h, int n_chains, const double* theta13,
+                        const int8_t* i_raw, const int8_t* waner, double* out_loglik,
+                        double* out_grad, void* stream);
+int abd_logp_dlogp_dev(abd_handle* h, int n_chains, const double* q17, const int8_t* i_raw,
+                       const int8_t* waner, double* out_logp, double* out_dlogp, void* stream);
+/* stats: device int64 [C][2] accumulated with atomics (caller zeroes), or NULL.  theta_is_q17:
+ * `theta` holds q17 and p / p_w are taken from it (p, p_w arguments ignored).                */
+int abd_gibbs_sweep_dev(abd_handle* h, int n_chains, const double* theta, int theta_is_q17,
+                        const double* p, const double* p_w, int8_t* i_raw, int8_t* waner,
+                        uint64_t seed, uint64_t sweep_idx, int mode, double transit_p,
+                        unsigned long long* stats, void* stream);
+int abd_deterministics_dev(abd_handle* h, int n_chains, const double* theta13,
+                           const int8_t* i_raw, const int8_t* waner, int8_t* out_i,
+                           double* out_mu_n, double* out_mu_s, void* stream);
+/* Pointers to the resident chain state (valid until the next call that changes n_chains).   */
+int abd_state_dev(abd_handle* h, int n_chains, int8_t** i_raw, int8_t** waner);
+
+/* Tuning knob: rows per CTA tile of the log-likelihood kernel (0 = automatic).              */
+int abd_set_tile_rows(abd_handle* h, int rows_per_tile);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABD_B200_H */

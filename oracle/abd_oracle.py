@@ -477,3 +477,75 @@ def binary_gibbs_metropolis_sweep(oracle, theta13, p, p_w, i_raw, w, rng, transi
         else:
             w[n] = old
     return i_raw, w
+
+
+# ---------------------------------------------------------------------------------------
+# The device sweep, restated: same visiting order, same random numbers, same decisions as
+# abd_gibbs_sweep (include/abd_b200.h), so a CUDA sweep can be checked bit-for-bit.
+# ---------------------------------------------------------------------------------------
+_M32 = 0xFFFFFFFF
+
+
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011).  ctr: 4 x u32, key: 2 x u32."""
+    c = [int(v) & _M32 for v in ctr]
+    k = [int(v) & _M32 for v in key]
+    for _ in range(10):
+        p0 = 0xD2511F53 * c[0]
+        p1 = 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & _M32, p1 & _M32, ((p0 >> 32) ^ c[3] ^ k[1]) & _M32, p0 & _M32]
+        k = [(k[0] + 0x9E3779B9) & _M32, (k[1] + 0xBB67AE85) & _M32]
+    return c
+
+
+def _u01(r):
+    return (float(r) + 1.0) * 2.0**-32
+
+
+def device_gibbs_sweep(cohort, splits, ignore_pcrpos, theta13, p, p_w, i_raw, w, seed, sweep, chain,
+                       mode=0, transit_p=0.8, ind_offset=0):
+    """One sweep of one chain exactly as the CUDA kernel schedules it: for every individual n,
+    proposals j = 0..G (j < G flips i_raw[j, n], j == G flips waner[n]) are visited in the
+    order of their Philox keys; mode 0 = Metropolised flip with probability transit_p
+    (BinaryGibbsMetropolis semantics), mode 1 = heat bath.  Returns (i_raw, w, [proposals,
+    flips])."""
+    G, N = cohort.n_gaps, cohort.n_inds
+    i_raw = np.array(i_raw).reshape(G, N).astype(np.int8).copy()
+    w = np.array(w).astype(np.int8).copy()
+    lo_i, lo_w = np.log(p) - np.log1p(-p), np.log(p_w) - np.log1p(-p_w)
+    key = (seed & _M32, ((seed >> 32) ^ (sweep >> 32)) & _M32)
+    n_prop = n_flip = 0
+    for n in range(N):
+        sub = Oracle(cohort.take(np.array([n])), splits=splits, ignore_pcrpos=ignore_pcrpos, dense=False)
+
+        def ll(col, wn):
+            return sub.loglik(theta13, col.reshape(G, 1), np.array([wn]))
+
+        rnd = [philox4x32_10((j, n + ind_offset, chain, sweep & _M32), key) for j in range(G + 1)]
+        order = sorted(range(G + 1), key=lambda j: (rnd[j][0], j))
+        col, wn = i_raw[:, n].copy(), int(w[n])
+        cur = ll(col, wn)
+        for j in order:
+            u_t, u_a = _u01(rnd[j][1]), _u01(rnd[j][2])
+            if mode == 0 and not (u_t <= transit_p):
+                continue
+            col2, wn2 = col.copy(), wn
+            if j == G:
+                wn2 = 1 - wn
+                cur_bit, lo = wn, lo_w
+            else:
+                col2[j] = 1 - col[j]
+                cur_bit, lo = int(col[j]), lo_i
+            new = ll(col2, wn2)
+            d10 = (cur - new + lo) if cur_bit else (new - cur + lo)
+            if mode == 0:
+                delta = -d10 if cur_bit else d10
+                flip = bool(np.isfinite(delta) and np.log(u_a) < delta)
+            else:
+                flip = (u_a <= 1.0 / (1.0 + np.exp(-d10))) != bool(cur_bit)
+            n_prop += 1
+            if flip:
+                n_flip += 1
+                col, wn, cur = col2, wn2, new
+        i_raw[:, n], w[n] = col, wn
+    return i_raw, w, [n_prop, n_flip]

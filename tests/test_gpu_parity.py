@@ -1,0 +1,448 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): the CUDA path, called through the
+C ABI (abdpymc_b200.engine -> ctypes -> libabd_b200.so), against
+  * the committed goldens produced by executing the reference's own code
+    (tests/golden/model_goldens.npz), and
+  * the CPU oracle (oracle/abd_oracle.py) on the same seeded inputs.
+
+Tolerances (north star: <= 1e-10 relative in fp64):
+  logp / loglik      |gpu - ref| <= 1e-10 * |ref|
+  gradient entries   |gpu - ref| <= 1e-10 * max(|ref_k|, 1e-3 * max_j |ref_j|)
+                     (an entry that is ~0 by cancellation is judged against the gradient's scale)
+  conditional log-odds   |gpu - ref| <= 1e-9 * max(1, |ref|)  (both sides difference two sums)
+  integers (i, counts, Gibbs states)  bit-exact
+"""
+import numpy as np
+import pytest
+
+from oracle import abd_oracle as ora
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def grad_ok(g, ref, rtol=RTOL):
+    scale = np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max(axis=-1, keepdims=True))
+    return np.all(np.abs(g - ref) <= rtol * scale + 1e-300)
+
+
+@pytest.fixture(scope="module")
+def Engine():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from abdpymc_b200 import build
+
+    build.build()
+    from abdpymc_b200.engine import AbdEngine
+
+    return AbdEngine
+
+
+def case_engine(Engine, cohorts, c):
+    return Engine(cohorts[c["cohort"]], splits=c["splits"], ignore_pcrpos=c["ignore_pcrpos"])
+
+
+def group_cases(cases):
+    groups = {}
+    for c in cases:
+        groups.setdefault((c["cohort"], tuple(c["splits"]), c["ignore_pcrpos"]), []).append(c)
+    return groups
+
+
+# ------------------------------------------------------------------------------ vs reference goldens
+def test_joint_logp_dlogp_vs_reference_goldens(Engine, goldens, cohorts):
+    z, cases = goldens
+    for (_, _, _), cs in group_cases(cases).items():
+        with case_engine(Engine, cohorts, cs[0]) as eng:
+            q = np.stack([z[f"{c['key']}/q"] for c in cs])
+            i_raw = np.stack([z[f"{c['key']}/i_raw"] for c in cs])
+            w = np.stack([z[f"{c['key']}/w"] for c in cs])
+            ref = np.array([float(z[f"{c['key']}/logp"]) for c in cs])
+            gref = np.stack([z[f"{c['key']}/grad"] for c in cs])
+            # batched over chains ...
+            lp, g = eng.logp_dlogp(q, i_raw, w)
+            assert np.all(np.abs(lp - ref) <= RTOL * np.abs(ref)), (lp - ref) / ref
+            assert grad_ok(g, gref), np.abs(g - gref).max()
+            # ... and one chain at a time: bitwise the same numbers
+            for k in range(len(cs)):
+                lp1, g1 = eng.logp_dlogp(q[k], i_raw[k], w[k])
+                assert lp1 == lp[k] and np.array_equal(g1, g[k])
+
+
+def test_deterministics_vs_reference_goldens(Engine, goldens, cohorts):
+    z, cases = goldens
+    for c in cases:
+        k = c["key"]
+        with case_engine(Engine, cohorts, c) as eng:
+            vals = ora.backward(z[f"{k}/q"])[0]
+            th = np.array([vals[n] for n in ora.THETA13])
+            i, mu_n, mu_s = eng.deterministics(th, z[f"{k}/i_raw"], z[f"{k}/w"])
+            assert int(i.sum()) == int(z[f"{k}/i_sum"])
+            np.testing.assert_allclose(mu_n.sum(), float(z[f"{k}/mu_n_sum"]), rtol=1e-12)
+            np.testing.assert_allclose(mu_s.sum(), float(z[f"{k}/mu_s_sum"]), rtol=1e-12)
+            if f"{k}/i" in z:
+                assert np.array_equal(i, z[f"{k}/i"])
+                np.testing.assert_allclose(mu_n, z[f"{k}/mu_n"], rtol=1e-12, atol=1e-12)
+                np.testing.assert_allclose(mu_s, z[f"{k}/mu_s"], rtol=1e-12, atol=1e-12)
+
+
+def test_cond_logodds_vs_reference_goldens(Engine, goldens, cohorts):
+    z, cases = goldens
+    n = 0
+    for c in cases:
+        k = c["key"]
+        if f"{k}/cond" not in z:
+            continue
+        with case_engine(Engine, cohorts, c) as eng:
+            vals = ora.backward(z[f"{k}/q"])[0]
+            th = np.array([vals[m] for m in ora.THETA13])
+            lo, lo_w = eng.cond_logodds(th, vals["p"], vals["ab_s_p_waner"], z[f"{k}/i_raw"], z[f"{k}/w"])
+            ref, ref_w = z[f"{k}/cond"], z[f"{k}/cond_w"]
+            assert np.all(np.abs(lo - ref) <= 3e-9 * np.maximum(1, np.abs(ref)))
+            assert np.all(np.abs(lo_w - ref_w) <= 3e-9 * np.maximum(1, np.abs(ref_w)))
+            n += 1
+    assert n >= 8
+
+
+def test_constrained_infections_vs_reference_kats(Engine, kats):
+    """K1 -> K2 -> K3 through the deterministics kernel on the reference-generated cases."""
+    from abdpymc_b200.cohort import CohortArrays
+
+    th = np.array([2.0, 1.0, 0.9, -2.0, 2.0, 0.9, -2.0, -1.0, 2.0, 1.0, -1.0, 2.0, 1.0])
+    done = 0
+    for k in kats["constrain"]:
+        i_raw, pcr, want = np.array(k["i_raw"]), np.array(k["pcrpos"]), np.array(k["out"])
+        g, n = i_raw.shape
+        if g > 63:
+            continue
+        co = CohortArrays(vacs=np.zeros((n, g)), pcrpos=pcr.T, ind=[0], gap=[0], antigen=[0], x=[0.0], od=[0.0])
+        with Engine(co, splits=tuple(k["splits"])) as eng:
+            i, _, _ = eng.deterministics(th, i_raw, np.zeros(n))
+        assert np.array_equal(i, want), k["splits"]
+        done += 1
+    assert done >= 40
+
+
+# ------------------------------------------------------------------------------ vs oracle, seeded sweeps
+def draw_points(rng, G, N, n_points):
+    q = np.stack([ora.forward(ora.sample_prior(rng, G)) for _ in range(n_points)])
+    dens = np.where(rng.random(n_points) < 0.5, 0.05, 1.0 / G)
+    i_raw = (rng.random((n_points, G, N)) < dens[:, None, None]).astype(np.int8)
+    w = (rng.random((n_points, N)) < 0.5).astype(np.int8)
+    # adversarial points
+    if n_points >= 6:
+        i_raw[0] = 0
+        i_raw[1] = 1
+        w[2] = 0
+        q[3, 3] = 18.0   # ab_n_rho -> 1
+        q[3, 6] = 25.0   # ab_s_rho -> 1
+        q[4, 11] = 1e-9  # it_n_b ~ 0
+        q[5, 13] = np.log(0.02)  # small sigma
+    return q, i_raw, w
+
+
+@pytest.mark.parametrize("splits", [(), (14,), (20,), (14, 20)])
+def test_parity_sweep_1k_cohort(Engine, splits):
+    """configs[1]: simulated 1k-individual cohort, 256 parameter points per split config."""
+    from abdpymc_b200.cohort import synthetic_cohort
+
+    co = synthetic_cohort(1000)
+    rng = np.random.default_rng(100 + len(splits) + sum(splits))
+    q, i_raw, w = draw_points(rng, co.n_gaps, co.n_inds, 256)
+    o = ora.Oracle(co, splits=splits, dense=False)
+    ref = [o.logp_dlogp(q[k], i_raw[k], w[k]) for k in range(len(q))]
+    ref_lp = np.array([r[0] for r in ref])
+    ref_g = np.stack([r[1] for r in ref])
+    with Engine(co, splits=splits) as eng:
+        lp, g = eng.logp_dlogp(q, i_raw, w)
+        assert np.all(np.abs(lp - ref_lp) <= RTOL * np.abs(ref_lp)), np.abs((lp - ref_lp) / ref_lp).max()
+        assert grad_ok(g, ref_g), np.abs(g - ref_g).max()
+        # the constrained-space entry point agrees with its own oracle too
+        vals = np.array([[ora.backward(q[k])[0][n] for n in ora.THETA13] for k in range(8)])
+        ll, g13, cnt = eng.loglik_grad(vals, i_raw[:8], w[:8])
+        for k in range(8):
+            rl, rg = o.loglik_grad(vals[k], i_raw[k], w[k])
+            assert abs(ll[k] - rl) <= RTOL * abs(rl)
+            assert grad_ok(g13[k], rg)
+            assert cnt[k, 0] == i_raw[k].sum() and cnt[k, 1] == w[k].sum()
+        # tile size must not change the result beyond rounding
+        eng.set_tile_rows(300)
+        lp2, g2 = eng.logp_dlogp(q[:16], i_raw[:16], w[:16])
+        assert np.all(np.abs(lp2 - ref_lp[:16]) <= RTOL * np.abs(ref_lp[:16]))
+        assert grad_ok(g2, ref_g[:16])
+
+
+def random_cohort(rng, G, N, rows_per_ind=6, p_empty=0.2):
+    from abdpymc_b200.cohort import CohortArrays
+
+    counts = rng.poisson(rows_per_ind, size=N) * (rng.random(N) > p_empty)
+    ind = np.repeat(np.arange(N), counts)
+    r = len(ind)
+    perm = rng.permutation(r)  # rows need not be sorted at the boundary
+    return CohortArrays(
+        vacs=rng.random((N, G)) < 0.05, pcrpos=rng.random((N, G)) < 0.03, ind=ind[perm],
+        gap=rng.integers(0, G, size=r), antigen=rng.integers(0, 2, size=r),
+        x=rng.integers(0, 8, size=r).astype(float) + rng.random(r) * (rng.random(r) < 0.2),
+        od=rng.normal(0.8, 0.5, size=r),
+    )
+
+
+@pytest.mark.parametrize("G,N,splits", [(40, 70, (14, 20)), (63, 33, (30,)), (31, 1, (14, 20)), (2, 5, ()),
+                                        (32, 64, (0, 32)), (12, 300, (5, 5 + 3))])
+def test_ragged_and_wide_cohorts(Engine, G, N, splits):
+    """Edge cases: G > 31 (64-bit masks), N = 1, G = 1, individuals without rows, unsorted rows,
+    empty chunks, non-integer dilutions."""
+    rng = np.random.default_rng(G * 1000 + N)
+    co = random_cohort(rng, G, N)
+    q, i_raw, w = draw_points(rng, G, N, 8)
+    o = ora.Oracle(co, splits=splits, dense=True)
+    with Engine(co, splits=splits) as eng:
+        lp, g = eng.logp_dlogp(q, i_raw, w)
+        for k in range(len(q)):
+            rl, rg = o.logp_dlogp(q[k], i_raw[k], w[k])
+            assert abs(lp[k] - rl) <= RTOL * abs(rl), (k, lp[k], rl)
+            assert grad_ok(g[k], rg), (k, g[k] - rg)
+        vals = ora.backward(q[6])[0]
+        th = np.array([vals[n] for n in ora.THETA13])
+        i, mu_n, mu_s = eng.deterministics(th, i_raw[6], w[6])
+        ri, rn, rs = o.deterministics(th, i_raw[6], w[6])
+        assert np.array_equal(i, ri)
+        np.testing.assert_allclose(mu_n, rn, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(mu_s, rs, rtol=1e-12, atol=1e-12)
+        lo, lo_w = eng.cond_logodds(th, vals["p"], vals["ab_s_p_waner"], i_raw[6], w[6])
+        rlo, rlo_w = o.cond_logodds(th, vals["p"], vals["ab_s_p_waner"], i_raw[6], w[6])
+        assert np.all(np.abs(lo - rlo) <= 1e-9 * np.maximum(1, np.abs(rlo)))
+        assert np.all(np.abs(lo_w - rlo_w) <= 1e-9 * np.maximum(1, np.abs(rlo_w)))
+
+
+def test_empty_antigen_and_no_rows(Engine):
+    from abdpymc_b200.cohort import CohortArrays
+
+    rng = np.random.default_rng(5)
+    co = random_cohort(rng, 20, 12)
+    only_s = CohortArrays(vacs=co.vacs, pcrpos=co.pcrpos, ind=co.ind[co.antigen == 1], gap=co.gap[co.antigen == 1],
+                          antigen=co.antigen[co.antigen == 1], x=co.x[co.antigen == 1], od=co.od[co.antigen == 1])
+    none = CohortArrays(vacs=co.vacs, pcrpos=co.pcrpos, ind=[], gap=[], antigen=[], x=[], od=[])
+    q, i_raw, w = draw_points(rng, 20, 12, 7)
+    for c2 in (only_s, none):
+        o = ora.Oracle(c2, splits=(7,))
+        with Engine(c2, splits=(7,)) as eng:
+            lp, g = eng.logp_dlogp(q, i_raw, w)
+            for k in range(len(q)):
+                rl, rg = o.logp_dlogp(q[k], i_raw[k], w[k])
+                assert abs(lp[k] - rl) <= RTOL * abs(rl)
+                assert grad_ok(g[k], rg)
+
+
+def test_error_behaviour(Engine, cohorts):
+    from abdpymc_b200._lib import AbdError
+
+    co = cohorts["test_cohort"]
+    with pytest.raises(AbdError, match="ascending"):  # abd.py:613-614
+        Engine(co, splits=(20, 14))
+    with pytest.raises(AbdError, match="unique"):  # abd.py:619-620
+        Engine(co, splits=(14, 14))
+    with pytest.raises(AbdError, match="positive"):  # abd.py:611-612
+        Engine(co, splits=(-1,))
+    with pytest.raises(AbdError, match="largest split"):  # abd.py:615-618
+        Engine(co, splits=(27,))
+    with pytest.raises(NotImplementedError):  # abd.py:881-882
+        Engine(co, splits=(1, 2, 3))
+    with pytest.raises(ValueError, match="ints"):  # abd.py:621-622
+        Engine(co, splits=(1.5,))
+    with Engine(co) as eng:
+        with pytest.raises(ValueError):
+            eng.logp_dlogp(np.zeros(16))
+        with pytest.raises(AbdError):
+            eng.gibbs_sweep(np.ones(13), 0.1, 0.5, np.zeros((26, 10)), np.zeros(10), mode=7)
+
+
+# ------------------------------------------------------------------------------ Gibbs
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("splits", [(), (14, 20)])
+def test_gibbs_sweep_bit_exact_vs_restated_device_sweep(Engine, cohorts, mode, splits):
+    """Same Philox stream, same visiting order, same accept rule on the CPU: the states after
+    three consecutive sweeps must be identical bit for bit."""
+    co = cohorts["test_cohort"]
+    rng = np.random.default_rng(11 + mode)
+    C = 3
+    vals = [ora.sample_prior(rng, co.n_gaps) for _ in range(C)]
+    th = np.array([[v[n] for n in ora.THETA13] for v in vals])
+    p = np.array([v["p"] for v in vals])
+    pw = np.array([v["ab_s_p_waner"] for v in vals])
+    i_raw = (rng.random((C, co.n_gaps, co.n_inds)) < 0.05).astype(np.int8)
+    w = (rng.random((C, co.n_inds)) < 0.5).astype(np.int8)
+    seed = 0x1234_5678_9ABC_DEF0
+    with Engine(co, splits=splits) as eng:
+        gi, gw = i_raw, w
+        ri, rw = i_raw.copy(), w.copy()
+        for sweep in range(3):
+            gi, gw, st = eng.gibbs_sweep(th, p, pw, gi, gw, seed=seed, sweep=sweep, mode=mode, transit_p=0.8)
+            for c in range(C):
+                ri[c], rw[c], rst = ora.device_gibbs_sweep(co, splits, False, th[c], p[c], pw[c], ri[c], rw[c],
+                                                           seed, sweep, c, mode=mode, transit_p=0.8)
+                assert list(st[c]) == rst, (sweep, c, st[c], rst)
+            assert np.array_equal(gi, ri) and np.array_equal(gw, rw), sweep
+        assert not np.array_equal(gi, i_raw)  # something moved
+
+
+def test_gibbs_sweep_wide_mask_bit_exact(Engine):
+    rng = np.random.default_rng(77)
+    co = random_cohort(rng, 45, 9, rows_per_ind=10, p_empty=0.0)
+    v = ora.sample_prior(rng, 45)
+    th = np.array([v[n] for n in ora.THETA13])
+    i_raw = (rng.random((45, 9)) < 0.05).astype(np.int8)
+    w = (rng.random(9) < 0.5).astype(np.int8)
+    with Engine(co, splits=(14, 20)) as eng:
+        gi, gw, st = eng.gibbs_sweep(th, v["p"], v["ab_s_p_waner"], i_raw, w, seed=5, sweep=9, mode=0)
+    ri, rw, rst = ora.device_gibbs_sweep(co, (14, 20), False, th, v["p"], v["ab_s_p_waner"], i_raw, w, 5, 9, 0)
+    assert np.array_equal(gi, ri) and np.array_equal(gw, rw) and list(st) == rst
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gibbs_stationary_distribution_small_model(Engine, mode):
+    """Statistical parity: on a G = 5 cohort every individual has 2^6 binary states, so the exact
+    conditional posterior given theta is enumerable with the oracle.  Both update rules must
+    leave it invariant: compare empirical state frequencies over many sweeps x chains."""
+    from abdpymc_b200.cohort import CohortArrays
+
+    rng = np.random.default_rng(2024)
+    G, N, C, sweeps = 5, 6, 256, 400
+    co = random_cohort(rng, G, N, rows_per_ind=5, p_empty=0.0)
+    co = CohortArrays(vacs=co.vacs, pcrpos=np.zeros((N, G)), ind=co.ind, gap=co.gap, antigen=co.antigen, x=co.x,
+                      od=rng.normal(0.9, 0.4, size=co.n_rows))
+    v = ora.sample_prior(rng, G)
+    v.update(it_n_sigma=0.8, it_s_sigma=0.8, p=0.3, ab_s_p_waner=0.4)
+    th = np.array([v[n] for n in ora.THETA13])
+    splits = (2,)
+    # exact distribution per individual
+    states = [(np.array([(s >> t) & 1 for t in range(G)]), (s >> G) & 1) for s in range(2 ** (G + 1))]
+    exact = np.empty((N, len(states)))
+    for n in range(N):
+        sub = ora.Oracle(co.take(np.array([n])), splits=splits, dense=False)
+        for s, (col, wn) in enumerate(states):
+            k = col.sum()
+            exact[n, s] = (sub.loglik(th, col.reshape(G, 1), np.array([wn])) + k * np.log(v["p"])
+                           + (G - k) * np.log1p(-v["p"]) + (np.log(v["ab_s_p_waner"]) if wn else np.log1p(-v["ab_s_p_waner"])))
+    exact = np.exp(exact - exact.max(axis=1, keepdims=True))
+    exact /= exact.sum(axis=1, keepdims=True)
+
+    counts = np.zeros_like(exact)
+    thC = np.tile(th, (C, 1))
+    pC, pwC = np.full(C, v["p"]), np.full(C, v["ab_s_p_waner"])
+    weights = 1 << np.arange(G)
+    with Engine(co, splits=splits) as eng:
+        eng.upload_state(np.zeros((C, G, N), np.int8), np.zeros((C, N), np.int8))
+        for sweep in range(sweeps + 50):
+            gi, gw, _ = eng.gibbs_sweep(thC, pC, pwC, seed=99, sweep=sweep, mode=mode, transit_p=0.8)
+            if sweep < 50:
+                continue
+            code = (gi.astype(np.int64) * weights[None, :, None]).sum(axis=1) + (gw.astype(np.int64) << G)  # (C, N)
+            for n in range(N):
+                counts[n] += np.bincount(code[:, n], minlength=exact.shape[1])
+    freq = counts / counts.sum(axis=1, keepdims=True)
+    # total-variation distance per individual; sampling noise at 102 400 (correlated) draws is ~1e-2
+    tv = 0.5 * np.abs(freq - exact).sum(axis=1)
+    assert np.all(tv < 0.05), tv
+
+
+# ------------------------------------------------------------------------------ size-independent properties
+def test_full_size_properties_10k(Engine):
+    """BASELINE config sizes (10k individuals): additivity over shards of individuals (the
+    multi-GPU decomposition), invariance to the order of individuals, chain-batch consistency,
+    and the identity  logp_dlogp == finalize(sums)  through the device-pointer API."""
+    import torch
+
+    from abdpymc_b200.cohort import shard_bounds, synthetic_cohort
+
+    co = synthetic_cohort(10_000)
+    rng = np.random.default_rng(8)
+    C = 4
+    q, i_raw, w = draw_points(rng, co.n_gaps, co.n_inds, C)
+    splits = (14, 20)
+    with Engine(co, splits=splits) as eng:
+        lp, g = eng.logp_dlogp(q, i_raw, w)
+        # oracle on the first chain (recurrence form, a few seconds)
+        o = ora.Oracle(co, splits=splits, dense=False)
+        rl, rg = o.logp_dlogp(q[0], i_raw[0], w[0])
+        assert abs(lp[0] - rl) <= RTOL * abs(rl)
+        assert grad_ok(g[0], rg)
+
+        # device-pointer API: sums -> finalize equals the fused single launch
+        dev = torch.device("cuda:0")
+        tq = torch.from_numpy(q).to(dev)
+        ti = torch.from_numpy(i_raw).to(dev)
+        tw = torch.from_numpy(w).to(dev)
+        sums = torch.zeros(C, 16, dtype=torch.float64, device=dev)
+        out = torch.zeros(C, dtype=torch.float64, device=dev)
+        outg = torch.zeros(C, 17, dtype=torch.float64, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        eng.sums_dev(C, tq.data_ptr(), 1, ti.data_ptr(), tw.data_ptr(), sums.data_ptr(), st)
+        eng.finalize_logp_dev(C, tq.data_ptr(), sums.data_ptr(), out.data_ptr(), outg.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), lp) and np.array_equal(outg.cpu().numpy(), g)
+        whole = sums.cpu().numpy()
+
+    # shards of individuals: raw sums add up to the whole cohort's
+    totals = (co.n_inds, int((co.antigen == 1).sum()), int((co.antigen == 0).sum()))
+    acc = np.zeros_like(whole)
+    world = 3
+    for r in range(world):
+        lo, hi = shard_bounds(co.n_inds, r, world)
+        with Engine(co.shard(r, world), splits=splits, totals=totals, ind_offset=lo) as eng:
+            tis = torch.from_numpy(np.ascontiguousarray(i_raw[:, :, lo:hi])).to(dev)
+            tws = torch.from_numpy(np.ascontiguousarray(w[:, lo:hi])).to(dev)
+            s = torch.zeros(C, 16, dtype=torch.float64, device=dev)
+            eng.sums_dev(C, tq.data_ptr(), 1, tis.data_ptr(), tws.data_ptr(), s.data_ptr(), st)
+            torch.cuda.synchronize()
+            acc += s.cpu().numpy()
+            if r == world - 1:
+                # finalising the all-reduced sums on any shard gives the whole-cohort answer
+                ts = torch.from_numpy(acc).to(dev)
+                eng.finalize_logp_dev(C, tq.data_ptr(), ts.data_ptr(), out.data_ptr(), outg.data_ptr(), st)
+                torch.cuda.synchronize()
+                assert np.all(np.abs(out.cpu().numpy() - lp) <= 1e-12 * np.abs(lp))
+                assert grad_ok(outg.cpu().numpy(), g, 1e-11)
+    np.testing.assert_allclose(acc, whole, rtol=1e-12, atol=1e-9)
+
+    # permuting individuals permutes nothing in the answer
+    perm = rng.permutation(co.n_inds)
+    with Engine(co.take(perm), splits=splits) as eng:
+        lp_p, g_p = eng.logp_dlogp(q, i_raw[:, :, perm], w[:, perm])
+    assert np.all(np.abs(lp_p - lp) <= 1e-12 * np.abs(lp))
+    assert grad_ok(g_p, g, 1e-11)
+
+
+def test_gibbs_properties_10k(Engine):
+    """At 10k individuals: a sweep only ever produces 0/1 states, is reproducible for a given
+    (seed, sweep), differs across sweeps, is independent of chain batching and of sharding
+    (ind_offset), and its flip statistics are plausible."""
+    from abdpymc_b200.cohort import synthetic_cohort
+
+    co = synthetic_cohort(10_000)
+    rng = np.random.default_rng(9)
+    C = 2
+    vals = [ora.sample_prior(rng, co.n_gaps) for _ in range(C)]
+    th = np.array([[v[n] for n in ora.THETA13] for v in vals])
+    p = np.array([0.04, 0.03])
+    pw = np.array([0.5, 0.6])
+    i_raw = (rng.random((C, co.n_gaps, co.n_inds)) < 0.04).astype(np.int8)
+    w = (rng.random((C, co.n_inds)) < 0.5).astype(np.int8)
+    with Engine(co, splits=(14, 20)) as eng:
+        a_i, a_w, st = eng.gibbs_sweep(th, p, pw, i_raw, w, seed=1, sweep=0)
+        b_i, b_w, _ = eng.gibbs_sweep(th, p, pw, i_raw, w, seed=1, sweep=0)
+        c_i, c_w, _ = eng.gibbs_sweep(th, p, pw, i_raw, w, seed=1, sweep=1)
+        assert set(np.unique(a_i)) <= {0, 1} and set(np.unique(a_w)) <= {0, 1}
+        assert np.array_equal(a_i, b_i) and np.array_equal(a_w, b_w)
+        assert not np.array_equal(a_i, c_i)
+        n_bits = co.n_gaps * co.n_inds + co.n_inds
+        assert np.all(np.abs(st[:, 0] / n_bits - 0.8) < 0.01)  # transit_p
+        assert np.all(st[:, 1] > 0) and np.all(st[:, 1] < st[:, 0])
+        # chain 1 alone, as chain index 0, differs (streams are keyed by chain) but a shard with
+        # the right offset reproduces the whole-cohort update of its individuals
+    lo, hi = 2500, 5000
+    with Engine(co.take(np.arange(lo, hi)), splits=(14, 20), ind_offset=lo) as eng:
+        s_i, s_w, _ = eng.gibbs_sweep(th, p, pw, i_raw[:, :, lo:hi], w[:, lo:hi], seed=1, sweep=0)
+    assert np.array_equal(s_i, a_i[:, :, lo:hi]) and np.array_equal(s_w, a_w[:, lo:hi])
