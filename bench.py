@@ -1,0 +1,454 @@
+#!/usr/bin/env python3
+"""Benchmark of the abdpymc inference hot path on B200 ("Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): the simulated
+10 000-individual cohort of SURVEY.md section 8d (bootstrap of the bundled 1520-individual
+schedule, forward-simulated with the reference's default dynamics), 31 monthly gaps, splits
+(14, 20), 4 chains per GPU.  With N > 1 GPUs every rank holds the whole cohort and its own 4
+chains (chain sharding: no data-path collective, weak scaling).
+
+One STEP = EVALS_PER_STEP (256) consecutive batched logp+grad evaluations of all 4 chains --
+a block of NUTS leapfrogs -- replayed as one CUDA graph.  Consecutive evaluations rotate over
+independent replicas of the cohort + chain state whose total footprint exceeds twice the L2
+(126 MB), so every evaluation streams its inputs from HBM ("inputs larger than L2").
+`value` = chain evaluations per second (C * 256 * K / device time, max over ranks, CUDA events).
+`e2e` = the same metric through the host-pointer C-ABI call abd_logp_dlogp(q17, i_raw, waner)
+with pinned HOST buffers: every call copies all three inputs to the device and the results back.
+The `gibbs` object reports abd_gibbs_sweep the same way (its own timed regions).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_INDS = 10_000
+N_CHAINS = 4
+SPLITS = (14, 20)
+EVALS_PER_STEP = 256
+L2_BYTES = 126e6
+METRIC = "logp+grad evals/s (10k individuals, joint logp + 17-dim gradient, per chain)"
+
+
+# ------------------------------------------------------------------------------------------
+def workload(n_inds=N_INDS, n_chains=N_CHAINS, seed=0, chain_offset=0):
+    from abdpymc_b200.cohort import synthetic_cohort
+    from abdpymc_b200.engine import forward
+
+    co = synthetic_cohort(n_inds)
+    rng = np.random.default_rng(1000 + seed + chain_offset)
+
+    def gam(mu, sd, size):
+        return rng.gamma(mu * mu / sd**2, sd**2 / mu, size)
+
+    C = n_chains
+    vals = np.stack([
+        np.clip(rng.beta(1, co.n_gaps - 1, C), 1e-4, 1 - 1e-4), gam(2, .5, C), gam(1, .5, C), rng.beta(10, 1, C),
+        rng.normal(-2, 1, C), gam(2, .5, C), rng.beta(10, 1, C), np.clip(rng.beta(1, 1, C), 1e-4, 1 - 1e-4),
+        gam(1, .5, C), gam(1, .5, C), rng.normal(-2, 1, C), rng.normal(-1, .5, C), rng.normal(2, .5, C),
+        rng.exponential(1, C) + 0.05, rng.normal(-1, .5, C), rng.normal(2, .5, C), rng.exponential(1, C) + 0.05,
+    ], axis=1)  # fmt: skip
+    q = forward(vals)
+    i_raw = (rng.random((C, co.n_gaps, co.n_inds)) < 0.04).astype(np.int8)
+    w = (rng.random((C, co.n_inds)) < 0.5).astype(np.int8)
+    return co, q, vals, i_raw, w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's restatement of the reference's dense (G,G,N) formulation
+# ------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(n_sub, dense):
+    from oracle import abd_oracle as ora
+
+    os.environ["OMP_NUM_THREADS"] = "1"
+    co, q, vals, i_raw, w = workload()
+    sub = co.take(np.arange(n_sub))
+    _CPU.update(o=ora.Oracle(sub, splits=SPLITS, dense=dense), q=q, i_raw=i_raw[:, :, :n_sub], w=w[:, :n_sub])
+
+
+def _cpu_eval(k):
+    c = k % N_CHAINS
+    t = time.perf_counter()
+    _CPU["o"].logp_dlogp(_CPU["q"][c], _CPU["i_raw"][c], _CPU["w"][c])
+    return time.perf_counter() - t
+
+
+def cpu_throughput(n_sub, dense, cores, steps, warmup):
+    """steps x (one logp+grad evaluation on n_sub individuals on each of `cores` processes).
+    Returns (chain-evals/s extrapolated linearly to N_INDS individuals, seconds per step)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(n_sub, dense)) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_eval, range(cores), chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_eval, range(cores), chunksize=1)
+        dt = time.perf_counter() - t0
+    evals = steps * cores * (n_sub / N_INDS)
+    return evals / dt, dt / steps
+
+
+def cpu_baseline():
+    """The bounded CPU sample reported next to the GPU number (rank 0, N = 1 only).  Runs
+    before CUDA is initialised in this process (the pool forks)."""
+    cores = min(os.cpu_count() or 1, 64)
+    n_sub, steps = 5000, 20
+    v_dense, _ = cpu_throughput(n_sub, True, cores, steps, 1)
+    v_scan, _ = cpu_throughput(N_INDS, False, cores, steps, 1)
+    return {"value": v_dense, "unit": "evals/s", "cores": cores, "kind": "port",
+            "sample": (f"{steps} steps x {cores} processes x 1 dense-formulation logp+grad evaluation on the first {n_sub} of "
+                       f"{N_INDS} individuals, scaled by {n_sub}/{N_INDS}; PyMC is not installable offline, so this is "
+                       "the NumPy restatement of the reference graph (oracle/abd_oracle.py)"),
+            "recurrence_port_evals_per_s": v_scan}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU formulation (restated: PyMC is not installable
+    offline), all host cores, same metric / config; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = min(os.cpu_count() or 1, 64)
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    # one dense evaluation costs ~65 us per individual per core: bound the whole run to ~100 s
+    budget_s = 100.0
+    n_sub = int(min(N_INDS, max(250, budget_s / ((steps + warmup) * 65e-6 * 1.5))))
+    value, s_per_step = cpu_throughput(n_sub, True, cores, steps, warmup)
+    sample = (f"each step = 1 logp+grad evaluation of the dense (G,G,N) formulation on the first {n_sub} of the "
+              f"{N_INDS} individuals on each of {cores} processes; throughput scaled by {n_sub}/{N_INDS} (cost is linear in N)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"simulated {N_INDS}-individual cohort, {N_CHAINS} chains, splits {list(SPLITS)}",
+                   "reference": "NumPy restatement of abd.py's dense formulation (oracle/abd_oracle.py); PyMC unavailable offline"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+
+    from abdpymc_b200 import build
+    from abdpymc_b200.engine import AbdEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    C, K, W = N_CHAINS, args.steps, max(args.warmup, 3)
+    cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline and not args.profile) else None
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if dist:
+        dist.barrier()
+
+    co, q, vals, i_raw, w = workload(chain_offset=rank * N_CHAINS)
+    G, N = co.n_gaps, co.n_inds
+    th13 = vals[:, [1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14, 15, 16]].copy()
+    p, pw = vals[:, 0].copy(), vals[:, 7].copy()
+
+    eng0 = AbdEngine(co, splits=SPLITS, device=local)
+    a_logp = eng0.algorithmic_bytes_logp(C)
+    a_gibbs = eng0.algorithmic_bytes_gibbs(C)
+    n_rep = int(np.ceil(2 * L2_BYTES / a_logp)) + 1
+    engines = [eng0] + [AbdEngine(co, splits=SPLITS, device=local) for _ in range(n_rep - 1)]
+    states = []
+    for e in engines:
+        e.upload_state(i_raw, w)
+        states.append(e.state_dev(C))
+
+    tq = torch.from_numpy(q).to(dev)
+    if args.profile:
+        tth = torch.from_numpy(th13).to(dev)
+        tp, tpw = torch.from_numpy(p).to(dev), torch.from_numpy(pw).to(dev)
+        o1 = torch.zeros(C, dtype=torch.float64, device=dev)
+        o2 = torch.zeros(C, 17, dtype=torch.float64, device=dev)
+        for k in range(max(K, 1) * 8):
+            j = k % n_rep
+            engines[j].logp_dlogp_dev(C, tq.data_ptr(), states[j][0], states[j][1], o1.data_ptr(), o2.data_ptr(), 0)
+        for k in range(max(K, 1)):
+            j = k % n_rep
+            engines[j].gibbs_sweep_dev(C, tth.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), states[j][0], states[j][1], 1, k)
+        torch.cuda.synchronize()
+        print("profile run done:", o1.cpu().numpy())
+        return
+    out = torch.zeros(C, dtype=torch.float64, device=dev)
+    outg = torch.zeros(C, 17, dtype=torch.float64, device=dev)
+    side = torch.cuda.Stream(device=dev)
+
+    def enqueue_block(stream_handle, start=0):
+        for k in range(EVALS_PER_STEP):
+            j = (start + k) % n_rep
+            engines[j].logp_dlogp_dev(C, tq.data_ptr(), states[j][0], states[j][1], out.data_ptr(), outg.data_ptr(),
+                                      stream_handle)
+
+    # warm every replica outside capture (first call allocates scratch), then capture one step
+    with torch.cuda.stream(side):
+        enqueue_block(side.cuda_stream)
+    side.synchronize()
+    check_lp = out.cpu().numpy().copy()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        enqueue_block(side.cuda_stream)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = sum(e.launch_count for e in engines)
+    for _ in range(W):
+        graph.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(K):
+            graph.replay()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # keep the sampler alive long enough for at least a few samples under load
+        t_end = time.time() + max(0.0, 0.6 - ms / 1e3)
+        while time.time() < t_end:
+            graph.replay()
+        torch.cuda.synchronize()
+    clocks = clk.summary()
+    assert np.array_equal(out.cpu().numpy(), check_lp), "graph replay changed the result"
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_launch = K * EVALS_PER_STEP
+    value = world * C * n_launch / (ms / 1e3)
+    t_kernel = ms / 1e3 / n_launch
+
+    # ---- L2-resident variant (what consecutive NUTS leapfrogs on ONE cohort see) ----
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2, stream=side):
+        for _ in range(EVALS_PER_STEP):
+            eng0.logp_dlogp_dev(C, tq.data_ptr(), states[0][0], states[0][1], out.data_ptr(), outg.data_ptr(), side.cuda_stream)
+    for _ in range(W):
+        g2.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(K):
+        g2.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_l2 = e0.elapsed_time(e1)
+
+    # ---- e2e: host-pointer C-ABI call, pinned host buffers, all inputs copied every call ----
+    hq = torch.from_numpy(q).pin_memory()
+    hi = torch.from_numpy(i_raw).pin_memory()
+    hw = torch.from_numpy(w).pin_memory()
+    n_e2e = max(50, min(2000, K * 8))
+    for k in range(W * 4):
+        engines[k % n_rep].logp_dlogp(hq.numpy(), hi.numpy(), hw.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        lp, gr = engines[k % n_rep].logp_dlogp(hq.numpy(), hi.numpy(), hw.numpy())
+    dt_e2e = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        lp2, gr2 = engines[k % n_rep].logp_dlogp(hq.numpy())  # chain state already resident
+    dt_res = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([dt_e2e, dt_res], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_e2e, dt_res = (float(v) for v in t.tolist())
+    assert np.array_equal(lp, check_lp) and np.array_equal(lp2, check_lp)
+
+    # ---- Gibbs sweeps ----
+    tth = torch.from_numpy(th13).to(dev)
+    tp, tpw = torch.from_numpy(p).to(dev), torch.from_numpy(pw).to(dev)
+    n_sw = max(10, min(200, K))
+    for k in range(3):
+        engines[k % n_rep].gibbs_sweep_dev(C, tth.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), states[k % n_rep][0],
+                                           states[k % n_rep][1], 1, k, stream=side.cuda_stream)
+    barrier()
+    with torch.cuda.stream(side):
+        e0.record()
+        for k in range(n_sw):
+            j = k % n_rep
+            engines[j].gibbs_sweep_dev(C, tth.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), states[j][0], states[j][1],
+                                       1, 3 + k, stream=side.cuda_stream)
+        e1.record()
+    barrier()
+    ms_gibbs = e0.elapsed_time(e1)
+    for e in engines:
+        e.upload_state(i_raw, w)
+    n_sw_e2e = max(5, min(50, K))
+    t0 = time.perf_counter()
+    for k in range(n_sw_e2e):
+        engines[k % n_rep].gibbs_sweep(th13, p, pw, hi.numpy(), hw.numpy(), seed=1, sweep=k)
+    dt_gibbs_e2e = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([ms_gibbs, dt_gibbs_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_gibbs, dt_gibbs_e2e = (float(v) for v in t.tolist())
+    launches = sum(e.launch_count for e in engines) - launches0
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    ach = a_logp / t_kernel / 1e9
+    t_sweep = ms_gibbs / 1e3 / n_sw
+    ach_g = a_gibbs / t_sweep / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"simulated {N_INDS}-individual cohort (G={G}, {co.n_rows} OD rows), {C} chains per GPU, splits {list(SPLITS)}",
+            "step": f"{EVALS_PER_STEP} consecutive batched logp+grad evaluations (one CUDA graph replay)",
+            "l2": f"inputs larger than L2: evaluations rotate over {n_rep} cohort+state replicas ({n_rep * a_logp / 1e6:.0f} MB > 2 x 126 MB L2)",
+            "parallelism": "chains sharded across GPUs, cohort replicated, no collective" if world > 1 else "1 GPU",
+        },
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": ncu_traffic("k_sums"), "kernel": "k_sums", "algorithmic_bytes_per_launch": a_logp,
+                     "avg_launch_us": t_kernel * 1e6, "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": {"value": world * C * n_e2e / dt_e2e, "unit": "evals/s",
+                "h2d_bytes_per_step": int(C * (17 * 8 + G * N + N)), "d2h_bytes_per_step": int(C * 18 * 8),
+                "call": "abd_logp_dlogp(q17, i_raw, waner) with pinned host buffers, one call per step"},
+        "e2e_resident_state": {"value": world * C * n_e2e / dt_res, "unit": "evals/s",
+                               "h2d_bytes_per_step": int(C * 17 * 8), "d2h_bytes_per_step": int(C * 18 * 8),
+                               "call": "abd_logp_dlogp(q17, NULL, NULL): chain state left on the device by the Gibbs sweep"},
+        "l2_resident": {"value": world * C * n_launch / (ms_l2 / 1e3), "unit": "evals/s",
+                        "avg_launch_us": ms_l2 / n_launch * 1e3,
+                        "note": "same cohort re-evaluated back to back (the access pattern of consecutive NUTS leapfrogs)"},
+        "gibbs": {"metric": "Gibbs sweeps/s (all G*N+N binary variables of one chain)", "value": world * C * n_sw / (ms_gibbs / 1e3),
+                  "unit": "sweeps/s", "avg_launch_us": t_sweep * 1e6,
+                  "roofline": {"bound": "hbm", "achieved": ach_g, "peak": peak, "unit": "GB/s", "frac": ach_g / peak,
+                               "traffic": ncu_traffic("k_gibbs"), "kernel": "k_gibbs", "algorithmic_bytes_per_launch": a_gibbs},
+                  "e2e": {"value": world * C * n_sw_e2e / dt_gibbs_e2e, "unit": "sweeps/s",
+                          "h2d_bytes_per_step": int(C * (G * N + N + 15 * 8)), "d2h_bytes_per_step": int(C * (G * N + N + 16))}},
+        "gpu_launches": int(n_launch), "gpu_launches_total": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="short run for ncu: a few un-captured logp+grad launches and Gibbs sweeps, no JSON line")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
