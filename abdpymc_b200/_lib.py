@@ -70,7 +70,8 @@ SIGNATURES = {
                                       C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "abd_deterministics_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 7),
     "abd_state_dev": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
-    "abd_set_tile_rows": (C.c_int, [H, C.c_int]),
+    "abd_set_tuning": (C.c_int, [H, C.c_int, C.c_int]),
+    "abd_debug_fast_math": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }  # fmt: skip
 
 _lib = None

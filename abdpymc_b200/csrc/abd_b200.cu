@@ -66,37 +66,50 @@ struct DevCohort {
 };
 
 constexpr int kSumsBlock = 256;
+constexpr int kSumsWarps = kSumsBlock / 32;
 constexpr int kTileMaxInds = 128;
 constexpr int kGibbsWarps = 8;
 constexpr int kGibbsTile = 32;  // individuals per Gibbs CTA
 
-template <int NV>
-__device__ __forceinline__ void warp_reduce(double (&v)[NV]) {
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+// per-individual state staged in shared memory: constrained infections, vaccinations, waner
+// (packed in the top bit of the vaccination mask; usable gaps <= width - 1)
+template <typename M>
+struct IndState {
+  M inf, vacw;
+};
+template <typename M>
+__device__ __forceinline__ M top_bit() { return (M)1 << (sizeof(M) * 8 - 1); }
+
+__device__ __forceinline__ double load_param(const double* theta, int theta_is_q, int c, int k13) {
+  if (theta_is_q) {
+    const int j = kQOfTheta[k13];
+    return backward(theta[(size_t)c * 17 + j], kQTransform[j]);
   }
+  return theta[(size_t)c * 13 + k13];
 }
 
-__device__ __forceinline__ void load_theta(const double* theta, int theta_is_q, int c, int tid,
-                                           double* s_th) {
-  if (tid < 13) {
-    if (theta_is_q) {
-      const int j = kQOfTheta[tid];
-      s_th[tid] = backward(theta[(size_t)c * 17 + j], kQTransform[j]);
-    } else {
-      s_th[tid] = theta[(size_t)c * 13 + tid];
+// One warp: pw[k] = rho^k and (optionally) dpw[k] = k rho^(k-1) for k < G by a shuffle scan.
+__device__ __forceinline__ void fill_pow_warp(double rho, int G, int lane, double* pw, double* dpw) {
+  double v = rho;  // inclusive prefix product: rho^(lane+1)
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double u = __shfl_up_sync(0xffffffffu, v, off);
+    if (lane >= off) v *= u;
+  }
+  const double r32 = __shfl_sync(0xffffffffu, v, 31);  // rho^32
+  double prev = __shfl_up_sync(0xffffffffu, v, 1);      // rho^lane
+  if (lane == 0) prev = 1.0;
+  if (lane == 0) {
+    pw[0] = 1.0;
+    if (dpw) dpw[0] = 0.0;
+  }
+  for (int blk = 0; blk * 32 < G; ++blk) {
+    const int k = blk * 32 + lane + 1;
+    const double scale = blk ? r32 : 1.0;  // G <= 63: at most two blocks
+    if (k < G) {
+      pw[k] = v * scale;
+      if (dpw) dpw[k] = (double)k * prev * scale;
     }
-  }
-}
-
-// pw[k] = rho^k, dpw[k] = k rho^(k-1), k < G
-__device__ __forceinline__ void fill_pow(double rho, int G, int lane, double* pw, double* dpw) {
-  for (int k = lane; k < G; k += 32) {
-    const double pkm1 = ipow(rho, k > 0 ? k - 1 : 0);
-    pw[k] = k > 0 ? pkm1 * rho : 1.0;
-    if (dpw) dpw[k] = k > 0 ? (double)k * pkm1 : 0.0;
   }
 }
 
@@ -110,162 +123,222 @@ struct FinalizeCfg {
   double* out_grad;  // [C][13] or [C][17] (may be null)
 };
 
+struct SumsCfg {
+  int ntiles;
+  int cap_n, cap_s;      // staged doubles per antigen (even)
+  int capm_n, capm_s;    // staged meta words per antigen (multiple of 4)
+  int chains_per_cta;
+  int C;
+};
+
 template <typename M>
-__global__ void __launch_bounds__(kSumsBlock)
-k_sums(const DevCohort dc, const int* __restrict__ tile_ind, const int ntiles,
+__global__ void __launch_bounds__(kSumsBlock, 3)
+k_sums(const DevCohort dc, const int* __restrict__ tile_ind, const SumsCfg cfg,
        const double* __restrict__ theta, const int theta_is_q,
        const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
        double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ sums,
        const FinalizeCfg fin, const Priors* __restrict__ priors) {
-  const int tile = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+  const int tile = blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int G = dc.G, N = dc.N;
+  const int G = dc.G, N = dc.N, ntiles = cfg.ntiles;
   const int i0 = tile_ind[tile], i1 = tile_ind[tile + 1];
   const int ni = i1 - i0;
 
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  double* s_od_n = reinterpret_cast<double*>(dyn_smem);
+  double* s_x_n = s_od_n + cfg.cap_n;
+  double* s_od_s = s_x_n + cfg.cap_n;
+  double* s_x_s = s_od_s + cfg.cap_s;
+  uint32_t* s_m_n = reinterpret_cast<uint32_t*>(s_x_s + cfg.cap_s);
+  uint32_t* s_m_s = s_m_n + cfg.capm_n;
+
   __shared__ double s_th[16];
   __shared__ double s_pw[4][kMaxGaps];  // rho_n^k, d/drho; rho_s^k, d/drho
-  __shared__ M s_inf[kTileMaxInds];
-  __shared__ M s_vac[kTileMaxInds];
-  __shared__ unsigned char s_w[kTileMaxInds];
-  __shared__ double s_red[kSumsBlock / 32][kNSums];
+  __shared__ double s_tab[kExpTab];
+  __shared__ unsigned s_bits[kMaxGaps][kTileMaxInds / 32];
+  __shared__ IndState<M> s_ind[kTileMaxInds];
+  __shared__ double s_red[kSumsWarps][kNSums];
+  __shared__ double s_fin[kSumsBlock / 16][kNSums];
   __shared__ int s_last;
+  __shared__ __align__(8) uint64_t s_bar;
 
-  load_theta(theta, theta_is_q, c, tid, s_th);
-
-  // ---- phase 0: int8 columns -> bit masks (coalesced over individuals for every gap) ----
-  M raw = 0;
-  int w = 0;
-  if (tid < ni) {
-    const int8_t* col = i_raw + (size_t)c * G * N + (i0 + tid);
-#pragma unroll 8
-    for (int t = 0; t < G; ++t) raw |= (M)(col[(size_t)t * N] != 0) << t;
-    w = waner[(size_t)c * N + i0 + tid] != 0;
-  }
-  __syncthreads();
-  if (warp == 0) fill_pow(s_th[N_RHO], G, lane, s_pw[0], s_pw[1]);
-  if (warp == 1) fill_pow(s_th[S_RHO], G, lane, s_pw[2], s_pw[3]);
-  double acc[kNSums];
-#pragma unroll
-  for (int k = 0; k < kNSums; ++k) acc[k] = 0.0;
-  if (tid < ni) {
-    const M pcr = reinterpret_cast<const M*>(dc.pcr)[i0 + tid];
-    s_inf[tid] = constrain<M>(raw, pcr, dc.ch);
-    s_vac[tid] = reinterpret_cast<const M*>(dc.vac)[i0 + tid];
-    s_w[tid] = (unsigned char)w;
-    acc[S_KI] = (double)popc(raw);
-    acc[S_KW] = (double)w;
-  }
-  __syncthreads();
-
-  // ---- phase 1: one thread per OD row ----
-  {
-    const double init = s_th[N_INIT], perm = s_th[N_PERM], temp = s_th[N_TEMP];
-    const double b = s_th[N_B], d = s_th[N_D];
-    const int r0 = dc.rp[0][i0], r1 = dc.rp[0][i1];
-    const double* __restrict__ od = dc.od[0];
-    const double* __restrict__ xs = dc.x[0];
-    const uint32_t* __restrict__ meta = dc.meta[0];
-#pragma unroll 2
-    for (int r = r0 + tid; r < r1; r += kSumsBlock) {
-      const uint32_t mt = meta[r];
-      const int t = mt & 63, li = (int)(mt >> 6) - i0;
-      double P, T, dT, s, res, q, xm;
-      traj_n<M>(s_inf[li], t, s_pw[0], s_pw[1], P, T, dT);
-      row_eval(xs[r], od[r], init + perm * P + temp * T, b, d, s, res, q, xm);
-      acc[SN_0] += res * res;
-      acc[SN_1] += res * s;
-      acc[SN_2] += q * xm;
-      acc[SN_QINIT] += q;
-      acc[SN_QPERM] += q * P;
-      acc[SN_QTEMP] += q * T;
-      acc[SN_QRHO] += q * dT;
+  // ---- stage this tile's OD rows in shared memory: one thread, six bulk async copies ----
+  const int rn0 = dc.rp[0][i0], rn1 = dc.rp[0][i1], rs0 = dc.rp[1][i0], rs1 = dc.rp[1][i1];
+  const int an0 = rn0 & ~1, as0 = rs0 & ~1, mn0 = rn0 & ~3, ms0 = rs0 & ~3;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    const uint32_t bn = (uint32_t)(((rn1 + 1) & ~1) - an0) * 8u, bs = (uint32_t)(((rs1 + 1) & ~1) - as0) * 8u;
+    const uint32_t bmn = (uint32_t)(((rn1 + 3) & ~3) - mn0) * 4u, bms = (uint32_t)(((rs1 + 3) & ~3) - ms0) * 4u;
+    mbar_expect_tx(&s_bar, 2 * bn + 2 * bs + bmn + bms);
+    if (bn) {
+      bulk_g2s(s_od_n, dc.od[0] + an0, bn, &s_bar);
+      bulk_g2s(s_x_n, dc.x[0] + an0, bn, &s_bar);
     }
-  }
-  {
-    const double init = s_th[S_INIT], perm = s_th[S_PERM];
-    const double b = s_th[S_B], d = s_th[S_D];
-    const int r0 = dc.rp[1][i0], r1 = dc.rp[1][i1];
-    const double* __restrict__ od = dc.od[1];
-    const double* __restrict__ xs = dc.x[1];
-    const uint32_t* __restrict__ meta = dc.meta[1];
-#pragma unroll 2
-    for (int r = r0 + tid; r < r1; r += kSumsBlock) {
-      const uint32_t mt = meta[r];
-      const int t = mt & 63, li = (int)(mt >> 6) - i0;
-      double P, U, dU, s, res, q, xm;
-      traj_s<M>(s_inf[li], s_vac[li], s_w[li], t, s_pw[2], s_pw[3], P, U, dU);
-      row_eval(xs[r], od[r], init + perm * P + U, b, d, s, res, q, xm);
-      acc[SS_0] += res * res;
-      acc[SS_1] += res * s;
-      acc[SS_2] += q * xm;
-      acc[SS_QINIT] += q;
-      acc[SS_QPERM] += q * P;
-      acc[SS_QRHO] += q * dU;
+    if (bs) {
+      bulk_g2s(s_od_s, dc.od[1] + as0, bs, &s_bar);
+      bulk_g2s(s_x_s, dc.x[1] + as0, bs, &s_bar);
     }
+    if (bmn) bulk_g2s(s_m_n, dc.meta[0] + mn0, bmn, &s_bar);
+    if (bms) bulk_g2s(s_m_s, dc.meta[1] + ms0, bms, &s_bar);
   }
+  fill_exp_table(s_tab, tid, kSumsBlock);
 
-  // ---- block reduction: shuffles inside a warp, shared memory across warps ----
-  warp_reduce<kNSums>(acc);
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < kNSums; ++k) s_red[warp][k] = acc[k];
-  }
-  __syncthreads();
-  if (tid < kNSums) {
-    double v = 0.0;
-#pragma unroll
-    for (int wv = 0; wv < kSumsBlock / 32; ++wv) v += s_red[wv][tid];
-    partial[((size_t)c * ntiles + tile) * kNSums + tid] = v;
-  }
+  const int ngrp = (ni + 31) >> 5;
+  const int nitems = G * ngrp;
 
-  // ---- last CTA of this chain: ordered reduction over tiles, then finalise ----
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&ticket[c], 1u) == (unsigned)(ntiles - 1));
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  {
-    const int k = tid & 15, g = tid >> 4;  // 16 groups of 16 values
-    double v = 0.0;
-    for (int tl = g; tl < ntiles; tl += kSumsBlock / 16)
-      v += __ldcg(&partial[((size_t)c * ntiles + tl) * kNSums + k]);
-    __shared__ double s_fin[kSumsBlock / 16][kNSums];
-    s_fin[g][k] = v;
+  for (int cc = 0; cc < cfg.chains_per_cta; ++cc) {
+    const int c = blockIdx.y * cfg.chains_per_cta + cc;
+    if (c >= cfg.C) break;
+
+    // ---- phase 0a: int8 columns -> per-gap ballots (every warp; coalesced over individuals) ----
+    {
+      const int8_t* base = i_raw + (size_t)c * G * N + i0;
+      for (int it0 = warp; it0 < nitems; it0 += 4 * kSumsWarps) {
+        int8_t b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int item = it0 + u * kSumsWarps;
+          const int t = item / ngrp, j = (item - t * ngrp) * 32 + lane;
+          b[u] = (item < nitems && j < ni) ? base[(size_t)t * N + j] : (int8_t)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int item = it0 + u * kSumsWarps;
+          const unsigned bal = __ballot_sync(0xffffffffu, b[u] != 0);
+          if (lane == 0 && item < nitems) {
+            const int t = item / ngrp;
+            s_bits[t][item - t * ngrp] = bal;
+          }
+        }
+      }
+    }
+    // ---- phase 0b: parameters and power tables (warps 0-2) ----
+    if (warp == 0) fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw[0], s_pw[1]);
+    if (warp == 1) fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw[2], s_pw[3]);
+    if (warp == 2 && lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
+    __syncthreads();
+
+    // ---- phase 0c: one thread per individual: mask over gaps, constraints ----
+    double acc[kNSums];
+#pragma unroll
+    for (int k = 0; k < kNSums; ++k) acc[k] = 0.0;
+    if (tid < ni) {
+      M raw = 0;
+      const int jg = tid >> 5, jb = tid & 31;
+      for (int t = 0; t < G; ++t) raw |= (M)((s_bits[t][jg] >> jb) & 1u) << t;
+      const int w = waner[(size_t)c * N + i0 + tid] != 0;
+      const M pcr = reinterpret_cast<const M*>(dc.pcr)[i0 + tid];
+      IndState<M> st;
+      st.inf = constrain<M>(raw, pcr, dc.ch);
+      st.vacw = reinterpret_cast<const M*>(dc.vac)[i0 + tid] | (w ? top_bit<M>() : (M)0);
+      s_ind[tid] = st;
+      acc[S_KI] = (double)popc(raw);
+      acc[S_KW] = (double)w;
+    }
+    __syncthreads();
+    if (cc == 0) mbar_wait(&s_bar, 0);
+
+    // ---- phase 1: one thread per OD row, rows read from shared memory ----
+    {
+      const double init = s_th[N_INIT], perm = s_th[N_PERM], temp = s_th[N_TEMP];
+      const double b = s_th[N_B], d = s_th[N_D];
+      for (int r = rn0 + tid; r < rn1; r += kSumsBlock) {
+        const uint32_t mt = s_m_n[r - mn0];
+        const int t = mt & 63, li = (int)(mt >> 6) - i0;
+        double P, T, dT, s, res, q, xm;
+        traj_n<M>(s_ind[li].inf, t, s_pw[0], s_pw[1], P, T, dT);
+        row_eval(s_x_n[r - an0], s_od_n[r - an0], init + perm * P + temp * T, b, d, s_tab, s, res, q, xm);
+        acc[SN_0] = fma(res, res, acc[SN_0]);
+        acc[SN_1] = fma(res, s, acc[SN_1]);
+        acc[SN_2] = fma(q, xm, acc[SN_2]);
+        acc[SN_QINIT] += q;
+        acc[SN_QPERM] = fma(q, P, acc[SN_QPERM]);
+        acc[SN_QTEMP] = fma(q, T, acc[SN_QTEMP]);
+        acc[SN_QRHO] = fma(q, dT, acc[SN_QRHO]);
+      }
+    }
+    {
+      const double init = s_th[S_INIT], perm = s_th[S_PERM];
+      const double b = s_th[S_B], d = s_th[S_D];
+      for (int r = rs0 + tid; r < rs1; r += kSumsBlock) {
+        const uint32_t mt = s_m_s[r - ms0];
+        const int t = mt & 63, li = (int)(mt >> 6) - i0;
+        const IndState<M> st = s_ind[li];
+        double P, U, dU, s, res, q, xm;
+        traj_s<M>(st.inf, st.vacw & ~top_bit<M>(), (st.vacw & top_bit<M>()) != 0, t, s_pw[2], s_pw[3], P, U, dU);
+        row_eval(s_x_s[r - as0], s_od_s[r - as0], init + perm * P + U, b, d, s_tab, s, res, q, xm);
+        acc[SS_0] = fma(res, res, acc[SS_0]);
+        acc[SS_1] = fma(res, s, acc[SS_1]);
+        acc[SS_2] = fma(q, xm, acc[SS_2]);
+        acc[SS_QINIT] += q;
+        acc[SS_QPERM] = fma(q, P, acc[SS_QPERM]);
+        acc[SS_QRHO] = fma(q, dU, acc[SS_QRHO]);
+      }
+    }
+
+    // ---- block reduction: butterfly inside a warp, shared memory across warps ----
+    {
+      const double tot = warp_reduce16(acc, lane);
+      if ((lane & 1) == 0) s_red[warp][warp_reduce16_index(lane)] = tot;
+    }
     __syncthreads();
     if (tid < kNSums) {
-      double tot = 0.0;
+      double v = 0.0;
 #pragma unroll
-      for (int gg = 0; gg < kSumsBlock / 16; ++gg) tot += s_fin[gg][tid];
-      s_red[0][tid] = tot;
-      if (sums) sums[(size_t)c * kNSums + tid] = tot;
+      for (int wv = 0; wv < kSumsWarps; ++wv) v += s_red[wv][tid];
+      partial[((size_t)c * ntiles + tile) * kNSums + tid] = v;
     }
+
+    // ---- last CTA of this chain: ordered reduction over tiles, then finalise ----
+    __threadfence();
     __syncthreads();
-  }
-  if (tid == 0) {
-    ticket[c] = 0;  // re-arm for the next launch
-    if (fin.mode == 1) {
-      finalize_loglik(s_th, s_red[0], fin.tot, &fin.out_val[c],
-                      fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
-    } else if (fin.mode == 2) {
-      finalize_logp(&theta[(size_t)c * 17], s_red[0], fin.tot, *priors, &fin.out_val[c],
-                    fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
+    if (tid == 0) s_last = (atomicAdd(&ticket[c], 1u) == (unsigned)(ntiles - 1));
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int k = tid & 15, g = tid >> 4;  // 16 groups of 16 values
+      double v = 0.0;
+      for (int tl = g; tl < ntiles; tl += kSumsBlock / 16)
+        v += __ldcg(&partial[((size_t)c * ntiles + tl) * kNSums + k]);
+      s_fin[g][k] = v;
+      __syncthreads();
+      if (tid < kNSums) {
+        double tot = 0.0;
+#pragma unroll
+        for (int gg = 0; gg < kSumsBlock / 16; ++gg) tot += s_fin[gg][tid];
+        s_red[0][tid] = tot;
+        if (sums) sums[(size_t)c * kNSums + tid] = tot;
+      }
+      __syncthreads();
+      if (tid == 0) ticket[c] = 0;  // re-arm for the next launch
+      if (warp == 0) {
+        if (fin.mode == 1) {
+          if (lane == 0)
+            finalize_loglik(s_th, s_red[0], fin.tot, &fin.out_val[c],
+                            fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
+        } else if (fin.mode == 2) {
+          finalize_logp_warp(lane, &theta[(size_t)c * 17], s_red[0], fin.tot, *priors, &fin.out_val[c],
+                             fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
+        }
+      }
     }
+    __syncthreads();  // shared memory is reused by the next chain
   }
 }
 
+// one warp per chain
 __global__ void k_finalize(const int C, const double* __restrict__ theta,
                            const double* __restrict__ sums, const FinalizeCfg fin,
                            const Priors* __restrict__ priors) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   if (fin.mode == 1) {
-    finalize_loglik(&theta[(size_t)c * 13], &sums[(size_t)c * kNSums], fin.tot, &fin.out_val[c],
-                    fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
+    if (lane == 0)
+      finalize_loglik(&theta[(size_t)c * 13], &sums[(size_t)c * kNSums], fin.tot, &fin.out_val[c],
+                      fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
   } else {
-    finalize_logp(&theta[(size_t)c * 17], &sums[(size_t)c * kNSums], fin.tot, *priors,
-                  &fin.out_val[c], fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
+    finalize_logp_warp(lane, &theta[(size_t)c * 17], &sums[(size_t)c * kNSums], fin.tot, *priors,
+                       &fin.out_val[c], fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
   }
 }
 
@@ -281,39 +354,33 @@ struct GibbsCfg {
   unsigned long long* stats;  // [C][2] proposals, accepted flips (may be null)
 };
 
-// log-likelihood of one individual's rows (up to the additive constant), all lanes return it
+// One OD row of one individual under a candidate state (value only, times -1/(2 sigma^2)).
+// N and S rows share one code path: lanes differ only in their per-lane parameters.
+struct RowPar {
+  double init, perm, tfac, b, d, nh;
+};
 template <typename M>
-__device__ __forceinline__ double indiv_ll(const DevCohort& dc, int n, M inf, M vac, int w,
-                                           const double* s_th, const double (*s_pw)[kMaxGaps],
-                                           int lane, int rn0, int rn1, int rs0, int rs1) {
-  double a = 0.0;
-  {
-    const double init = s_th[N_INIT], perm = s_th[N_PERM], temp = s_th[N_TEMP];
-    const double b = s_th[N_B], d = s_th[N_D];
-    double sub = 0.0;
-    for (int r = rn0 + lane; r < rn1; r += 32) {
-      const int t = dc.meta[0][r] & 63;
-      sub += row_resid2(dc.x[0][r], dc.od[0][r], mu_n_at<M>(inf, t, s_pw[0], init, perm, temp), b, d);
-    }
-    a += sub * s_th[13];  // -1 / (2 sigma_n^2)
+__device__ __forceinline__ double gibbs_row(double x, double od, int t, bool is_s, M inf, M vac, int w,
+                                            const RowPar& rp, const double (*s_pw)[kMaxGaps],
+                                            const double* __restrict__ s_tab) {
+  const M lm = low_mask<M>(t);
+  M e = inf & lm, v = is_s ? (vac & lm) : (M)0;
+  const double P = (e | v) ? rp.perm : 0.0;
+  const double* pw = is_s ? (w ? s_pw[1] : s_pw[2]) : s_pw[0];  // s_pw[2] = all ones (rho_ind = 1)
+  double T = 0.0;
+  while (e) {
+    T += pw[t - ctz(e)];
+    e &= e - 1;
   }
-  {
-    const double init = s_th[S_INIT], perm = s_th[S_PERM];
-    const double b = s_th[S_B], d = s_th[S_D];
-    double sub = 0.0;
-    for (int r = rs0 + lane; r < rs1; r += 32) {
-      const int t = dc.meta[1][r] & 63;
-      sub += row_resid2(dc.x[1][r], dc.od[1][r], mu_s_at<M>(inf, vac, w, t, s_pw[1], init, perm), b, d);
-    }
-    a += sub * s_th[14];  // -1 / (2 sigma_s^2)
+  while (v) {
+    T += pw[t - ctz(v)];
+    v &= v - 1;
   }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-  return a;
+  return rp.nh * row_resid2(x, od, fma(rp.tfac, T, rp.init + P), rp.b, rp.d, s_tab);
 }
 
 template <typename M>
-__global__ void __launch_bounds__(kGibbsWarps * 32)
+__global__ void __launch_bounds__(kGibbsWarps * 32, 3)
 k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is_q,
         const double* __restrict__ p_arr, const double* __restrict__ pw_arr,
         int8_t* __restrict__ i_raw, int8_t* __restrict__ waner, const GibbsCfg cfg) {
@@ -324,42 +391,56 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
   const int ni = min(kGibbsTile, N - i0);
 
   __shared__ double s_th[16];
-  __shared__ double s_pw[2][kMaxGaps];
+  __shared__ double s_pw[3][kMaxGaps];
+  __shared__ double s_tab[kExpTab];
   __shared__ double s_lo[2];  // logit(p), logit(p_w)
   __shared__ unsigned char s_bytes[kMaxGaps][kGibbsTile];
+  __shared__ unsigned char s_ord[kGibbsWarps][kMaxGaps];
   __shared__ unsigned s_stat[2];
+  __shared__ int s_next;
 
-  load_theta(theta, theta_is_q, c, tid, s_th);
-  if (tid == 32) {
-    if (theta_is_q) {  // logit of a logodds-transformed value is the value itself
-      s_lo[0] = theta[(size_t)c * 17 + kQ_P];
-      s_lo[1] = theta[(size_t)c * 17 + kQ_PW];
-    } else {
-      const double p = p_arr[c], pw = pw_arr[c];
-      s_lo[0] = log(p) - log1p(-p);
-      s_lo[1] = log(pw) - log1p(-pw);
+  if (warp == 0) fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw[0], nullptr);
+  if (warp == 1) fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw[1], nullptr);
+  if (warp == 2) {
+    if (lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
+    if (lane == 13) {
+      const double sg = load_param(theta, theta_is_q, c, N_SIGMA);
+      s_th[13] = -0.5 / (sg * sg);
+    }
+    if (lane == 14) {
+      const double sg = load_param(theta, theta_is_q, c, S_SIGMA);
+      s_th[14] = -0.5 / (sg * sg);
+    }
+    if (lane == 15 || lane == 16) {
+      const int which = lane - 15;
+      double lo;
+      if (theta_is_q) {  // logit of a logodds-transformed value is the value itself
+        lo = theta[(size_t)c * 17 + (which ? kQ_PW : kQ_P)];
+      } else {
+        const double p = which ? pw_arr[c] : p_arr[c];
+        lo = log(p) - log1p(-p);
+      }
+      s_lo[which] = lo;
     }
   }
-  if (tid < 2) s_stat[tid] = 0;
+  if (warp == 3) {
+    for (int k = lane; k < kMaxGaps; k += 32) s_pw[2][k] = 1.0;
+    if (lane < 2) s_stat[lane] = 0;
+    if (lane == 2) s_next = kGibbsWarps;
+  }
+  fill_exp_table(s_tab, tid, kGibbsWarps * 32);
   for (int idx = tid; idx < G * kGibbsTile; idx += kGibbsWarps * 32) {
     const int t = idx / kGibbsTile, j = idx % kGibbsTile;
     s_bytes[t][j] = (j < ni) ? (unsigned char)(i_raw[((size_t)c * G + t) * N + i0 + j] != 0) : 0;
-  }
-  __syncthreads();
-  if (warp == 0) fill_pow(s_th[N_RHO], G, lane, s_pw[0], nullptr);
-  if (warp == 1) fill_pow(s_th[S_RHO], G, lane, s_pw[1], nullptr);
-  if (tid == 64) {
-    s_th[13] = -0.5 / (s_th[N_SIGMA] * s_th[N_SIGMA]);
-    s_th[14] = -0.5 / (s_th[S_SIGMA] * s_th[S_SIGMA]);
   }
   __syncthreads();
 
   const int nprop = G + 1;  // proposal j < G flips i_raw[j, n]; j == G flips waner[n]
   unsigned n_prop = 0, n_acc = 0;
 
-  for (int j = warp; j < ni; j += kGibbsWarps) {
+  int j = warp;  // individuals are handed out dynamically: row counts differ a lot
+  while (j < ni) {
     const int n = i0 + j;
-    // column -> mask
     M raw = 0;
 #pragma unroll
     for (int sl = 0; sl < NSLOT; ++sl) {
@@ -370,24 +451,79 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
     int w = waner[(size_t)c * N + n] != 0;
     const M pcr = reinterpret_cast<const M*>(dc.pcr)[n];
     const M vac = reinterpret_cast<const M*>(dc.vac)[n];
-    const int rn0 = dc.rp[0][n], rn1 = dc.rp[0][n + 1], rs0 = dc.rp[1][n], rs1 = dc.rp[1][n + 1];
+    const int rn0 = dc.rp[0][n], cnt_n = dc.rp[0][n + 1] - rn0;
+    const int rs0 = dc.rp[1][n], cnt_s = dc.rp[1][n + 1] - rs0;
+    const int nrows = cnt_n + cnt_s;
+
+    // rows of this individual, one per lane (N rows first, then S rows); kept in registers
+    auto load_row = [&](int l, double& x, double& od, int& t, bool& is_s) {
+      is_s = l >= cnt_n;
+      const int a = is_s ? 1 : 0;
+      const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
+      if (l < nrows) {
+        x = dc.x[a][r];
+        od = dc.od[a][r];
+        t = (int)(dc.meta[a][r] & 63u);
+      } else {
+        x = 0.0;
+        od = 0.0;
+        t = -1;
+      }
+    };
+    auto row_par = [&](bool is_s) {
+      RowPar rp;
+      rp.init = s_th[is_s ? S_INIT : N_INIT];
+      rp.perm = s_th[is_s ? S_PERM : N_PERM];
+      rp.tfac = is_s ? 1.0 : s_th[N_TEMP];
+      rp.b = s_th[is_s ? S_B : N_B];
+      rp.d = s_th[is_s ? S_D : N_D];
+      rp.nh = s_th[is_s ? 14 : 13];
+      return rp;
+    };
+    double x0, od0;
+    int t0;
+    bool s0;
+    load_row(lane, x0, od0, t0, s0);
+    const RowPar rp0 = row_par(s0);
+
+    auto indiv_ll = [&](M inf_, int w_) {
+      double a = (t0 >= 0) ? gibbs_row<M>(x0, od0, t0, s0, inf_, vac, w_, rp0, s_pw, s_tab) : 0.0;
+      for (int l = lane + 32; l < nrows; l += 32) {  // individuals with more than 32 rows
+        double x, od;
+        int t;
+        bool is_s;
+        load_row(l, x, od, t, is_s);
+        a += gibbs_row<M>(x, od, t, is_s, inf_, vac, w_, row_par(is_s), s_pw, s_tab);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      return a;
+    };
 
     M inf = constrain<M>(raw, pcr, dc.ch);
-    double ll = indiv_ll<M>(dc, n, inf, vac, w, s_th, s_pw, lane, rn0, rn1, rs0, rs1);
+    double ll = indiv_ll(inf, w);
 
-    // random visiting order: rank of a 32-bit Philox key per proposal (ties by index)
-    uint32_t rnd_t[NSLOT], rnd_a[NSLOT];
-    int rank[NSLOT];
+    // lane-owned proposals: random key (visiting order), transit / accept uniforms
+    bool skip[NSLOT];
+    double acc_u[NSLOT];  // log(u) (Metropolis) or u (heat bath) of the proposals this lane owns
+    M inf2_own[NSLOT];    // constrained infections if this lane's proposal were flipped
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; ++sl) {
+      skip[sl] = false;
+      acc_u[sl] = 0.0;
+    }
     if (cfg.mode >= 0) {
       uint32_t key[NSLOT];
+      int rank[NSLOT];
 #pragma unroll
       for (int sl = 0; sl < NSLOT; ++sl) {
         const uint4 r = philox4x32_10(
             make_uint4((uint32_t)(lane + 32 * sl), (uint32_t)n + dc.ind_offset, (uint32_t)c, (uint32_t)cfg.sweep),
             make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32) ^ (uint32_t)(cfg.sweep >> 32)));
         key[sl] = r.x;
-        rnd_t[sl] = r.y;
-        rnd_a[sl] = r.z;
+        const double u_t = u01(r.y), u_a = u01(r.z);
+        skip[sl] = (cfg.mode == ABD_GIBBS_METROPOLIS) && !(u_t <= cfg.transit_p);
+        acc_u[sl] = (cfg.mode == ABD_GIBBS_METROPOLIS) ? log(u_a) : u_a;
         rank[sl] = 0;
       }
       for (int jj = 0; jj < nprop; ++jj) {
@@ -398,39 +534,44 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
           rank[sl] += (kj < key[sl]) || (kj == key[sl] && jj < me);
         }
       }
+      __syncwarp();
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const int me = lane + 32 * sl;
+        if (me < nprop) s_ord[warp][rank[sl]] = (unsigned char)me;
+      }
+      __syncwarp();
     }
+    auto refresh_inf2 = [&]() {
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const int me = lane + 32 * sl;
+        inf2_own[sl] = (me < G) ? constrain<M>(raw ^ ((M)1 << me), pcr, dc.ch) : inf;
+      }
+    };
+    refresh_inf2();
 
     for (int step = 0; step < nprop; ++step) {
-      int jp;  // proposal visited at this step
-      double u_t = 0.0, u_a = 1.0;
-      if (cfg.mode >= 0) {
-        jp = 0;
-#pragma unroll
-        for (int sl = 0; sl < NSLOT; ++sl) {
-          const int me = lane + 32 * sl;
-          const unsigned bal = __ballot_sync(0xffffffffu, me < nprop && rank[sl] == step);
-          if (bal) {
-            const int src = __ffs(bal) - 1;
-            jp = src + 32 * sl;
-            u_t = u01(__shfl_sync(0xffffffffu, rnd_t[sl], src));
-            u_a = u01(__shfl_sync(0xffffffffu, rnd_a[sl], src));
-          }
-        }
-        if (cfg.mode == ABD_GIBBS_METROPOLIS && !(u_t <= cfg.transit_p)) continue;
-      } else {
-        jp = step;
+      const int jp = (cfg.mode >= 0) ? (int)s_ord[warp][step] : step;  // proposal visited now
+      const int owner = jp & 31, slot = jp >> 5;
+      bool skp = skip[0];
+      double au = acc_u[0];
+      M inf2 = inf2_own[0];
+      if (NSLOT > 1 && slot) {
+        skp = skip[NSLOT - 1];
+        au = acc_u[NSLOT - 1];
+        inf2 = inf2_own[NSLOT - 1];
       }
+      if (__shfl_sync(0xffffffffu, (int)skp, owner)) continue;
       const bool is_w = (jp == G);
+      inf2 = __shfl_sync(0xffffffffu, inf2, owner);
       const M raw2 = is_w ? raw : (raw ^ ((M)1 << jp));
       const int w2 = is_w ? (w ^ 1) : w;
-      const M inf2 = is_w ? inf : constrain<M>(raw2, pcr, dc.ch);
       const int cur_bit = is_w ? w : (int)((raw >> jp) & 1);
       double ll2 = ll;
-      if (inf2 != inf || is_w)
-        ll2 = indiv_ll<M>(dc, n, inf2, vac, w2, s_th, s_pw, lane, rn0, rn1, rs0, rs1);
+      if (inf2 != inf || is_w) ll2 = indiv_ll(inf2, w2);
       const double lo = s_lo[is_w ? 1 : 0];
-      // log-odds of bit = 1 versus bit = 0
-      const double d10 = cur_bit ? (ll - ll2 + lo) : (ll2 - ll + lo);
+      const double d10 = cur_bit ? (ll - ll2 + lo) : (ll2 - ll + lo);  // log-odds of 1 versus 0
       if (cfg.mode < 0) {
         if (lane == 0) {
           if (is_w) cfg.out_w[(size_t)c * N + n] = d10;
@@ -438,14 +579,14 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
         }
         continue;
       }
+      au = __shfl_sync(0xffffffffu, au, owner);
       bool flip;
       if (cfg.mode == ABD_GIBBS_METROPOLIS) {
         const double delta = cur_bit ? -d10 : d10;  // logp(proposed) - logp(current)
-        flip = isfinite(delta) && (log(u_a) < delta);
+        flip = isfinite(delta) && (au < delta);
       } else {
         const double p1 = 1.0 / (1.0 + exp(-d10));
-        const int nb = u_a <= p1;
-        flip = (nb != cur_bit);
+        flip = ((au <= p1) ? 1 : 0) != cur_bit;
       }
       ++n_prop;
       if (flip) {
@@ -454,6 +595,7 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
         w = w2;
         inf = inf2;
         ll = ll2;
+        if (!is_w) refresh_inf2();
       }
     }
 
@@ -465,6 +607,8 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
       }
       if (lane == 0) waner[(size_t)c * N + n] = (int8_t)w;
     }
+    if (lane == 0) j = atomicAdd(&s_next, 1);
+    j = __shfl_sync(0xffffffffu, j, 0);
   }
   if (cfg.mode < 0) return;
   if (lane == 0 && cfg.stats) {
@@ -473,8 +617,8 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
   }
   __syncthreads();
   for (int idx = tid; idx < G * kGibbsTile; idx += kGibbsWarps * 32) {
-    const int t = idx / kGibbsTile, j = idx % kGibbsTile;
-    if (j < ni) i_raw[((size_t)c * G + t) * N + i0 + j] = (int8_t)s_bytes[t][j];
+    const int t = idx / kGibbsTile, jj = idx % kGibbsTile;
+    if (jj < ni) i_raw[((size_t)c * G + t) * N + i0 + jj] = (int8_t)s_bytes[t][jj];
   }
   if (cfg.stats && tid < 2) atomicAdd(&cfg.stats[(size_t)c * 2 + tid], (unsigned long long)s_stat[tid]);
 }
@@ -490,7 +634,7 @@ k_determ(const DevCohort dc, const double* __restrict__ theta13, const int8_t* _
   const int c = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
   const int G = dc.G, N = dc.N;
   __shared__ double s_th[16];
-  load_theta(theta13, 0, c, threadIdx.x, s_th);
+  if (threadIdx.x < 13) s_th[threadIdx.x] = theta13[(size_t)c * 13 + threadIdx.x];
   __syncthreads();
   if (n >= N) return;
   M raw = 0;
@@ -511,6 +655,17 @@ k_determ(const DevCohort dc, const double* __restrict__ theta13, const int8_t* _
     if (out_i) out_i[o] = (int8_t)it;
     if (out_mu_n) out_mu_n[o] = s_th[N_PERM] * Pn + s_th[N_TEMP] * T + s_th[N_INIT];
     if (out_mu_s) out_mu_s[o] = s_th[S_PERM] * Ps + U + s_th[S_INIT];
+  }
+}
+
+__global__ void k_debug_fast_math(const long long n, const double* __restrict__ z, double* __restrict__ out_exp,
+                                  double* __restrict__ out_rcp) {
+  __shared__ double s_tab[kExpTab];
+  fill_exp_table(s_tab, threadIdx.x, blockDim.x);
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    out_exp[i] = fast_exp(z[i], s_tab);
+    out_rcp[i] = fast_rcp(1.0 + fabs(z[i]));
   }
 }
 
@@ -535,9 +690,14 @@ struct abd_handle {
   struct Tiling {
     int ntiles = 0;
     int* d_tile_ind = nullptr;
+    int cap_n = 0, cap_s = 0, capm_n = 0, capm_s = 0;  // staging capacities (elements)
+    size_t smem = 0;                                     // dynamic shared memory per CTA
   };
-  std::map<int, Tiling> tilings;  // keyed by rows per tile
-  int tile_rows_override = 0;
+  std::map<int, Tiling> tilings;  // keyed by number of tiles requested
+  int tile_rows_override = 0;     // 0 = automatic
+  int chains_per_cta_override = 0;
+  int n_sms = 148;
+  size_t smem_optin = 0;
 
   // per-chain scratch
   int cap_chains = 0;
@@ -628,8 +788,9 @@ int build_rows(abd_handle* h, int a, int64_t R, const double* x, const double* o
   for (int n = 0; n < N; ++n)
     std::stable_sort(order.begin() + rp[n], order.begin() + rp[n + 1],
                      [&](int64_t p, int64_t q) { return gap[p] < gap[q]; });
-  std::vector<double> xs((size_t)R), ods((size_t)R);
-  std::vector<uint32_t> meta((size_t)R);
+  // padded so that the 16-byte-aligned bulk copies of k_sums may read past the last row
+  std::vector<double> xs((size_t)R + 2, 0.0), ods((size_t)R + 2, 0.0);
+  std::vector<uint32_t> meta((size_t)R + 4, 0u);
   for (int64_t k = 0; k < R; ++k) {
     const int64_t r = order[(size_t)k];
     xs[(size_t)k] = x[r];
@@ -652,27 +813,46 @@ int build_rows(abd_handle* h, int a, int64_t R, const double* x, const double* o
   return ABD_OK;
 }
 
-int get_tiling(abd_handle* h, int rows_per_tile, abd_handle::Tiling** out) {
-  auto it = h->tilings.find(rows_per_tile);
+// Split the individuals into `want` contiguous tiles of (nearly) equal OD-row count, at most
+// kTileMaxInds individuals each, and size the shared-memory staging buffers for the largest.
+int get_tiling(abd_handle* h, int want, abd_handle::Tiling** out) {
+  auto it = h->tilings.find(want);
   if (it == h->tilings.end()) {
+    const int N = h->N;
+    const std::vector<int>&rn = h->h_rp[0], &rs = h->h_rp[1];
+    const double total = (double)rn[N] + (double)rs[N];
     std::vector<int> ti{0};
-    int rows = 0, inds = 0;
-    for (int n = 0; n < h->N; ++n) {
-      const int rn = (h->h_rp[0][n + 1] - h->h_rp[0][n]) + (h->h_rp[1][n + 1] - h->h_rp[1][n]);
-      if (inds > 0 && (inds == kTileMaxInds || rows + rn > rows_per_tile)) {
+    int inds = 0;
+    for (int n = 0; n < N; ++n) {
+      // boundary before individual n if the running row count passed the next multiple of total/want
+      const double before = (double)rn[n] + (double)rs[n];
+      const double target = total * (double)ti.size() / (double)want;
+      if (inds > 0 && (inds == kTileMaxInds || (before >= target && (int)ti.size() < want))) {
         ti.push_back(n);
-        rows = 0;
         inds = 0;
       }
-      rows += rn;
       ++inds;
     }
-    ti.push_back(h->N);
+    ti.push_back(N);
     abd_handle::Tiling t;
     t.ntiles = (int)ti.size() - 1;
+    for (int k = 0; k < t.ntiles; ++k) {
+      const int a = ti[k], b = ti[k + 1];
+      t.cap_n = std::max(t.cap_n, ((rn[b] + 1) & ~1) - (rn[a] & ~1));
+      t.cap_s = std::max(t.cap_s, ((rs[b] + 1) & ~1) - (rs[a] & ~1));
+      t.capm_n = std::max(t.capm_n, ((rn[b] + 3) & ~3) - (rn[a] & ~3));
+      t.capm_s = std::max(t.capm_s, ((rs[b] + 3) & ~3) - (rs[a] & ~3));
+    }
+    t.cap_n = std::max(t.cap_n, 2);
+    t.cap_s = std::max(t.cap_s, 2);
+    t.capm_n = std::max(t.capm_n, 4);
+    t.capm_s = std::max(t.capm_s, 4);
+    t.smem = (size_t)(2 * t.cap_n + 2 * t.cap_s) * 8 + (size_t)(t.capm_n + t.capm_s) * 4;
+    if (t.smem + 12 * 1024 > h->smem_optin)
+      return fail(ABD_ERR_INVALID, "an individual tile does not fit in shared memory (too many OD rows per 128 individuals)");
     int rc = upload(h, &t.d_tile_ind, ti);
     if (rc) return rc;
-    it = h->tilings.emplace(rows_per_tile, t).first;
+    it = h->tilings.emplace(want, t).first;
   }
   *out = &it->second;
   return ABD_OK;
@@ -714,36 +894,65 @@ int ensure_chains(abd_handle* h, int C) {
   return ABD_OK;
 }
 
-int auto_tile_rows(const abd_handle* h, int C) {
-  if (h->tile_rows_override > 0) return h->tile_rows_override;
-  const double row_evals = (double)(h->R[0] + h->R[1]) * C;
-  // aim for >= ~4 CTAs per SM while keeping >= 4 rows per thread
-  if (row_evals < 148.0 * 4 * 1024) return 1024;
-  if (row_evals < 148.0 * 16 * 2048) return 2048;
-  return 4096;
+// Grid plan: CTAs = tiles x chain groups.  While the whole grid fits in a few waves, make it a
+// multiple of the SM count (one CTA wave of equal work per SM: no tail); rows per tile are kept
+// near `target` so that each of the 256 threads owns a handful of OD rows.
+void plan_grid(const abd_handle* h, int C, int* want_tiles, int* chains_per_cta) {
+  const double rows = (double)(h->R[0] + h->R[1]);
+  const int target = h->tile_rows_override > 0 ? h->tile_rows_override : 1600;
+  int cpc = h->chains_per_cta_override > 0 ? h->chains_per_cta_override : (C >= 256 ? 4 : 1);
+  cpc = std::min(cpc, C);
+  const int groups = (C + cpc - 1) / cpc;
+  int tiles = std::max(1, (int)std::ceil(rows / target));
+  tiles = std::max(tiles, (h->N + kTileMaxInds - 1) / kTileMaxInds);
+  const long ctas = (long)tiles * groups;
+  if (ctas < 8L * h->n_sms) {
+    // smallest multiple of the SM count that keeps rows per tile <= target
+    for (int k = 1; k <= 8; ++k) {
+      const int t = std::max(1, (h->n_sms * k) / groups);
+      if (rows / t <= target * 1.05 || k == 8) {
+        tiles = std::max(t, (h->N + kTileMaxInds - 1) / kTileMaxInds);
+        break;
+      }
+    }
+  }
+  tiles = std::min(tiles, h->N);
+  *want_tiles = tiles;
+  *chains_per_cta = cpc;
+}
+
+template <typename M>
+int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cfg, dim3 grid, const double* theta,
+                  int theta_is_q, const int8_t* i_raw, const int8_t* waner, double* sums, const FinalizeCfg& fin,
+                  cudaStream_t st) {
+  if (tl.smem > 40 * 1024)
+    CU(cudaFuncSetAttribute(k_sums<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem));
+  k_sums<M><<<grid, kSumsBlock, tl.smem, st>>>(h->dc, tl.d_tile_ind, cfg, theta, theta_is_q, i_raw, waner,
+                                                h->d_partial, h->d_ticket, sums, fin, h->d_priors);
+  return ABD_OK;
 }
 
 int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const int8_t* i_raw,
                 const int8_t* waner, double* sums, const FinalizeCfg& fin, cudaStream_t st) {
+  int want, cpc;
+  plan_grid(h, C, &want, &cpc);
   abd_handle::Tiling* tl;
-  int rc = get_tiling(h, auto_tile_rows(h, C), &tl);
+  int rc = get_tiling(h, want, &tl);
   if (rc) return rc;
   const size_t need = (size_t)C * tl->ntiles * kNSums;
   if (need > h->cap_partial) {
     CU(cudaStreamSynchronize(st));
     if (h->d_partial) cudaFree(h->d_partial);
+    h->d_partial = nullptr;
+    h->cap_partial = 0;
     if ((rc = dev_alloc(h, &h->d_partial, need, false))) return rc;
     h->cap_partial = need;
   }
-  dim3 grid(tl->ntiles, C);
-  if (h->wide)
-    k_sums<uint64_t><<<grid, kSumsBlock, 0, st>>>(h->dc, tl->d_tile_ind, tl->ntiles, theta, theta_is_q,
-                                                  i_raw, waner, h->d_partial, h->d_ticket, sums, fin,
-                                                  h->d_priors);
-  else
-    k_sums<uint32_t><<<grid, kSumsBlock, 0, st>>>(h->dc, tl->d_tile_ind, tl->ntiles, theta, theta_is_q,
-                                                  i_raw, waner, h->d_partial, h->d_ticket, sums, fin,
-                                                  h->d_priors);
+  SumsCfg cfg{tl->ntiles, tl->cap_n, tl->cap_s, tl->capm_n, tl->capm_s, cpc, C};
+  dim3 grid(tl->ntiles, (C + cpc - 1) / cpc);
+  rc = h->wide ? launch_sums_t<uint64_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st)
+               : launch_sums_t<uint32_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st);
+  if (rc) return rc;
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;
@@ -815,6 +1024,11 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
 
   abd_handle* h = new abd_handle();
   h->device = device;
+  {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->n_sms = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess) h->smem_optin = (size_t)v;
+  }
   h->G = G;
   h->N = N;
   h->wide = G > 31;
@@ -911,10 +1125,11 @@ int64_t abd_algorithmic_bytes_gibbs(const abd_handle* h, int C) {
 }
 int64_t abd_launch_count(const abd_handle* h) { return h ? h->launches : 0; }
 
-int abd_set_tile_rows(abd_handle* h, int rows) {
+int abd_set_tuning(abd_handle* h, int rows_per_tile, int chains_per_cta) {
   if (!h) return fail(ABD_ERR_INVALID, "NULL handle");
-  if (rows < 0) return fail(ABD_ERR_INVALID, "rows_per_tile must be >= 0");
-  h->tile_rows_override = rows;
+  if (rows_per_tile < 0 || chains_per_cta < 0) return fail(ABD_ERR_INVALID, "tuning values must be >= 0");
+  h->tile_rows_override = rows_per_tile;
+  h->chains_per_cta_override = chains_per_cta;
   return ABD_OK;
 }
 
@@ -1106,7 +1321,7 @@ int abd_finalize_loglik_dev(abd_handle* h, int C, const double* theta13, const d
   PROLOGUE(h, C);
   if (!theta13 || !sums || !out_loglik) return fail(ABD_ERR_INVALID, "NULL argument");
   FinalizeCfg fin{1, h->tot, out_loglik, out_grad};
-  k_finalize<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(C, theta13, sums, fin, h->d_priors);
+  k_finalize<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, theta13, sums, fin, h->d_priors);
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;
@@ -1117,7 +1332,7 @@ int abd_finalize_logp_dev(abd_handle* h, int C, const double* q17, const double*
   PROLOGUE(h, C);
   if (!q17 || !sums || !out_logp) return fail(ABD_ERR_INVALID, "NULL argument");
   FinalizeCfg fin{2, h->tot, out_logp, out_dlogp};
-  k_finalize<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(C, q17, sums, fin, h->d_priors);
+  k_finalize<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, q17, sums, fin, h->d_priors);
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;
@@ -1161,6 +1376,28 @@ int abd_deterministics_dev(abd_handle* h, int C, const double* theta13, const in
     k_determ<uint32_t><<<grid, 128, 0, (cudaStream_t)stream>>>(h->dc, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s);
   CU(cudaGetLastError());
   h->launches++;
+  return ABD_OK;
+}
+
+int abd_debug_fast_math(int device, int64_t n, const double* z, double* out_exp, double* out_rcp) {
+  if (n < 0 || !z || !out_exp || !out_rcp) return fail(ABD_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(device));
+  double *dz = nullptr, *de = nullptr, *dr = nullptr;
+  const size_t bytes = (size_t)std::max<int64_t>(n, 1) * sizeof(double);
+  CU(cudaMalloc((void**)&dz, bytes));
+  CU(cudaMalloc((void**)&de, bytes));
+  CU(cudaMalloc((void**)&dr, bytes));
+  cudaError_t e = cudaMemcpy(dz, z, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_debug_fast_math<<<296, 256>>>(n, dz, de, dr);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_exp, de, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out_rcp, dr, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dz);
+  cudaFree(de);
+  cudaFree(dr);
+  CU(e);
   return ABD_OK;
 }
 

@@ -185,24 +185,141 @@ __device__ __forceinline__ double mu_s_at(M inf, M vac, int w, int t, const doub
   return init + P + U;
 }
 
+// ---- fast fp64 exp / reciprocal for the OD-row hot loop -------------------------------------
+// exp(z) = 2^(k/64) * exp(r),  k = rint(z * 64/ln2),  r = z - k ln2/64  (|r| <= ln2/128):
+// 64-entry table of 2^(j/64) (shared memory) x degree-5 polynomial; < 1.5 ulp for -745 <= z
+// <= 709 (checked against libm in tests/test_gpu_parity.py::test_fast_math).  Results below
+// 2^-1021 are flushed to 0 (the caller only needs 1/(1+E)).  NaN in -> NaN out.
+constexpr int kExpTab = 64;
+// 2^(j/64), j = 0..63, correctly rounded (generated with 60-digit decimal arithmetic)
+__device__ const double kExp2Tab[kExpTab] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+__device__ __forceinline__ void fill_exp_table(double* tab, int tid, int nthreads) {
+  for (int j = tid; j < kExpTab; j += nthreads) tab[j] = kExp2Tab[j];
+}
+__device__ __forceinline__ double fast_exp(double z, const double* __restrict__ tab) {
+  constexpr double kInv = 92.33248261689366;            // 64 / ln 2
+  constexpr double kMagic = 6755399441055744.0;         // 1.5 * 2^52
+  constexpr double kLn2Hi = 0.01083042469326756;        // ln2/64, low 21 mantissa bits zero
+  constexpr double kLn2Lo = 2.9815858269852933e-12;     // ln2/64 - kLn2Hi
+  const double zc = (z < -750.0) ? -750.0 : z;
+  const double t = fma(zc, kInv, kMagic);
+  const int k = __double2loint(t);
+  const double kd = t - kMagic;
+  double r = fma(kd, -kLn2Hi, zc);
+  r = fma(kd, -kLn2Lo, r);
+  double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p * r, r, r);
+  const double T = tab[k & (kExpTab - 1)];
+  double res = fma(T, p, T);
+  const int e = k >> 6;
+  res = __hiloint2double(__double2hiint(res) + (e << 20), __double2loint(res));
+  res = (e < -1021) ? 0.0 : res;
+  return (z != z) ? z : res;
+}
+// 1/x for normal x >= 1: MUFU seed + two Newton steps (full fp64 accuracy to ~1 ulp)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
 // One OD row: s = 1/(1+E), E = exp(-b (x - m));  r = od - d s;  q = r s (1 - s).
 // 1 - s is formed as E s (no cancellation); E is capped so that E s stays finite.
 __device__ __forceinline__ void row_eval(double x, double od, double m, double b, double d,
-                                         double& s, double& r, double& q, double& xm) {
+                                         const double* __restrict__ tab, double& s, double& r,
+                                         double& q, double& xm) {
   xm = x - m;
   double z = -b * xm;
   z = (z > 700.0) ? 700.0 : z;  // NaN stays NaN
-  const double E = exp(z);
-  s = 1.0 / (1.0 + E);
+  const double E = fast_exp(z, tab);
+  s = fast_rcp(1.0 + E);
   r = fma(-d, s, od);
   q = r * s * (E * s);
 }
-__device__ __forceinline__ double row_resid2(double x, double od, double m, double b, double d) {
+__device__ __forceinline__ double row_resid2(double x, double od, double m, double b, double d,
+                                             const double* __restrict__ tab) {
   double z = -b * (x - m);
   z = (z > 700.0) ? 700.0 : z;
-  const double s = 1.0 / (1.0 + exp(z));
+  const double s = fast_rcp(1.0 + fast_exp(z, tab));
   const double r = fma(-d, s, od);
   return r * r;
+}
+
+// ---- warp reduction of 16 doubles with 16 (not 80) 64-bit shuffles ----------------------------
+// Butterfly that halves the number of values a lane carries at every step.  Afterwards lane l
+// holds the warp total of value  k(l) = 8 b4 + 4 b3 + 2 b2 + b1  (b_i = bit i of l); both lanes
+// of a pair (l, l^1) hold the same total.  Summation order is fixed => deterministic.
+__device__ __forceinline__ double warp_reduce16(const double (&v)[16], int lane) {
+  double a8[8], a4[4], a2[2], a1;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double send = h16 ? v[k] : v[k + 8], keep = h16 ? v[k + 8] : v[k];
+    a8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double send = h8 ? a8[k] : a8[k + 4], keep = h8 ? a8[k + 4] : a8[k];
+    a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double send = h4 ? a4[k] : a4[k + 2], keep = h4 ? a4[k + 2] : a4[k];
+    a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const double send = h2 ? a2[0] : a2[1], keep = h2 ? a2[1] : a2[0];
+    a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return a1 + __shfl_xor_sync(0xffffffffu, a1, 1);
+}
+__device__ __forceinline__ int warp_reduce16_index(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA) -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, size and both addresses multiples of 16 bytes; completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 __device__ __forceinline__ double softplus(double y) {  // log(1 + e^y)
@@ -242,25 +359,26 @@ __device__ inline void finalize_loglik(const double* th, const double* S, const 
 }
 
 // Joint logp over (q17, i_raw, waner) in PyMC's unconstrained space and d logp / d q17.
-__device__ inline void finalize_logp(const double* q, const double* S, const Totals& tot,
-                                     const Priors& pr, double* logp, double* dlogp) {
+// Executed by one full warp: lane k < 17 owns value variable k (prior, transform, Jacobian and
+// chain rule); the 17 terms are summed by a fixed-order shuffle tree (deterministic).
+__device__ inline void finalize_logp_warp(int lane, const double* q, const double* S, const Totals& tot,
+                                          const Priors& pr, double* logp, double* dlogp) {
   double th[13], g13[13], ll;
   for (int k = 0; k < 13; ++k) th[k] = backward(q[kQOfTheta[k]], kQTransform[kQOfTheta[k]]);
   finalize_loglik(th, S, tot, &ll, g13);
-  double gl[17];  // d loglik / d (constrained value) scattered to the 17 slots
-  for (int k = 0; k < 17; ++k) gl[k] = 0.0;
-  for (int k = 0; k < 13; ++k) gl[kQOfTheta[k]] = g13[k];
-
-  double total = ll;
-  for (int k = 0; k < 17; ++k) {
+  double lp = 0.0, d = 0.0;
+  if (lane < 17) {
+    const int k = lane;
+    double gl = 0.0;  // d loglik / d (constrained value of slot k)
+#pragma unroll
+    for (int j = 0; j < 13; ++j) gl = (kQOfTheta[j] == k) ? g13[j] : gl;
     const double y = q[k];
     const PriorSpec ps = pr.v[k];
     const int tr = kQTransform[k];
-    double lp = 0.0, d = 0.0;
     if (tr == 0) {  // Normal, no transform
       const double z = (y - ps.a) / ps.b;
       lp = -0.5 * z * z + ps.c;
-      d = -z / ps.b + gl[k];
+      d = -z / ps.b + gl;
     } else if (tr == 1) {  // log transform: x = e^y, log|J| = y
       const double x = exp(y);
       if (ps.kind == 1) {  // Gamma(alpha, beta)
@@ -271,7 +389,7 @@ __device__ inline void finalize_logp(const double* q, const double* S, const Tot
         d = -ps.a * x;
       }
       lp += y;
-      d += 1.0 + gl[k] * x;
+      d += 1.0 + gl * x;
     } else {  // logodds transform: x = sigmoid(y), log|J| = log x + log(1 - x)
       const double lx = -softplus(-y), l1mx = -softplus(y);
       const double x = exp(lx), omx = exp(l1mx);
@@ -283,14 +401,15 @@ __device__ inline void finalize_logp(const double* q, const double* S, const Tot
         ca += S[S_KW];
         cb += tot.bits_w - S[S_KW];
       }
-      // (ca + 1) lx + (cb + 1) l1mx: prior, Bernoulli counts and the Jacobian share one form
+      // prior, Bernoulli counts and the Jacobian share the form  a' lx + b' l1mx
       lp = ps.c + (ca == 0.0 ? 0.0 : ca * lx) + (cb == 0.0 ? 0.0 : cb * l1mx) + lx + l1mx;
-      d = (ca + 1.0) * omx - (cb + 1.0) * x + gl[k] * x * omx;
+      d = (ca + 1.0) * omx - (cb + 1.0) * x + gl * x * omx;
     }
-    total += lp;
     if (dlogp) dlogp[k] = d;
   }
-  *logp = total;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) lp += __shfl_down_sync(0xffffffffu, lp, off);
+  if (lane == 0) *logp = ll + lp;
 }
 
 // Philox4x32-10 (Salmon et al. 2011), counter-based: one call yields 4 x 32 random bits.

@@ -159,8 +159,8 @@ class AbdEngine:
     def launch_count(self):
         return int(self._lib.abd_launch_count(self._h))
 
-    def set_tile_rows(self, rows):
-        check(self._lib.abd_set_tile_rows(self._h, int(rows)))
+    def set_tuning(self, rows_per_tile=0, chains_per_cta=0):
+        check(self._lib.abd_set_tuning(self._h, int(rows_per_tile), int(chains_per_cta)))
 
     # ------------------------------------------------------------------------------ state
     def upload_state(self, i_raw, waner):

@@ -188,8 +188,13 @@ int abd_deterministics_dev(abd_handle* h, int n_chains, const double* theta13,
 /* Pointers to the resident chain state (valid until the next call that changes n_chains).   */
 int abd_state_dev(abd_handle* h, int n_chains, int8_t** i_raw, int8_t** waner);
 
-/* Tuning knob: rows per CTA tile of the log-likelihood kernel (0 = automatic).              */
-int abd_set_tile_rows(abd_handle* h, int rows_per_tile);
+/* Tuning knobs of the log-likelihood kernel (0 = automatic): target OD rows per CTA tile and
+ * chains looped over inside one CTA (reusing the rows staged in shared memory).             */
+int abd_set_tuning(abd_handle* h, int rows_per_tile, int chains_per_cta);
+
+/* Test hook: out_exp[i] = the kernels' fast exp(z[i]), out_rcp[i] = their fast 1/(1 + |z[i]|)
+ * (host pointers; checked against libm in tests/test_gpu_parity.py).                        */
+int abd_debug_fast_math(int device, int64_t n, const double* z, double* out_exp, double* out_rcp);
 
 #ifdef __cplusplus
 }

@@ -168,7 +168,7 @@ def test_parity_sweep_1k_cohort(Engine, splits):
             assert grad_ok(g13[k], rg)
             assert cnt[k, 0] == i_raw[k].sum() and cnt[k, 1] == w[k].sum()
         # tile size must not change the result beyond rounding
-        eng.set_tile_rows(300)
+        eng.set_tuning(300, 3)
         lp2, g2 = eng.logp_dlogp(q[:16], i_raw[:16], w[:16])
         assert np.all(np.abs(lp2 - ref_lp[:16]) <= RTOL * np.abs(ref_lp[:16]))
         assert grad_ok(g2, ref_g[:16])
@@ -446,3 +446,26 @@ def test_gibbs_properties_10k(Engine):
     with Engine(co.take(np.arange(lo, hi)), splits=(14, 20), ind_offset=lo) as eng:
         s_i, s_w, _ = eng.gibbs_sweep(th, p, pw, i_raw[:, :, lo:hi], w[:, lo:hi], seed=1, sweep=0)
     assert np.array_equal(s_i, a_i[:, :, lo:hi]) and np.array_equal(s_w, a_w[:, lo:hi])
+
+
+def test_fast_math(Engine):
+    """The kernels' table-based exp and Newton reciprocal against libm: <= 2 ulp over the whole
+    range the OD-row code can produce (z is capped at 700 by the caller)."""
+    import ctypes as C
+
+    from abdpymc_b200 import _lib
+
+    rng = np.random.default_rng(1)
+    z = np.concatenate([rng.uniform(-745, 700, 400_000), rng.uniform(-40, 40, 400_000), rng.normal(0, 1e-3, 50_000),
+                        np.array([0.0, -0.0, 700.0, -708.0, -745.0, -800.0, -1e6, -1e300, np.nan, 1e-300, -1e-300])])
+    e = np.empty_like(z)
+    r = np.empty_like(z)
+    _lib.check(_lib.load().abd_debug_fast_math(0, len(z), z.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p),
+                                               r.ctypes.data_as(C.c_void_p)))
+    ref = np.exp(z)
+    ok = np.isfinite(z) & (z > -700)
+    assert np.max(np.abs(e[ok] - ref[ok]) / ref[ok]) < 4.5e-16
+    assert np.all(e[np.isfinite(z) & (z <= -700)] <= 1e-300)  # flushed towards 0, never negative / NaN
+    assert np.all(e[np.isfinite(z)] >= 0) and np.isnan(e[np.isnan(z)]).all()
+    x = 1.0 + np.abs(z[np.isfinite(z)])
+    assert np.max(np.abs(r[np.isfinite(z)] * x - 1.0)) < 4.5e-16
