@@ -8,10 +8,11 @@ every entry point fails loudly.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libabd_b200.so"
+LIB_PATH = Path(os.environ.get("ABD_B200_LIB", PKG / "libabd_b200.so"))  # override: developer builds only
 
 N_THETA, N_Q, N_SUMS, MAX_GAPS = 13, 17, 16, 63
 GIBBS_METROPOLIS, GIBBS_HEATBATH = 0, 1

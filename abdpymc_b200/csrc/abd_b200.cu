@@ -61,7 +61,9 @@ struct DevCohort {
   const int* rp[2];          // [0] = N antigen, [1] = S antigen
   const double* od[2];
   const double* x[2];
-  const uint32_t* meta[2];
+  const uint32_t* meta[2];     // per row: individual << 6 | gap
+  const uint32_t* rowcell[2];  // per row: index of its (individual, gap) cell
+  const uint32_t* cmeta[2];    // per cell: individual << 6 | gap
   Chunks ch;
 };
 
@@ -69,7 +71,6 @@ constexpr int kSumsBlock = 256;
 constexpr int kSumsWarps = kSumsBlock / 32;
 constexpr int kTileMaxInds = 128;
 constexpr int kGibbsWarps = 8;
-constexpr int kGibbsTile = 32;  // individuals per Gibbs CTA
 
 // per-individual state staged in shared memory: constrained infections, vaccinations, waner
 // (packed in the top bit of the vaccination mask; usable gaps <= width - 1)
@@ -126,14 +127,45 @@ struct FinalizeCfg {
 struct SumsCfg {
   int ntiles;
   int cap_n, cap_s;      // staged doubles per antigen (even)
-  int capm_n, capm_s;    // staged meta words per antigen (multiple of 4)
+  int capr_n, capr_s;    // staged row->cell words per antigen (multiple of 4)
+  int capk_n, capk_s;    // staged cell-meta words per antigen (multiple of 4)
   int chains_per_cta;
   int C;
 };
 
+// tile descriptor (48 bytes, three 16-byte loads): individuals [i0, i1); per antigen the OD rows
+// [r0, r1) and the (individual, gap) cells [c0, c1) of those individuals
+struct __align__(16) TileDesc {
+  int i0, i1, rn0, rn1;
+  int rs0, rs1, cn0, cn1;
+  int cs0, cs1, pad0, pad1;
+};
+
+// trajectory of one cell: titer m, decaying part T (or U) and its rho-derivative
+struct CellVal {
+  double m, T, dT;
+};
+
+#ifdef ABD_PHASE_TIMING
+__device__ unsigned long long g_phase[4096][12];
+#define PHASE(i)                                                                         \
+  do {                                                                                   \
+    if (tid == 0 && blockIdx.y == 0 && blockIdx.x < 4096) {                              \
+      unsigned long long t_;                                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+      g_phase[blockIdx.x][i] = t_;                                                       \
+    }                                                                                    \
+  } while (0)
+#else
+#define PHASE(i)
+#endif
+
+#ifndef ABD_SUMS_MINB
+#define ABD_SUMS_MINB 3
+#endif
 template <typename M>
-__global__ void __launch_bounds__(kSumsBlock, 3)
-k_sums(const DevCohort dc, const int* __restrict__ tile_ind, const SumsCfg cfg,
+__global__ void __launch_bounds__(kSumsBlock, ABD_SUMS_MINB)
+k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg,
        const double* __restrict__ theta, const int theta_is_q,
        const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
        double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ sums,
@@ -141,35 +173,51 @@ k_sums(const DevCohort dc, const int* __restrict__ tile_ind, const SumsCfg cfg,
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int G = dc.G, N = dc.N, ntiles = cfg.ntiles;
-  const int i0 = tile_ind[tile], i1 = tile_ind[tile + 1];
-  const int ni = i1 - i0;
 
+  // dynamic shared memory: staged rows (od, x, row->cell), staged cell meta, per-cell values
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double* s_od_n = reinterpret_cast<double*>(dyn_smem);
   double* s_x_n = s_od_n + cfg.cap_n;
   double* s_od_s = s_x_n + cfg.cap_n;
   double* s_x_s = s_od_s + cfg.cap_s;
-  uint32_t* s_m_n = reinterpret_cast<uint32_t*>(s_x_s + cfg.cap_s);
-  uint32_t* s_m_s = s_m_n + cfg.capm_n;
+  CellVal* s_cv_n = reinterpret_cast<CellVal*>(s_x_s + cfg.cap_s);
+  CellVal* s_cv_s = s_cv_n + cfg.capk_n;
+  uint32_t* s_rc_n = reinterpret_cast<uint32_t*>(s_cv_s + cfg.capk_s);
+  uint32_t* s_rc_s = s_rc_n + cfg.capr_n;
+  uint32_t* s_cm_n = s_rc_s + cfg.capr_s;
+  uint32_t* s_cm_s = s_cm_n + cfg.capk_n;
 
   __shared__ double s_th[16];
   __shared__ double s_pw[4][kMaxGaps];  // rho_n^k, d/drho; rho_s^k, d/drho
   __shared__ double s_tab[kExpTab];
-  __shared__ unsigned s_bits[kMaxGaps][kTileMaxInds / 32];
   __shared__ IndState<M> s_ind[kTileMaxInds];
   __shared__ double s_red[kSumsWarps][kNSums];
   __shared__ double s_fin[kSumsBlock / 16][kNSums];
   __shared__ int s_last;
   __shared__ __align__(8) uint64_t s_bar;
+  __shared__ PriorPre s_pre[17];
+  __shared__ LikPre s_lik;
 
-  // ---- stage this tile's OD rows in shared memory: one thread, six bulk async copies ----
-  const int rn0 = dc.rp[0][i0], rn1 = dc.rp[0][i1], rs0 = dc.rp[1][i0], rs1 = dc.rp[1][i1];
-  const int an0 = rn0 & ~1, as0 = rs0 & ~1, mn0 = rn0 & ~3, ms0 = rs0 & ~3;
+  PHASE(0);
+  const int4 d0 = reinterpret_cast<const int4*>(tiles + tile)[0];
+  const int4 d1 = reinterpret_cast<const int4*>(tiles + tile)[1];
+  const int2 d2 = reinterpret_cast<const int2*>(tiles + tile)[4];
+  const int i0 = d0.x, ni = d0.y - d0.x;
+  const int rn0 = d0.z, rn1 = d0.w, rs0 = d1.x, rs1 = d1.y;
+  const int cn0 = d1.z, cn1 = d1.w, cs0 = d2.x, cs1 = d2.y;
+
+  // ---- stage this tile's rows and cell table in shared memory: one thread, bulk async copies ----
+  const int an0 = rn0 & ~1, as0 = rs0 & ~1;      // 16-byte aligned starts (doubles)
+  const int qn0 = rn0 & ~3, qs0 = rs0 & ~3;      // (32-bit words)
+  const int kn0 = cn0 & ~3, ks0 = cs0 & ~3;
   if (tid == 0) {
     mbar_init(&s_bar, 1);
     const uint32_t bn = (uint32_t)(((rn1 + 1) & ~1) - an0) * 8u, bs = (uint32_t)(((rs1 + 1) & ~1) - as0) * 8u;
-    const uint32_t bmn = (uint32_t)(((rn1 + 3) & ~3) - mn0) * 4u, bms = (uint32_t)(((rs1 + 3) & ~3) - ms0) * 4u;
-    mbar_expect_tx(&s_bar, 2 * bn + 2 * bs + bmn + bms);
+    const uint32_t bqn = (uint32_t)(((rn1 + 3) & ~3) - qn0) * 4u, bqs = (uint32_t)(((rs1 + 3) & ~3) - qs0) * 4u;
+    const uint32_t bkn = (uint32_t)(((cn1 + 3) & ~3) - kn0) * 4u, bks = (uint32_t)(((cs1 + 3) & ~3) - ks0) * 4u;
+    mbar_expect_tx(&s_bar, 2 * bn + 2 * bs + bqn + bqs + bkn + bks);
+    if (bkn) bulk_g2s(s_cm_n, dc.cmeta[0] + kn0, bkn, &s_bar);
+    if (bks) bulk_g2s(s_cm_s, dc.cmeta[1] + ks0, bks, &s_bar);
     if (bn) {
       bulk_g2s(s_od_n, dc.od[0] + an0, bn, &s_bar);
       bulk_g2s(s_x_n, dc.x[0] + an0, bn, &s_bar);
@@ -178,104 +226,125 @@ k_sums(const DevCohort dc, const int* __restrict__ tile_ind, const SumsCfg cfg,
       bulk_g2s(s_od_s, dc.od[1] + as0, bs, &s_bar);
       bulk_g2s(s_x_s, dc.x[1] + as0, bs, &s_bar);
     }
-    if (bmn) bulk_g2s(s_m_n, dc.meta[0] + mn0, bmn, &s_bar);
-    if (bms) bulk_g2s(s_m_s, dc.meta[1] + ms0, bms, &s_bar);
+    if (bqn) bulk_g2s(s_rc_n, dc.rowcell[0] + qn0, bqn, &s_bar);
+    if (bqs) bulk_g2s(s_rc_s, dc.rowcell[1] + qs0, bqs, &s_bar);
   }
   fill_exp_table(s_tab, tid, kSumsBlock);
-
-  const int ngrp = (ni + 31) >> 5;
-  const int nitems = G * ngrp;
+  PHASE(1);
 
   for (int cc = 0; cc < cfg.chains_per_cta; ++cc) {
     const int c = blockIdx.y * cfg.chains_per_cta + cc;
     if (c >= cfg.C) break;
 
-    // ---- phase 0a: int8 columns -> per-gap ballots (every warp; coalesced over individuals) ----
-    {
-      const int8_t* base = i_raw + (size_t)c * G * N + i0;
-      for (int it0 = warp; it0 < nitems; it0 += 4 * kSumsWarps) {
-        int8_t b[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int item = it0 + u * kSumsWarps;
-          const int t = item / ngrp, j = (item - t * ngrp) * 32 + lane;
-          b[u] = (item < nitems && j < ni) ? base[(size_t)t * N + j] : (int8_t)0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int item = it0 + u * kSumsWarps;
-          const unsigned bal = __ballot_sync(0xffffffffu, b[u] != 0);
-          if (lane == 0 && item < nitems) {
-            const int t = item / ngrp;
-            s_bits[t][item - t * ngrp] = bal;
-          }
-        }
-      }
-    }
-    // ---- phase 0b: parameters and power tables (warps 0-2) ----
-    if (warp == 0) fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw[0], s_pw[1]);
-    if (warp == 1) fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw[2], s_pw[3]);
-    if (warp == 2 && lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
-    __syncthreads();
-
-    // ---- phase 0c: one thread per individual: mask over gaps, constraints ----
     double acc[kNSums];
 #pragma unroll
     for (int k = 0; k < kNSums; ++k) acc[k] = 0.0;
-    if (tid < ni) {
-      M raw = 0;
-      const int jg = tid >> 5, jb = tid & 31;
-      for (int t = 0; t < G; ++t) raw |= (M)((s_bits[t][jg] >> jb) & 1u) << t;
-      const int w = waner[(size_t)c * N + i0 + tid] != 0;
-      const M pcr = reinterpret_cast<const M*>(dc.pcr)[i0 + tid];
-      IndState<M> st;
-      st.inf = constrain<M>(raw, pcr, dc.ch);
-      st.vacw = reinterpret_cast<const M*>(dc.vac)[i0 + tid] | (w ? top_bit<M>() : (M)0);
-      s_ind[tid] = st;
-      acc[S_KI] = (double)popc(raw);
-      acc[S_KW] = (double)w;
+
+    // ---- phase 0: warps 0-3: one thread per individual reads its int8 column (every load of
+    //      the warp is one coalesced 32-byte segment; all gaps in flight at once) and applies
+    //      the infection constraints; warps 4-6: parameters and power tables ----
+    if (tid < kTileMaxInds) {
+      if (tid < ni) {
+        // issue every load of the column before the first use (one memory round trip)
+        const int8_t* col = i_raw + (size_t)c * G * N + i0 + tid;
+        int8_t bytes[sizeof(M) * 8];
+#pragma unroll
+        for (int t = 0; t < (int)sizeof(M) * 8; ++t) {
+          bytes[t] = (t < G) ? __ldg(col) : (int8_t)0;
+          col += N;
+        }
+        M raw = 0;
+#pragma unroll
+        for (int t = 0; t < (int)sizeof(M) * 8; ++t) raw |= (M)(bytes[t] != 0) << t;
+        const int w = waner[(size_t)c * N + i0 + tid] != 0;
+        const M pcr = reinterpret_cast<const M*>(dc.pcr)[i0 + tid];
+        IndState<M> st;
+        st.inf = constrain<M>(raw, pcr, dc.ch);
+        st.vacw = reinterpret_cast<const M*>(dc.vac)[i0 + tid] | (w ? top_bit<M>() : (M)0);
+        s_ind[tid] = st;
+        acc[S_KI] = (double)popc(raw);
+        acc[S_KW] = (double)w;
+      }
+    } else if (warp == 4) {
+      fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw[0], s_pw[1]);
+    } else if (warp == 5) {
+      fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw[2], s_pw[3]);
+    } else if (warp == 6) {
+      if (lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
     }
     __syncthreads();
+    PHASE(2);
     if (cc == 0) mbar_wait(&s_bar, 0);
+    PHASE(3);
 
-    // ---- phase 1: one thread per OD row, rows read from shared memory ----
+    // ---- phase 1: one thread per (individual, gap) cell: titer in closed form from the masks ----
     {
       const double init = s_th[N_INIT], perm = s_th[N_PERM], temp = s_th[N_TEMP];
-      const double b = s_th[N_B], d = s_th[N_D];
-      for (int r = rn0 + tid; r < rn1; r += kSumsBlock) {
-        const uint32_t mt = s_m_n[r - mn0];
+      for (int k = cn0 + tid; k < cn1; k += kSumsBlock) {
+        const uint32_t mt = s_cm_n[k - kn0];
         const int t = mt & 63, li = (int)(mt >> 6) - i0;
-        double P, T, dT, s, res, q, xm;
+        double P, T, dT;
         traj_n<M>(s_ind[li].inf, t, s_pw[0], s_pw[1], P, T, dT);
-        row_eval(s_x_n[r - an0], s_od_n[r - an0], init + perm * P + temp * T, b, d, s_tab, s, res, q, xm);
-        acc[SN_0] = fma(res, res, acc[SN_0]);
-        acc[SN_1] = fma(res, s, acc[SN_1]);
-        acc[SN_2] = fma(q, xm, acc[SN_2]);
-        acc[SN_QINIT] += q;
-        acc[SN_QPERM] = fma(q, P, acc[SN_QPERM]);
-        acc[SN_QTEMP] = fma(q, T, acc[SN_QTEMP]);
-        acc[SN_QRHO] = fma(q, dT, acc[SN_QRHO]);
+        CellVal cv;
+        cv.m = init + perm * P + temp * T;
+        cv.T = T;
+        cv.dT = (P != 0.0) ? dT : -0.0;  // sign bit of dT carries "never exposed" (P = 0)
+        s_cv_n[k - cn0] = cv;
       }
     }
     {
       const double init = s_th[S_INIT], perm = s_th[S_PERM];
-      const double b = s_th[S_B], d = s_th[S_D];
-      for (int r = rs0 + tid; r < rs1; r += kSumsBlock) {
-        const uint32_t mt = s_m_s[r - ms0];
+      for (int k = cs0 + tid; k < cs1; k += kSumsBlock) {
+        const uint32_t mt = s_cm_s[k - ks0];
         const int t = mt & 63, li = (int)(mt >> 6) - i0;
         const IndState<M> st = s_ind[li];
-        double P, U, dU, s, res, q, xm;
+        double P, U, dU;
         traj_s<M>(st.inf, st.vacw & ~top_bit<M>(), (st.vacw & top_bit<M>()) != 0, t, s_pw[2], s_pw[3], P, U, dU);
-        row_eval(s_x_s[r - as0], s_od_s[r - as0], init + perm * P + U, b, d, s_tab, s, res, q, xm);
+        CellVal cv;
+        cv.m = init + perm * P + U;
+        cv.T = U;
+        cv.dT = (P != 0.0) ? dU : -0.0;
+        s_cv_s[k - cs0] = cv;
+      }
+    }
+    __syncthreads();
+    PHASE(4);
+
+    // ---- phase 2: one thread per OD row; everything comes from shared memory, no divergence.
+    //      P (ever exposed) travels in the sign bit of dT ----
+    {
+      const double b = s_th[N_B], d = s_th[N_D];
+#pragma unroll 2
+      for (int r = rn0 + tid; r < rn1; r += kSumsBlock) {
+        const CellVal cv = s_cv_n[s_rc_n[r - qn0] - cn0];
+        double s, res, q, xm;
+        row_eval(s_x_n[r - an0], s_od_n[r - an0], cv.m, b, d, s_tab, s, res, q, xm);
+        acc[SN_0] = fma(res, res, acc[SN_0]);
+        acc[SN_1] = fma(res, s, acc[SN_1]);
+        acc[SN_2] = fma(q, xm, acc[SN_2]);
+        acc[SN_QINIT] += q;
+        acc[SN_QPERM] += (__double2hiint(cv.dT) < 0) ? 0.0 : q;
+        acc[SN_QTEMP] = fma(q, cv.T, acc[SN_QTEMP]);
+        acc[SN_QRHO] = fma(q, cv.dT, acc[SN_QRHO]);
+      }
+    }
+    {
+      const double b = s_th[S_B], d = s_th[S_D];
+#pragma unroll 2
+      for (int r = rs0 + tid; r < rs1; r += kSumsBlock) {
+        const CellVal cv = s_cv_s[s_rc_s[r - qs0] - cs0];
+        double s, res, q, xm;
+        row_eval(s_x_s[r - as0], s_od_s[r - as0], cv.m, b, d, s_tab, s, res, q, xm);
         acc[SS_0] = fma(res, res, acc[SS_0]);
         acc[SS_1] = fma(res, s, acc[SS_1]);
         acc[SS_2] = fma(q, xm, acc[SS_2]);
         acc[SS_QINIT] += q;
-        acc[SS_QPERM] = fma(q, P, acc[SS_QPERM]);
-        acc[SS_QRHO] = fma(q, dU, acc[SS_QRHO]);
+        acc[SS_QPERM] += (__double2hiint(cv.dT) < 0) ? 0.0 : q;
+        acc[SS_QRHO] = fma(q, cv.dT, acc[SS_QRHO]);
       }
     }
 
+    PHASE(5);
     // ---- block reduction: butterfly inside a warp, shared memory across warps ----
     {
       const double tot = warp_reduce16(acc, lane);
@@ -289,18 +358,36 @@ k_sums(const DevCohort dc, const int* __restrict__ tile_ind, const SumsCfg cfg,
       partial[((size_t)c * ntiles + tile) * kNSums + tid] = v;
     }
 
+    PHASE(6);
     // ---- last CTA of this chain: ordered reduction over tiles, then finalise ----
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&ticket[c], 1u) == (unsigned)(ntiles - 1));
     __syncthreads();
+    PHASE(7);
     if (s_last) {
       __threadfence();
+      // warp 7 prepares what the finaliser needs besides the sums while the partials arrive
+      // (kept out of the prologue: its cold libm code would sit on every CTA's critical path)
+      if (warp == kSumsWarps - 1) {
+        if (fin.mode == 2 && lane < 17) s_pre[lane] = prior_pre(lane, theta[(size_t)c * 17 + lane], priors->v[lane]);
+        if (lane == 17) s_lik = lik_pre(s_th[N_SIGMA], s_th[S_SIGMA]);
+      }
       const int k = tid & 15, g = tid >> 4;  // 16 groups of 16 values
       double v = 0.0;
-      for (int tl = g; tl < ntiles; tl += kSumsBlock / 16)
-        v += __ldcg(&partial[((size_t)c * ntiles + tl) * kNSums + k]);
+      const double* src = partial + (size_t)c * ntiles * kNSums + k;
+      for (int tl = g; tl < ntiles; tl += 8 * (kSumsBlock / 16)) {  // 8 loads in flight, fixed order
+        double ld[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int tt = tl + u * (kSumsBlock / 16);
+          ld[u] = (tt < ntiles) ? __ldcg(src + (size_t)tt * kNSums) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v += ld[u];
+      }
       s_fin[g][k] = v;
+      PHASE(9);
       __syncthreads();
       if (tid < kNSums) {
         double tot = 0.0;
@@ -310,18 +397,21 @@ k_sums(const DevCohort dc, const int* __restrict__ tile_ind, const SumsCfg cfg,
         if (sums) sums[(size_t)c * kNSums + tid] = tot;
       }
       __syncthreads();
+      PHASE(10);
       if (tid == 0) ticket[c] = 0;  // re-arm for the next launch
       if (warp == 0) {
         if (fin.mode == 1) {
           if (lane == 0)
-            finalize_loglik(s_th, s_red[0], fin.tot, &fin.out_val[c],
-                            fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
+            finalize_loglik_post(s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
+                                 fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
         } else if (fin.mode == 2) {
-          finalize_logp_warp(lane, &theta[(size_t)c * 17], s_red[0], fin.tot, *priors, &fin.out_val[c],
+          finalize_logp_post(lane, s_pre, s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
                              fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
         }
       }
     }
+    if (s_last) PHASE(11);
+    PHASE(8);
     __syncthreads();  // shared memory is reused by the next chain
   }
 }
@@ -337,8 +427,15 @@ __global__ void k_finalize(const int C, const double* __restrict__ theta,
       finalize_loglik(&theta[(size_t)c * 13], &sums[(size_t)c * kNSums], fin.tot, &fin.out_val[c],
                       fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
   } else {
-    finalize_logp_warp(lane, &theta[(size_t)c * 17], &sums[(size_t)c * kNSums], fin.tot, *priors,
-                       &fin.out_val[c], fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
+    __shared__ double s_th[4][16];  // 128 threads = 4 chains per CTA
+    __shared__ PriorPre s_pre[4][17];
+    const int wv = threadIdx.x >> 5;
+    if (lane < 13) s_th[wv][lane] = load_param(theta, 1, c, lane);
+    if (lane < 17) s_pre[wv][lane] = prior_pre(lane, theta[(size_t)c * 17 + lane], priors->v[lane]);
+    __syncwarp();
+    finalize_logp_post(lane, s_pre[wv], s_th[wv], lik_pre(s_th[wv][N_SIGMA], s_th[wv][S_SIGMA]),
+                       &sums[(size_t)c * kNSums], fin.tot, &fin.out_val[c],
+                       fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
   }
 }
 
@@ -379,76 +476,85 @@ __device__ __forceinline__ double gibbs_row(double x, double od, int t, bool is_
   return rp.nh * row_resid2(x, od, fma(rp.tfac, T, rp.init + P), rp.b, rp.d, s_tab);
 }
 
+// Persistent warps: every warp repeatedly claims the next (chain, individual) from a global
+// counter.  Items are ordered chain-major and, inside a chain, by decreasing OD-row count
+// (longest job first), so the tail at the end of the launch is one short job.
 template <typename M>
 __global__ void __launch_bounds__(kGibbsWarps * 32, 3)
-k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is_q,
+k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
+        const double* __restrict__ theta, const int theta_is_q,
         const double* __restrict__ p_arr, const double* __restrict__ pw_arr,
-        int8_t* __restrict__ i_raw, int8_t* __restrict__ waner, const GibbsCfg cfg) {
+        int8_t* __restrict__ i_raw, int8_t* __restrict__ waner, unsigned* __restrict__ queue,
+        const GibbsCfg cfg) {
   constexpr int NSLOT = sizeof(M) / 4;  // proposals owned per lane
-  const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = dc.G, N = dc.N;
-  const int i0 = blockIdx.x * kGibbsTile;
-  const int ni = min(kGibbsTile, N - i0);
 
-  __shared__ double s_th[16];
-  __shared__ double s_pw[3][kMaxGaps];
   __shared__ double s_tab[kExpTab];
-  __shared__ double s_lo[2];  // logit(p), logit(p_w)
-  __shared__ unsigned char s_bytes[kMaxGaps][kGibbsTile];
+  __shared__ double s_th_all[kGibbsWarps][18];            // theta13, -1/(2 sigma^2) x 2, logit p, logit p_w
+  __shared__ double s_pw_all[kGibbsWarps][3][kMaxGaps];   // rho_n^k, rho_s^k, ones
   __shared__ unsigned char s_ord[kGibbsWarps][kMaxGaps];
-  __shared__ unsigned s_stat[2];
-  __shared__ int s_next;
+  double* s_th = s_th_all[warp];
+  const double (*s_pw)[kMaxGaps] = s_pw_all[warp];
 
-  if (warp == 0) fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw[0], nullptr);
-  if (warp == 1) fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw[1], nullptr);
-  if (warp == 2) {
-    if (lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
-    if (lane == 13) {
-      const double sg = load_param(theta, theta_is_q, c, N_SIGMA);
-      s_th[13] = -0.5 / (sg * sg);
-    }
-    if (lane == 14) {
-      const double sg = load_param(theta, theta_is_q, c, S_SIGMA);
-      s_th[14] = -0.5 / (sg * sg);
-    }
-    if (lane == 15 || lane == 16) {
-      const int which = lane - 15;
-      double lo;
-      if (theta_is_q) {  // logit of a logodds-transformed value is the value itself
-        lo = theta[(size_t)c * 17 + (which ? kQ_PW : kQ_P)];
-      } else {
-        const double p = which ? pw_arr[c] : p_arr[c];
-        lo = log(p) - log1p(-p);
-      }
-      s_lo[which] = lo;
-    }
-  }
-  if (warp == 3) {
-    for (int k = lane; k < kMaxGaps; k += 32) s_pw[2][k] = 1.0;
-    if (lane < 2) s_stat[lane] = 0;
-    if (lane == 2) s_next = kGibbsWarps;
-  }
   fill_exp_table(s_tab, tid, kGibbsWarps * 32);
-  for (int idx = tid; idx < G * kGibbsTile; idx += kGibbsWarps * 32) {
-    const int t = idx / kGibbsTile, j = idx % kGibbsTile;
-    s_bytes[t][j] = (j < ni) ? (unsigned char)(i_raw[((size_t)c * G + t) * N + i0 + j] != 0) : 0;
-  }
+  for (int k = lane; k < kMaxGaps; k += 32) s_pw_all[warp][2][k] = 1.0;
   __syncthreads();
 
   const int nprop = G + 1;  // proposal j < G flips i_raw[j, n]; j == G flips waner[n]
+  const unsigned n_items = (unsigned)C * (unsigned)N;
   unsigned n_prop = 0, n_acc = 0;
+  int cur_c = -1;
 
-  int j = warp;  // individuals are handed out dynamically: row counts differ a lot
-  while (j < ni) {
-    const int n = i0 + j;
+  while (true) {
+    unsigned item = 0;
+    if (lane == 0) item = atomicAdd(queue, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    const int c = (int)(item / (unsigned)N);
+    const int n = order[item - (unsigned)c * (unsigned)N];
+
+    if (c != cur_c) {  // (re)load this chain's parameters into the warp's shared-memory slot
+      if (cur_c >= 0 && cfg.stats && lane == 0) {
+        atomicAdd(&cfg.stats[(size_t)cur_c * 2], (unsigned long long)n_prop);
+        atomicAdd(&cfg.stats[(size_t)cur_c * 2 + 1], (unsigned long long)n_acc);
+      }
+      n_prop = n_acc = 0;
+      cur_c = c;
+      __syncwarp();
+      fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw_all[warp][0], nullptr);
+      fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw_all[warp][1], nullptr);
+      if (lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
+      if (lane == 13 || lane == 14) {
+        const double sg = load_param(theta, theta_is_q, c, lane == 13 ? N_SIGMA : S_SIGMA);
+        s_th[lane] = -0.5 / (sg * sg);
+      }
+      if (lane == 15 || lane == 16) {
+        const int which = lane - 15;
+        double lo;
+        if (theta_is_q) {  // logit of a logodds-transformed value is the value itself
+          lo = theta[(size_t)c * 17 + (which ? kQ_PW : kQ_P)];
+        } else {
+          const double p = which ? pw_arr[c] : p_arr[c];
+          lo = log(p) - log1p(-p);
+        }
+        s_th[lane] = lo;
+      }
+      __syncwarp();
+    }
+
+    // ---- this individual's column of i_raw (lane t reads gap t), waner, masks, rows ----
+    int8_t* col = i_raw + (size_t)c * G * N + n;
     M raw = 0;
 #pragma unroll
     for (int sl = 0; sl < NSLOT; ++sl) {
       const int t = lane + 32 * sl;
-      const unsigned bal = __ballot_sync(0xffffffffu, t < G && s_bytes[t][j]);
-      raw |= (M)bal << (32 * sl);
+      const int8_t b = (t < G) ? col[(size_t)t * N] : (int8_t)0;
+      raw |= (M)__ballot_sync(0xffffffffu, b != 0) << (32 * sl);
     }
+    const M raw_in = raw;
     int w = waner[(size_t)c * N + n] != 0;
+    const int w_in = w;
     const M pcr = reinterpret_cast<const M*>(dc.pcr)[n];
     const M vac = reinterpret_cast<const M*>(dc.vac)[n];
     const int rn0 = dc.rp[0][n], cnt_n = dc.rp[0][n + 1] - rn0;
@@ -458,12 +564,11 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
     // rows of this individual, one per lane (N rows first, then S rows); kept in registers
     auto load_row = [&](int l, double& x, double& od, int& t, bool& is_s) {
       is_s = l >= cnt_n;
-      const int a = is_s ? 1 : 0;
       const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
       if (l < nrows) {
-        x = dc.x[a][r];
-        od = dc.od[a][r];
-        t = (int)(dc.meta[a][r] & 63u);
+        x = (is_s ? dc.x[1] : dc.x[0])[r];
+        od = (is_s ? dc.od[1] : dc.od[0])[r];
+        t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
       } else {
         x = 0.0;
         od = 0.0;
@@ -485,6 +590,17 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
     bool s0;
     load_row(lane, x0, od0, t0, s0);
     const RowPar rp0 = row_par(s0);
+    // latest sampled gap of either antigen / of the S antigen (rows are sorted by gap)
+    int t_last = t0, t_last_s = s0 ? t0 : -1;
+    for (int l = lane + 32; l < nrows; l += 32) {
+      const bool is_s = l >= cnt_n;
+      const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
+      const int t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
+      t_last = max(t_last, t);
+      if (is_s) t_last_s = max(t_last_s, t);
+    }
+    t_last = __reduce_max_sync(0xffffffffu, t_last);
+    t_last_s = __reduce_max_sync(0xffffffffu, t_last_s);
 
     auto indiv_ll = [&](M inf_, int w_) {
       double a = (t0 >= 0) ? gibbs_row<M>(x0, od0, t0, s0, inf_, vac, w_, rp0, s_pw, s_tab) : 0.0;
@@ -503,18 +619,16 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
     M inf = constrain<M>(raw, pcr, dc.ch);
     double ll = indiv_ll(inf, w);
 
-    // lane-owned proposals: random key (visiting order), transit / accept uniforms
-    bool skip[NSLOT];
-    double acc_u[NSLOT];  // log(u) (Metropolis) or u (heat bath) of the proposals this lane owns
-    M inf2_own[NSLOT];    // constrained infections if this lane's proposal were flipped
-#pragma unroll
-    for (int sl = 0; sl < NSLOT; ++sl) {
-      skip[sl] = false;
-      acc_u[sl] = 0.0;
-    }
+    // ---- lane-owned proposals: Philox key (visiting order), transit / accept uniforms ----
+    M act = 0;              // steps that are not skipped
+    int jp_step[NSLOT];     // lane k (+32 sl): proposal visited at step k
+    double au_step[NSLOT];  // its log(u) (Metropolis) or u (heat bath)
+    M inf2_own[NSLOT];      // constrained infections if this lane's own proposal were flipped
     if (cfg.mode >= 0) {
       uint32_t key[NSLOT];
       int rank[NSLOT];
+      bool skip[NSLOT];
+      double acc_u[NSLOT];
 #pragma unroll
       for (int sl = 0; sl < NSLOT; ++sl) {
         const uint4 r = philox4x32_10(
@@ -541,6 +655,33 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
         if (me < nprop) s_ord[warp][rank[sl]] = (unsigned char)me;
       }
       __syncwarp();
+      // gather, for the step this lane stands for, the proposal and its random numbers
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const int step = lane + 32 * sl;
+        const int jp = (step < nprop) ? (int)s_ord[warp][step] : 0;
+        jp_step[sl] = jp;
+        const int owner = jp & 31;
+        bool sk = __shfl_sync(0xffffffffu, (int)skip[0], owner);
+        double au = __shfl_sync(0xffffffffu, acc_u[0], owner);
+        if (NSLOT > 1) {
+          const bool sk1 = __shfl_sync(0xffffffffu, (int)skip[NSLOT - 1], owner);
+          const double au1 = __shfl_sync(0xffffffffu, acc_u[NSLOT - 1], owner);
+          if (jp >> 5) {
+            sk = sk1;
+            au = au1;
+          }
+        }
+        au_step[sl] = au;
+        act |= (M)__ballot_sync(0xffffffffu, step < nprop && !sk) << (32 * sl);
+      }
+    } else {
+#pragma unroll
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        jp_step[sl] = lane + 32 * sl;
+        au_step[sl] = 0.0;
+      }
+      act = low_mask<M>(G);  // every proposal 0..G, in order
     }
     auto refresh_inf2 = [&]() {
 #pragma unroll
@@ -551,26 +692,35 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
     };
     refresh_inf2();
 
-    for (int step = 0; step < nprop; ++step) {
-      const int jp = (cfg.mode >= 0) ? (int)s_ord[warp][step] : step;  // proposal visited now
-      const int owner = jp & 31, slot = jp >> 5;
-      bool skp = skip[0];
-      double au = acc_u[0];
-      M inf2 = inf2_own[0];
-      if (NSLOT > 1 && slot) {
-        skp = skip[NSLOT - 1];
-        au = acc_u[NSLOT - 1];
-        inf2 = inf2_own[NSLOT - 1];
+    while (act) {
+      const int step = ctz(act);
+      act &= act - 1;
+      int jp = jp_step[0];
+      double au = au_step[0];
+      if (NSLOT > 1 && (step >> 5)) {
+        jp = jp_step[NSLOT - 1];
+        au = au_step[NSLOT - 1];
       }
-      if (__shfl_sync(0xffffffffu, (int)skp, owner)) continue;
+      jp = __shfl_sync(0xffffffffu, jp, step & 31);
       const bool is_w = (jp == G);
-      inf2 = __shfl_sync(0xffffffffu, inf2, owner);
+      M inf2 = inf2_own[0];
+      if (NSLOT > 1 && (jp >> 5)) inf2 = inf2_own[NSLOT - 1];
+      inf2 = __shfl_sync(0xffffffffu, inf2, jp & 31);
       const M raw2 = is_w ? raw : (raw ^ ((M)1 << jp));
       const int w2 = is_w ? (w ^ 1) : w;
       const int cur_bit = is_w ? w : (int)((raw >> jp) & 1);
-      double ll2 = ll;
-      if (inf2 != inf || is_w) ll2 = indiv_ll(inf2, w2);
-      const double lo = s_lo[is_w ? 1 : 0];
+      // the data term changes only if the constrained infections differ at or before the last
+      // sampled gap (or, for the waner bit, if there is an S sample after the first exposure)
+      bool affected;
+      if (is_w) {
+        const M ex = inf | vac;
+        affected = ex != 0 && ctz(ex | top_bit<M>()) < t_last_s;
+      } else {
+        const M diff = inf ^ inf2;
+        affected = diff != 0 && ctz(diff | top_bit<M>()) <= t_last;
+      }
+      const double ll2 = affected ? indiv_ll(inf2, w2) : ll;
+      const double lo = s_th[is_w ? 16 : 15];
       const double d10 = cur_bit ? (ll - ll2 + lo) : (ll2 - ll + lo);  // log-odds of 1 versus 0
       if (cfg.mode < 0) {
         if (lane == 0) {
@@ -579,7 +729,7 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
         }
         continue;
       }
-      au = __shfl_sync(0xffffffffu, au, owner);
+      au = __shfl_sync(0xffffffffu, au, step & 31);
       bool flip;
       if (cfg.mode == ABD_GIBBS_METROPOLIS) {
         const double delta = cur_bit ? -d10 : d10;  // logp(proposed) - logp(current)
@@ -599,28 +749,20 @@ k_gibbs(const DevCohort dc, const double* __restrict__ theta, const int theta_is
       }
     }
 
-    if (cfg.mode >= 0) {
+    if (cfg.mode >= 0) {  // write back only what changed
+      const M changed = raw ^ raw_in;
 #pragma unroll
       for (int sl = 0; sl < NSLOT; ++sl) {
         const int t = lane + 32 * sl;
-        if (t < G) s_bytes[t][j] = (unsigned char)((raw >> t) & 1);
+        if (t < G && ((changed >> t) & 1)) col[(size_t)t * N] = (int8_t)((raw >> t) & 1);
       }
-      if (lane == 0) waner[(size_t)c * N + n] = (int8_t)w;
+      if (lane == 0 && w != w_in) waner[(size_t)c * N + n] = (int8_t)w;
     }
-    if (lane == 0) j = atomicAdd(&s_next, 1);
-    j = __shfl_sync(0xffffffffu, j, 0);
   }
-  if (cfg.mode < 0) return;
-  if (lane == 0 && cfg.stats) {
-    atomicAdd(&s_stat[0], n_prop);
-    atomicAdd(&s_stat[1], n_acc);
+  if (cfg.mode >= 0 && cfg.stats && lane == 0 && cur_c >= 0) {
+    atomicAdd(&cfg.stats[(size_t)cur_c * 2], (unsigned long long)n_prop);
+    atomicAdd(&cfg.stats[(size_t)cur_c * 2 + 1], (unsigned long long)n_acc);
   }
-  __syncthreads();
-  for (int idx = tid; idx < G * kGibbsTile; idx += kGibbsWarps * 32) {
-    const int t = idx / kGibbsTile, jj = idx % kGibbsTile;
-    if (jj < ni) i_raw[((size_t)c * G + t) * N + i0 + jj] = (int8_t)s_bytes[t][jj];
-  }
-  if (cfg.stats && tid < 2) atomicAdd(&cfg.stats[(size_t)c * 2 + tid], (unsigned long long)s_stat[tid]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -682,15 +824,16 @@ struct abd_handle {
   Totals tot{};
   DevCohort dc{};
   std::vector<void*> owned;   // device allocations freed in abd_destroy
-  std::vector<int> h_rp[2];   // host copy of the CSR pointers (for tilings)
+  std::vector<int> h_rp[2];   // host copy of the row CSR pointers (for tilings)
+  std::vector<int> h_cp[2];   // host copy of the cell CSR pointers
   cudaStream_t stream = nullptr;
   Priors* d_priors = nullptr;
   int64_t launches = 0;
 
   struct Tiling {
     int ntiles = 0;
-    int* d_tile_ind = nullptr;
-    int cap_n = 0, cap_s = 0, capm_n = 0, capm_s = 0;  // staging capacities (elements)
+    void* d_tiles = nullptr;   // TileDesc[ntiles]
+    int cap_n = 0, cap_s = 0, capr_n = 0, capr_s = 0, capk_n = 0, capk_s = 0;  // staging capacities (elements)
     size_t smem = 0;                                     // dynamic shared memory per CTA
   };
   std::map<int, Tiling> tilings;  // keyed by number of tiles requested
@@ -698,6 +841,9 @@ struct abd_handle {
   int chains_per_cta_override = 0;
   int n_sms = 148;
   size_t smem_optin = 0;
+  int* d_order = nullptr;       // individuals by decreasing OD-row count (Gibbs work queue)
+  unsigned* d_queue = nullptr;  // Gibbs work-queue counter
+  int gibbs_ctas = 0;
 
   // per-chain scratch
   int cap_chains = 0;
@@ -791,24 +937,40 @@ int build_rows(abd_handle* h, int a, int64_t R, const double* x, const double* o
   // padded so that the 16-byte-aligned bulk copies of k_sums may read past the last row
   std::vector<double> xs((size_t)R + 2, 0.0), ods((size_t)R + 2, 0.0);
   std::vector<uint32_t> meta((size_t)R + 4, 0u);
+  // cells: the distinct (individual, gap) pairs, in row order; every row points at its cell
+  std::vector<uint32_t> rowcell((size_t)R + 4, 0u), cmeta;
+  std::vector<int>& cp = h->h_cp[a];
+  cp.assign((size_t)N + 1, 0);
   for (int64_t k = 0; k < R; ++k) {
     const int64_t r = order[(size_t)k];
     xs[(size_t)k] = x[r];
     ods[(size_t)k] = od[r];
-    meta[(size_t)k] = ((uint32_t)ind[r] << 6) | (uint32_t)gap[r];
+    const uint32_t m = ((uint32_t)ind[r] << 6) | (uint32_t)gap[r];
+    meta[(size_t)k] = m;
+    if (cmeta.empty() || cmeta.back() != m) {
+      cmeta.push_back(m);
+      cp[(size_t)ind[r] + 1]++;
+    }
+    rowcell[(size_t)k] = (uint32_t)cmeta.size() - 1;
   }
+  for (int n = 0; n < N; ++n) cp[n + 1] += cp[n];
+  cmeta.resize(cmeta.size() + 4, 0u);
   int rc;
   int* d_rp;
   double *d_x, *d_od;
-  uint32_t* d_meta;
+  uint32_t *d_meta, *d_rowcell, *d_cmeta;
   if ((rc = upload(h, &d_rp, rp))) return rc;
   if ((rc = upload(h, &d_x, xs))) return rc;
   if ((rc = upload(h, &d_od, ods))) return rc;
   if ((rc = upload(h, &d_meta, meta))) return rc;
+  if ((rc = upload(h, &d_rowcell, rowcell))) return rc;
+  if ((rc = upload(h, &d_cmeta, cmeta))) return rc;
   h->dc.rp[a] = d_rp;
   h->dc.x[a] = d_x;
   h->dc.od[a] = d_od;
   h->dc.meta[a] = d_meta;
+  h->dc.rowcell[a] = d_rowcell;
+  h->dc.cmeta[a] = d_cmeta;
   h->R[a] = R;
   return ABD_OK;
 }
@@ -836,22 +998,36 @@ int get_tiling(abd_handle* h, int want, abd_handle::Tiling** out) {
     ti.push_back(N);
     abd_handle::Tiling t;
     t.ntiles = (int)ti.size() - 1;
+    const std::vector<int>&cn = h->h_cp[0], &cs = h->h_cp[1];
+    auto span = [](int lo, int hi, int al) { return ((hi + al - 1) & ~(al - 1)) - (lo & ~(al - 1)); };
     for (int k = 0; k < t.ntiles; ++k) {
       const int a = ti[k], b = ti[k + 1];
-      t.cap_n = std::max(t.cap_n, ((rn[b] + 1) & ~1) - (rn[a] & ~1));
-      t.cap_s = std::max(t.cap_s, ((rs[b] + 1) & ~1) - (rs[a] & ~1));
-      t.capm_n = std::max(t.capm_n, ((rn[b] + 3) & ~3) - (rn[a] & ~3));
-      t.capm_s = std::max(t.capm_s, ((rs[b] + 3) & ~3) - (rs[a] & ~3));
+      t.cap_n = std::max(t.cap_n, span(rn[a], rn[b], 2));
+      t.cap_s = std::max(t.cap_s, span(rs[a], rs[b], 2));
+      t.capr_n = std::max(t.capr_n, span(rn[a], rn[b], 4));
+      t.capr_s = std::max(t.capr_s, span(rs[a], rs[b], 4));
+      t.capk_n = std::max(t.capk_n, span(cn[a], cn[b], 4));
+      t.capk_s = std::max(t.capk_s, span(cs[a], cs[b], 4));
     }
     t.cap_n = std::max(t.cap_n, 2);
     t.cap_s = std::max(t.cap_s, 2);
-    t.capm_n = std::max(t.capm_n, 4);
-    t.capm_s = std::max(t.capm_s, 4);
-    t.smem = (size_t)(2 * t.cap_n + 2 * t.cap_s) * 8 + (size_t)(t.capm_n + t.capm_s) * 4;
+    t.capr_n = std::max(t.capr_n, 4);
+    t.capr_s = std::max(t.capr_s, 4);
+    t.capk_n = std::max(t.capk_n, 4);
+    t.capk_s = std::max(t.capk_s, 4);
+    t.smem = (size_t)(2 * t.cap_n + 2 * t.cap_s) * 8 + (size_t)(t.capk_n + t.capk_s) * (sizeof(CellVal) + 4) +
+             (size_t)(t.capr_n + t.capr_s) * 4;
     if (t.smem + 12 * 1024 > h->smem_optin)
       return fail(ABD_ERR_INVALID, "an individual tile does not fit in shared memory (too many OD rows per 128 individuals)");
-    int rc = upload(h, &t.d_tile_ind, ti);
+    std::vector<TileDesc> desc((size_t)t.ntiles);
+    for (int k = 0; k < t.ntiles; ++k) {
+      const int a = ti[k], b = ti[k + 1];
+      desc[(size_t)k] = TileDesc{a, b, rn[a], rn[b], rs[a], rs[b], cn[a], cn[b], cs[a], cs[b], 0, 0};
+    }
+    TileDesc* d_desc = nullptr;
+    int rc = upload(h, &d_desc, desc);
     if (rc) return rc;
+    t.d_tiles = d_desc;
     it = h->tilings.emplace(want, t).first;
   }
   *out = &it->second;
@@ -894,30 +1070,29 @@ int ensure_chains(abd_handle* h, int C) {
   return ABD_OK;
 }
 
-// Grid plan: CTAs = tiles x chain groups.  While the whole grid fits in a few waves, make it a
-// multiple of the SM count (one CTA wave of equal work per SM: no tail); rows per tile are kept
-// near `target` so that each of the 256 threads owns a handful of OD rows.
+// Grid plan: CTAs = tiles x chain groups.  Up to a few waves' worth of work the grid is sized
+// to exactly `waves` full waves of resident CTAs (n_sms x CTAs-per-SM), so every SM gets the
+// same number of equally sized tiles and there is no partial last wave; beyond that the tail is
+// negligible and tiles simply hold ~`target` OD rows (a handful per thread).
 void plan_grid(const abd_handle* h, int C, int* want_tiles, int* chains_per_cta) {
   const double rows = (double)(h->R[0] + h->R[1]);
-  const int target = h->tile_rows_override > 0 ? h->tile_rows_override : 1600;
-  int cpc = h->chains_per_cta_override > 0 ? h->chains_per_cta_override : (C >= 256 ? 4 : 1);
+  const int target = h->tile_rows_override > 0 ? h->tile_rows_override : 2200;
+  int cpc = h->chains_per_cta_override > 0 ? h->chains_per_cta_override : (C >= 32 ? 4 : 1);
   cpc = std::min(cpc, C);
   const int groups = (C + cpc - 1) / cpc;
-  int tiles = std::max(1, (int)std::ceil(rows / target));
-  tiles = std::max(tiles, (h->N + kTileMaxInds - 1) / kTileMaxInds);
-  const long ctas = (long)tiles * groups;
-  if (ctas < 8L * h->n_sms) {
-    // smallest multiple of the SM count that keeps rows per tile <= target
-    for (int k = 1; k <= 8; ++k) {
-      const int t = std::max(1, (h->n_sms * k) / groups);
-      if (rows / t <= target * 1.05 || k == 8) {
-        tiles = std::max(t, (h->N + kTileMaxInds - 1) / kTileMaxInds);
+  const int min_tiles = (h->N + kTileMaxInds - 1) / kTileMaxInds;
+  const int resident = h->n_sms * ABD_SUMS_MINB;  // __launch_bounds__(256, ABD_SUMS_MINB)
+  int tiles = std::max(min_tiles, (int)std::ceil(rows / target));
+  if ((long)tiles * groups <= 6L * resident) {
+    for (int waves = 1; waves <= 6; ++waves) {
+      const int t = (resident * waves) / groups;
+      if (t >= min_tiles && t >= 1 && rows / t <= target * 1.02) {
+        tiles = t;
         break;
       }
     }
   }
-  tiles = std::min(tiles, h->N);
-  *want_tiles = tiles;
+  *want_tiles = std::max(1, std::min(tiles, h->N));
   *chains_per_cta = cpc;
 }
 
@@ -925,9 +1100,13 @@ template <typename M>
 int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cfg, dim3 grid, const double* theta,
                   int theta_is_q, const int8_t* i_raw, const int8_t* waner, double* sums, const FinalizeCfg& fin,
                   cudaStream_t st) {
-  if (tl.smem > 40 * 1024)
-    CU(cudaFuncSetAttribute(k_sums<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem));
-  k_sums<M><<<grid, kSumsBlock, tl.smem, st>>>(h->dc, tl.d_tile_ind, cfg, theta, theta_is_q, i_raw, waner,
+  static thread_local size_t configured = 0;
+  if (tl.smem > configured) {
+    CU(cudaFuncSetAttribute(k_sums<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(tl.smem, 48 * 1024)));
+    CU(cudaFuncSetAttribute(k_sums<M>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = std::max<size_t>(tl.smem, 48 * 1024);
+  }
+  k_sums<M><<<grid, kSumsBlock, tl.smem, st>>>(h->dc, reinterpret_cast<const TileDesc*>(tl.d_tiles), cfg, theta, theta_is_q, i_raw, waner,
                                                 h->d_partial, h->d_ticket, sums, fin, h->d_priors);
   return ABD_OK;
 }
@@ -948,7 +1127,7 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
     if ((rc = dev_alloc(h, &h->d_partial, need, false))) return rc;
     h->cap_partial = need;
   }
-  SumsCfg cfg{tl->ntiles, tl->cap_n, tl->cap_s, tl->capm_n, tl->capm_s, cpc, C};
+  SumsCfg cfg{tl->ntiles, tl->cap_n, tl->cap_s, tl->capr_n, tl->capr_s, tl->capk_n, tl->capk_s, cpc, C};
   dim3 grid(tl->ntiles, (C + cpc - 1) / cpc);
   rc = h->wide ? launch_sums_t<uint64_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st)
                : launch_sums_t<uint32_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st);
@@ -960,11 +1139,23 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
 
 int launch_gibbs(abd_handle* h, int C, const double* theta, int theta_is_q, const double* p,
                  const double* pw, int8_t* i_raw, int8_t* waner, const GibbsCfg& cfg, cudaStream_t st) {
-  dim3 grid((h->N + kGibbsTile - 1) / kGibbsTile, C);
+  if (!h->gibbs_ctas) {
+    int occ = 0;
+    if (h->wide)
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gibbs<uint64_t>, kGibbsWarps * 32, 0));
+    else
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gibbs<uint32_t>, kGibbsWarps * 32, 0));
+    h->gibbs_ctas = h->n_sms * std::max(occ, 1);
+  }
+  const long items = (long)C * h->N;
+  const int grid = (int)std::min<long>(h->gibbs_ctas, (items + kGibbsWarps - 1) / kGibbsWarps);
+  CU(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
   if (h->wide)
-    k_gibbs<uint64_t><<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, theta, theta_is_q, p, pw, i_raw, waner, cfg);
+    k_gibbs<uint64_t><<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, h->d_order, C, theta, theta_is_q, p, pw, i_raw, waner,
+                                                          h->d_queue, cfg);
   else
-    k_gibbs<uint32_t><<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, theta, theta_is_q, p, pw, i_raw, waner, cfg);
+    k_gibbs<uint32_t><<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, h->d_order, C, theta, theta_is_q, p, pw, i_raw, waner,
+                                                          h->d_queue, cfg);
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;
@@ -1075,6 +1266,16 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
   if ((rc = build_rows(h, 0, co->n_rows_n, co->x_n, co->od_n, co->gap_n, co->ind_n))) return bail(rc);
   if ((rc = build_rows(h, 1, co->n_rows_s, co->x_s, co->od_s, co->gap_s, co->ind_s))) return bail(rc);
 
+  {
+    std::vector<int> order((size_t)N);
+    for (int n = 0; n < N; ++n) order[(size_t)n] = n;
+    auto nrows = [&](int n) {
+      return (h->h_rp[0][n + 1] - h->h_rp[0][n]) + (h->h_rp[1][n + 1] - h->h_rp[1][n]);
+    };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nrows(a) > nrows(b); });
+    if ((rc = upload(h, &h->d_order, order))) return bail(rc);
+    if ((rc = dev_alloc(h, &h->d_queue, 1))) return bail(rc);
+  }
   const double tn = co->total_inds > 0 ? (double)co->total_inds : (double)N;
   h->tot.rows_n = co->total_rows_n > 0 ? (double)co->total_rows_n : (double)co->n_rows_n;
   h->tot.rows_s = co->total_rows_s > 0 ? (double)co->total_rows_s : (double)co->n_rows_s;
@@ -1400,5 +1601,12 @@ int abd_debug_fast_math(int device, int64_t n, const double* z, double* out_exp,
   CU(e);
   return ABD_OK;
 }
+
+#ifdef ABD_PHASE_TIMING
+int abd_debug_phase_times(unsigned long long* out, int n_ctas) {
+  CU(cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 12 * (size_t)n_ctas));
+  return ABD_OK;
+}
+#endif
 
 }  // extern "C"

@@ -333,78 +333,113 @@ __device__ __forceinline__ double backward(double y, int transform) {
   return y;
 }
 
+// ---- finalisation: raw sums -> loglik / joint logp and gradients ---------------------------------
+// Split in a "pre" part that depends only on the parameters (logs, exps, priors, transforms --
+// computed while the rows are still being processed) and a cheap "post" part that needs the sums.
+struct LikPre {
+  double lsn, lss;   // log sigma
+  double ivn, ivs;   // 1 / sigma^2
+  double isn, iss;   // 1 / sigma
+};
+__device__ __forceinline__ LikPre lik_pre(double sn, double ss) {
+  LikPre p;
+  p.lsn = log(sn);
+  p.lss = log(ss);
+  p.isn = 1.0 / sn;
+  p.iss = 1.0 / ss;
+  p.ivn = p.isn * p.isn;
+  p.ivs = p.iss * p.iss;
+  return p;
+}
+
 // Data log-likelihood and gradient w.r.t. theta13 from the raw sums.
-__device__ inline void finalize_loglik(const double* th, const double* S, const Totals& tot,
-                                       double* loglik, double* g) {
-  const double sn = th[N_SIGMA], ss = th[S_SIGMA];
-  const double ivn = 1.0 / (sn * sn), ivs = 1.0 / (ss * ss);
-  *loglik = -0.5 * S[SN_0] * ivn - tot.rows_n * (kHalfLog2Pi + log(sn)) +
-            -0.5 * S[SS_0] * ivs - tot.rows_s * (kHalfLog2Pi + log(ss));
+__device__ __forceinline__ void finalize_loglik_post(const double* th, const LikPre& lp, const double* S,
+                                                     const Totals& tot, double* loglik, double* g) {
+  *loglik = -0.5 * S[SN_0] * lp.ivn - tot.rows_n * (kHalfLog2Pi + lp.lsn) +
+            -0.5 * S[SS_0] * lp.ivs - tot.rows_s * (kHalfLog2Pi + lp.lss);
   if (!g) return;
-  g[N_D] = S[SN_1] * ivn;
-  g[N_B] = th[N_D] * S[SN_2] * ivn;
-  g[N_SIGMA] = S[SN_0] * ivn / sn - tot.rows_n / sn;
-  const double cn = -th[N_D] * th[N_B] * ivn;
+  g[N_D] = S[SN_1] * lp.ivn;
+  g[N_B] = th[N_D] * S[SN_2] * lp.ivn;
+  g[N_SIGMA] = (S[SN_0] * lp.ivn - tot.rows_n) * lp.isn;
+  const double cn = -th[N_D] * th[N_B] * lp.ivn;
   g[N_INIT] = cn * S[SN_QINIT];
   g[N_PERM] = cn * S[SN_QPERM];
   g[N_TEMP] = cn * S[SN_QTEMP];
   g[N_RHO] = cn * th[N_TEMP] * S[SN_QRHO];
-  g[S_D] = S[SS_1] * ivs;
-  g[S_B] = th[S_D] * S[SS_2] * ivs;
-  g[S_SIGMA] = S[SS_0] * ivs / ss - tot.rows_s / ss;
-  const double cs = -th[S_D] * th[S_B] * ivs;
+  g[S_D] = S[SS_1] * lp.ivs;
+  g[S_B] = th[S_D] * S[SS_2] * lp.ivs;
+  g[S_SIGMA] = (S[SS_0] * lp.ivs - tot.rows_s) * lp.iss;
+  const double cs = -th[S_D] * th[S_B] * lp.ivs;
   g[S_INIT] = cs * S[SS_QINIT];
   g[S_PERM] = cs * S[SS_QPERM];
   g[S_RHO] = cs * S[SS_QRHO];
 }
+__device__ inline void finalize_loglik(const double* th, const double* S, const Totals& tot,
+                                       double* loglik, double* g) {
+  finalize_loglik_post(th, lik_pre(th[N_SIGMA], th[S_SIGMA]), S, tot, loglik, g);
+}
 
-// Joint logp over (q17, i_raw, waner) in PyMC's unconstrained space and d logp / d q17.
-// Executed by one full warp: lane k < 17 owns value variable k (prior, transform, Jacobian and
-// chain rule); the 17 terms are summed by a fixed-order shuffle tree (deterministic).
-__device__ inline void finalize_logp_warp(int lane, const double* q, const double* S, const Totals& tot,
-                                          const Priors& pr, double* logp, double* dlogp) {
-  double th[13], g13[13], ll;
-  for (int k = 0; k < 13; ++k) th[k] = backward(q[kQOfTheta[k]], kQTransform[kQOfTheta[k]]);
-  finalize_loglik(th, S, tot, &ll, g13);
-  double lp = 0.0, d = 0.0;
+// Prior + transform of value variable k at unconstrained value y, minus what needs the sums:
+//   logp_k = lpA (+ K lx + (n - K) l1mx   for the two Bernoulli probabilities)
+//   dlogp_k = dA (+ K omx - (n - K) x) + f * d loglik / d x_k
+struct PriorPre {
+  double lpA, dA, f, lx, l1mx, x, omx;
+};
+__device__ inline PriorPre prior_pre(int k, double y, const PriorSpec& ps) {
+  PriorPre o;
+  o.lx = o.l1mx = o.x = o.omx = 0.0;
+  const int tr = kQTransform[k];
+  if (tr == 0) {  // Normal, no transform
+    const double z = (y - ps.a) / ps.b;
+    o.lpA = -0.5 * z * z + ps.c;
+    o.dA = -z / ps.b;
+    o.f = 1.0;
+  } else if (tr == 1) {  // log transform: x = e^y, log|J| = y
+    const double x = exp(y);
+    if (ps.kind == 1) {  // Gamma(alpha, beta)
+      o.lpA = ps.c - ps.b * x + (ps.a - 1.0) * y + y;
+      o.dA = -ps.b * x + (ps.a - 1.0) + 1.0;
+    } else {  // Exponential(lam)
+      o.lpA = ps.c - ps.a * x + y;
+      o.dA = -ps.a * x + 1.0;
+    }
+    o.f = x;
+  } else {  // logodds transform: x = sigmoid(y), log|J| = log x + log(1 - x); Beta(a, b) prior
+    o.lx = -softplus(-y);
+    o.l1mx = -softplus(y);
+    o.x = exp(o.lx);
+    o.omx = exp(o.l1mx);
+    const double ca = ps.a - 1.0, cb = ps.b - 1.0;
+    o.lpA = ps.c + (ca == 0.0 ? 0.0 : ca * o.lx) + (cb == 0.0 ? 0.0 : cb * o.l1mx) + o.lx + o.l1mx;
+    o.dA = (ca + 1.0) * o.omx - (cb + 1.0) * o.x;
+    o.f = o.x * o.omx;
+  }
+  return o;
+}
+
+// Joint logp over (q17, i_raw, waner) in PyMC's unconstrained space and d logp / d q17, by one
+// full warp: lane k < 17 owns value variable k; the 17 terms are summed by a fixed-order shuffle
+// tree (deterministic).  pre[k] = prior_pre(k, q[k], ...), th = the 13 constrained parameters.
+__device__ inline void finalize_logp_post(int lane, const PriorPre* pre, const double* th, const LikPre& lk,
+                                          const double* S, const Totals& tot, double* logp, double* dlogp) {
+  double g13[13], ll;
+  finalize_loglik_post(th, lk, S, tot, &ll, g13);
+  double lp = 0.0;
   if (lane < 17) {
     const int k = lane;
     double gl = 0.0;  // d loglik / d (constrained value of slot k)
 #pragma unroll
     for (int j = 0; j < 13; ++j) gl = (kQOfTheta[j] == k) ? g13[j] : gl;
-    const double y = q[k];
-    const PriorSpec ps = pr.v[k];
-    const int tr = kQTransform[k];
-    if (tr == 0) {  // Normal, no transform
-      const double z = (y - ps.a) / ps.b;
-      lp = -0.5 * z * z + ps.c;
-      d = -z / ps.b + gl;
-    } else if (tr == 1) {  // log transform: x = e^y, log|J| = y
-      const double x = exp(y);
-      if (ps.kind == 1) {  // Gamma(alpha, beta)
-        lp = ps.c - ps.b * x + (ps.a - 1.0) * y;
-        d = -ps.b * x + (ps.a - 1.0);
-      } else {  // Exponential(lam)
-        lp = ps.c - ps.a * x;
-        d = -ps.a * x;
-      }
-      lp += y;
-      d += 1.0 + gl * x;
-    } else {  // logodds transform: x = sigmoid(y), log|J| = log x + log(1 - x)
-      const double lx = -softplus(-y), l1mx = -softplus(y);
-      const double x = exp(lx), omx = exp(l1mx);
-      double ca = ps.a - 1.0, cb = ps.b - 1.0;  // Beta(a, b)
-      if (k == kQ_P) {  // + Bernoulli(i_raw | p)      abd.py:427
-        ca += S[S_KI];
-        cb += tot.bits_i - S[S_KI];
-      } else if (k == kQ_PW) {  // + Bernoulli(ab_s_waner | p_waner)   abd.py:373
-        ca += S[S_KW];
-        cb += tot.bits_w - S[S_KW];
-      }
-      // prior, Bernoulli counts and the Jacobian share the form  a' lx + b' l1mx
-      lp = ps.c + (ca == 0.0 ? 0.0 : ca * lx) + (cb == 0.0 ? 0.0 : cb * l1mx) + lx + l1mx;
-      d = (ca + 1.0) * omx - (cb + 1.0) * x + gl * x * omx;
+    const PriorPre p = pre[k];
+    lp = p.lpA;
+    double d = p.dA;
+    if (k == kQ_P || k == kQ_PW) {  // Bernoulli(i_raw | p) abd.py:427, Bernoulli(waner | p_waner) abd.py:373
+      const double K = (k == kQ_P) ? S[S_KI] : S[S_KW];
+      const double nK = ((k == kQ_P) ? tot.bits_i : tot.bits_w) - K;
+      lp += (K == 0.0 ? 0.0 : K * p.lx) + (nK == 0.0 ? 0.0 : nK * p.l1mx);
+      d += K * p.omx - nK * p.x;
     }
+    d = fma(gl, p.f, d);
     if (dlogp) dlogp[k] = d;
   }
 #pragma unroll

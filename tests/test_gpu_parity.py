@@ -65,10 +65,13 @@ def test_joint_logp_dlogp_vs_reference_goldens(Engine, goldens, cohorts):
             lp, g = eng.logp_dlogp(q, i_raw, w)
             assert np.all(np.abs(lp - ref) <= RTOL * np.abs(ref)), (lp - ref) / ref
             assert grad_ok(g, gref), np.abs(g - gref).max()
-            # ... and one chain at a time: bitwise the same numbers
-            for k in range(len(cs)):
+            # ... and one chain at a time (another grid plan, so another summation order: equal
+            # to rounding), and the same call twice: bitwise the same numbers
+            for k in range(0, len(cs), 3):
                 lp1, g1 = eng.logp_dlogp(q[k], i_raw[k], w[k])
-                assert lp1 == lp[k] and np.array_equal(g1, g[k])
+                assert abs(lp1 - lp[k]) <= 1e-13 * abs(lp[k]) and grad_ok(g1, g[k], 1e-12)
+            lp_again, g_again = eng.logp_dlogp(q, i_raw, w)
+            assert np.array_equal(lp_again, lp) and np.array_equal(g_again, g)
 
 
 def test_deterministics_vs_reference_goldens(Engine, goldens, cohorts):
