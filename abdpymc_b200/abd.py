@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference interface for the inference hot path (abdpymc/abd.py).
+
+Same names, argument meaning and error behaviour as the reference for this path:
+
+  ``model(data, splits=None, ignore_pcrpos=False)``   abd.py:396-442  -> pm.Model with the same RV
+      names / dims (p, i_raw, ab_n_*, ab_s_*, it_*; Deterministics i, ab_n_mu, ab_s_mu with dims
+      ("gap", "ind")), but the data likelihood is ONE opaque PyTensor Op backed by the CUDA
+      library (``AbdLogLik``) wrapped in ``pm.Potential("loglik", ...)``.
+  ``GpuBinaryGibbs``  the step method that replaces PyMC's BinaryGibbsMetropolis for ``i_raw`` and
+      ``ab_s_waner`` (assigned implicitly by ``pm.sample`` at abd.py:922).
+  ``main()``          ``abdpymc-infer`` with the reference's flags (abd.py:885-924).
+
+PyMC / PyTensor / ArviZ are import-guarded: they are not installable in the offline build image,
+so everything PyMC-facing here is written against the PyMC 5 API and exercised only where PyMC
+exists (tests/test_pymc_parity.py, skipped otherwise).  Without PyMC, ``main()`` drives the
+built-in sampler (abdpymc_b200.sampler) on the same model terms and writes the same variable
+names to an .npz (or NetCDF when ArviZ is importable).  There is no CPU fallback for the
+numerics: every path goes through libabd_b200.so.
+"""
+
+from __future__ import annotations
+
+import argparse
+import sys
+
+import numpy as np
+
+from .cohort import CohortArrays
+from .engine import Q17, Q17_RV, Q_OF_THETA, Q_P, Q_PW, THETA13, AbdEngine, backward, forward
+
+GAP_IND = "gap", "ind"  # abd.py:18
+
+try:  # pragma: no cover - PyMC is absent from the build image
+    import pymc as pm
+    import pytensor.tensor as pt
+    from pytensor.gradient import grad_undefined
+    from pytensor.graph.basic import Apply
+    from pytensor.graph.op import Op
+
+    HAVE_PYMC = True
+except ImportError:
+    pm = pt = None
+    Op = object
+    HAVE_PYMC = False
+
+
+def check_splits(splits, data=None):
+    """abd.py:604-622, same messages."""
+    if splits is not None:
+        if any(split < 0 for split in splits):
+            raise ValueError("split indexes must be positive")
+        if sorted(splits) != list(splits):
+            raise ValueError("splits must be in ascending order")
+        if data is not None and splits and splits[-1] > data.n_gaps:
+            raise ValueError(f"largest split must be less than n_gaps - 1, ({splits[-1]})")
+        if len(splits) != len(set(splits)):
+            raise ValueError("splits not unique")
+        if any(not isinstance(split, (int, np.integer)) for split in splits):
+            raise ValueError("splits must be ints")
+
+
+def as_cohort(data) -> CohortArrays:
+    """Accepts a CohortArrays or the reference's ``TiterData`` (abd.py:46-126: ``vacs``, ``pcrpos``
+    (n_inds, n_gaps) and ``s.df`` / ``n.df`` with individual_i, elapsed_months, log_dilution, od)."""
+    if isinstance(data, CohortArrays):
+        return data
+    rows = []
+    for a, ag in ((0, data.n), (1, data.s)):
+        df = ag.df
+        rows.append((np.asarray(ag.idx_ind), np.asarray(ag.idx_gap), np.full(len(df), a),
+                     df["log_dilution"].to_numpy(float), df["od"].to_numpy(float)))
+    ind, gap, antigen, x, od = (np.concatenate(c) for c in zip(*rows))
+    return CohortArrays(vacs=np.asarray(data.vacs), pcrpos=np.asarray(data.pcrpos), ind=ind, gap=gap, antigen=antigen,
+                        x=x, od=od, t0=str(getattr(data, "t0", "2020-05")))
+
+
+def make_engine(data, splits=None, ignore_pcrpos=False, device=0, **kw) -> AbdEngine:
+    cohort = as_cohort(data)
+    check_splits(splits, cohort)
+    if splits is not None and len(splits) > 2:
+        raise NotImplementedError("only implemented 1-3 time chunks (0-2 splits)")  # abd.py:881-882
+    return AbdEngine(cohort, splits=splits, ignore_pcrpos=ignore_pcrpos, device=device, **kw)
+
+
+# ------------------------------------------------------------------------------------------
+# PyTensor Ops
+# ------------------------------------------------------------------------------------------
+class _Cache:
+    """Value and gradient come out of one kernel launch; NUTS asks for both at the same point."""
+
+    def __init__(self, engine):
+        self.engine, self.key, self.val = engine, None, None
+
+    def get(self, inputs):
+        th = np.array([float(v) for v in inputs[:13]], dtype=np.float64)
+        i_raw, waner = np.asarray(inputs[13]), np.asarray(inputs[14])
+        key = (th.tobytes(), i_raw.tobytes(), waner.tobytes())
+        if key != self.key:
+            ll, g, _ = self.engine.loglik_grad(th, i_raw, waner)
+            self.key, self.val = key, (float(ll), np.asarray(g, dtype=np.float64))
+        return self.val
+
+
+class AbdLogLik(Op):
+    """loglik(theta13..., i_raw, ab_s_waner) -> scalar: the sum of the two observed Normal
+    log-densities of abd.py:445-469 given the response model of abd.py:309-393."""
+
+    __props__ = ()
+
+    def __init__(self, engine, cache=None):
+        self.engine = engine
+        self.cache = cache or _Cache(engine)
+        self.grad_op = None
+
+    def make_node(self, *inputs):
+        if len(inputs) != 15:
+            raise ValueError("AbdLogLik takes the 13 likelihood scalars, i_raw and ab_s_waner")
+        theta = [pt.as_tensor_variable(v).astype("float64") for v in inputs[:13]]
+        binaries = [pt.as_tensor_variable(v) for v in inputs[13:]]
+        return Apply(self, [*theta, *binaries], [pt.dscalar()])
+
+    def perform(self, node, inputs, output_storage):
+        output_storage[0][0] = np.asarray(self.cache.get(inputs)[0], dtype=np.float64)
+
+    def grad(self, inputs, output_grads):
+        if self.grad_op is None:
+            self.grad_op = AbdLogLikGrad(self.engine, self.cache)
+        (gz,) = output_grads
+        parts = self.grad_op(*inputs)
+        return [gz * g for g in parts] + [grad_undefined(self, 13, inputs[13]), grad_undefined(self, 14, inputs[14])]
+
+
+class AbdLogLikGrad(Op):
+    """d loglik / d theta13 (13 scalars), from the same launch as the value."""
+
+    __props__ = ()
+
+    def __init__(self, engine, cache):
+        self.engine, self.cache = engine, cache
+
+    def make_node(self, *inputs):
+        inputs = [pt.as_tensor_variable(v) for v in inputs]
+        return Apply(self, inputs, [pt.dscalar() for _ in range(13)])
+
+    def perform(self, node, inputs, output_storage):
+        g = self.cache.get(inputs)[1]
+        for k in range(13):
+            output_storage[k][0] = np.asarray(g[k], dtype=np.float64)
+
+
+class AbdDeterministics(Op):
+    """(i, ab_n_mu, ab_s_mu), each (gap, ind): abd.py:649 / 667, :341, :389-391."""
+
+    __props__ = ()
+
+    def __init__(self, engine):
+        self.engine = engine
+
+    def make_node(self, *inputs):
+        inputs = [pt.as_tensor_variable(v) for v in inputs]
+        return Apply(self, inputs, [pt.bmatrix(), pt.dmatrix(), pt.dmatrix()])
+
+    def perform(self, node, inputs, output_storage):
+        th = np.array([float(v) for v in inputs[:13]], dtype=np.float64)
+        i, mn, ms = self.engine.deterministics(th, inputs[13], inputs[14])
+        output_storage[0][0], output_storage[1][0], output_storage[2][0] = i, mn, ms
+
+
+def model(data, splits=None, ignore_pcrpos=False, device=0):
+    """Set up the antibody dynamics model (abd.py:396-442) with the GPU likelihood.
+
+    Same RVs, priors and names as the reference; the only structural difference is that
+    ``it_n_lik`` / ``it_s_lik`` (observed Normals) are replaced by ``pm.Potential("loglik")``.
+    The engine is attached as ``model.abd_engine`` for ``GpuBinaryGibbs``."""
+    if not HAVE_PYMC:
+        raise ImportError("abdpymc_b200.abd.model needs PyMC; use abdpymc_b200.sampler without it")
+    cohort = as_cohort(data)
+    engine = make_engine(cohort, splits=splits, ignore_pcrpos=ignore_pcrpos, device=device)
+    coords = dict(ind=np.arange(cohort.n_inds), gap=np.arange(cohort.n_gaps))  # abd.py:126
+    with pm.Model(coords=coords) as m:
+        p = pm.Beta("p", alpha=1, beta=cohort.n_gaps - 1)  # abd.py:424
+        i_raw = pm.Bernoulli("i_raw", p, dims=GAP_IND)  # abd.py:427
+        n_perm = pm.Gamma("ab_n_perm", mu=2.0, sigma=0.5)  # abd.py:329
+        n_temp = pm.Gamma("ab_n_temp", mu=1.0, sigma=0.5)  # abd.py:333
+        n_rho = pm.Beta("ab_n_rho", alpha=10.0, beta=1.0)  # abd.py:334
+        n_init = pm.Normal("ab_n_init", -2, 1)  # abd.py:340
+        s_perm = pm.Gamma("ab_s_perm", mu=2.0, sigma=0.5)  # abd.py:367
+        s_rho = pm.Beta("ab_s_rho", alpha=10.0, beta=1.0)  # abd.py:371
+        p_waner = pm.Beta("ab_s_p_waner", alpha=1.0, beta=1.0)  # abd.py:372
+        waner = pm.Bernoulli("ab_s_waner", p=p_waner, dims="ind")  # abd.py:373
+        pm.Gamma("ab_s_tempinf", mu=1.0, sigma=0.5)  # abd.py:377 -- prior only (abd.py:263-274 ignores temp)
+        pm.Gamma("ab_s_tempvac", mu=1.0, sigma=0.5)  # abd.py:383
+        s_init = pm.Normal("ab_s_init", -2, 1)  # abd.py:388
+        n_b, n_d = pm.Normal("it_n_b", -1, 0.5), pm.Normal("it_n_d", 2, 0.5)  # abd.py:464-465
+        n_sigma = pm.Exponential("it_n_sigma", 1)  # abd.py:467
+        s_b, s_d = pm.Normal("it_s_b", -1, 0.5), pm.Normal("it_s_d", 2, 0.5)
+        s_sigma = pm.Exponential("it_s_sigma", 1)
+        theta = [n_perm, n_temp, n_rho, n_init, s_perm, s_rho, s_init, n_b, n_d, n_sigma, s_b, s_d, s_sigma]
+        pm.Potential("loglik", AbdLogLik(engine)(*theta, i_raw, waner))
+        i, mu_n, mu_s = AbdDeterministics(engine)(*theta, i_raw, waner)
+        pm.Deterministic("i", i, dims=GAP_IND)
+        pm.Deterministic("ab_n_mu", mu_n, dims=GAP_IND)
+        pm.Deterministic("ab_s_mu", mu_s, dims=GAP_IND)
+    m.abd_engine = engine
+    return m
+
+
+# ------------------------------------------------------------------------------------------
+# PyMC step method
+# ------------------------------------------------------------------------------------------
+def point_to_q17(point) -> np.ndarray:
+    """PyMC point dict (value-variable names, abd.py declaration order) -> q17."""
+    return np.array([float(point[name]) for name in Q17], dtype=np.float64)
+
+
+if HAVE_PYMC:  # pragma: no cover
+    from pymc.step_methods.arraystep import BlockedStep
+
+    class GpuBinaryGibbs(BlockedStep):
+        """Drop-in for BinaryGibbsMetropolis over ``i_raw`` and ``ab_s_waner``:
+        ``pm.sample(step=[GpuBinaryGibbs([m["i_raw"], m["ab_s_waner"]], model=m)])``.
+        One ``step`` = one ``abd_gibbs_sweep`` (same per-bit transition kernel: flip proposed
+        w.p. ``transit_p``, Metropolis accept; individuals updated in parallel, each in a
+        uniformly random order)."""
+
+        name = "gpu_binary_gibbs"
+        stats_dtypes_shapes = {"p_jump": (float, []), "tune": (bool, [])}
+        stats_dtypes = [{"p_jump": float, "tune": bool}]  # PyMC < 5.7 spelling
+
+        def __init__(self, vars=None, model=None, transit_p=0.8, mode=0, seed=None, **kwargs):
+            model = pm.modelcontext(model)
+            vars = vars or [model["i_raw"], model["ab_s_waner"]]
+            self.vars = [model.rvs_to_values.get(v, v) for v in vars]
+            self.engine = model.abd_engine
+            self.transit_p, self.mode = transit_p, mode
+            self.seed = int(np.random.SeedSequence(seed).generate_state(1, dtype=np.uint64)[0])
+            self.sweep, self.tune = 0, True
+            self.model = model
+
+        def step(self, point):
+            q = point_to_q17(point)
+            x = backward(q)
+            i_raw, waner, st = self.engine.gibbs_sweep(x[Q_OF_THETA], x[Q_P], x[Q_PW], point["i_raw"],
+                                                       point["ab_s_waner"], seed=self.seed, sweep=self.sweep,
+                                                       mode=self.mode, transit_p=self.transit_p)
+            self.sweep += 1
+            new = dict(point)
+            new["i_raw"] = i_raw.astype(np.asarray(point["i_raw"]).dtype)
+            new["ab_s_waner"] = waner.astype(np.asarray(point["ab_s_waner"]).dtype)
+            return new, [{"p_jump": float(st[1]) / max(float(st[0]), 1.0), "tune": self.tune}]
+
+        def stop_tuning(self):
+            self.tune = False
+
+        @staticmethod
+        def competence(var, has_grad):
+            from pymc.step_methods.compound import Competence
+
+            return Competence.COMPATIBLE if var.name in ("i_raw", "ab_s_waner") else Competence.INCOMPATIBLE
+
+
+# ------------------------------------------------------------------------------------------
+# abdpymc-infer
+# ------------------------------------------------------------------------------------------
+def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0, seed=0, progress=None):
+    """tune + draws iterations of the built-in HMC + GPU-Gibbs sampler.  Returns (result,
+    {name: array (chain, draw, ...)}) with the reference's posterior variable names."""
+    import torch
+
+    from .sampler import AbdTarget, SamplerConfig, sample
+
+    engine = make_engine(cohort, splits=splits, ignore_pcrpos=ignore_pcrpos, device=device)
+    rng = np.random.default_rng(seed)
+    G, N = engine.G, engine.N
+    # PyMC-like initial point: prior means on the constrained scale, jittered in q space
+    x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
+    q0 = forward(x0)[None, :] + rng.uniform(-1, 1, size=(chains, 17))
+    target = AbdTarget(engine, chains, np.zeros((chains, G, N), np.int8), np.zeros((chains, N), np.int8), seed=seed)
+    cfg = SamplerConfig(tune=tune, draws=draws, seed=seed, record_deterministics_every=1)
+    res = sample(target, torch.from_numpy(q0).to(target.device), cfg, progress=progress)
+    post = res.posterior()
+    i_raw, waner = target.state()
+    post_last = dict(i_raw=i_raw, ab_s_waner=waner)
+    engine.close()
+    return res, post, post_last
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser("abdpymc-infer")  # flags of abd.py:888-911
+    parser.add_argument("--tune", help="Number of tuning steps.", type=int, required=True)
+    parser.add_argument("--draws", help="Number of draws.", type=int, required=True)
+    parser.add_argument("--cores", help="Number of cores", type=int)
+    parser.add_argument("--ititers_data", help="Path to directory for generating TiterData object.", default="cohort_data")
+    parser.add_argument("--split_delta", help="Split time chunk between delta and pre-delta", action="store_true")
+    parser.add_argument("--split_omicron", help="Split time chunk between omicron and delta", action="store_true")
+    parser.add_argument("--ignore_pcrpos", help="Ignore PCR+ data", action="store_true")
+    parser.add_argument("--netcdf", help="Path of netCDF file to save.")
+    parser.add_argument("--chains", type=int, default=4, help="(extension) chains batched on the GPU")
+    parser.add_argument("--device", type=int, default=0, help="(extension) CUDA device")
+    args = parser.parse_args(argv)
+
+    data = CohortArrays.from_disk(args.ititers_data)
+    splits = (None if (not args.split_delta) and (not args.split_omicron)
+              else data.calculate_splits(delta=args.split_delta, omicron=args.split_omicron))
+
+    if HAVE_PYMC:  # pragma: no cover
+        import arviz as az
+
+        with model(data, splits=splits, ignore_pcrpos=args.ignore_pcrpos, device=args.device) as m:
+            step = GpuBinaryGibbs([m["i_raw"], m["ab_s_waner"]], model=m)
+            # chains run in this process: CUDA contexts do not survive pm.sample's fork
+            idata = pm.sample(tune=args.tune, draws=args.draws, cores=1, chains=args.chains, step=[step])
+        az.to_netcdf(idata, args.netcdf)
+        return idata
+
+    res, post, last = infer_builtin(data, splits, args.ignore_pcrpos, args.tune, args.draws, chains=args.chains,
+                                    device=args.device, progress=max(1, (args.tune + args.draws) // 10))
+    out = args.netcdf or "abd_posterior.npz"
+    np.savez_compressed(out if out.endswith(".npz") else out + ".npz", **post, **{f"mean_{k}": v for k, v in res.means.items()},
+                        **{f"last_{k}": v for k, v in last.items()}, step_size=res.step_size, wall_s=res.wall_s)
+    print(f"PyMC not installed: sampled with the built-in HMC+Gibbs driver in {res.wall_s:.1f} s; wrote {out}", file=sys.stderr)
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,25 @@ class CohortArrays:
             x=df["log_dilution"].to_numpy(float), od=df["od"].to_numpy(float), t0=str(t0),
         )
 
+    def to_disk(self, directory) -> None:
+        """Write df.csv / vacs.txt / pcrpos.txt / t0.txt in the layout TiterData.to_disk uses
+        (abd.py:149-169), with the columns TiterData.__init__ reads (abd.py:75-126)."""
+        import pandas as pd
+
+        d = Path(directory)
+        d.mkdir(parents=True, exist_ok=True)
+        meas = np.where(self.antigen == ANTIGEN_S, MEASUREMENT_S, MEASUREMENT_N)
+        sample = np.array([f"S{i:06d}-G{g:02d}" for i, g in zip(self.ind, self.gap)])
+        df = pd.DataFrame(dict(
+            sample=sample, measurement=meas, od=self.od, dilution=40.0 * 4.0**self.x, record_id=self.ind + 1000,
+            elapsed_months=self.gap, individual_i=self.ind, log_dilution=self.x,
+            sample_i=pd.factorize(sample)[0],
+        ))
+        df.to_csv(d / "df.csv")
+        np.savetxt(d / "vacs.txt", self.vacs, fmt="%1.0f")
+        np.savetxt(d / "pcrpos.txt", self.pcrpos, fmt="%1.0f")
+        (d / "t0.txt").write_text(self.t0)
+
     def calculate_splits(self, delta: bool, omicron: bool) -> tuple:
         """abd.py:204-221: gaps from t0 to 2021-07 (delta) and 2022-01 (omicron)."""
         y, m = (int(v) for v in self.t0.split("-")[:2])

@@ -1,0 +1,224 @@
+"""Built-in compound sampler: batched HMC over the 17 continuous value variables + the GPU
+Gibbs sweep over the binary variables, for C chains in lockstep on one device.
+
+The reference delegates sampling to PyMC (``pm.sample`` -> CompoundStep[NUTS,
+BinaryGibbsMetropolis], abd.py:921-922).  PyMC is not installable offline, and even where it
+is, a host round trip per leapfrog dominates once an evaluation costs microseconds (SURVEY.md
+section 8f rank 1).  This driver keeps every chain's position, momentum, step size and mass
+matrix in device tensors and calls the C ABI's device-pointer entry points directly; the model
+terms it samples are exactly those of ``abd.model`` (same value variables, transforms, priors).
+
+Kernel: Hamiltonian Monte Carlo with a diagonal mass matrix, jittered trajectory length, step
+size by dual averaging (Nesterov; Hoffman & Gelman 2014, the scheme PyMC's NUTS uses) and
+Stan-style windowed variance adaptation.  It is *not* NUTS: trajectory length is fixed up to
+jitter, which keeps all chains of a batch in lockstep (one kernel launch per leapfrog for all
+chains).  The binary block is updated by ``abd_gibbs_sweep`` (Metropolised flips with
+BinaryGibbsMetropolis semantics by default).
+
+The sampler is generic over a ``target`` (see ``AbdTarget``), so its host logic is tested on
+CPU against a Gaussian with known moments (tests/test_sampler.py).
+"""
+
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from .engine import Q17_RV, Q_OF_THETA, backward
+
+
+class AbdTarget:
+    """The antibody-dynamics posterior on one GPU: joint logp + gradient over q17 for C chains
+    with the chain state (i_raw, waner) resident on the device, and the Gibbs sweep over it."""
+
+    def __init__(self, engine, n_chains, i_raw, waner, seed=0, gibbs_mode=0, transit_p=0.8):
+        self.engine, self.C = engine, n_chains
+        self.device = torch.device("cuda", engine.device)
+        engine.upload_state(i_raw, waner)
+        self.d_i, self.d_w = engine.state_dev(n_chains)
+        self.out = torch.zeros(n_chains, dtype=torch.float64, device=self.device)
+        self.outg = torch.zeros(n_chains, 17, dtype=torch.float64, device=self.device)
+        self.seed, self.gibbs_mode, self.transit_p = seed, gibbs_mode, transit_p
+        self.dim = 17
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def logp_dlogp(self, q):
+        q = q.contiguous()
+        self.engine.logp_dlogp_dev(self.C, q.data_ptr(), self.d_i, self.d_w, self.out.data_ptr(), self.outg.data_ptr(),
+                                   self._stream())
+        return self.out.clone(), self.outg.clone()
+
+    def gibbs(self, q, sweep):
+        q = q.contiguous()
+        self.engine.gibbs_sweep_dev(self.C, q.data_ptr(), 1, None, None, self.d_i, self.d_w, self.seed, sweep,
+                                    mode=self.gibbs_mode, transit_p=self.transit_p, stream=self._stream())
+
+    def deterministics(self, q):
+        """(i, ab_n_mu, ab_s_mu) of the current state, device tensors (C, G, N)."""
+        G, N, C = self.engine.G, self.engine.N, self.C
+        th = torch.from_numpy(backward(q.cpu().numpy())[:, Q_OF_THETA].copy()).to(self.device)
+        oi = torch.empty(C, G, N, dtype=torch.int8, device=self.device)
+        mn = torch.empty(C, G, N, dtype=torch.float64, device=self.device)
+        ms = torch.empty(C, G, N, dtype=torch.float64, device=self.device)
+        self.engine.deterministics_dev(C, th.data_ptr(), self.d_i, self.d_w, oi.data_ptr(), mn.data_ptr(), ms.data_ptr(),
+                                       self._stream())
+        return oi, mn, ms
+
+    def state(self):
+        torch.cuda.synchronize(self.device)
+        return self.engine.download_state(self.C)
+
+
+@dataclass
+class SamplerConfig:
+    tune: int = 500
+    draws: int = 500
+    n_leapfrog: int = 12           # mean trajectory length in steps (jittered uniformly in [0.6, 1.4] x)
+    target_accept: float = 0.8
+    init_step: float = 0.05
+    record_deterministics_every: int = 0   # 0 = never; k = accumulate means every k-th draw
+    seed: int = 0
+
+
+@dataclass
+class SamplerResult:
+    q: np.ndarray                      # (chains, draws, dim) unconstrained draws
+    logp: np.ndarray                   # (chains, draws)
+    accept: np.ndarray                 # (chains, draws) acceptance probability of each HMC step
+    step_size: np.ndarray              # (chains,)
+    inv_mass: np.ndarray               # (dim,)
+    wall_s: float
+    n_grad_evals: int
+    means: dict = field(default_factory=dict)   # posterior means of i, ab_n_mu, ab_s_mu (G, N)
+
+    def posterior(self):
+        """{RV name: (chains, draws)} on the constrained scale, named as abd.model names them."""
+        x = backward(self.q)
+        return {name: x[:, :, k] for k, (name, _) in enumerate(Q17_RV)} if x.shape[-1] == 17 else {}
+
+
+class _DualAveraging:
+    """Nesterov dual averaging of log step size, per chain (vectorised)."""
+
+    def __init__(self, eps0, target, device, gamma=0.05, t0=10.0, kappa=0.75):
+        self.mu = torch.log(10.0 * eps0)
+        self.target, self.gamma, self.t0, self.kappa = target, gamma, t0, kappa
+        self.h = torch.zeros_like(eps0)
+        self.log_avg = torch.zeros_like(eps0)
+        self.t = 0
+
+    def update(self, accept):
+        self.t += 1
+        eta = 1.0 / (self.t + self.t0)
+        self.h = (1 - eta) * self.h + eta * (self.target - accept)
+        log_eps = self.mu - (self.t**0.5 / self.gamma) * self.h
+        w = self.t ** (-self.kappa)
+        self.log_avg = w * log_eps + (1 - w) * self.log_avg
+        return torch.exp(log_eps)
+
+    def final(self):
+        return torch.exp(self.log_avg)
+
+
+def _windows(tune):
+    """Stan's warm-up schedule: fast initial buffer, doubling slow windows, fast final buffer.
+    Returns the list of iteration indexes at which a slow window ends."""
+    if tune < 150:
+        return [int(tune * 0.5)] if tune >= 20 else []
+    start, end, size, ends = 75, tune - 50, 25, []
+    while start + size <= end:
+        nxt = start + size
+        if nxt + 2 * size > end:
+            nxt = end
+        ends.append(nxt)
+        start, size = nxt, size * 2
+    return ends
+
+
+def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> SamplerResult:
+    """Run tune + draws iterations of [HMC on q | binaries] then [Gibbs on binaries | q]."""
+    dev = q0.device
+    C, D = q0.shape
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(cfg.seed)
+    q = q0.clone().to(torch.float64)
+    logp, grad = target.logp_dlogp(q)
+    inv_mass = torch.ones(D, dtype=torch.float64, device=dev)
+    eps = torch.full((C,), cfg.init_step, dtype=torch.float64, device=dev)
+    da = _DualAveraging(eps, cfg.target_accept, dev)
+    ends = _windows(cfg.tune)
+    win_start = 75 if cfg.tune >= 150 else 0
+    win_draws = []
+    total = cfg.tune + cfg.draws
+    out_q = torch.empty(cfg.draws, C, D, dtype=torch.float64, device=dev)
+    out_lp = torch.empty(cfg.draws, C, dtype=torch.float64, device=dev)
+    out_acc = torch.empty(cfg.draws, C, dtype=torch.float64, device=dev)
+    means, n_means, n_grad = {}, 0, 0
+    has_gibbs = hasattr(target, "gibbs")
+    t0 = time.perf_counter()
+    for it in range(total):
+        # ---- HMC over q given the binaries -------------------------------------------------
+        p = torch.randn(C, D, dtype=torch.float64, device=dev, generator=gen) / torch.sqrt(inv_mass)
+        h0 = -logp + 0.5 * (p * p * inv_mass).sum(dim=1)
+        jitter = 0.6 + 0.8 * torch.rand((), device=dev, generator=gen).item()
+        L = max(1, int(round(cfg.n_leapfrog * jitter)))
+        qn, pn, gn, lpn = q, p, grad, logp
+        e = eps[:, None]
+        for _ in range(L):
+            pn = pn + 0.5 * e * gn
+            qn = qn + e * pn * inv_mass
+            lpn, gn = target.logp_dlogp(qn)
+            pn = pn + 0.5 * e * gn
+        n_grad += L
+        h1 = -lpn + 0.5 * (pn * pn * inv_mass).sum(dim=1)
+        dh = h0 - h1
+        dh = torch.where(torch.isfinite(dh), dh, torch.full_like(dh, -float("inf")))
+        acc_p = torch.exp(torch.clamp(dh, max=0.0))
+        take = torch.rand(C, dtype=torch.float64, device=dev, generator=gen) < acc_p
+        q = torch.where(take[:, None], qn, q)
+        grad = torch.where(take[:, None], gn, grad)
+        logp = torch.where(take, lpn, logp)
+        # ---- Gibbs over the binaries given q (then logp / grad at the new state) -------------
+        if has_gibbs:
+            target.gibbs(q, it)
+            logp, grad = target.logp_dlogp(q)
+            n_grad += 1
+        # ---- adaptation / recording -----------------------------------------------------------
+        if it < cfg.tune:
+            eps = da.update(acc_p)
+            if ends and win_start <= it:
+                win_draws.append(q.clone())
+            if ends and it + 1 == ends[0]:
+                x = torch.stack(win_draws).reshape(-1, D)
+                n = x.shape[0]
+                var = x.var(dim=0, unbiased=True)
+                inv_mass = (n / (n + 5.0)) * var + 1e-3 * (5.0 / (n + 5.0))  # Stan's shrinkage
+                win_draws, win_start = [], ends.pop(0)
+                eps = da.final()  # restart step-size adaptation under the new metric
+                da = _DualAveraging(eps, cfg.target_accept, dev)
+            if it + 1 == cfg.tune and da.t:
+                eps = da.final()
+        else:
+            k = it - cfg.tune
+            out_q[k], out_lp[k], out_acc[k] = q, logp, acc_p
+            every = cfg.record_deterministics_every
+            if every and hasattr(target, "deterministics") and k % every == 0:
+                oi, mn, ms = target.deterministics(q)
+                for name, v in (("i", oi.to(torch.float64)), ("ab_n_mu", mn), ("ab_s_mu", ms)):
+                    means[name] = v.mean(dim=0) if name not in means else means[name] + v.mean(dim=0)
+                n_means += 1
+        if progress and (it + 1) % progress == 0:
+            print(f"  iter {it + 1}/{total}  step {eps.mean().item():.4f}  accept {acc_p.mean().item():.2f}", flush=True)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    return SamplerResult(
+        q=out_q.permute(1, 0, 2).cpu().numpy(), logp=out_lp.T.cpu().numpy(), accept=out_acc.T.cpu().numpy(),
+        step_size=eps.cpu().numpy(), inv_mass=inv_mass.cpu().numpy(), wall_s=wall, n_grad_evals=n_grad,
+        means={k: (v / n_means).cpu().numpy() for k, v in means.items()},
+    )

@@ -233,6 +233,28 @@ def make_model_goldens():
     return out
 
 
+def make_sim_goldens():
+    """Deterministic part of the reference simulator (simulation.py:222-279): with lam0 = 0 the
+    only infections are the PCR+ ones, so titers depend on pcrpos / vacs alone."""
+    sim = sys.modules["abdpymc.simulation"]
+    out = {}
+    for name, path in (("test_cohort", REF_DATA / "test_data" / "cohort_data"), ("cohort", REF_DATA / "cohort_data")):
+        data = abd.TiterData.from_disk(str(path))
+        n, g = data.vacs.shape
+        take = np.arange(n) if n <= 10 else np.arange(0, n, 40)
+        s_t, n_t, inf = [], [], []
+        for k in take:
+            r = sim.Individual(pcrpos=data.pcrpos[k], vacs=data.vacs[k]).infection_responses(lam0=np.zeros(g))
+            s_t.append(r.s_response)
+            n_t.append(r.n_response)
+            inf.append(r.infections)
+        out[f"sim/{name}/individuals"] = take
+        out[f"sim/{name}/s_titer"] = np.array(s_t)
+        out[f"sim/{name}/n_titer"] = np.array(n_t)
+        out[f"sim/{name}/infections"] = np.array(inf)
+    return out
+
+
 if __name__ == "__main__":
     info = run_reference_tests()
     kats = make_kats()
@@ -240,5 +262,6 @@ if __name__ == "__main__":
     (HERE / "reference_kats.json").write_text(json.dumps(kats, separators=(",", ":")))
     print("wrote reference_kats.json", {k: len(v) for k, v in kats.items() if isinstance(v, list)})
     gold = make_model_goldens()
+    gold.update(make_sim_goldens())
     np.savez_compressed(HERE / "model_goldens.npz", **gold)
     print("wrote model_goldens.npz", len(gold), "arrays")
