@@ -8,9 +8,10 @@ section 8f rank 1).  This driver keeps every chain's position, momentum, step si
 matrix in device tensors and calls the C ABI's device-pointer entry points directly; the model
 terms it samples are exactly those of ``abd.model`` (same value variables, transforms, priors).
 
-Kernel: Hamiltonian Monte Carlo with a diagonal mass matrix, jittered trajectory length, step
-size by dual averaging (Nesterov; Hoffman & Gelman 2014, the scheme PyMC's NUTS uses) and
-Stan-style windowed variance adaptation.  It is *not* NUTS: trajectory length is fixed up to
+Kernel: Hamiltonian Monte Carlo with a dense mass matrix (the 17 scalars are strongly correlated,
+e.g. ab_n_init against ab_n_perm), jittered trajectory length, step size by dual averaging
+(Nesterov; Hoffman & Gelman 2014, the scheme PyMC's NUTS uses) and Stan-style windowed covariance
+adaptation pooled over the chains of the batch.  It is *not* NUTS: trajectory length is fixed up to
 jitter, which keeps all chains of a batch in lockstep (one kernel launch per leapfrog for all
 chains).  The binary block is updated by ``abd_gibbs_sweep`` (Metropolised flips with
 BinaryGibbsMetropolis semantics by default).
@@ -91,7 +92,7 @@ class SamplerResult:
     logp: np.ndarray                   # (chains, draws)
     accept: np.ndarray                 # (chains, draws) acceptance probability of each HMC step
     step_size: np.ndarray              # (chains,)
-    inv_mass: np.ndarray               # (dim,)
+    inv_mass: np.ndarray               # (dim, dim) adapted covariance (inverse mass matrix)
     wall_s: float
     n_grad_evals: int
     means: dict = field(default_factory=dict)   # posterior means of i, ab_n_mu, ab_s_mu (G, N)
@@ -148,7 +149,8 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     gen.manual_seed(cfg.seed)
     q = q0.clone().to(torch.float64)
     logp, grad = target.logp_dlogp(q)
-    inv_mass = torch.ones(D, dtype=torch.float64, device=dev)
+    inv_mass = torch.eye(D, dtype=torch.float64, device=dev)   # Sigma = M^-1 (dense)
+    chol = torch.eye(D, dtype=torch.float64, device=dev)       # Sigma = chol chol^T
     eps = torch.full((C,), cfg.init_step, dtype=torch.float64, device=dev)
     da = _DualAveraging(eps, cfg.target_accept, dev)
     ends = _windows(cfg.tune)
@@ -163,19 +165,21 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     t0 = time.perf_counter()
     for it in range(total):
         # ---- HMC over q given the binaries -------------------------------------------------
-        p = torch.randn(C, D, dtype=torch.float64, device=dev, generator=gen) / torch.sqrt(inv_mass)
-        h0 = -logp + 0.5 * (p * p * inv_mass).sum(dim=1)
+        # p ~ N(0, M) with M = Sigma^-1:  p = chol^-T z
+        z = torch.randn(C, D, dtype=torch.float64, device=dev, generator=gen)
+        p = torch.linalg.solve_triangular(chol.T, z.T, upper=True).T
+        h0 = -logp + 0.5 * (z * z).sum(dim=1)
         jitter = 0.6 + 0.8 * torch.rand((), device=dev, generator=gen).item()
         L = max(1, int(round(cfg.n_leapfrog * jitter)))
         qn, pn, gn, lpn = q, p, grad, logp
         e = eps[:, None]
         for _ in range(L):
             pn = pn + 0.5 * e * gn
-            qn = qn + e * pn * inv_mass
+            qn = qn + e * (pn @ inv_mass)
             lpn, gn = target.logp_dlogp(qn)
             pn = pn + 0.5 * e * gn
         n_grad += L
-        h1 = -lpn + 0.5 * (pn * pn * inv_mass).sum(dim=1)
+        h1 = -lpn + 0.5 * ((pn @ inv_mass) * pn).sum(dim=1)
         dh = h0 - h1
         dh = torch.where(torch.isfinite(dh), dh, torch.full_like(dh, -float("inf")))
         acc_p = torch.exp(torch.clamp(dh, max=0.0))
@@ -196,8 +200,9 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
             if ends and it + 1 == ends[0]:
                 x = torch.stack(win_draws).reshape(-1, D)
                 n = x.shape[0]
-                var = x.var(dim=0, unbiased=True)
-                inv_mass = (n / (n + 5.0)) * var + 1e-3 * (5.0 / (n + 5.0))  # Stan's shrinkage
+                cov = torch.cov(x.T)
+                inv_mass = (n / (n + 5.0)) * cov + 1e-3 * (5.0 / (n + 5.0)) * torch.eye(D, dtype=cov.dtype, device=dev)
+                chol = torch.linalg.cholesky(inv_mass)  # Stan's shrinkage keeps it positive definite
                 win_draws, win_start = [], ends.pop(0)
                 eps = da.final()  # restart step-size adaptation under the new metric
                 da = _DualAveraging(eps, cfg.target_accept, dev)
