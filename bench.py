@@ -129,7 +129,8 @@ def ncu_traffic(kernel):
     p = ROOT / "profiles" / "ncu_traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(kernel)
+            d = json.loads(p.read_text()).get(kernel)
+            return None if d is None else int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
         except Exception:
             return None
     return None
@@ -388,6 +389,57 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_gibbs, dt_gibbs_e2e = (float(v) for v in t.tolist())
     launches = sum(e.launch_count for e in engines) - launches0
+    for e in engines[1:]:
+        e.close()
+
+    # ---- individual sharding (BASELINE configs[3]): 100k-individual cohort split over the ranks,
+    #      one all-reduce of C x 16 doubles per evaluation (NCCL), host-driven loop ----
+    sharded = None
+    if dist:
+        from abdpymc_b200.cohort import synthetic_cohort
+        from abdpymc_b200.distributed import ShardedEngine
+
+        big = synthetic_cohort(100_000)
+        rngb = np.random.default_rng(77)
+        ib = (rngb.random((C, big.n_gaps, big.n_inds)) < 0.04).astype(np.int8)
+        wb = (rngb.random((C, big.n_inds)) < 0.5).astype(np.int8)
+        se = ShardedEngine(big, splits=SPLITS, device_index=local, rank=rank, world=world)
+        se.upload_state(ib, wb)
+        tqs = torch.from_numpy(workload(chain_offset=0)[1]).to(dev)  # identical q on every rank
+        for _ in range(10):
+            se.logp_dlogp(tqs)
+        barrier()
+        n_sh = max(50, min(500, K * 10))
+        e0.record()
+        for _ in range(n_sh):
+            lp_sh, _ = se.logp_dlogp(tqs)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sharded = {"workload": "simulated 100000-individual cohort sharded by individual, 4 chains",
+                   "value": C * n_sh / (float(t.item()) / 1e3), "unit": "evals/s", "ms_per_eval_batch": float(t.item()) / n_sh,
+                   "collective": "torch.distributed all_reduce(SUM) of 4 x 16 float64 per evaluation (NCCL)",
+                   "logp_chain0": float(lp_sh[0].item())}
+        se.close()
+
+    # ---- ESS/s of the built-in HMC + GPU-Gibbs sampler on the same cohort (bounded run) ----
+    ess = None
+    if world == 1 and not args.no_ess:
+        from abdpymc_b200 import diagnostics as dg
+        from abdpymc_b200.sampler import AbdTarget, SamplerConfig, sample
+
+        tgt = AbdTarget(eng0, C, np.zeros_like(i_raw), np.zeros_like(w), seed=1)
+        cfg = SamplerConfig(tune=300, draws=300, seed=1)
+        res = sample(tgt, torch.from_numpy(q).to(dev), cfg)
+        summ = dg.summary(res.posterior())
+        vals_ess = sorted(v["ess_bulk"] for v in summ.values())
+        # wall time of the whole run (tune + draws) is charged to the draws kept
+        ess = {"sampler": "built-in batched HMC (dense metric) + GPU Metropolised-Gibbs sweep, 4 chains x (300 tune + 300 draws)",
+               "wall_s": res.wall_s, "min_bulk_ess_per_s": vals_ess[0] / res.wall_s,
+               "median_bulk_ess_per_s": vals_ess[len(vals_ess) // 2] / res.wall_s,
+               "max_rhat": max(v["rhat"] for v in summ.values()), "grad_evals": res.n_grad_evals,
+               "note": "PyMC is not installable offline, so there is no PyMC-CPU ESS/s beside it"}
 
     if rank != 0:
         if dist:
@@ -427,7 +479,8 @@ def run_gpu(args):
                                "traffic": ncu_traffic("k_gibbs"), "kernel": "k_gibbs", "algorithmic_bytes_per_launch": a_gibbs},
                   "e2e": {"value": world * C * n_sw_e2e / dt_gibbs_e2e, "unit": "sweeps/s",
                           "h2d_bytes_per_step": int(C * (G * N + N + 15 * 8)), "d2h_bytes_per_step": int(C * (G * N + N + 16))}},
-        "gpu_launches": int(n_launch), "gpu_launches_total": int(launches), "clocks": clocks,
+        "sharded_100k": sharded, "ess": ess,
+        "gpu_launches": int(n_launch), "gpu_launches_host_api": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))
     if dist:
@@ -441,6 +494,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: a few un-captured logp+grad launches and Gibbs sweeps, no JSON line")
     args = ap.parse_args()
