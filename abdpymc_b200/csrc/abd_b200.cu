@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -61,6 +62,7 @@ struct DevCohort {
   const int* rp[2];          // [0] = N antigen, [1] = S antigen
   const double* od[2];
   const double* x[2];
+  const float* x32[2];         // the same values as float when every one is exactly representable
   const uint32_t* meta[2];     // per row: individual << 6 | gap
   const uint32_t* rowcell[2];  // per row: index of its (individual, gap) cell
   const uint32_t* cmeta[2];    // per cell: individual << 6 | gap
@@ -69,6 +71,7 @@ struct DevCohort {
 
 constexpr int kSumsBlock = 256;
 constexpr int kSumsWarps = kSumsBlock / 32;
+constexpr int kAuxDoubles = 128;  // 17 x PriorPre (7) + LikPre (6), padded
 constexpr int kTileMaxInds = 128;
 constexpr int kGibbsWarps = 8;
 
@@ -148,41 +151,68 @@ struct CellVal {
 
 #ifdef ABD_PHASE_TIMING
 __device__ unsigned long long g_phase[4096][12];
+__device__ unsigned long long g_span[256][2];  // per launch: first CTA start, last CTA end
+__device__ unsigned g_span_idx, g_span_done;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t_;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+  return t_;
+}
+#define SPAN_BEGIN()                                                                      \
+  unsigned span_slot_ = 0;                                                                \
+  if (threadIdx.x == 0) {                                                                 \
+    span_slot_ = *(volatile unsigned*)&g_span_idx & 255u;                                 \
+    atomicMin(&g_span[span_slot_][0], gtime());                                           \
+  }
+#define SPAN_END()                                                                        \
+  if (threadIdx.x == 0) {                                                                 \
+    atomicMax(&g_span[span_slot_][1], gtime());                                           \
+    if (atomicAdd(&g_span_done, 1u) == gridDim.x * gridDim.y - 1) {                       \
+      g_span_done = 0;                                                                    \
+      __threadfence();                                                                    \
+      atomicAdd(&g_span_idx, 1u);                                                         \
+    }                                                                                     \
+  }
 #define PHASE(i)                                                                         \
   do {                                                                                   \
-    if (tid == 0 && blockIdx.y == 0 && blockIdx.x < 4096) {                              \
+    if (tid == 0 && blockIdx.y * gridDim.x + blockIdx.x < 4096) {                        \
       unsigned long long t_;                                                             \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
-      g_phase[blockIdx.x][i] = t_;                                                       \
+      g_phase[blockIdx.y * gridDim.x + blockIdx.x][i] = t_;                              \
     }                                                                                    \
   } while (0)
 #else
 #define PHASE(i)
+#define SPAN_BEGIN()
+#define SPAN_END()
 #endif
 
 #ifndef ABD_SUMS_MINB
 #define ABD_SUMS_MINB 3
 #endif
-template <typename M>
+// XT: how the dilutions are staged in shared memory -- float when every log_dilution of the cohort
+// is exactly representable in fp32 (the usual case: small integers), double otherwise.
+template <typename M, typename XT>
 __global__ void __launch_bounds__(kSumsBlock, ABD_SUMS_MINB)
 k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg,
        const double* __restrict__ theta, const int theta_is_q,
        const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
        double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ sums,
-       const FinalizeCfg fin, const Priors* __restrict__ priors) {
+       const FinalizeCfg fin, const Priors* __restrict__ priors, double* __restrict__ aux) {
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int G = dc.G, N = dc.N, ntiles = cfg.ntiles;
 
   // dynamic shared memory: staged rows (od, x, row->cell), staged cell meta, per-cell values
   extern __shared__ __align__(16) unsigned char dyn_smem[];
+  constexpr bool kX32 = sizeof(XT) == 4;
   double* s_od_n = reinterpret_cast<double*>(dyn_smem);
-  double* s_x_n = s_od_n + cfg.cap_n;
-  double* s_od_s = s_x_n + cfg.cap_n;
-  double* s_x_s = s_od_s + cfg.cap_s;
-  CellVal* s_cv_n = reinterpret_cast<CellVal*>(s_x_s + cfg.cap_s);
+  double* s_od_s = s_od_n + cfg.cap_n;
+  CellVal* s_cv_n = reinterpret_cast<CellVal*>(s_od_s + cfg.cap_s);
   CellVal* s_cv_s = s_cv_n + cfg.capk_n;
-  uint32_t* s_rc_n = reinterpret_cast<uint32_t*>(s_cv_s + cfg.capk_s);
+  XT* s_x_n = reinterpret_cast<XT*>(s_cv_s + cfg.capk_s);   // cap_n doubles or capr_n floats
+  XT* s_x_s = s_x_n + (kX32 ? cfg.capr_n : cfg.cap_n);
+  uint32_t* s_rc_n = reinterpret_cast<uint32_t*>(s_x_s + (kX32 ? cfg.capr_s : cfg.cap_s));
   uint32_t* s_rc_s = s_rc_n + cfg.capr_n;
   uint32_t* s_cm_n = s_rc_s + cfg.capr_s;
   uint32_t* s_cm_s = s_cm_n + cfg.capk_n;
@@ -199,6 +229,8 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
   __shared__ LikPre s_lik;
 
   PHASE(0);
+  SPAN_BEGIN();
+  griddep_launch_dependents();
   const int4 d0 = reinterpret_cast<const int4*>(tiles + tile)[0];
   const int4 d1 = reinterpret_cast<const int4*>(tiles + tile)[1];
   const int2 d2 = reinterpret_cast<const int2*>(tiles + tile)[4];
@@ -215,21 +247,26 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     const uint32_t bn = (uint32_t)(((rn1 + 1) & ~1) - an0) * 8u, bs = (uint32_t)(((rs1 + 1) & ~1) - as0) * 8u;
     const uint32_t bqn = (uint32_t)(((rn1 + 3) & ~3) - qn0) * 4u, bqs = (uint32_t)(((rs1 + 3) & ~3) - qs0) * 4u;
     const uint32_t bkn = (uint32_t)(((cn1 + 3) & ~3) - kn0) * 4u, bks = (uint32_t)(((cs1 + 3) & ~3) - ks0) * 4u;
-    mbar_expect_tx(&s_bar, 2 * bn + 2 * bs + bqn + bqs + bkn + bks);
+    mbar_expect_tx(&s_bar, (kX32 ? bn + bqn + bs + bqs : 2 * bn + 2 * bs) + bqn + bqs + bkn + bks);
     if (bkn) bulk_g2s(s_cm_n, dc.cmeta[0] + kn0, bkn, &s_bar);
     if (bks) bulk_g2s(s_cm_s, dc.cmeta[1] + ks0, bks, &s_bar);
     if (bn) {
       bulk_g2s(s_od_n, dc.od[0] + an0, bn, &s_bar);
-      bulk_g2s(s_x_n, dc.x[0] + an0, bn, &s_bar);
+      if (kX32) bulk_g2s(s_x_n, dc.x32[0] + qn0, bqn, &s_bar);
+      else bulk_g2s(s_x_n, dc.x[0] + an0, bn, &s_bar);
     }
     if (bs) {
       bulk_g2s(s_od_s, dc.od[1] + as0, bs, &s_bar);
-      bulk_g2s(s_x_s, dc.x[1] + as0, bs, &s_bar);
+      if (kX32) bulk_g2s(s_x_s, dc.x32[1] + qs0, bqs, &s_bar);
+      else bulk_g2s(s_x_s, dc.x[1] + as0, bs, &s_bar);
     }
     if (bqn) bulk_g2s(s_rc_n, dc.rowcell[0] + qn0, bqn, &s_bar);
     if (bqs) bulk_g2s(s_rc_s, dc.rowcell[1] + qs0, bqs, &s_bar);
   }
   fill_exp_table(s_tab, tid, kSumsBlock);
+  // everything above reads only the immutable cohort; parameters, chain state and the reduction
+  // scratch may be written by the previous kernel in the stream
+  griddep_wait();
   PHASE(1);
 
   for (int cc = 0; cc < cfg.chains_per_cta; ++cc) {
@@ -274,13 +311,31 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     }
     __syncthreads();
     PHASE(2);
+    // The finaliser's parameter-only part (priors, transforms, logs: ~2 us of cold libm code) is
+    // taken off the critical path: warp 7 of the chain's first tile computes it now, instead of
+    // processing cells / rows, and parks it in global memory for whichever CTA finishes last.
+    const bool aux_cta = (tile == 0) && fin.mode != 0;
+    const int nwork = aux_cta ? kSumsBlock - 32 : kSumsBlock;
+    if (aux_cta && warp == kSumsWarps - 1) {
+      double* a = aux + (size_t)c * kAuxDoubles;
+      if (fin.mode == 2 && lane < 17) {
+        const PriorPre pp = prior_pre(lane, theta[(size_t)c * 17 + lane], priors->v[lane]);
+        double* o = a + lane * 7;
+        o[0] = pp.lpA, o[1] = pp.dA, o[2] = pp.f, o[3] = pp.lx, o[4] = pp.l1mx, o[5] = pp.x, o[6] = pp.omx;
+      }
+      if (lane == 17) {
+        const LikPre lk = lik_pre(s_th[N_SIGMA], s_th[S_SIGMA]);
+        double* o = a + 17 * 7;
+        o[0] = lk.lsn, o[1] = lk.lss, o[2] = lk.ivn, o[3] = lk.ivs, o[4] = lk.isn, o[5] = lk.iss;
+      }
+    }
     if (cc == 0) mbar_wait(&s_bar, 0);
     PHASE(3);
 
     // ---- phase 1: one thread per (individual, gap) cell: titer in closed form from the masks ----
     {
       const double init = s_th[N_INIT], perm = s_th[N_PERM], temp = s_th[N_TEMP];
-      for (int k = cn0 + tid; k < cn1; k += kSumsBlock) {
+      for (int k = cn0 + tid; k < cn1 && tid < nwork; k += nwork) {
         const uint32_t mt = s_cm_n[k - kn0];
         const int t = mt & 63, li = (int)(mt >> 6) - i0;
         double P, T, dT;
@@ -294,7 +349,7 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     }
     {
       const double init = s_th[S_INIT], perm = s_th[S_PERM];
-      for (int k = cs0 + tid; k < cs1; k += kSumsBlock) {
+      for (int k = cs0 + tid; k < cs1 && tid < nwork; k += nwork) {
         const uint32_t mt = s_cm_s[k - ks0];
         const int t = mt & 63, li = (int)(mt >> 6) - i0;
         const IndState<M> st = s_ind[li];
@@ -315,10 +370,10 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     {
       const double b = s_th[N_B], d = s_th[N_D];
 #pragma unroll 2
-      for (int r = rn0 + tid; r < rn1; r += kSumsBlock) {
+      for (int r = rn0 + tid; r < rn1 && tid < nwork; r += nwork) {
         const CellVal cv = s_cv_n[s_rc_n[r - qn0] - cn0];
         double s, res, q, xm;
-        row_eval(s_x_n[r - an0], s_od_n[r - an0], cv.m, b, d, s_tab, s, res, q, xm);
+        row_eval((double)s_x_n[r - (kX32 ? qn0 : an0)], s_od_n[r - an0], cv.m, b, d, s_tab, s, res, q, xm);
         acc[SN_0] = fma(res, res, acc[SN_0]);
         acc[SN_1] = fma(res, s, acc[SN_1]);
         acc[SN_2] = fma(q, xm, acc[SN_2]);
@@ -331,10 +386,10 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     {
       const double b = s_th[S_B], d = s_th[S_D];
 #pragma unroll 2
-      for (int r = rs0 + tid; r < rs1; r += kSumsBlock) {
+      for (int r = rs0 + tid; r < rs1 && tid < nwork; r += nwork) {
         const CellVal cv = s_cv_s[s_rc_s[r - qs0] - cs0];
         double s, res, q, xm;
-        row_eval(s_x_s[r - as0], s_od_s[r - as0], cv.m, b, d, s_tab, s, res, q, xm);
+        row_eval((double)s_x_s[r - (kX32 ? qs0 : as0)], s_od_s[r - as0], cv.m, b, d, s_tab, s, res, q, xm);
         acc[SS_0] = fma(res, res, acc[SS_0]);
         acc[SS_1] = fma(res, s, acc[SS_1]);
         acc[SS_2] = fma(q, xm, acc[SS_2]);
@@ -367,11 +422,11 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     PHASE(7);
     if (s_last) {
       __threadfence();
-      // warp 7 prepares what the finaliser needs besides the sums while the partials arrive
-      // (kept out of the prologue: its cold libm code would sit on every CTA's critical path)
-      if (warp == kSumsWarps - 1) {
-        if (fin.mode == 2 && lane < 17) s_pre[lane] = prior_pre(lane, theta[(size_t)c * 17 + lane], priors->v[lane]);
-        if (lane == 17) s_lik = lik_pre(s_th[N_SIGMA], s_th[S_SIGMA]);
+      // the parameter-only part of the finaliser was parked in `aux` by the chain's first tile
+      if (fin.mode && tid < kAuxDoubles) {
+        const double v = __ldcg(aux + (size_t)c * kAuxDoubles + tid);
+        if (tid < 17 * 7) reinterpret_cast<double*>(s_pre)[tid] = v;
+        else if (tid < 17 * 7 + 6) reinterpret_cast<double*>(&s_lik)[tid - 17 * 7] = v;
       }
       const int k = tid & 15, g = tid >> 4;  // 16 groups of 16 values
       double v = 0.0;
@@ -414,6 +469,7 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     PHASE(8);
     __syncthreads();  // shared memory is reused by the next chain
   }
+  SPAN_END();
 }
 
 // one warp per chain
@@ -835,6 +891,7 @@ struct abd_handle {
     void* d_tiles = nullptr;   // TileDesc[ntiles]
     int cap_n = 0, cap_s = 0, capr_n = 0, capr_s = 0, capk_n = 0, capk_s = 0;  // staging capacities (elements)
     size_t smem = 0;                                     // dynamic shared memory per CTA
+    int occ = 0;                                         // resident CTAs per SM (0 = not queried yet)
   };
   std::map<int, Tiling> tilings;  // keyed by number of tiles requested
   int tile_rows_override = 0;     // 0 = automatic
@@ -844,6 +901,8 @@ struct abd_handle {
   int* d_order = nullptr;       // individuals by decreasing OD-row count (Gibbs work queue)
   unsigned* d_queue = nullptr;  // Gibbs work-queue counter
   int gibbs_ctas = 0;
+  bool x_exact_f32 = true;      // every log_dilution is exactly representable as float
+  bool use_pdl = true;          // programmatic dependent launch (ABD_B200_NO_PDL=1 disables)
 
   // per-chain scratch
   int cap_chains = 0;
@@ -854,6 +913,7 @@ struct abd_handle {
   double* d_sums = nullptr;    // [C][16]
   double* d_out = nullptr;     // [C][18]
   unsigned* d_ticket = nullptr;
+  double* d_aux = nullptr;     // [C][kAuxDoubles] finaliser inputs that depend on parameters only
   unsigned long long* d_stats = nullptr;
   double* d_partial = nullptr;
   size_t cap_partial = 0;
@@ -965,6 +1025,18 @@ int build_rows(abd_handle* h, int a, int64_t R, const double* x, const double* o
   if ((rc = upload(h, &d_meta, meta))) return rc;
   if ((rc = upload(h, &d_rowcell, rowcell))) return rc;
   if ((rc = upload(h, &d_cmeta, cmeta))) return rc;
+  {
+    bool exact = true;
+    std::vector<float> xf(xs.size() + 2, 0.0f);  // same padding as the 32-bit word arrays (R + 4)
+    for (size_t k = 0; k < xs.size(); ++k) {
+      xf[k] = (float)xs[k];
+      exact = exact && ((double)xf[k] == xs[k]);
+    }
+    h->x_exact_f32 = h->x_exact_f32 && exact;
+    float* d_xf;
+    if ((rc = upload(h, &d_xf, xf))) return rc;
+    h->dc.x32[a] = d_xf;
+  }
   h->dc.rp[a] = d_rp;
   h->dc.x[a] = d_x;
   h->dc.od[a] = d_od;
@@ -1015,8 +1087,9 @@ int get_tiling(abd_handle* h, int want, abd_handle::Tiling** out) {
     t.capr_s = std::max(t.capr_s, 4);
     t.capk_n = std::max(t.capk_n, 4);
     t.capk_s = std::max(t.capk_s, 4);
-    t.smem = (size_t)(2 * t.cap_n + 2 * t.cap_s) * 8 + (size_t)(t.capk_n + t.capk_s) * (sizeof(CellVal) + 4) +
-             (size_t)(t.capr_n + t.capr_s) * 4;
+    t.smem = (size_t)(t.cap_n + t.cap_s) * 8 + (size_t)(t.capk_n + t.capk_s) * (sizeof(CellVal) + 4) +
+             (size_t)(t.capr_n + t.capr_s) * 4 +
+             (h->x_exact_f32 ? (size_t)(t.capr_n + t.capr_s) * 4 : (size_t)(t.cap_n + t.cap_s) * 8);
     if (t.smem + 12 * 1024 > h->smem_optin)
       return fail(ABD_ERR_INVALID, "an individual tile does not fit in shared memory (too many OD rows per 128 individuals)");
     std::vector<TileDesc> desc((size_t)t.ntiles);
@@ -1053,7 +1126,7 @@ int ensure_chains(abd_handle* h, int C) {
     CU(cudaMemcpy(nw, old_w, (size_t)oldC * h->N, cudaMemcpyDeviceToDevice));
   }
   for (void* p : {(void*)old_i, (void*)old_w, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
-                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats})
+                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_aux})
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   h->d_iraw = ni;
@@ -1063,6 +1136,7 @@ int ensure_chains(abd_handle* h, int C) {
   if ((rc = dev_alloc(h, &h->d_sums, (size_t)C * kNSums, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_out, (size_t)C * 18, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_ticket, (size_t)C, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_aux, (size_t)C * kAuxDoubles, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_stats, (size_t)C * 2, false))) return rc;
   CU(cudaMemset(h->d_ticket, 0, (size_t)C * sizeof(unsigned)));
   CU(cudaMallocHost((void**)&h->h_pin, (size_t)C * 40 * sizeof(double)));
@@ -1074,14 +1148,14 @@ int ensure_chains(abd_handle* h, int C) {
 // to exactly `waves` full waves of resident CTAs (n_sms x CTAs-per-SM), so every SM gets the
 // same number of equally sized tiles and there is no partial last wave; beyond that the tail is
 // negligible and tiles simply hold ~`target` OD rows (a handful per thread).
-void plan_grid(const abd_handle* h, int C, int* want_tiles, int* chains_per_cta) {
+void plan_grid(const abd_handle* h, int C, int ctas_per_sm, int* want_tiles, int* chains_per_cta) {
   const double rows = (double)(h->R[0] + h->R[1]);
   const int target = h->tile_rows_override > 0 ? h->tile_rows_override : 2200;
   int cpc = h->chains_per_cta_override > 0 ? h->chains_per_cta_override : (C >= 32 ? 4 : 1);
   cpc = std::min(cpc, C);
   const int groups = (C + cpc - 1) / cpc;
   const int min_tiles = (h->N + kTileMaxInds - 1) / kTileMaxInds;
-  const int resident = h->n_sms * ABD_SUMS_MINB;  // __launch_bounds__(256, ABD_SUMS_MINB)
+  const int resident = h->n_sms * ctas_per_sm;
   int tiles = std::max(min_tiles, (int)std::ceil(rows / target));
   if ((long)tiles * groups <= 6L * resident) {
     for (int waves = 1; waves <= 6; ++waves) {
@@ -1096,28 +1170,66 @@ void plan_grid(const abd_handle* h, int C, int* want_tiles, int* chains_per_cta)
   *chains_per_cta = cpc;
 }
 
-template <typename M>
+template <typename M, typename XT>
+cudaError_t sums_occupancy(size_t smem, int* occ) {
+  cudaError_t e = cudaFuncSetAttribute(k_sums<M, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_sums<M, XT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sums<M, XT>, kSumsBlock, smem);
+}
+
+template <typename M, typename XT>
 int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cfg, dim3 grid, const double* theta,
                   int theta_is_q, const int8_t* i_raw, const int8_t* waner, double* sums, const FinalizeCfg& fin,
                   cudaStream_t st) {
+  if (std::getenv("ABD_B200_VERBOSE")) {
+    const int occ = tl.occ;
+    std::fprintf(stderr, "[abd_b200] k_sums grid (%u, %u) dyn smem %zu B, occupancy %d CTAs/SM, caps rows %d/%d cells %d/%d\n",
+                 grid.x, grid.y, tl.smem, occ, tl.cap_n, tl.cap_s, tl.capk_n, tl.capk_s);
+  }
   static thread_local size_t configured = 0;
   if (tl.smem > configured) {
-    CU(cudaFuncSetAttribute(k_sums<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(tl.smem, 48 * 1024)));
-    CU(cudaFuncSetAttribute(k_sums<M>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_sums<M, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(tl.smem, 48 * 1024)));
+    CU(cudaFuncSetAttribute(k_sums<M, XT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = std::max<size_t>(tl.smem, 48 * 1024);
   }
-  k_sums<M><<<grid, kSumsBlock, tl.smem, st>>>(h->dc, reinterpret_cast<const TileDesc*>(tl.d_tiles), cfg, theta, theta_is_q, i_raw, waner,
-                                                h->d_partial, h->d_ticket, sums, fin, h->d_priors);
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid;
+  lc.blockDim = dim3(kSumsBlock);
+  lc.dynamicSmemBytes = tl.smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = h->use_pdl ? 1 : 0;
+  CU(cudaLaunchKernelEx(&lc, k_sums<M, XT>, h->dc, reinterpret_cast<const TileDesc*>(tl.d_tiles), cfg, theta, theta_is_q, i_raw,
+                        waner, h->d_partial, h->d_ticket, sums, fin, (const Priors*)h->d_priors, h->d_aux));
   return ABD_OK;
 }
 
 int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const int8_t* i_raw,
                 const int8_t* waner, double* sums, const FinalizeCfg& fin, cudaStream_t st) {
-  int want, cpc;
-  plan_grid(h, C, &want, &cpc);
-  abd_handle::Tiling* tl;
-  int rc = get_tiling(h, want, &tl);
-  if (rc) return rc;
+  // plan for the kernel's register-limited occupancy first; if the tiles that plan needs do not
+  // fit that many CTAs per SM (shared memory), plan again for what actually fits
+  int want, cpc, rc;
+  abd_handle::Tiling* tl = nullptr;
+  for (int occ = ABD_SUMS_MINB; occ >= 1; --occ) {
+    plan_grid(h, C, occ, &want, &cpc);
+    if ((rc = get_tiling(h, want, &tl))) return rc;
+    if (!tl->occ) {
+      int o = 0;
+      cudaError_t e;
+      if (h->wide)
+        e = h->x_exact_f32 ? sums_occupancy<uint64_t, float>(tl->smem, &o) : sums_occupancy<uint64_t, double>(tl->smem, &o);
+      else
+        e = h->x_exact_f32 ? sums_occupancy<uint32_t, float>(tl->smem, &o) : sums_occupancy<uint32_t, double>(tl->smem, &o);
+      CU(e);
+      tl->occ = std::max(o, 1);
+    }
+    if (tl->occ >= occ) break;
+  }
   const size_t need = (size_t)C * tl->ntiles * kNSums;
   if (need > h->cap_partial) {
     CU(cudaStreamSynchronize(st));
@@ -1129,8 +1241,12 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
   }
   SumsCfg cfg{tl->ntiles, tl->cap_n, tl->cap_s, tl->capr_n, tl->capr_s, tl->capk_n, tl->capk_s, cpc, C};
   dim3 grid(tl->ntiles, (C + cpc - 1) / cpc);
-  rc = h->wide ? launch_sums_t<uint64_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st)
-               : launch_sums_t<uint32_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st);
+  if (h->wide)
+    rc = h->x_exact_f32 ? launch_sums_t<uint64_t, float>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st)
+                        : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st);
+  else
+    rc = h->x_exact_f32 ? launch_sums_t<uint32_t, float>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st)
+                        : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st);
   if (rc) return rc;
   CU(cudaGetLastError());
   h->launches++;
@@ -1215,6 +1331,7 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
 
   abd_handle* h = new abd_handle();
   h->device = device;
+  if (const char* e = std::getenv("ABD_B200_NO_PDL")) h->use_pdl = !(e[0] == '1');
   {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->n_sms = v;
@@ -1296,7 +1413,7 @@ int abd_destroy(abd_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->owned) cudaFree(p);
   for (void* p : {(void*)h->d_iraw, (void*)h->d_waner, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
-                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_partial})
+                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_partial, (void*)h->d_aux})
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1603,6 +1720,19 @@ int abd_debug_fast_math(int device, int64_t n, const double* z, double* out_exp,
 }
 
 #ifdef ABD_PHASE_TIMING
+int abd_debug_spans(unsigned long long* out, int reset) {
+  if (reset) {
+    unsigned long long init[256][2];
+    for (auto& r : init) { r[0] = ~0ull; r[1] = 0; }
+    unsigned z = 0;
+    CU(cudaMemcpyToSymbol(g_span, init, sizeof(init)));
+    CU(cudaMemcpyToSymbol(g_span_idx, &z, sizeof(z)));
+    CU(cudaMemcpyToSymbol(g_span_done, &z, sizeof(z)));
+    return ABD_OK;
+  }
+  CU(cudaMemcpyFromSymbol(out, g_span, sizeof(unsigned long long) * 512));
+  return ABD_OK;
+}
 int abd_debug_phase_times(unsigned long long* out, int n_ctas) {
   CU(cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 12 * (size_t)n_ctas));
   return ABD_OK;

@@ -299,6 +299,13 @@ __device__ __forceinline__ int warp_reduce16_index(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// launch_dependents: the next kernel in the stream may start being scheduled (it still blocks in
+// its own griddep_wait until this grid has completed and flushed).  wait: block until every
+// kernel this launch depends on has completed.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier + 1-D bulk async copy (TMA) -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {

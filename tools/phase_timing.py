@@ -36,7 +36,7 @@ for rep in range(4):
     torch.cuda.synchronize()
     eng.logp_dlogp_dev(C_, tq.data_ptr(), di, dw, out.data_ptr(), outg.data_ptr(), 0)
     torch.cuda.synchronize()
-n = 444
+n = 4096
 buf = np.zeros((n, 12), np.uint64)
 lib.abd_debug_phase_times.argtypes = [C.c_void_p, C.c_int]
 lib.abd_debug_phase_times(buf.ctypes.data_as(C.c_void_p), n)
@@ -44,10 +44,14 @@ buf = buf[buf[:, 0] > 0].astype(np.int64)
 t0 = buf[:, 0].min()
 rel = (buf[:, :9] - t0) / 1e3
 names = ["start", "staged+tab", "phase0 done", "tma arrived", "cells done", "rows done", "partial written", "ticket", "end"]
-print(f"{len(buf)} CTAs of chain 0; times in us relative to the first CTA start")
+print(f"{len(buf)} CTAs (all chains); times in us relative to the first CTA start")
 for k, nm in enumerate(names):
     col = rel[:, k]
     print(f"  {nm:16s} min {col.min():7.2f}  median {np.median(col):7.2f}  max {col.max():7.2f}")
+per = len(buf) // C_
+for c in range(C_):
+    blk = rel[c * per:(c + 1) * per]
+    print(f"  chain {c}: start median {np.median(blk[:, 0]):.2f}  phase0 done {np.median(blk[:, 2]):.2f}  rows done {np.median(blk[:, 5]):.2f}  end max {blk[:, 8].max():.2f}")
 last = buf[buf[:, 11] > buf[:, 0]]
 if len(last):
     r = (last[0, [7, 9, 10, 11, 8]] - t0) / 1e3
