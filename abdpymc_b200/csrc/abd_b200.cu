@@ -136,6 +136,24 @@ struct SumsCfg {
   int C;
 };
 
+// Trajectory mode (n_steps > 0): the kernel stays resident for n_steps leapfrog steps of
+// Hamiltonian dynamics over q17 with the binary state fixed.  Per step every CTA evaluates its
+// tile at the current position; the CTA that finishes a chain last finalises logp / gradient,
+// advances (q, p) and publishes them with a per-chain generation counter the other CTAs of that
+// chain wait on -- no kernel launch, no re-staging of the cohort between evaluations.
+struct TrajCfg {
+  int n_steps;             // 0 = plain evaluation
+  double* q;               // [C][17] in: start position, out: end position
+  double* p;               // [C][17] in/out momentum
+  double* grad;            // [C][17] in: gradient at q, out: gradient at the end position
+  double* logp;            // [C]     out: logp at the end position
+  const double* eps;       // [C] step sizes
+  const double* inv_mass;  // [17][17] (symmetric) inverse mass matrix, shared by all chains
+  double* state;           // [C][34] scratch: position and half-step momentum of the current step
+  unsigned* gen;           // [C] generation counters (zeroed before the launch)
+  unsigned* err;           // set to 1 if a wait timed out
+};
+
 // tile descriptor (48 bytes, three 16-byte loads): individuals [i0, i1); per antigen the OD rows
 // [r0, r1) and the (individual, gap) cells [c0, c1) of those individuals
 struct __align__(16) TileDesc {
@@ -192,13 +210,13 @@ __device__ __forceinline__ unsigned long long gtime() {
 #endif
 // XT: how the dilutions are staged in shared memory -- float when every log_dilution of the cohort
 // is exactly representable in fp32 (the usual case: small integers), double otherwise.
-template <typename M, typename XT>
+template <typename M, typename XT, bool TRAJ>
 __global__ void __launch_bounds__(kSumsBlock, ABD_SUMS_MINB)
 k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg,
        const double* __restrict__ theta, const int theta_is_q,
        const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
        double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ sums,
-       const FinalizeCfg fin, const Priors* __restrict__ priors, double* __restrict__ aux) {
+       const FinalizeCfg fin, const Priors* __restrict__ priors, double* __restrict__ aux, const TrajCfg traj) {
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int G = dc.G, N = dc.N, ntiles = cfg.ntiles;
@@ -227,6 +245,8 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ PriorPre s_pre[17];
   __shared__ LikPre s_lik;
+  __shared__ double s_q[17], s_ph[17], s_out[18];  // trajectory mode: position, half-step momentum, logp + gradient
+  __shared__ double s_im[TRAJ ? 17 * 17 : 1];       // trajectory mode: inverse mass matrix
 
   PHASE(0);
   SPAN_BEGIN();
@@ -267,21 +287,70 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
   // everything above reads only the immutable cohort; parameters, chain state and the reduction
   // scratch may be written by the previous kernel in the stream
   griddep_wait();
+  if (TRAJ) {
+    for (int k = tid; k < 17 * 17; k += kSumsBlock) s_im[k] = traj.inv_mass[k];
+    __syncthreads();
+  }
   PHASE(1);
 
   for (int cc = 0; cc < cfg.chains_per_cta; ++cc) {
     const int c = blockIdx.y * cfg.chains_per_cta + cc;
     if (c >= cfg.C) break;
 
+    const int nsteps = TRAJ ? traj.n_steps : 1;
+    double cnt_i = 0.0, cnt_w = 0.0;  // this thread's individual: sum(i_raw), waner
+    for (int step = 0; step < nsteps; ++step) {
     double acc[kNSums];
 #pragma unroll
     for (int k = 0; k < kNSums; ++k) acc[k] = 0.0;
+    acc[S_KI] = cnt_i;
+    acc[S_KW] = cnt_w;
+
+    // trajectory mode: this step's position.  Step 0: every warp that needs it advances the
+    // start point itself (p_half = p + eps/2 g, q' = q + eps Sigma p_half: 17 FMAs per lane);
+    // later steps: wait for the chain's previous finaliser to publish (q', p_half).
+    double q_lane = 0.0, ph_lane = 0.0;  // lane k < 17: component k
+    if (TRAJ) {
+      if (step > 0) {
+        if (tid == 0) {
+          unsigned seen, polls = 0;
+          do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(traj.gen + c) : "memory");
+          } while (seen < (unsigned)step && ++polls < (1u << 26));
+          if (seen < (unsigned)step) *traj.err = 1u;  // watchdog: never hang the GPU
+        }
+        __syncthreads();
+        if (lane < 17) {
+          q_lane = __ldcg(traj.state + (size_t)c * 34 + lane);
+          ph_lane = __ldcg(traj.state + (size_t)c * 34 + 17 + lane);
+        }
+      } else if (warp >= 4) {
+        const double e = traj.eps[c];
+        double mine = 0.0;
+        if (lane < 17) mine = fma(0.5 * e, traj.grad[(size_t)c * 17 + lane], traj.p[(size_t)c * 17 + lane]);
+        double dot = 0.0;
+        for (int j = 0; j < 17; ++j) {
+          const double pj = __shfl_sync(0xffffffffu, mine, j);
+          if (lane < 17) dot = fma(s_im[lane * 17 + j], pj, dot);
+        }
+        ph_lane = mine;
+        if (lane < 17) q_lane = fma(e, dot, traj.q[(size_t)c * 17 + lane]);
+      }
+    }
+    // parameter k13 of this chain for the calling warp (uniform over the warp)
+    auto param13 = [&](int k13) -> double {
+      if (TRAJ) {
+        const int j = kQOfTheta[k13];
+        return backward(__shfl_sync(0xffffffffu, q_lane, j), kQTransform[j]);
+      }
+      return load_param(theta, theta_is_q, c, k13);
+    };
 
     // ---- phase 0: warps 0-3: one thread per individual reads its int8 column (every load of
     //      the warp is one coalesced 32-byte segment; all gaps in flight at once) and applies
     //      the infection constraints; warps 4-6: parameters and power tables ----
     if (tid < kTileMaxInds) {
-      if (tid < ni) {
+      if (tid < ni && step == 0) {
         // issue every load of the column before the first use (one memory round trip)
         const int8_t* col = i_raw + (size_t)c * G * N + i0 + tid;
         int8_t bytes[sizeof(M) * 8];
@@ -299,15 +368,24 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         st.inf = constrain<M>(raw, pcr, dc.ch);
         st.vacw = reinterpret_cast<const M*>(dc.vac)[i0 + tid] | (w ? top_bit<M>() : (M)0);
         s_ind[tid] = st;
-        acc[S_KI] = (double)popc(raw);
-        acc[S_KW] = (double)w;
+        acc[S_KI] = cnt_i = (double)popc(raw);
+        acc[S_KW] = cnt_w = (double)w;
       }
     } else if (warp == 4) {
-      fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw[0], s_pw[1]);
+      fill_pow_warp(param13(N_RHO), G, lane, s_pw[0], s_pw[1]);
     } else if (warp == 5) {
-      fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw[2], s_pw[3]);
+      fill_pow_warp(param13(S_RHO), G, lane, s_pw[2], s_pw[3]);
     } else if (warp == 6) {
-      if (lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
+      if (TRAJ) {
+        const int j = kQOfTheta[lane < 13 ? lane : 0];
+        const double v = backward(__shfl_sync(0xffffffffu, q_lane, j), kQTransform[j]);
+        if (lane < 13) s_th[lane] = v;
+      } else if (lane < 13) {
+        s_th[lane] = load_param(theta, theta_is_q, c, lane);
+      }
+    } else if (TRAJ && lane < 17) {  // warp 7 keeps (q, p_half) for the finaliser
+      s_q[lane] = q_lane;
+      s_ph[lane] = ph_lane;
     }
     __syncthreads();
     PHASE(2);
@@ -319,7 +397,7 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     if (aux_cta && warp == kSumsWarps - 1) {
       double* a = aux + (size_t)c * kAuxDoubles;
       if (fin.mode == 2 && lane < 17) {
-        const PriorPre pp = prior_pre(lane, theta[(size_t)c * 17 + lane], priors->v[lane]);
+        const PriorPre pp = prior_pre(lane, TRAJ ? s_q[lane] : theta[(size_t)c * 17 + lane], priors->v[lane]);
         double* o = a + lane * 7;
         o[0] = pp.lpA, o[1] = pp.dA, o[2] = pp.f, o[3] = pp.lx, o[4] = pp.l1mx, o[5] = pp.x, o[6] = pp.omx;
       }
@@ -329,7 +407,7 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         o[0] = lk.lsn, o[1] = lk.lss, o[2] = lk.ivn, o[3] = lk.ivs, o[4] = lk.isn, o[5] = lk.iss;
       }
     }
-    if (cc == 0) mbar_wait(&s_bar, 0);
+    if (cc == 0 && step == 0) mbar_wait(&s_bar, 0);
     PHASE(3);
 
     // ---- phase 1: one thread per (individual, gap) cell: titer in closed form from the masks ----
@@ -459,15 +537,49 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
           if (lane == 0)
             finalize_loglik_post(s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
                                  fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
-        } else if (fin.mode == 2) {
+        } else if (fin.mode == 2 && !TRAJ) {
           finalize_logp_post(lane, s_pre, s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
                              fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
+        } else if (TRAJ && fin.mode == 2) {
+          // trajectory mode: finish this leapfrog step and either publish the next position or
+          // write the end point
+          finalize_logp_post(lane, s_pre, s_th, s_lik, s_red[0], fin.tot, &s_out[0], &s_out[1]);
+          __syncwarp();
+          const double e = traj.eps[c];
+          const double g = lane < 17 ? s_out[1 + lane] : 0.0;
+          const double ph = lane < 17 ? s_ph[lane] : 0.0;
+          if (step == nsteps - 1) {
+            if (lane < 17) {
+              traj.q[(size_t)c * 17 + lane] = s_q[lane];
+              traj.p[(size_t)c * 17 + lane] = fma(0.5 * e, g, ph);
+              traj.grad[(size_t)c * 17 + lane] = g;
+            }
+            if (lane == 0) traj.logp[c] = s_out[0];
+          } else {
+            const double ph2 = fma(e, g, ph);  // two half steps: end of this step + start of the next
+            double dot = 0.0;
+            for (int j = 0; j < 17; ++j) {
+              const double pj = __shfl_sync(0xffffffffu, ph2, j);
+              if (lane < 17) dot = fma(s_im[lane * 17 + j], pj, dot);
+            }
+            if (lane < 17) {
+              traj.state[(size_t)c * 34 + lane] = fma(e, dot, s_q[lane]);
+              traj.state[(size_t)c * 34 + 17 + lane] = ph2;
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+              const unsigned nxt = (unsigned)step + 1u;
+              asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(traj.gen + c), "r"(nxt) : "memory");
+            }
+          }
         }
       }
     }
     if (s_last) PHASE(11);
     PHASE(8);
-    __syncthreads();  // shared memory is reused by the next chain
+    __syncthreads();  // shared memory is reused by the next step / chain
+    }  // step
   }
   SPAN_END();
 }
@@ -914,6 +1026,8 @@ struct abd_handle {
   double* d_out = nullptr;     // [C][18]
   unsigned* d_ticket = nullptr;
   double* d_aux = nullptr;     // [C][kAuxDoubles] finaliser inputs that depend on parameters only
+  double* d_traj = nullptr;    // [C][34] trajectory-mode scratch (position, half-step momentum)
+  unsigned* d_gen = nullptr;   // [C + 1] generation counters + error flag
   unsigned long long* d_stats = nullptr;
   double* d_partial = nullptr;
   size_t cap_partial = 0;
@@ -1126,7 +1240,7 @@ int ensure_chains(abd_handle* h, int C) {
     CU(cudaMemcpy(nw, old_w, (size_t)oldC * h->N, cudaMemcpyDeviceToDevice));
   }
   for (void* p : {(void*)old_i, (void*)old_w, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
-                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_aux})
+                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_aux, (void*)h->d_traj, (void*)h->d_gen})
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   h->d_iraw = ni;
@@ -1137,6 +1251,8 @@ int ensure_chains(abd_handle* h, int C) {
   if ((rc = dev_alloc(h, &h->d_out, (size_t)C * 18, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_ticket, (size_t)C, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_aux, (size_t)C * kAuxDoubles, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_traj, (size_t)C * 34, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_gen, (size_t)C + 1, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_stats, (size_t)C * 2, false))) return rc;
   CU(cudaMemset(h->d_ticket, 0, (size_t)C * sizeof(unsigned)));
   CU(cudaMallocHost((void**)&h->h_pin, (size_t)C * 40 * sizeof(double)));
@@ -1172,27 +1288,34 @@ void plan_grid(const abd_handle* h, int C, int ctas_per_sm, int* want_tiles, int
 
 template <typename M, typename XT>
 cudaError_t sums_occupancy(size_t smem, int* occ) {
-  cudaError_t e = cudaFuncSetAttribute(k_sums<M, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+  cudaError_t e = cudaFuncSetAttribute(k_sums<M, XT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_sums<M, XT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(k_sums<M, XT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sums<M, XT>, kSumsBlock, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sums<M, XT, false>, kSumsBlock, smem);
 }
 
 template <typename M, typename XT>
 int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cfg, dim3 grid, const double* theta,
                   int theta_is_q, const int8_t* i_raw, const int8_t* waner, double* sums, const FinalizeCfg& fin,
-                  cudaStream_t st) {
+                  const TrajCfg& traj, cudaStream_t st) {
   if (std::getenv("ABD_B200_VERBOSE")) {
     const int occ = tl.occ;
     std::fprintf(stderr, "[abd_b200] k_sums grid (%u, %u) dyn smem %zu B, occupancy %d CTAs/SM, caps rows %d/%d cells %d/%d\n",
                  grid.x, grid.y, tl.smem, occ, tl.cap_n, tl.cap_s, tl.capk_n, tl.capk_s);
   }
-  static thread_local size_t configured = 0;
-  if (tl.smem > configured) {
-    CU(cudaFuncSetAttribute(k_sums<M, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(tl.smem, 48 * 1024)));
-    CU(cudaFuncSetAttribute(k_sums<M, XT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    configured = std::max<size_t>(tl.smem, 48 * 1024);
+  static thread_local size_t configured[2] = {0, 0};
+  const int tj = traj.n_steps > 0 ? 1 : 0;
+  if (tl.smem > configured[tj]) {
+    const int want = (int)std::max<size_t>(tl.smem, 48 * 1024);
+    if (tj) {
+      CU(cudaFuncSetAttribute(k_sums<M, XT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+      CU(cudaFuncSetAttribute(k_sums<M, XT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    } else {
+      CU(cudaFuncSetAttribute(k_sums<M, XT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+      CU(cudaFuncSetAttribute(k_sums<M, XT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    configured[tj] = (size_t)want;
   }
   cudaLaunchConfig_t lc{};
   lc.gridDim = grid;
@@ -1200,23 +1323,46 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
   lc.dynamicSmemBytes = tl.smem;
   lc.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  lc.attrs = attr;
-  lc.numAttrs = h->use_pdl ? 1 : 0;
-  CU(cudaLaunchKernelEx(&lc, k_sums<M, XT>, h->dc, reinterpret_cast<const TileDesc*>(tl.d_tiles), cfg, theta, theta_is_q, i_raw,
-                        waner, h->d_partial, h->d_ticket, sums, fin, (const Priors*)h->d_priors, h->d_aux));
+  const TileDesc* tiles = reinterpret_cast<const TileDesc*>(tl.d_tiles);
+  const Priors* pri = h->d_priors;
+  if (tj) {  // CTAs wait on one another: they must all be resident
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sums<M, XT, true>, kSumsBlock, tl.smem));
+    if ((long)grid.x * grid.y > (long)occ * h->n_sms)
+      return fail(ABD_ERR_INVALID, "abd_leapfrog_dev: the grid does not fit on the device at once");
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, true>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, h->d_partial,
+                          h->d_ticket, sums, fin, pri, h->d_aux, traj));
+  } else {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = h->use_pdl ? 1 : 0;
+    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, false>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, h->d_partial,
+                          h->d_ticket, sums, fin, pri, h->d_aux, traj));
+  }
   return ABD_OK;
 }
 
 int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const int8_t* i_raw,
-                const int8_t* waner, double* sums, const FinalizeCfg& fin, cudaStream_t st) {
+                const int8_t* waner, double* sums, const FinalizeCfg& fin, cudaStream_t st,
+                const TrajCfg* traj_in = nullptr) {
+  TrajCfg traj{};
+  if (traj_in) traj = *traj_in;
   // plan for the kernel's register-limited occupancy first; if the tiles that plan needs do not
   // fit that many CTAs per SM (shared memory), plan again for what actually fits
   int want, cpc, rc;
   abd_handle::Tiling* tl = nullptr;
   for (int occ = ABD_SUMS_MINB; occ >= 1; --occ) {
     plan_grid(h, C, occ, &want, &cpc);
+    if (traj.n_steps > 0 && cpc != 1) {  // re-plan with one chain per CTA, exactly one wave
+      cpc = 1;
+      want = std::max((h->N + kTileMaxInds - 1) / kTileMaxInds, (h->n_sms * occ) / C);
+      want = std::max(1, std::min(want, h->N));
+    }
     if ((rc = get_tiling(h, want, &tl))) return rc;
     if (!tl->occ) {
       int o = 0;
@@ -1230,6 +1376,12 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
     }
     if (tl->occ >= occ) break;
   }
+  if (traj.n_steps > 0) {
+    // persistent mode: one chain per CTA and every CTA resident at once
+    if (cpc != 1 || (long)tl->ntiles * C > (long)h->n_sms * tl->occ)
+      return fail(ABD_ERR_INVALID, "abd_leapfrog_dev: too many chains for one resident grid on this cohort; "
+                                   "use abd_logp_dlogp_dev per step");
+  }
   const size_t need = (size_t)C * tl->ntiles * kNSums;
   if (need > h->cap_partial) {
     CU(cudaStreamSynchronize(st));
@@ -1242,11 +1394,11 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
   SumsCfg cfg{tl->ntiles, tl->cap_n, tl->cap_s, tl->capr_n, tl->capr_s, tl->capk_n, tl->capk_s, cpc, C};
   dim3 grid(tl->ntiles, (C + cpc - 1) / cpc);
   if (h->wide)
-    rc = h->x_exact_f32 ? launch_sums_t<uint64_t, float>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st)
-                        : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st);
+    rc = h->x_exact_f32 ? launch_sums_t<uint64_t, float>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st)
+                        : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st);
   else
-    rc = h->x_exact_f32 ? launch_sums_t<uint32_t, float>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st)
-                        : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, st);
+    rc = h->x_exact_f32 ? launch_sums_t<uint32_t, float>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st)
+                        : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st);
   if (rc) return rc;
   CU(cudaGetLastError());
   h->launches++;
@@ -1413,7 +1565,8 @@ int abd_destroy(abd_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->owned) cudaFree(p);
   for (void* p : {(void*)h->d_iraw, (void*)h->d_waner, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
-                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_partial, (void*)h->d_aux})
+                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_partial, (void*)h->d_aux, (void*)h->d_traj,
+                  (void*)h->d_gen})
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1695,6 +1848,25 @@ int abd_deterministics_dev(abd_handle* h, int C, const double* theta13, const in
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;
+}
+
+int abd_leapfrog_dev(abd_handle* h, int C, int n_steps, double* q17, double* p17, double* grad17, double* logp,
+                     const double* eps, const double* inv_mass, const int8_t* i_raw, const int8_t* waner, void* stream) {
+  PROLOGUE(h, C);
+  if (!q17 || !p17 || !grad17 || !logp || !eps || !inv_mass || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
+  if (n_steps < 1 || n_steps > 4096) return fail(ABD_ERR_INVALID, "n_steps must be in [1, 4096]");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(h->d_gen, 0, ((size_t)C + 1) * sizeof(unsigned), st));
+  TrajCfg traj{n_steps, q17, p17, grad17, logp, eps, inv_mass, h->d_traj, h->d_gen, h->d_gen + C};
+  FinalizeCfg fin{2, h->tot, nullptr, nullptr};
+  return launch_sums(h, C, q17, 1, i_raw, waner, nullptr, fin, st, &traj);
+}
+
+int abd_leapfrog_status(abd_handle* h, int C) {
+  PROLOGUE(h, C);
+  unsigned err = 0;
+  CU(cudaMemcpy(&err, h->d_gen + C, sizeof(unsigned), cudaMemcpyDeviceToHost));
+  return err ? fail(ABD_ERR_CUDA, "abd_leapfrog_dev: a CTA timed out waiting for its chain (grid not co-resident?)") : ABD_OK;
 }
 
 int abd_debug_fast_math(int device, int64_t n, const double* z, double* out_exp, double* out_rcp) {

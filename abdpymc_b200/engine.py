@@ -261,5 +261,11 @@ class AbdEngine:
         check(self._lib.abd_gibbs_sweep_dev(self._h, C_, theta, int(theta_is_q17), p, p_w, i_raw, waner,
                                             int(seed), int(sweep), int(mode), float(transit_p), stats, stream))
 
+    def leapfrog_dev(self, C_, n_steps, q17, p17, grad17, logp, eps, inv_mass, i_raw, waner, stream=0):
+        check(self._lib.abd_leapfrog_dev(self._h, C_, int(n_steps), q17, p17, grad17, logp, eps, inv_mass, i_raw, waner, stream))
+
+    def leapfrog_status(self, C_):
+        check(self._lib.abd_leapfrog_status(self._h, C_))
+
     def deterministics_dev(self, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream=0):
         check(self._lib.abd_deterministics_dev(self._h, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream))

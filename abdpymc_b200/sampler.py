@@ -54,6 +54,16 @@ class AbdTarget:
                                    self._stream())
         return self.out.clone(), self.outg.clone()
 
+    def leapfrog(self, q, p, grad, eps, inv_mass, n_steps):
+        """n_steps leapfrog steps for all chains in one persistent launch (abd_leapfrog_dev).
+        Returns (q, p, logp, grad) at the end point; inputs are not modified."""
+        q, p, grad = q.clone().contiguous(), p.clone().contiguous(), grad.clone().contiguous()
+        eps, inv_mass = eps.contiguous(), inv_mass.contiguous()
+        lp = torch.empty(self.C, dtype=torch.float64, device=self.device)
+        self.engine.leapfrog_dev(self.C, n_steps, q.data_ptr(), p.data_ptr(), grad.data_ptr(), lp.data_ptr(),
+                                 eps.data_ptr(), inv_mass.data_ptr(), self.d_i, self.d_w, self._stream())
+        return q, p, lp, grad
+
     def gibbs(self, q, sweep):
         q = q.contiguous()
         self.engine.gibbs_sweep_dev(self.C, q.data_ptr(), 1, None, None, self.d_i, self.d_w, self.seed, sweep,
@@ -83,6 +93,7 @@ class SamplerConfig:
     target_accept: float = 0.8
     init_step: float = 0.05
     record_deterministics_every: int = 0   # 0 = never; k = accumulate means every k-th draw
+    persistent_trajectories: bool = True   # one abd_leapfrog_dev launch per trajectory when it fits
     seed: int = 0
 
 
@@ -162,6 +173,7 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     out_acc = torch.empty(cfg.draws, C, dtype=torch.float64, device=dev)
     means, n_means, n_grad = {}, 0, 0
     has_gibbs = hasattr(target, "gibbs")
+    use_traj = hasattr(target, "leapfrog") and cfg.persistent_trajectories
     t0 = time.perf_counter()
     for it in range(total):
         # ---- HMC over q given the binaries -------------------------------------------------
@@ -171,13 +183,19 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
         h0 = -logp + 0.5 * (z * z).sum(dim=1)
         jitter = 0.6 + 0.8 * torch.rand((), device=dev, generator=gen).item()
         L = max(1, int(round(cfg.n_leapfrog * jitter)))
-        qn, pn, gn, lpn = q, p, grad, logp
-        e = eps[:, None]
-        for _ in range(L):
-            pn = pn + 0.5 * e * gn
-            qn = qn + e * (pn @ inv_mass)
-            lpn, gn = target.logp_dlogp(qn)
-            pn = pn + 0.5 * e * gn
+        if use_traj:
+            try:
+                qn, pn, lpn, gn = target.leapfrog(q, p, grad, eps, inv_mass, L)
+            except Exception:  # too many chains for one resident grid: per-step launches
+                use_traj = False
+        if not use_traj:
+            qn, pn, gn, lpn = q, p, grad, logp
+            e = eps[:, None]
+            for _ in range(L):
+                pn = pn + 0.5 * e * gn
+                qn = qn + e * (pn @ inv_mass)
+                lpn, gn = target.logp_dlogp(qn)
+                pn = pn + 0.5 * e * gn
         n_grad += L
         h1 = -lpn + 0.5 * ((pn @ inv_mass) * pn).sum(dim=1)
         dh = h0 - h1

@@ -185,6 +185,19 @@ int abd_gibbs_sweep_dev(abd_handle* h, int n_chains, const double* theta, int th
 int abd_deterministics_dev(abd_handle* h, int n_chains, const double* theta13,
                            const int8_t* i_raw, const int8_t* waner, int8_t* out_i,
                            double* out_mu_n, double* out_mu_s, void* stream);
+/* n_steps leapfrog steps of Hamiltonian dynamics over q17 for C chains with the binary state
+ * fixed, in ONE persistent launch (what a NUTS / HMC trajectory of pm.sample, abd.py:922, costs
+ * n_steps calls of logp_dlogp_function for).  Per step: p += eps/2 grad; q += eps inv_mass p;
+ * (logp, grad) = joint logp + gradient at q; p += eps/2 grad.  q17, p17, grad17 (C x 17, in/out;
+ * grad17 holds the gradient at q17 on entry), logp (C, out), eps (C), inv_mass (17 x 17 row-major,
+ * symmetric).  The grid must be resident at once: C x tiles <= SMs x CTAs/SM, otherwise
+ * ABD_ERR_INVALID (use abd_logp_dlogp_dev per step).  abd_leapfrog_status: synchronous check that
+ * no CTA timed out in the last trajectory.                                                    */
+int abd_leapfrog_dev(abd_handle* h, int n_chains, int n_steps, double* q17, double* p17,
+                     double* grad17, double* logp, const double* eps, const double* inv_mass,
+                     const int8_t* i_raw, const int8_t* waner, void* stream);
+int abd_leapfrog_status(abd_handle* h, int n_chains);
+
 /* Pointers to the resident chain state (valid until the next call that changes n_chains).   */
 int abd_state_dev(abd_handle* h, int n_chains, int8_t** i_raw, int8_t** waner);
 

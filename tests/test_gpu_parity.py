@@ -472,3 +472,47 @@ def test_fast_math(Engine):
     assert np.all(e[np.isfinite(z)] >= 0) and np.isnan(e[np.isnan(z)]).all()
     x = 1.0 + np.abs(z[np.isfinite(z)])
     assert np.max(np.abs(r[np.isfinite(z)] * x - 1.0)) < 4.5e-16
+
+
+@pytest.mark.parametrize("n_inds,C,L", [(10_000, 4, 7), (1000, 2, 1), (1000, 3, 12)])
+def test_persistent_leapfrog_matches_stepwise(Engine, n_inds, C, L):
+    """abd_leapfrog_dev (one persistent launch, CTAs hand the position over through a generation
+    counter) against the same L leapfrog steps done with one abd_logp_dlogp call per step."""
+    import torch
+
+    from abdpymc_b200.cohort import synthetic_cohort
+
+    co = synthetic_cohort(n_inds)
+    rng = np.random.default_rng(4 + L)
+    q = np.stack([ora.forward(ora.sample_prior(rng, co.n_gaps)) for _ in range(C)])
+    i_raw = (rng.random((C, co.n_gaps, co.n_inds)) < 0.04).astype(np.int8)
+    w = (rng.random((C, co.n_inds)) < 0.5).astype(np.int8)
+    a = rng.normal(size=(17, 17))
+    inv_mass = 1e-4 * (a @ a.T / 17 + np.eye(17))
+    eps = rng.uniform(0.05, 0.2, size=C)
+    p = rng.normal(size=(C, 17)) * 30
+    with Engine(co, splits=(14, 20)) as eng:
+        eng.upload_state(i_raw, w)
+        lp0, g0 = eng.logp_dlogp(q)
+        # reference: host leapfrog, one evaluation per step
+        qr, pr, gr = q.copy(), p.copy(), g0.copy()
+        for _ in range(L):
+            pr = pr + 0.5 * eps[:, None] * gr
+            qr = qr + eps[:, None] * (pr @ inv_mass)
+            lpr, gr = eng.logp_dlogp(qr)
+            pr = pr + 0.5 * eps[:, None] * gr
+        dev = torch.device("cuda:0")
+        tq, tp, tg = (torch.from_numpy(v.copy()).to(dev) for v in (q, p, g0))
+        te, tm = torch.from_numpy(eps).to(dev), torch.from_numpy(inv_mass).to(dev)
+        tl = torch.zeros(C, dtype=torch.float64, device=dev)
+        di, dw = eng.state_dev(C)
+        for rep in range(2):  # twice: the generation counters are re-armed per launch
+            tq.copy_(torch.from_numpy(q)), tp.copy_(torch.from_numpy(p)), tg.copy_(torch.from_numpy(g0))
+            eng.leapfrog_dev(C, L, tq.data_ptr(), tp.data_ptr(), tg.data_ptr(), tl.data_ptr(), te.data_ptr(), tm.data_ptr(),
+                             di, dw, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            eng.leapfrog_status(C)
+            np.testing.assert_allclose(tq.cpu().numpy(), qr, rtol=1e-11, atol=1e-11)
+            np.testing.assert_allclose(tp.cpu().numpy(), pr, rtol=1e-9, atol=1e-7)
+            np.testing.assert_allclose(tl.cpu().numpy(), lpr, rtol=1e-11)
+            assert grad_ok(tg.cpu().numpy(), gr, 1e-9)

@@ -32,9 +32,20 @@ tq = torch.from_numpy(q).to(dev)
 out = torch.zeros(C_, dtype=torch.float64, device=dev)
 outg = torch.zeros(C_, 17, dtype=torch.float64, device=dev)
 lib = _lib.load()
+L = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+if L:
+    a = np.random.default_rng(0).normal(size=(17, 17))
+    tm = torch.from_numpy(1e-6 * (a @ a.T / 17 + np.eye(17))).to(dev)
+    te = torch.full((C_,), 1e-3, dtype=torch.float64, device=dev)
+    eng.logp_dlogp_dev(C_, tq.data_ptr(), di, dw, out.data_ptr(), outg.data_ptr(), 0)
+    torch.cuda.synchronize()
 for rep in range(4):
     torch.cuda.synchronize()
-    eng.logp_dlogp_dev(C_, tq.data_ptr(), di, dw, out.data_ptr(), outg.data_ptr(), 0)
+    if L:
+        qq, pp, gg = tq.clone(), torch.zeros_like(tq), outg.clone()
+        eng.leapfrog_dev(C_, L, qq.data_ptr(), pp.data_ptr(), gg.data_ptr(), out.data_ptr(), te.data_ptr(), tm.data_ptr(), di, dw, 0)
+    else:
+        eng.logp_dlogp_dev(C_, tq.data_ptr(), di, dw, out.data_ptr(), outg.data_ptr(), 0)
     torch.cuda.synchronize()
 n = 4096
 buf = np.zeros((n, 12), np.uint64)

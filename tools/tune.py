@@ -60,6 +60,28 @@ def main():
                                    n_inner=64 if C <= 16 else 4)
                     print(f"N={n_inds} C={C} rows/tile={rows} chains/cta={cpc}: {t:.2f} us/launch, {C / t * 1e6:.0f} evals/s, "
                           f"{eng.algorithmic_bytes_logp(C) / t / 1e3:.1f} GB/s")
+        elif what == "traj":
+            a = np.random.default_rng(0).normal(size=(17, 17))
+            tm = torch.from_numpy(1e-6 * (a @ a.T / 17 + np.eye(17))).to(dev)
+            te = torch.full((C,), 1e-3, dtype=torch.float64, device=dev)
+            eng.logp_dlogp_dev(C, tq.data_ptr(), di, dw, out.data_ptr(), outg.data_ptr(), 0)
+            torch.cuda.synchronize()
+            g0 = outg.clone()
+            for L in [int(v) for v in (sys.argv[4].split(",") if len(sys.argv) > 4 else ["1", "16", "64", "256"])]:
+                qq, pp, gg = tq.clone(), torch.zeros_like(tq), g0.clone()
+                lp = torch.zeros(C, dtype=torch.float64, device=dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ts = []
+                for rep in range(6):
+                    qq.copy_(tq), pp.zero_(), gg.copy_(g0)
+                    e0.record()
+                    eng.leapfrog_dev(C, L, qq.data_ptr(), pp.data_ptr(), gg.data_ptr(), lp.data_ptr(), te.data_ptr(), tm.data_ptr(), di, dw, 0)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+                eng.leapfrog_status(C)
+                t = float(np.median(ts[1:]))
+                print(f"N={n_inds} C={C} persistent trajectory L={L}: {t:.1f} us/launch, {t / L:.2f} us/step, {C * L / t * 1e6:.0f} evals/s, logp {lp[0].item():.3f}")
         elif what == "gibbs":
             th = torch.from_numpy(vals[:, [1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14, 15, 16]].copy()).to(dev)
             p = torch.from_numpy(vals[:, 0].copy()).to(dev)
