@@ -212,7 +212,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -482,7 +482,7 @@ def run_gpu(args):
         "sharded_100k": sharded, "ess": ess,
         "gpu_launches": int(n_launch), "gpu_launches_host_api": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
 
@@ -498,10 +498,25 @@ def main():
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: a few un-captured logp+grad launches and Gibbs sweeps, no JSON line")
     args = ap.parse_args()
+    # Exactly ONE line goes to stdout (rank 0's JSON): libraries that chat on stdout (NCCL prints its
+    # version there) are sent to stderr for the whole run.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":
