@@ -492,14 +492,19 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     }
 
     PHASE(6);
-    // ---- last CTA of this chain: ordered reduction over tiles, then finalise ----
-    __threadfence();
+    // ---- last CTA of this chain: ordered reduction over tiles, then finalise.  One thread
+    //      releases the CTA's partials (barrier, then fence + ticket) and acquires the others'
+    //      (fence after the ticket, then barrier): the grid-sync idiom, one fence pair per CTA ----
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&ticket[c], 1u) == (unsigned)(ntiles - 1));
+    if (tid == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(&ticket[c], 1u);
+      __threadfence();
+      s_last = (prev == (unsigned)(ntiles - 1));
+    }
     __syncthreads();
     PHASE(7);
     if (s_last) {
-      __threadfence();
       // the parameter-only part of the finaliser was parked in `aux` by the chain's first tile
       if (fin.mode && tid < kAuxDoubles) {
         const double v = __ldcg(aux + (size_t)c * kAuxDoubles + tid);
@@ -659,7 +664,7 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
   const int G = dc.G, N = dc.N;
 
   __shared__ double s_tab[kExpTab];
-  __shared__ double s_th_all[kGibbsWarps][18];            // theta13, -1/(2 sigma^2) x 2, logit p, logit p_w
+  __shared__ double s_th_all[kGibbsWarps][20];            // theta13, -1/(2 sigma^2) x 2, logit p / p_w, p / p_w
   __shared__ double s_pw_all[kGibbsWarps][3][kMaxGaps];   // rho_n^k, rho_s^k, ones
   __shared__ unsigned char s_ord[kGibbsWarps][kMaxGaps];
   double* s_th = s_th_all[warp];
@@ -707,6 +712,7 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
           lo = log(p) - log1p(-p);
         }
         s_th[lane] = lo;
+        s_th[lane + 2] = 1.0 / (1.0 + exp(-lo));
       }
       __syncwarp();
     }
@@ -790,13 +796,13 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
     // ---- lane-owned proposals: Philox key (visiting order), transit / accept uniforms ----
     M act = 0;              // steps that are not skipped
     int jp_step[NSLOT];     // lane k (+32 sl): proposal visited at step k
-    double au_step[NSLOT];  // its log(u) (Metropolis) or u (heat bath)
-    M inf2_own[NSLOT];      // constrained infections if this lane's own proposal were flipped
+    double acc_u[NSLOT];    // log(u) (Metropolis) or u (heat bath) of the proposals this lane owns
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; ++sl) acc_u[sl] = 0.0;
     if (cfg.mode >= 0) {
       uint32_t key[NSLOT];
       int rank[NSLOT];
       bool skip[NSLOT];
-      double acc_u[NSLOT];
 #pragma unroll
       for (int sl = 0; sl < NSLOT; ++sl) {
         const uint4 r = philox4x32_10(
@@ -823,97 +829,112 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
         if (me < nprop) s_ord[warp][rank[sl]] = (unsigned char)me;
       }
       __syncwarp();
-      // gather, for the step this lane stands for, the proposal and its random numbers
+      // the proposal visited at the step this lane stands for; skipped steps drop out of `act`
 #pragma unroll
       for (int sl = 0; sl < NSLOT; ++sl) {
         const int step = lane + 32 * sl;
         const int jp = (step < nprop) ? (int)s_ord[warp][step] : 0;
         jp_step[sl] = jp;
-        const int owner = jp & 31;
-        bool sk = __shfl_sync(0xffffffffu, (int)skip[0], owner);
-        double au = __shfl_sync(0xffffffffu, acc_u[0], owner);
+        bool sk = __shfl_sync(0xffffffffu, (int)skip[0], jp & 31);
         if (NSLOT > 1) {
-          const bool sk1 = __shfl_sync(0xffffffffu, (int)skip[NSLOT - 1], owner);
-          const double au1 = __shfl_sync(0xffffffffu, acc_u[NSLOT - 1], owner);
-          if (jp >> 5) {
-            sk = sk1;
-            au = au1;
-          }
+          const bool sk1 = __shfl_sync(0xffffffffu, (int)skip[NSLOT - 1], jp & 31);
+          if (jp >> 5) sk = sk1;
         }
-        au_step[sl] = au;
         act |= (M)__ballot_sync(0xffffffffu, step < nprop && !sk) << (32 * sl);
       }
     } else {
 #pragma unroll
-      for (int sl = 0; sl < NSLOT; ++sl) {
-        jp_step[sl] = lane + 32 * sl;
-        au_step[sl] = 0.0;
-      }
+      for (int sl = 0; sl < NSLOT; ++sl) jp_step[sl] = lane + 32 * sl;
       act = low_mask<M>(G);  // every proposal 0..G, in order
     }
-    auto refresh_inf2 = [&]() {
+
+    // Everything about a proposal that depends only on the current state lives in the lane that
+    // owns it and is refreshed (lane-parallel) after an accepted flip of an infection bit:
+    //   inf2  constrained infections if the flip were accepted
+    //   code  2: the data term changes, the individual's likelihood must be evaluated;
+    //         1 / 0: it cannot change (the constrained infections differ only after the last
+    //         sampled gap, or -- waner bit -- there is no S sample after the first exposure), so
+    //         logp(prop) - logp(cur) = +-logit(p) and the flip decision (1 / 0) is already known
+    M inf2_own[NSLOT];
+    int code_own[NSLOT];
+    auto refresh = [&]() {
 #pragma unroll
       for (int sl = 0; sl < NSLOT; ++sl) {
         const int me = lane + 32 * sl;
-        inf2_own[sl] = (me < G) ? constrain<M>(raw ^ ((M)1 << me), pcr, dc.ch) : inf;
+        const bool is_w = (me == G);
+        const M i2 = (me < G) ? constrain<M>(raw ^ ((M)1 << me), pcr, dc.ch) : inf;
+        inf2_own[sl] = i2;
+        const int cur_bit = is_w ? w : (int)((raw >> (me < G ? me : 0)) & 1);
+        bool affected;
+        if (is_w) {
+          const M ex = inf | vac;
+          affected = ex != 0 && ctz(ex | top_bit<M>()) < t_last_s;
+        } else {
+          const M diff = inf ^ i2;
+          affected = diff != 0 && ctz(diff | top_bit<M>()) <= t_last;
+        }
+        bool flip0;
+        if (cfg.mode == ABD_GIBBS_METROPOLIS) {
+          const double lo = s_th[is_w ? 16 : 15];
+          const double delta = cur_bit ? -lo : lo;
+          flip0 = isfinite(delta) && (acc_u[sl] < delta);
+        } else {
+          flip0 = ((acc_u[sl] <= s_th[is_w ? 18 : 17]) ? 1 : 0) != cur_bit;  // s_th[17 / 18] = sigmoid(logit)
+        }
+        code_own[sl] = affected ? 2 : (flip0 ? 1 : 0);
       }
     };
-    refresh_inf2();
+    refresh();
 
     while (act) {
       const int step = ctz(act);
       act &= act - 1;
       int jp = jp_step[0];
-      double au = au_step[0];
-      if (NSLOT > 1 && (step >> 5)) {
-        jp = jp_step[NSLOT - 1];
-        au = au_step[NSLOT - 1];
-      }
+      if (NSLOT > 1 && (step >> 5)) jp = jp_step[NSLOT - 1];
       jp = __shfl_sync(0xffffffffu, jp, step & 31);
+      const int owner = jp & 31;
+      const bool hi = NSLOT > 1 && (jp >> 5);
+      const int code = __shfl_sync(0xffffffffu, hi ? code_own[NSLOT - 1] : code_own[0], owner);
       const bool is_w = (jp == G);
-      M inf2 = inf2_own[0];
-      if (NSLOT > 1 && (jp >> 5)) inf2 = inf2_own[NSLOT - 1];
-      inf2 = __shfl_sync(0xffffffffu, inf2, jp & 31);
-      const M raw2 = is_w ? raw : (raw ^ ((M)1 << jp));
+      if (cfg.mode >= 0) {
+        ++n_prop;
+        if (code == 0) continue;
+      }
+      const M inf2 = __shfl_sync(0xffffffffu, hi ? inf2_own[NSLOT - 1] : inf2_own[0], owner);
       const int w2 = is_w ? (w ^ 1) : w;
-      const int cur_bit = is_w ? w : (int)((raw >> jp) & 1);
-      // the data term changes only if the constrained infections differ at or before the last
-      // sampled gap (or, for the waner bit, if there is an S sample after the first exposure)
-      bool affected;
-      if (is_w) {
-        const M ex = inf | vac;
-        affected = ex != 0 && ctz(ex | top_bit<M>()) < t_last_s;
-      } else {
-        const M diff = inf ^ inf2;
-        affected = diff != 0 && ctz(diff | top_bit<M>()) <= t_last;
-      }
-      const double ll2 = affected ? indiv_ll(inf2, w2) : ll;
-      const double lo = s_th[is_w ? 16 : 15];
-      const double d10 = cur_bit ? (ll - ll2 + lo) : (ll2 - ll + lo);  // log-odds of 1 versus 0
-      if (cfg.mode < 0) {
-        if (lane == 0) {
-          if (is_w) cfg.out_w[(size_t)c * N + n] = d10;
-          else cfg.out_i[((size_t)c * G + jp) * N + n] = d10;
+      double ll2 = ll;
+      bool flip = true;
+      if (code == 2 || cfg.mode < 0) {
+        const int cur_bit = is_w ? w : (int)((raw >> jp) & 1);
+        if (code == 2) ll2 = indiv_ll(inf2, w2);
+        const double lo = s_th[is_w ? 16 : 15];
+        const double d10 = cur_bit ? (ll - ll2 + lo) : (ll2 - ll + lo);  // log-odds of 1 versus 0
+        if (cfg.mode < 0) {
+          if (lane == 0) {
+            if (is_w) cfg.out_w[(size_t)c * N + n] = d10;
+            else cfg.out_i[((size_t)c * G + jp) * N + n] = d10;
+          }
+          continue;
         }
-        continue;
+        const double au = __shfl_sync(0xffffffffu, hi ? acc_u[NSLOT - 1] : acc_u[0], owner);
+        if (cfg.mode == ABD_GIBBS_METROPOLIS) {
+          const double delta = cur_bit ? -d10 : d10;  // logp(proposed) - logp(current)
+          flip = isfinite(delta) && (au < delta);
+        } else {
+          const double p1 = 1.0 / (1.0 + exp(-d10));
+          flip = ((au <= p1) ? 1 : 0) != cur_bit;
+        }
       }
-      au = __shfl_sync(0xffffffffu, au, step & 31);
-      bool flip;
-      if (cfg.mode == ABD_GIBBS_METROPOLIS) {
-        const double delta = cur_bit ? -d10 : d10;  // logp(proposed) - logp(current)
-        flip = isfinite(delta) && (au < delta);
-      } else {
-        const double p1 = 1.0 / (1.0 + exp(-d10));
-        flip = ((au <= p1) ? 1 : 0) != cur_bit;
-      }
-      ++n_prop;
       if (flip) {
         ++n_acc;
-        raw = raw2;
-        w = w2;
-        inf = inf2;
         ll = ll2;
-        if (!is_w) refresh_inf2();
+        if (is_w) {
+          w = w2;
+        } else {
+          raw ^= (M)1 << jp;
+          inf = inf2;
+          refresh();
+        }
       }
     }
 

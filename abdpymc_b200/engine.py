@@ -138,9 +138,17 @@ class AbdEngine:
             return None, None
         if i_raw is None or waner is None:
             raise ValueError("pass both i_raw and waner, or neither (resident state)")
-        i8 = np.ascontiguousarray(np.asarray(i_raw) != 0, dtype=np.int8).reshape(C_, self.G, self.N)
-        w8 = np.ascontiguousarray(np.asarray(waner) != 0, dtype=np.int8).reshape(C_, self.N)
-        return i8, w8
+        return self._as_int8(i_raw, (C_, self.G, self.N)), self._as_int8(waner, (C_, self.N))
+
+    @staticmethod
+    def _as_int8(a, shape):
+        """0/1 bytes for the C ABI.  One-byte inputs are passed through untouched (the kernels treat
+        any non-zero byte as 1; a pinned buffer stays pinned); wider dtypes (PyMC holds the Bernoulli
+        values as int64) are converted once."""
+        a = np.asarray(a)
+        if a.dtype.itemsize == 1 and a.flags.c_contiguous:
+            return a.view(np.int8).reshape(shape)
+        return np.ascontiguousarray(a != 0, dtype=np.int8).reshape(shape)
 
     @staticmethod
     def _chains(a, width):
