@@ -72,6 +72,10 @@ SIGNATURES = {
     "abd_deterministics_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 7),
     "abd_leapfrog_dev": (C.c_int, [H, C.c_int, C.c_int] + [C.c_void_p] * 9),
     "abd_leapfrog_status": (C.c_int, [H, C.c_int]),
+    "abd_xch_alloc": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "abd_xch_connect": (C.c_int, [H, C.c_void_p]),
+    "abd_logp_dlogp_sharded_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 6),
+    "abd_xch_status": (C.c_int, [H]),
     "abd_state_dev": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "abd_set_tuning": (C.c_int, [H, C.c_int, C.c_int]),
     "abd_debug_fast_math": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -136,6 +136,22 @@ struct SumsCfg {
   int C;
 };
 
+// Fused all-reduce over NVLink peer memory (individuals sharded over `world` GPUs of one node):
+// the CTA that finishes a chain last on each rank stores its 16 raw sums straight into every
+// peer's exchange buffer, raises a per-(rank, chain) flag there, waits for the flags the peers
+// raise in ITS buffer, adds the `world` contributions in rank order (bitwise the same result on
+// every rank) and finalises -- compute, exchange and finalisation in one launch, no NCCL call.
+// Buffers are double-buffered on the parity of a per-chain sequence number kept on the device.
+constexpr int kMaxPeers = 8;
+constexpr unsigned long long kXchTimeoutNs = 10ull * 1000 * 1000 * 1000;  // a peer that is 10 s late is declared lost
+struct XchCfg {
+  int world, rank, cmax;                 // world == 0: not sharded
+  double* data[kMaxPeers];               // peer r's buffer: [2][world][cmax][16] doubles ...
+  unsigned long long* flag[kMaxPeers];   // ... followed by [2][world][cmax] flags
+  unsigned* seq;                         // [cmax] local sequence numbers
+  unsigned* err;
+};
+
 // Trajectory mode (n_steps > 0): the kernel stays resident for n_steps leapfrog steps of
 // Hamiltonian dynamics over q17 with the binary state fixed.  Per step every CTA evaluates its
 // tile at the current position; the CTA that finishes a chain last finalises logp / gradient,
@@ -216,7 +232,8 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
        const double* __restrict__ theta, const int theta_is_q,
        const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
        double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ sums,
-       const FinalizeCfg fin, const Priors* __restrict__ priors, double* __restrict__ aux, const TrajCfg traj) {
+       const FinalizeCfg fin, const Priors* __restrict__ priors, double* __restrict__ aux, const TrajCfg traj,
+       const XchCfg xch) {
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int G = dc.G, N = dc.N, ntiles = cfg.ntiles;
@@ -535,6 +552,42 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         if (sums) sums[(size_t)c * kNSums + tid] = tot;
       }
       __syncthreads();
+      if (!TRAJ && xch.world > 1) {
+        __shared__ unsigned s_seq;
+        if (tid == 0) s_seq = xch.seq[c] + 1u;
+        __syncthreads();
+        const unsigned seq = s_seq, par = seq & 1u;
+        const size_t slot = ((size_t)par * xch.world + xch.rank) * xch.cmax + c;  // my slot in a peer's buffer
+        if (tid < kNSums * xch.world) {
+          const int r = tid >> 4, k = tid & 15;
+          xch.data[r][slot * kNSums + k] = s_red[0][k];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < xch.world) {
+          unsigned long long* f = xch.flag[tid] + slot;
+          asm volatile("st.release.sys.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)seq) : "memory");
+          // wait for peer `tid`'s contribution to arrive in MY buffer
+          const unsigned long long* mine = xch.flag[xch.rank] + ((size_t)par * xch.world + tid) * xch.cmax + c;
+          unsigned long long seen, t_start, t_now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+          do {
+            asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+          } while (seen != (unsigned long long)seq && t_now - t_start < kXchTimeoutNs);
+          if (seen != (unsigned long long)seq) *xch.err = 1u;  // watchdog: never hang the GPU
+        }
+        __syncthreads();
+        if (tid < kNSums) {
+          double tot = 0.0;
+          for (int r = 0; r < xch.world; ++r)
+            tot += __ldcg(xch.data[xch.rank] + (((size_t)par * xch.world + r) * xch.cmax + c) * kNSums + tid);
+          s_red[0][tid] = tot;
+          if (sums) sums[(size_t)c * kNSums + tid] = tot;
+        }
+        if (tid == 0) xch.seq[c] = seq;
+        __syncthreads();
+      }
       PHASE(10);
       if (tid == 0) ticket[c] = 0;  // re-arm for the next launch
       if (warp == 0) {
@@ -1034,6 +1087,11 @@ struct abd_handle {
   int* d_order = nullptr;       // individuals by decreasing OD-row count (Gibbs work queue)
   unsigned* d_queue = nullptr;  // Gibbs work-queue counter
   int gibbs_ctas = 0;
+  // peer exchange (individual sharding over NVLink)
+  XchCfg xch{};
+  void* xch_local = nullptr;
+  bool xch_active = false;  // set for the duration of a fused sharded launch
+  void* xch_peer[kMaxPeers] = {};
   bool x_exact_f32 = true;      // every log_dilution is exactly representable as float
   bool use_pdl = true;          // programmatic dependent launch (ABD_B200_NO_PDL=1 disables)
 
@@ -1356,14 +1414,14 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
     lc.attrs = attr;
     lc.numAttrs = 1;
     CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, true>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, h->d_partial,
-                          h->d_ticket, sums, fin, pri, h->d_aux, traj));
+                          h->d_ticket, sums, fin, pri, h->d_aux, traj, XchCfg{}));
   } else {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = h->use_pdl ? 1 : 0;
     CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, false>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, h->d_partial,
-                          h->d_ticket, sums, fin, pri, h->d_aux, traj));
+                          h->d_ticket, sums, fin, pri, h->d_aux, traj, h->xch_active ? h->xch : XchCfg{}));
   }
   return ABD_OK;
 }
@@ -1584,6 +1642,9 @@ int abd_destroy(abd_handle* h) {
   if (!h) return ABD_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->xch_peer)
+    if (p) cudaIpcCloseMemHandle(p);
+  if (h->xch_local) cudaFree(h->xch_local);
   for (void* p : h->owned) cudaFree(p);
   for (void* p : {(void*)h->d_iraw, (void*)h->d_waner, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
                   (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_partial, (void*)h->d_aux, (void*)h->d_traj,
@@ -1888,6 +1949,78 @@ int abd_leapfrog_status(abd_handle* h, int C) {
   unsigned err = 0;
   CU(cudaMemcpy(&err, h->d_gen + C, sizeof(unsigned), cudaMemcpyDeviceToHost));
   return err ? fail(ABD_ERR_CUDA, "abd_leapfrog_dev: a CTA timed out waiting for its chain (grid not co-resident?)") : ABD_OK;
+}
+
+int abd_xch_alloc(abd_handle* h, int world, int rank, int max_chains, void* out_ipc_handle) {
+  if (!h) return fail(ABD_ERR_INVALID, "NULL handle");
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world || max_chains < 1 || !out_ipc_handle)
+    return fail(ABD_ERR_INVALID, "abd_xch_alloc: need 2 <= world <= 8, 0 <= rank < world, max_chains >= 1");
+  if (world * kNSums > kSumsBlock) return fail(ABD_ERR_INVALID, "world too large");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (h->xch_local) return fail(ABD_ERR_INVALID, "abd_xch_alloc: already allocated");
+  const size_t nd = (size_t)2 * world * max_chains * kNSums, nf = (size_t)2 * world * max_chains;
+  const size_t bytes = nd * sizeof(double) + nf * sizeof(unsigned long long);
+  CU(cudaMalloc(&h->xch_local, bytes));
+  CU(cudaMemset(h->xch_local, 0, bytes));
+  unsigned* seq;
+  if ((rc = dev_alloc(h, &seq, (size_t)max_chains + 1))) return rc;
+  CU(cudaMemset(seq, 0, ((size_t)max_chains + 1) * sizeof(unsigned)));
+  h->xch = XchCfg{};
+  h->xch.world = world;
+  h->xch.rank = rank;
+  h->xch.cmax = max_chains;
+  h->xch.seq = seq;
+  h->xch.err = seq + max_chains;
+  cudaIpcMemHandle_t ipc;
+  CU(cudaIpcGetMemHandle(&ipc, h->xch_local));
+  static_assert(sizeof(ipc) == ABD_IPC_HANDLE_BYTES, "IPC handle size");
+  std::memcpy(out_ipc_handle, &ipc, sizeof(ipc));
+  return ABD_OK;
+}
+
+int abd_xch_connect(abd_handle* h, const void* all_ipc_handles) {
+  if (!h || !all_ipc_handles) return fail(ABD_ERR_INVALID, "NULL argument");
+  if (!h->xch_local) return fail(ABD_ERR_INVALID, "abd_xch_connect: call abd_xch_alloc first");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const int world = h->xch.world;
+  const size_t nd = (size_t)2 * world * h->xch.cmax * kNSums;
+  for (int r = 0; r < world; ++r) {
+    void* base = h->xch_local;
+    if (r != h->xch.rank) {
+      cudaIpcMemHandle_t ipc;
+      std::memcpy(&ipc, (const char*)all_ipc_handles + (size_t)r * sizeof(ipc), sizeof(ipc));
+      CU(cudaIpcOpenMemHandle(&base, ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->xch_peer[r] = base;
+    }
+    h->xch.data[r] = (double*)base;
+    h->xch.flag[r] = (unsigned long long*)((double*)base + nd);
+  }
+  return ABD_OK;
+}
+
+int abd_logp_dlogp_sharded_dev(abd_handle* h, int C, const double* q17, const int8_t* i_raw, const int8_t* waner,
+                               double* out_logp, double* out_dlogp, void* stream) {
+  PROLOGUE(h, C);
+  if (!q17 || !i_raw || !waner || !out_logp) return fail(ABD_ERR_INVALID, "NULL argument");
+  if (!h->xch_local || !h->xch.data[h->xch.world - 1] || !h->xch.data[0])
+    return fail(ABD_ERR_INVALID, "abd_logp_dlogp_sharded_dev: call abd_xch_alloc and abd_xch_connect first");
+  if (C > h->xch.cmax) return fail(ABD_ERR_INVALID, "more chains than abd_xch_alloc reserved");
+  FinalizeCfg fin{2, h->tot, out_logp, out_dlogp};
+  h->xch_active = true;
+  const int rc = launch_sums(h, C, q17, 1, i_raw, waner, h->d_sums, fin, (cudaStream_t)stream);
+  h->xch_active = false;
+  return rc;
+}
+
+int abd_xch_status(abd_handle* h) {
+  if (!h || !h->xch_local) return fail(ABD_ERR_INVALID, "no exchange buffer");
+  int rc = set_device(h);
+  if (rc) return rc;
+  unsigned err = 0;
+  CU(cudaMemcpy(&err, h->xch.err, sizeof(unsigned), cudaMemcpyDeviceToHost));
+  return err ? fail(ABD_ERR_CUDA, "a peer's contribution did not arrive (timeout)") : ABD_OK;
 }
 
 int abd_debug_fast_math(int device, int64_t n, const double* z, double* out_exp, double* out_rcp) {

@@ -84,7 +84,11 @@ class ShardedEngine:
     """
 
     def __init__(self, cohort: CohortArrays, splits=None, ignore_pcrpos=False, device_index=0, rank=None, world=None,
-                 group=None):
+                 group=None, fused=False, max_chains=64):
+        """``fused=True``: the all-reduce is done INSIDE the logp kernel over NVLink peer memory
+        (``abd_logp_dlogp_sharded_dev``: every rank's finishing CTA stores its sums into all peers'
+        exchange buffers and waits for theirs) -- one launch per evaluation, no NCCL call.  Needs
+        an initialised process group once, to exchange the CUDA IPC handles."""
         import torch
 
         from .engine import AbdEngine
@@ -99,6 +103,15 @@ class ShardedEngine:
                                 ind_offset=offset)
         self.G, self.N_local, self.N_total = self.engine.G, self.engine.N, cohort.n_inds
         self._bufs = {}
+        self.fused = bool(fused) and self.world > 1
+        if self.fused:
+            import torch.distributed as dist
+
+            mine = self.engine.xch_alloc(self.world, self.rank, max_chains)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            self.engine.xch_connect(handles)
+            dist.barrier(group=group)  # every rank has mapped every buffer before the first launch
 
     def _buffers(self, C):
         import torch
@@ -126,6 +139,9 @@ class ShardedEngine:
         sums, out, outg = self._buffers(C)
         st = torch.cuda.current_stream(self.device).cuda_stream
         d_i, d_w = self.engine.state_dev(C)
+        if self.fused:
+            self.engine.logp_dlogp_sharded_dev(C, q17.data_ptr(), d_i, d_w, out.data_ptr(), outg.data_ptr(), st)
+            return out, outg
         self.engine.sums_dev(C, q17.data_ptr(), 1, d_i, d_w, sums.data_ptr(), st)
         allreduce_sums(sums, self.group)
         self.engine.finalize_logp_dev(C, q17.data_ptr(), sums.data_ptr(), out.data_ptr(), outg.data_ptr(), st)

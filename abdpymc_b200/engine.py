@@ -275,5 +275,21 @@ class AbdEngine:
     def leapfrog_status(self, C_):
         check(self._lib.abd_leapfrog_status(self._h, C_))
 
+    # peer exchange (fused all-reduce over NVLink), see include/abd_b200.h
+    def xch_alloc(self, world, rank, max_chains) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self._lib.abd_xch_alloc(self._h, int(world), int(rank), int(max_chains), buf))
+        return buf.raw
+
+    def xch_connect(self, handles):
+        blob = b"".join(handles)
+        check(self._lib.abd_xch_connect(self._h, C.c_char_p(blob)))
+
+    def logp_dlogp_sharded_dev(self, C_, q17, i_raw, waner, out_logp, out_dlogp, stream=0):
+        check(self._lib.abd_logp_dlogp_sharded_dev(self._h, C_, q17, i_raw, waner, out_logp, out_dlogp, stream))
+
+    def xch_status(self):
+        check(self._lib.abd_xch_status(self._h))
+
     def deterministics_dev(self, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream=0):
         check(self._lib.abd_deterministics_dev(self._h, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream))

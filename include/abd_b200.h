@@ -198,6 +198,24 @@ int abd_leapfrog_dev(abd_handle* h, int n_chains, int n_steps, double* q17, doub
                      const int8_t* i_raw, const int8_t* waner, void* stream);
 int abd_leapfrog_status(abd_handle* h, int n_chains);
 
+/* Individual sharding over the GPUs of one node WITHOUT a separate collective: the all-reduce of
+ * the C x 16 raw sums is fused into the kernel through NVLink peer memory (each rank's finishing
+ * CTA stores its sums into every peer's buffer, waits for the peers' flags, adds in rank order,
+ * finalises).  One process per GPU:
+ *   abd_xch_alloc   allocates this rank's exchange buffer, returns its CUDA IPC handle (64 bytes);
+ *   (exchange the handles between the processes, e.g. torch.distributed.all_gather)
+ *   abd_xch_connect opens all peers' buffers (all_ipc_handles: world x 64 bytes, rank order);
+ *   abd_logp_dlogp_sharded_dev  is then a COLLECTIVE call: every rank must make the same sequence
+ *   of calls; all ranks obtain bitwise identical (logp, dlogp).  The handle must have been created
+ *   with total_* / ind_offset set.  abd_xch_status: synchronous check for a timed-out wait.   */
+#define ABD_IPC_HANDLE_BYTES 64
+int abd_xch_alloc(abd_handle* h, int world, int rank, int max_chains, void* out_ipc_handle);
+int abd_xch_connect(abd_handle* h, const void* all_ipc_handles);
+int abd_logp_dlogp_sharded_dev(abd_handle* h, int n_chains, const double* q17, const int8_t* i_raw,
+                               const int8_t* waner, double* out_logp, double* out_dlogp,
+                               void* stream);
+int abd_xch_status(abd_handle* h);
+
 /* Pointers to the resident chain state (valid until the next call that changes n_chains).   */
 int abd_state_dev(abd_handle* h, int n_chains, int8_t** i_raw, int8_t** waner);
 
