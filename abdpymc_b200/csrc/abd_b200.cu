@@ -62,7 +62,10 @@ struct DevCohort {
   const int* rp[2];          // [0] = N antigen, [1] = S antigen
   const double* od[2];
   const double* x[2];
-  const float* x32[2];         // the same values as float when every one is exactly representable
+  // factored mode (the cohort has <= 32 distinct log_dilution values, the usual case):
+  const uint32_t* rcx[2];      // per row: cell index << 5 | index of its dilution in xlev
+  const double* xlev;          // [32] the distinct dilutions, ascending (padded with 0)
+  int n_xlev;                  // 0: not available (k_sums stages the dilutions as doubles)
   const uint32_t* meta[2];     // per row: individual << 6 | gap
   const uint32_t* rowcell[2];  // per row: index of its (individual, gap) cell
   const uint32_t* cmeta[2];    // per cell: individual << 6 | gap
@@ -178,13 +181,20 @@ struct __align__(16) TileDesc {
   int cs0, cs1, pad0, pad1;
 };
 
-// trajectory of one cell: titer m, decaying part T (or U) and its rho-derivative
-struct CellVal {
+// trajectory of one cell: titer m, decaying part T (or U) and its rho-derivative; in factored mode
+// also Em = exp(b m) (capped so that exp(-b x) * Em <= e^700)
+template <bool FX>
+struct CellValT {
   double m, T, dT;
 };
+template <>
+struct __align__(16) CellValT<true> {
+  double m, T, dT, Em;
+};
+constexpr int kMaxXLevels = 32;
 
 #ifdef ABD_PHASE_TIMING
-__device__ unsigned long long g_phase[4096][12];
+__device__ unsigned long long g_phase[4096][16];
 __device__ unsigned long long g_span[256][2];  // per launch: first CTA start, last CTA end
 __device__ unsigned g_span_idx, g_span_done;
 __device__ __forceinline__ unsigned long long gtime() {
@@ -215,8 +225,17 @@ __device__ __forceinline__ unsigned long long gtime() {
       g_phase[blockIdx.y * gridDim.x + blockIdx.x][i] = t_;                              \
     }                                                                                    \
   } while (0)
+#define PHASEW(i, cond)                                                                  \
+  do {                                                                                   \
+    if ((cond) && blockIdx.y * gridDim.x + blockIdx.x < 4096) {                          \
+      unsigned long long t_;                                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
+      g_phase[blockIdx.y * gridDim.x + blockIdx.x][i] = t_;                              \
+    }                                                                                    \
+  } while (0)
 #else
 #define PHASE(i)
+#define PHASEW(i, cond)
 #define SPAN_BEGIN()
 #define SPAN_END()
 #endif
@@ -224,8 +243,10 @@ __device__ __forceinline__ unsigned long long gtime() {
 #ifndef ABD_SUMS_MINB
 #define ABD_SUMS_MINB 3
 #endif
-// XT: how the dilutions are staged in shared memory -- float when every log_dilution of the cohort
-// is exactly representable in fp32 (the usual case: small integers), double otherwise.
+// XT: how the dilutions reach the row loop.  uint8_t = factored mode: a row carries the index of
+// its dilution (packed with its cell index), exp(-b (x - m)) = exp(-b x) * exp(b m) costs one exp
+// per CELL plus a per-chain table over the distinct dilutions; double = general fallback, the
+// dilutions themselves are staged and every row evaluates its own exp.
 template <typename M, typename XT, bool TRAJ>
 __global__ void __launch_bounds__(kSumsBlock, ABD_SUMS_MINB)
 k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg,
@@ -240,14 +261,15 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
 
   // dynamic shared memory: staged rows (od, x, row->cell), staged cell meta, per-cell values
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  constexpr bool kX32 = sizeof(XT) == 4;
+  constexpr bool kFX = sizeof(XT) == 1;
+  using CellVal = CellValT<kFX>;
   double* s_od_n = reinterpret_cast<double*>(dyn_smem);
   double* s_od_s = s_od_n + cfg.cap_n;
   CellVal* s_cv_n = reinterpret_cast<CellVal*>(s_od_s + cfg.cap_s);
   CellVal* s_cv_s = s_cv_n + cfg.capk_n;
-  XT* s_x_n = reinterpret_cast<XT*>(s_cv_s + cfg.capk_s);   // cap_n doubles or capr_n floats
-  XT* s_x_s = s_x_n + (kX32 ? cfg.capr_n : cfg.cap_n);
-  uint32_t* s_rc_n = reinterpret_cast<uint32_t*>(s_x_s + (kX32 ? cfg.capr_s : cfg.cap_s));
+  double* s_x_n = reinterpret_cast<double*>(s_cv_s + cfg.capk_s);   // cap_n doubles (not in factored mode)
+  double* s_x_s = s_x_n + (kFX ? 0 : cfg.cap_n);
+  uint32_t* s_rc_n = reinterpret_cast<uint32_t*>(s_x_s + (kFX ? 0 : cfg.cap_s));
   uint32_t* s_rc_s = s_rc_n + cfg.capr_n;
   uint32_t* s_cm_n = s_rc_s + cfg.capr_s;
   uint32_t* s_cm_s = s_cm_n + cfg.capk_n;
@@ -264,6 +286,9 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
   __shared__ LikPre s_lik;
   __shared__ double s_q[17], s_ph[17], s_out[18];  // trajectory mode: position, half-step momentum, logp + gradient
   __shared__ double s_im[TRAJ ? 17 * 17 : 1];       // trajectory mode: inverse mass matrix
+  __shared__ double2 s_xe[kFX ? 2 : 1][kMaxXLevels];  // factored mode: {x_j, exp(-b x_j)} per antigen
+  __shared__ double s_zmax[2];                      // cap on b m so that exp(-b x) exp(b m) <= e^700
+  __shared__ int s_direct;                          // |b| x too large to factor: rows take their own exp
 
   PHASE(0);
   SPAN_BEGIN();
@@ -284,23 +309,30 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     const uint32_t bn = (uint32_t)(((rn1 + 1) & ~1) - an0) * 8u, bs = (uint32_t)(((rs1 + 1) & ~1) - as0) * 8u;
     const uint32_t bqn = (uint32_t)(((rn1 + 3) & ~3) - qn0) * 4u, bqs = (uint32_t)(((rs1 + 3) & ~3) - qs0) * 4u;
     const uint32_t bkn = (uint32_t)(((cn1 + 3) & ~3) - kn0) * 4u, bks = (uint32_t)(((cs1 + 3) & ~3) - ks0) * 4u;
-    mbar_expect_tx(&s_bar, (kX32 ? bn + bqn + bs + bqs : 2 * bn + 2 * bs) + bqn + bqs + bkn + bks);
+    mbar_expect_tx(&s_bar, (kFX ? bn + bs : 2 * bn + 2 * bs) + bqn + bqs + bkn + bks);
     if (bkn) bulk_g2s(s_cm_n, dc.cmeta[0] + kn0, bkn, &s_bar);
     if (bks) bulk_g2s(s_cm_s, dc.cmeta[1] + ks0, bks, &s_bar);
     if (bn) {
       bulk_g2s(s_od_n, dc.od[0] + an0, bn, &s_bar);
-      if (kX32) bulk_g2s(s_x_n, dc.x32[0] + qn0, bqn, &s_bar);
-      else bulk_g2s(s_x_n, dc.x[0] + an0, bn, &s_bar);
+      if (!kFX) bulk_g2s(s_x_n, dc.x[0] + an0, bn, &s_bar);
     }
     if (bs) {
       bulk_g2s(s_od_s, dc.od[1] + as0, bs, &s_bar);
-      if (kX32) bulk_g2s(s_x_s, dc.x32[1] + qs0, bqs, &s_bar);
-      else bulk_g2s(s_x_s, dc.x[1] + as0, bs, &s_bar);
+      if (!kFX) bulk_g2s(s_x_s, dc.x[1] + as0, bs, &s_bar);
     }
-    if (bqn) bulk_g2s(s_rc_n, dc.rowcell[0] + qn0, bqn, &s_bar);
-    if (bqs) bulk_g2s(s_rc_s, dc.rowcell[1] + qs0, bqs, &s_bar);
+    if (bqn) bulk_g2s(s_rc_n, (kFX ? dc.rcx[0] : dc.rowcell[0]) + qn0, bqn, &s_bar);
+    if (bqs) bulk_g2s(s_rc_s, (kFX ? dc.rcx[1] : dc.rowcell[1]) + qs0, bqs, &s_bar);
   }
   fill_exp_table(s_tab, tid, kSumsBlock);
+  // the immutable PCR+ / vaccination masks of this thread's individual (read before the wait)
+  M my_pcr = 0, my_vac = 0;
+  if (tid < ni) {
+    my_pcr = reinterpret_cast<const M*>(dc.pcr)[i0 + tid];
+    my_vac = reinterpret_cast<const M*>(dc.vac)[i0 + tid];
+  }
+  double x_lev = 0.0;  // factored mode, last warp: lane j holds the j-th distinct dilution
+  if (kFX && warp == kSumsWarps - 1) x_lev = dc.xlev[lane];
+  __syncthreads();  // the exp table is usable from here on (still before the dependency wait)
   // everything above reads only the immutable cohort; parameters, chain state and the reduction
   // scratch may be written by the previous kernel in the stream
   griddep_wait();
@@ -364,11 +396,12 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     };
 
     // ---- phase 0: warps 0-3: one thread per individual reads its int8 column (every load of
-    //      the warp is one coalesced 32-byte segment; all gaps in flight at once) and applies
-    //      the infection constraints; warps 4-6: parameters and power tables ----
+    //      the warp is one coalesced 32-byte segment) and applies the infection constraints;
+    //      warps 4-7: parameters, power tables, dilution table.  (Fetching the block as aligned
+    //      32-bit words + shared-memory atomics / ballots was measured: slower, the transposition
+    //      costs more than the byte loads save.) ----
     if (tid < kTileMaxInds) {
       if (tid < ni && step == 0) {
-        // issue every load of the column before the first use (one memory round trip)
         const int8_t* col = i_raw + (size_t)c * G * N + i0 + tid;
         int8_t bytes[sizeof(M) * 8];
 #pragma unroll
@@ -380,16 +413,17 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
 #pragma unroll
         for (int t = 0; t < (int)sizeof(M) * 8; ++t) raw |= (M)(bytes[t] != 0) << t;
         const int w = waner[(size_t)c * N + i0 + tid] != 0;
-        const M pcr = reinterpret_cast<const M*>(dc.pcr)[i0 + tid];
         IndState<M> st;
-        st.inf = constrain<M>(raw, pcr, dc.ch);
-        st.vacw = reinterpret_cast<const M*>(dc.vac)[i0 + tid] | (w ? top_bit<M>() : (M)0);
+        st.inf = constrain<M>(raw, my_pcr, dc.ch);
+        st.vacw = my_vac | (w ? top_bit<M>() : (M)0);
         s_ind[tid] = st;
         acc[S_KI] = cnt_i = (double)popc(raw);
         acc[S_KW] = cnt_w = (double)w;
       }
+      PHASEW(12, tid == 0);
     } else if (warp == 4) {
       fill_pow_warp(param13(N_RHO), G, lane, s_pw[0], s_pw[1]);
+      PHASEW(13, lane == 0);
     } else if (warp == 5) {
       fill_pow_warp(param13(S_RHO), G, lane, s_pw[2], s_pw[3]);
     } else if (warp == 6) {
@@ -400,18 +434,44 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
       } else if (lane < 13) {
         s_th[lane] = load_param(theta, theta_is_q, c, lane);
       }
-    } else if (TRAJ && lane < 17) {  // warp 7 keeps (q, p_half) for the finaliser
-      s_q[lane] = q_lane;
-      s_ph[lane] = ph_lane;
+      PHASEW(14, lane == 0);
+    } else if (warp == kSumsWarps - 1) {
+      if (kFX) {
+        // per-chain table {x_j, exp(-b x_j)} over the distinct dilutions, both antigens, and the
+        // cap on b m that keeps the product <= e^700 (b is not transformed: read it directly)
+        const double zn = -param13(N_B) * x_lev, zs = -param13(S_B) * x_lev;
+        double mn = (lane < dc.n_xlev) ? fabs(zn) : 0.0, ms = (lane < dc.n_xlev) ? fabs(zs) : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          mn = fmax(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+          ms = fmax(ms, __shfl_xor_sync(0xffffffffu, ms, off));
+        }
+        // NaN / huge |b| x: every row evaluates its own exponential (same arithmetic as the fallback)
+        const bool direct = !(mn < 300.0 && ms < 300.0);
+        s_xe[0][lane] = make_double2(x_lev, direct ? 0.0 : fast_exp(zn, s_tab));
+        s_xe[kFX ? 1 : 0][lane] = make_double2(x_lev, direct ? 0.0 : fast_exp(zs, s_tab));
+        if (lane == 0) {
+          s_zmax[0] = 700.0 - mn;
+          s_zmax[1] = 700.0 - ms;
+          s_direct = direct;
+        }
+      }
+      if (TRAJ && lane < 17) {  // keeps (q, p_half) for the finaliser
+        s_q[lane] = q_lane;
+        s_ph[lane] = ph_lane;
+      }
+      PHASEW(15, lane == 0);
     }
     __syncthreads();
     PHASE(2);
     // The finaliser's parameter-only part (priors, transforms, logs: ~2 us of cold libm code) is
     // taken off the critical path: warp 7 of the chain's first tile computes it now, instead of
     // processing cells / rows, and parks it in global memory for whichever CTA finishes last.
-    const bool aux_cta = (tile == 0) && fin.mode != 0;
+    // (the row -> thread assignment must not depend on fin.mode: abd_sums_dev + abd_finalize_* has
+    // to reproduce the fused launch bit for bit)
+    const bool aux_cta = (tile == 0);
     const int nwork = aux_cta ? kSumsBlock - 32 : kSumsBlock;
-    if (aux_cta && warp == kSumsWarps - 1) {
+    if (aux_cta && fin.mode != 0 && warp == kSumsWarps - 1) {
       double* a = aux + (size_t)c * kAuxDoubles;
       if (fin.mode == 2 && lane < 17) {
         const PriorPre pp = prior_pre(lane, TRAJ ? s_q[lane] : theta[(size_t)c * 17 + lane], priors->v[lane]);
@@ -430,6 +490,7 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     // ---- phase 1: one thread per (individual, gap) cell: titer in closed form from the masks ----
     {
       const double init = s_th[N_INIT], perm = s_th[N_PERM], temp = s_th[N_TEMP];
+      const double bn_fx = s_th[N_B], zmax_n = s_zmax[0];
       for (int k = cn0 + tid; k < cn1 && tid < nwork; k += nwork) {
         const uint32_t mt = s_cm_n[k - kn0];
         const int t = mt & 63, li = (int)(mt >> 6) - i0;
@@ -439,11 +500,16 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         cv.m = init + perm * P + temp * T;
         cv.T = T;
         cv.dT = (P != 0.0) ? dT : -0.0;  // sign bit of dT carries "never exposed" (P = 0)
+        if constexpr (kFX) {
+          const double z = bn_fx * cv.m;
+          cv.Em = fast_exp((z > zmax_n) ? zmax_n : z, s_tab);  // NaN stays NaN
+        }
         s_cv_n[k - cn0] = cv;
       }
     }
     {
       const double init = s_th[S_INIT], perm = s_th[S_PERM];
+      const double bs_fx = s_th[S_B], zmax_s = s_zmax[1];
       for (int k = cs0 + tid; k < cs1 && tid < nwork; k += nwork) {
         const uint32_t mt = s_cm_s[k - ks0];
         const int t = mt & 63, li = (int)(mt >> 6) - i0;
@@ -454,6 +520,10 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         cv.m = init + perm * P + U;
         cv.T = U;
         cv.dT = (P != 0.0) ? dU : -0.0;
+        if constexpr (kFX) {
+          const double z = bs_fx * cv.m;
+          cv.Em = fast_exp((z > zmax_s) ? zmax_s : z, s_tab);
+        }
         s_cv_s[k - cs0] = cv;
       }
     }
@@ -462,13 +532,22 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
 
     // ---- phase 2: one thread per OD row; everything comes from shared memory, no divergence.
     //      P (ever exposed) travels in the sign bit of dT ----
+    const bool direct = kFX && s_direct;
     {
       const double b = s_th[N_B], d = s_th[N_D];
 #pragma unroll 2
       for (int r = rn0 + tid; r < rn1 && tid < nwork; r += nwork) {
-        const CellVal cv = s_cv_n[s_rc_n[r - qn0] - cn0];
         double s, res, q, xm;
-        row_eval((double)s_x_n[r - (kX32 ? qn0 : an0)], s_od_n[r - an0], cv.m, b, d, s_tab, s, res, q, xm);
+        const uint32_t rc = s_rc_n[r - qn0];
+        const CellVal cv = s_cv_n[(kFX ? (rc >> 5) : rc) - cn0];
+        if constexpr (kFX) {
+          const double2 xe = s_xe[0][rc & 31];
+          xm = xe.x - cv.m;
+          if (direct) row_eval(xe.x, s_od_n[r - an0], cv.m, b, d, s_tab, s, res, q, xm);
+          else row_eval_E(xe.y * cv.Em, s_od_n[r - an0], d, s, res, q);
+        } else {
+          row_eval(s_x_n[r - an0], s_od_n[r - an0], cv.m, b, d, s_tab, s, res, q, xm);
+        }
         acc[SN_0] = fma(res, res, acc[SN_0]);
         acc[SN_1] = fma(res, s, acc[SN_1]);
         acc[SN_2] = fma(q, xm, acc[SN_2]);
@@ -482,9 +561,17 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
       const double b = s_th[S_B], d = s_th[S_D];
 #pragma unroll 2
       for (int r = rs0 + tid; r < rs1 && tid < nwork; r += nwork) {
-        const CellVal cv = s_cv_s[s_rc_s[r - qs0] - cs0];
         double s, res, q, xm;
-        row_eval((double)s_x_s[r - (kX32 ? qs0 : as0)], s_od_s[r - as0], cv.m, b, d, s_tab, s, res, q, xm);
+        const uint32_t rc = s_rc_s[r - qs0];
+        const CellVal cv = s_cv_s[(kFX ? (rc >> 5) : rc) - cs0];
+        if constexpr (kFX) {
+          const double2 xe = s_xe[1][rc & 31];
+          xm = xe.x - cv.m;
+          if (direct) row_eval(xe.x, s_od_s[r - as0], cv.m, b, d, s_tab, s, res, q, xm);
+          else row_eval_E(xe.y * cv.Em, s_od_s[r - as0], d, s, res, q);
+        } else {
+          row_eval(s_x_s[r - as0], s_od_s[r - as0], cv.m, b, d, s_tab, s, res, q, xm);
+        }
         acc[SS_0] = fma(res, res, acc[SS_0]);
         acc[SS_1] = fma(res, s, acc[SS_1]);
         acc[SS_2] = fma(q, xm, acc[SS_2]);
@@ -511,12 +598,12 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     PHASE(6);
     // ---- last CTA of this chain: ordered reduction over tiles, then finalise.  One thread
     //      releases the CTA's partials (barrier, then fence + ticket) and acquires the others'
-    //      (fence after the ticket, then barrier): the grid-sync idiom, one fence pair per CTA ----
+    //      (then barrier): the grid-sync idiom with ONE acq_rel atomic per CTA instead of a pair of
+    //      sequentially consistent fences around a relaxed one ----
     __syncthreads();
     if (tid == 0) {
-      __threadfence();
-      const unsigned prev = atomicAdd(&ticket[c], 1u);
-      __threadfence();
+      unsigned prev;
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ticket + c) : "memory");
       s_last = (prev == (unsigned)(ntiles - 1));
     }
     __syncthreads();
@@ -1092,7 +1179,8 @@ struct abd_handle {
   void* xch_local = nullptr;
   bool xch_active = false;  // set for the duration of a fused sharded launch
   void* xch_peer[kMaxPeers] = {};
-  bool x_exact_f32 = true;      // every log_dilution is exactly representable as float
+  std::vector<double> x_levels; // distinct log_dilution values (ascending) when there are <= 32 of them
+  bool fx = false;              // factored mode: rows carry (cell, dilution index), see k_sums
   bool use_pdl = true;          // programmatic dependent launch (ABD_B200_NO_PDL=1 disables)
 
   // per-chain scratch
@@ -1218,17 +1306,16 @@ int build_rows(abd_handle* h, int a, int64_t R, const double* x, const double* o
   if ((rc = upload(h, &d_meta, meta))) return rc;
   if ((rc = upload(h, &d_rowcell, rowcell))) return rc;
   if ((rc = upload(h, &d_cmeta, cmeta))) return rc;
-  {
-    bool exact = true;
-    std::vector<float> xf(xs.size() + 2, 0.0f);  // same padding as the 32-bit word arrays (R + 4)
-    for (size_t k = 0; k < xs.size(); ++k) {
-      xf[k] = (float)xs[k];
-      exact = exact && ((double)xf[k] == xs[k]);
+  h->dc.rcx[a] = nullptr;
+  if (h->fx) {
+    std::vector<uint32_t> rcx((size_t)R + 4, 0u);
+    for (int64_t k = 0; k < R; ++k) {
+      const int xi = (int)(std::lower_bound(h->x_levels.begin(), h->x_levels.end(), xs[(size_t)k]) - h->x_levels.begin());
+      rcx[(size_t)k] = (rowcell[(size_t)k] << 5) | (uint32_t)xi;
     }
-    h->x_exact_f32 = h->x_exact_f32 && exact;
-    float* d_xf;
-    if ((rc = upload(h, &d_xf, xf))) return rc;
-    h->dc.x32[a] = d_xf;
+    uint32_t* d_rcx;
+    if ((rc = upload(h, &d_rcx, rcx))) return rc;
+    h->dc.rcx[a] = d_rcx;
   }
   h->dc.rp[a] = d_rp;
   h->dc.x[a] = d_x;
@@ -1280,9 +1367,9 @@ int get_tiling(abd_handle* h, int want, abd_handle::Tiling** out) {
     t.capr_s = std::max(t.capr_s, 4);
     t.capk_n = std::max(t.capk_n, 4);
     t.capk_s = std::max(t.capk_s, 4);
-    t.smem = (size_t)(t.cap_n + t.cap_s) * 8 + (size_t)(t.capk_n + t.capk_s) * (sizeof(CellVal) + 4) +
-             (size_t)(t.capr_n + t.capr_s) * 4 +
-             (h->x_exact_f32 ? (size_t)(t.capr_n + t.capr_s) * 4 : (size_t)(t.cap_n + t.cap_s) * 8);
+    t.smem = (size_t)(t.cap_n + t.cap_s) * 8 + (size_t)(t.capr_n + t.capr_s) * 4 +
+             (h->fx ? (size_t)(t.capk_n + t.capk_s) * (sizeof(CellValT<true>) + 4)
+                    : (size_t)(t.capk_n + t.capk_s) * (sizeof(CellValT<false>) + 4) + (size_t)(t.cap_n + t.cap_s) * 8);
     if (t.smem + 12 * 1024 > h->smem_optin)
       return fail(ABD_ERR_INVALID, "an individual tile does not fit in shared memory (too many OD rows per 128 individuals)");
     std::vector<TileDesc> desc((size_t)t.ntiles);
@@ -1447,9 +1534,9 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
       int o = 0;
       cudaError_t e;
       if (h->wide)
-        e = h->x_exact_f32 ? sums_occupancy<uint64_t, float>(tl->smem, &o) : sums_occupancy<uint64_t, double>(tl->smem, &o);
+        e = h->fx ? sums_occupancy<uint64_t, uint8_t>(tl->smem, &o) : sums_occupancy<uint64_t, double>(tl->smem, &o);
       else
-        e = h->x_exact_f32 ? sums_occupancy<uint32_t, float>(tl->smem, &o) : sums_occupancy<uint32_t, double>(tl->smem, &o);
+        e = h->fx ? sums_occupancy<uint32_t, uint8_t>(tl->smem, &o) : sums_occupancy<uint32_t, double>(tl->smem, &o);
       CU(e);
       tl->occ = std::max(o, 1);
     }
@@ -1473,11 +1560,11 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
   SumsCfg cfg{tl->ntiles, tl->cap_n, tl->cap_s, tl->capr_n, tl->capr_s, tl->capk_n, tl->capk_s, cpc, C};
   dim3 grid(tl->ntiles, (C + cpc - 1) / cpc);
   if (h->wide)
-    rc = h->x_exact_f32 ? launch_sums_t<uint64_t, float>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st)
-                        : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st);
+    rc = h->fx ? launch_sums_t<uint64_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st)
+               : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st);
   else
-    rc = h->x_exact_f32 ? launch_sums_t<uint32_t, float>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st)
-                        : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st);
+    rc = h->fx ? launch_sums_t<uint32_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st)
+               : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st);
   if (rc) return rc;
   CU(cudaGetLastError());
   h->launches++;
@@ -1610,6 +1697,35 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
     for (int k = 0; k < 3; ++k) h->dc.ch.mask[k] = 0;
     for (int k = 0; k <= co->n_splits; ++k)
       for (int t = edges[k]; t < edges[k + 1]; ++t) h->dc.ch.mask[k] |= 1ull << t;
+  }
+  // distinct dilutions over both antigens: <= 32 of them (and no NaN) enables the factored mode
+  {
+    std::vector<double>& lv = h->x_levels;
+    bool ok = std::getenv("ABD_B200_NO_FACTORED") == nullptr;
+    for (int a = 0; a < 2 && ok; ++a) {
+      const double* xa = a ? co->x_s : co->x_n;
+      const int64_t Ra = a ? co->n_rows_s : co->n_rows_n;
+      if (Ra > 0 && !xa) break;  // build_rows reports the NULL
+      double last = std::nan("");
+      for (int64_t r = 0; r < Ra && ok; ++r) {
+        const double v = xa[r];
+        if (v == last) continue;
+        last = v;
+        auto it = std::lower_bound(lv.begin(), lv.end(), v);
+        if (it != lv.end() && *it == v) continue;
+        if (!(v == v) || (int)lv.size() == kMaxXLevels) ok = false;
+        else lv.insert(it, v);
+      }
+    }
+    // a row packs its cell index in 27 bits
+    h->fx = ok && (co->n_rows_n < ((int64_t)1 << 27)) && (co->n_rows_s < ((int64_t)1 << 27));
+    if (!h->fx) lv.clear();
+    std::vector<double> padded(lv);
+    padded.resize(kMaxXLevels, 0.0);
+    double* d_lv;
+    if ((rc = upload(h, &d_lv, padded))) return bail(rc);
+    h->dc.xlev = d_lv;
+    h->dc.n_xlev = h->fx ? (int)lv.size() : 0;
   }
   if ((rc = build_rows(h, 0, co->n_rows_n, co->x_n, co->od_n, co->gap_n, co->ind_n))) return bail(rc);
   if ((rc = build_rows(h, 1, co->n_rows_s, co->x_s, co->od_s, co->gap_s, co->ind_s))) return bail(rc);
@@ -2060,7 +2176,7 @@ int abd_debug_spans(unsigned long long* out, int reset) {
   return ABD_OK;
 }
 int abd_debug_phase_times(unsigned long long* out, int n_ctas) {
-  CU(cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 12 * (size_t)n_ctas));
+  CU(cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 16 * (size_t)n_ctas));
   return ABD_OK;
 }
 #endif

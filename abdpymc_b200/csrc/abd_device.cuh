@@ -245,6 +245,16 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
+// 1/x for normal x >= 1 with one cubic step: e = 1 - x r (|e| <= 2^-19.9 after the MUFU seed, which
+// reads only the high word of x), r' = r (1 + e + e^2): remaining error e^3 < 2^-59, < 1 ulp overall.
+__device__ __forceinline__ double fast_rcp3(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
+}
+
 // One OD row: s = 1/(1+E), E = exp(-b (x - m));  r = od - d s;  q = r s (1 - s).
 // 1 - s is formed as E s (no cancellation); E is capped so that E s stays finite.
 __device__ __forceinline__ void row_eval(double x, double od, double m, double b, double d,
@@ -255,6 +265,14 @@ __device__ __forceinline__ void row_eval(double x, double od, double m, double b
   z = (z > 700.0) ? 700.0 : z;  // NaN stays NaN
   const double E = fast_exp(z, tab);
   s = fast_rcp(1.0 + E);
+  r = fma(-d, s, od);
+  q = r * s * (E * s);
+}
+// The same with E handed in (factored mode: E = exp(-b x) * exp(b m), one exp per (individual,
+// gap) cell and a per-chain table over the cohort's few distinct dilutions instead of one exp per
+// row).  The caller guarantees E <= e^700 (or NaN).
+__device__ __forceinline__ void row_eval_E(double E, double od, double d, double& s, double& r, double& q) {
+  s = fast_rcp3(1.0 + E);
   r = fma(-d, s, od);
   q = r * s * (E * s);
 }
@@ -359,27 +377,32 @@ __device__ __forceinline__ LikPre lik_pre(double sn, double ss) {
   return p;
 }
 
-// Data log-likelihood and gradient w.r.t. theta13 from the raw sums.
+// Data log-likelihood and gradient w.r.t. theta13 from the raw sums.  The finaliser is inlined in
+// several kernels (k_sums, k_finalize) that must agree BITWISE, so every product / sum is spelled
+// with non-contractible intrinsics: the compiler may not pick different FMA contractions per copy.
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ void finalize_loglik_post(const double* th, const LikPre& lp, const double* S,
                                                      const Totals& tot, double* loglik, double* g) {
-  *loglik = -0.5 * S[SN_0] * lp.ivn - tot.rows_n * (kHalfLog2Pi + lp.lsn) +
-            -0.5 * S[SS_0] * lp.ivs - tot.rows_s * (kHalfLog2Pi + lp.lss);
+  const double ln = add_(mul_(mul_(-0.5, S[SN_0]), lp.ivn), -mul_(tot.rows_n, add_(kHalfLog2Pi, lp.lsn)));
+  const double ls = add_(mul_(mul_(-0.5, S[SS_0]), lp.ivs), -mul_(tot.rows_s, add_(kHalfLog2Pi, lp.lss)));
+  *loglik = add_(ln, ls);
   if (!g) return;
-  g[N_D] = S[SN_1] * lp.ivn;
-  g[N_B] = th[N_D] * S[SN_2] * lp.ivn;
-  g[N_SIGMA] = (S[SN_0] * lp.ivn - tot.rows_n) * lp.isn;
-  const double cn = -th[N_D] * th[N_B] * lp.ivn;
-  g[N_INIT] = cn * S[SN_QINIT];
-  g[N_PERM] = cn * S[SN_QPERM];
-  g[N_TEMP] = cn * S[SN_QTEMP];
-  g[N_RHO] = cn * th[N_TEMP] * S[SN_QRHO];
-  g[S_D] = S[SS_1] * lp.ivs;
-  g[S_B] = th[S_D] * S[SS_2] * lp.ivs;
-  g[S_SIGMA] = (S[SS_0] * lp.ivs - tot.rows_s) * lp.iss;
-  const double cs = -th[S_D] * th[S_B] * lp.ivs;
-  g[S_INIT] = cs * S[SS_QINIT];
-  g[S_PERM] = cs * S[SS_QPERM];
-  g[S_RHO] = cs * S[SS_QRHO];
+  g[N_D] = mul_(S[SN_1], lp.ivn);
+  g[N_B] = mul_(mul_(th[N_D], S[SN_2]), lp.ivn);
+  g[N_SIGMA] = mul_(add_(mul_(S[SN_0], lp.ivn), -tot.rows_n), lp.isn);
+  const double cn = mul_(mul_(-th[N_D], th[N_B]), lp.ivn);
+  g[N_INIT] = mul_(cn, S[SN_QINIT]);
+  g[N_PERM] = mul_(cn, S[SN_QPERM]);
+  g[N_TEMP] = mul_(cn, S[SN_QTEMP]);
+  g[N_RHO] = mul_(mul_(cn, th[N_TEMP]), S[SN_QRHO]);
+  g[S_D] = mul_(S[SS_1], lp.ivs);
+  g[S_B] = mul_(mul_(th[S_D], S[SS_2]), lp.ivs);
+  g[S_SIGMA] = mul_(add_(mul_(S[SS_0], lp.ivs), -tot.rows_s), lp.iss);
+  const double cs = mul_(mul_(-th[S_D], th[S_B]), lp.ivs);
+  g[S_INIT] = mul_(cs, S[SS_QINIT]);
+  g[S_PERM] = mul_(cs, S[SS_QPERM]);
+  g[S_RHO] = mul_(cs, S[SS_QRHO]);
 }
 __device__ inline void finalize_loglik(const double* th, const double* S, const Totals& tot,
                                        double* loglik, double* g) {
@@ -392,7 +415,8 @@ __device__ inline void finalize_loglik(const double* th, const double* S, const 
 struct PriorPre {
   double lpA, dA, f, lx, l1mx, x, omx;
 };
-__device__ inline PriorPre prior_pre(int k, double y, const PriorSpec& ps) {
+// (not inlined: one copy of this cold code per kernel, and the same arithmetic in every kernel)
+__device__ __noinline__ PriorPre prior_pre(int k, double y, const PriorSpec& ps) {
   PriorPre o;
   o.lx = o.l1mx = o.x = o.omx = 0.0;
   const int tr = kQTransform[k];
@@ -443,15 +467,15 @@ __device__ inline void finalize_logp_post(int lane, const PriorPre* pre, const d
     if (k == kQ_P || k == kQ_PW) {  // Bernoulli(i_raw | p) abd.py:427, Bernoulli(waner | p_waner) abd.py:373
       const double K = (k == kQ_P) ? S[S_KI] : S[S_KW];
       const double nK = ((k == kQ_P) ? tot.bits_i : tot.bits_w) - K;
-      lp += (K == 0.0 ? 0.0 : K * p.lx) + (nK == 0.0 ? 0.0 : nK * p.l1mx);
-      d += K * p.omx - nK * p.x;
+      lp = add_(lp, add_(K == 0.0 ? 0.0 : mul_(K, p.lx), nK == 0.0 ? 0.0 : mul_(nK, p.l1mx)));
+      d = add_(d, add_(mul_(K, p.omx), -mul_(nK, p.x)));
     }
     d = fma(gl, p.f, d);
     if (dlogp) dlogp[k] = d;
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) lp += __shfl_down_sync(0xffffffffu, lp, off);
-  if (lane == 0) *logp = ll + lp;
+  for (int off = 16; off > 0; off >>= 1) lp = add_(lp, __shfl_down_sync(0xffffffffu, lp, off));
+  if (lane == 0) *logp = add_(ll, lp);
 }
 
 // Philox4x32-10 (Salmon et al. 2011), counter-based: one call yields 4 x 32 random bits.

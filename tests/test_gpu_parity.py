@@ -177,6 +177,35 @@ def test_parity_sweep_1k_cohort(Engine, splits):
         assert grad_ok(g2, ref_g[:16])
 
 
+def test_factored_exponential_vs_fallback_and_direct_rows(Engine, monkeypatch):
+    """k_sums has three ways to obtain exp(-b (x - m)): factored (a cohort with <= 32 distinct
+    dilutions: exp(-b x_j) table x one exp(b m) per cell), the general fallback (dilutions staged as
+    doubles, one exp per row) and, inside the factored kernel, direct rows when |b| x is too large
+    to factor.  All three against the oracle, including extreme slopes and titers."""
+    from abdpymc_b200.cohort import synthetic_cohort
+
+    co = synthetic_cohort(1000)
+    rng = np.random.default_rng(77)
+    q, i_raw, w = draw_points(rng, co.n_gaps, co.n_inds, 24)
+    q[6, 11], q[6, 14] = -80.0, 55.0      # |b| x_max > 300: direct rows
+    q[7, 11], q[7, 14] = -42.0, -42.8     # just below the switch (|b| x = 294 .. 299.6)
+    q[8, 4], q[8, 10] = 90.0, -120.0      # ab_n_init / ab_s_init: b m far outside exp's range
+    q[9, 11], q[9, 4] = -40.0, 30.0       # b m beyond the cap
+    q[10, 14], q[10, 10] = 35.0, 25.0
+    o = ora.Oracle(co, splits=(14, 20), dense=False)
+    ref = [o.logp_dlogp(q[k], i_raw[k], w[k]) for k in range(len(q))]
+    ref_lp, ref_g = np.array([r[0] for r in ref]), np.stack([r[1] for r in ref])
+    assert np.all(np.isfinite(ref_lp)) and np.all(np.isfinite(ref_g))
+    with Engine(co, splits=(14, 20)) as eng:
+        lp, g = eng.logp_dlogp(q, i_raw, w)
+    monkeypatch.setenv("ABD_B200_NO_FACTORED", "1")
+    with Engine(co, splits=(14, 20)) as eng:
+        lp_fb, g_fb = eng.logp_dlogp(q, i_raw, w)
+    for a, b in ((lp, g), (lp_fb, g_fb)):
+        assert np.all(np.abs(a - ref_lp) <= RTOL * np.abs(ref_lp)), np.abs((a - ref_lp) / ref_lp).max()
+        assert grad_ok(b, ref_g), np.abs(b - ref_g).max()
+
+
 def random_cohort(rng, G, N, rows_per_ind=6, p_empty=0.2):
     from abdpymc_b200.cohort import CohortArrays
 

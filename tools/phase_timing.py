@@ -12,7 +12,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 dbg = ROOT / "gpurun_out" / "libabd_b200_dbg.so"
 dbg.parent.mkdir(exist_ok=True)
-subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DABD_PHASE_TIMING", "-Xcompiler", "-fPIC",
+import os
+subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DABD_PHASE_TIMING", *os.environ.get("ABD_EXTRA_FLAGS", "").split(), "-Xcompiler", "-fPIC",
                 "-shared", "-o", str(dbg), str(ROOT / "abdpymc_b200/csrc/abd_b200.cu")], check=True)
 from abdpymc_b200 import _lib  # noqa: E402
 
@@ -48,7 +49,7 @@ for rep in range(4):
         eng.logp_dlogp_dev(C_, tq.data_ptr(), di, dw, out.data_ptr(), outg.data_ptr(), 0)
     torch.cuda.synchronize()
 n = 4096
-buf = np.zeros((n, 12), np.uint64)
+buf = np.zeros((n, 16), np.uint64)
 lib.abd_debug_phase_times.argtypes = [C.c_void_p, C.c_int]
 lib.abd_debug_phase_times(buf.ctypes.data_as(C.c_void_p), n)
 buf = buf[buf[:, 0] > 0].astype(np.int64)
@@ -67,4 +68,7 @@ last = buf[buf[:, 11] > buf[:, 0]]
 if len(last):
     r = (last[0, [7, 9, 10, 11, 8]] - t0) / 1e3
     print(f"  last CTA: ticket {r[0]:.2f}  partials read {r[1]:.2f}  totals {r[2]:.2f}  finalised {r[3]:.2f}  end {r[4]:.2f}")
+for k, nm in ((12, "columns+constrain"), (13, "pow table (warp 4)"), (14, "params (warp 6)"), (15, "dilution table (warp 7)")):
+    col = (buf[:, k] - buf[:, 1]) / 1e3
+    print(f"  phase 0 detail, after the dependency wait: {nm:24s} median {np.median(col):6.2f}  max {col.max():6.2f}")
 print("  durations (median): " + ", ".join(f"{names[k + 1]} {np.median(rel[:, k + 1] - rel[:, k]):.2f}" for k in range(8)))
