@@ -1095,6 +1095,81 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
 }
 
 // ------------------------------------------------------------------------------------------
+// k_hmc_begin / k_hmc_end -- the two ends of an HMC transition, one warp per chain
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_hmc_begin(const int C, const double* __restrict__ q, const double* __restrict__ grad, const double* __restrict__ logp,
+            const double* __restrict__ linv_t, const uint64_t seed, const uint64_t iter, double* __restrict__ qw,
+            double* __restrict__ pw, double* __restrict__ gw, double* __restrict__ h0) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double z = 0.0;
+  if (lane < 17) {  // Box-Muller on two of the four Philox words
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)lane, (uint32_t)c, (uint32_t)iter, 0x484d4331u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iter >> 32)));
+    z = sqrt(-2.0 * log(u01(r.x))) * cospi(2.0 * u01(r.y));
+  }
+  double p = 0.0, kin = z * z;
+  for (int j = 0; j < 17; ++j) {
+    const double zj = __shfl_sync(0xffffffffu, z, j);
+    if (lane < 17) p = fma(linv_t[lane * 17 + j], zj, p);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) kin += __shfl_xor_sync(0xffffffffu, kin, off);
+  if (lane < 17) {
+    qw[(size_t)c * 17 + lane] = q[(size_t)c * 17 + lane];
+    gw[(size_t)c * 17 + lane] = grad[(size_t)c * 17 + lane];
+    pw[(size_t)c * 17 + lane] = p;
+  }
+  if (lane == 0) h0[c] = -logp[c] + 0.5 * kin;
+}
+
+__global__ void __launch_bounds__(128)
+k_hmc_end(const int C, double* __restrict__ q, double* __restrict__ grad, double* __restrict__ logp,
+          const double* __restrict__ qw, const double* __restrict__ pw, const double* __restrict__ gw,
+          const double* __restrict__ lpw, const double* __restrict__ inv_mass, const double* __restrict__ h0,
+          const uint64_t seed, const uint64_t iter, double* __restrict__ accept_out, double* __restrict__ da,
+          double* __restrict__ eps, const int adapt, const double target) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  const double p = lane < 17 ? pw[(size_t)c * 17 + lane] : 0.0;
+  double v = 0.0;
+  for (int j = 0; j < 17; ++j) {
+    const double pj = __shfl_sync(0xffffffffu, p, j);
+    if (lane < 17) v = fma(inv_mass[lane * 17 + j], pj, v);
+  }
+  double kin = p * v;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) kin += __shfl_xor_sync(0xffffffffu, kin, off);
+  const double h1 = -lpw[c] + 0.5 * kin;
+  double dh = h0[c] - h1;
+  if (!isfinite(dh)) dh = -INFINITY;
+  const double acc = exp(fmin(dh, 0.0));
+  const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)c, (uint32_t)iter, 0x41434331u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iter >> 32)));
+  const bool take = (u01(r.x) - 2.3283064365386963e-10) < acc;  // u in [0, 1)
+  if (take && lane < 17) {
+    q[(size_t)c * 17 + lane] = qw[(size_t)c * 17 + lane];
+    grad[(size_t)c * 17 + lane] = gw[(size_t)c * 17 + lane];
+  }
+  if (lane == 0) {
+    if (take) logp[c] = lpw[c];
+    accept_out[c] = acc;
+    if (adapt) {  // Nesterov dual averaging of log(step size): gamma 0.05, t0 10, kappa 0.75
+      double* s = da + (size_t)c * 4;
+      const double t = s[3] + 1.0, eta = 1.0 / (t + 10.0);
+      const double hbar = (1.0 - eta) * s[1] + eta * (target - acc);
+      const double log_eps = s[0] - sqrt(t) / 0.05 * hbar;
+      const double w = pow(t, -0.75);
+      s[1] = hbar;
+      s[2] = w * log_eps + (1.0 - w) * s[2];
+      s[3] = t;
+      eps[c] = exp(log_eps);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // k_determ
 // ------------------------------------------------------------------------------------------
 template <typename M>
@@ -2065,6 +2140,32 @@ int abd_leapfrog_status(abd_handle* h, int C) {
   unsigned err = 0;
   CU(cudaMemcpy(&err, h->d_gen + C, sizeof(unsigned), cudaMemcpyDeviceToHost));
   return err ? fail(ABD_ERR_CUDA, "abd_leapfrog_dev: a CTA timed out waiting for its chain (grid not co-resident?)") : ABD_OK;
+}
+
+int abd_hmc_begin_dev(abd_handle* h, int C, const double* q17, const double* grad17, const double* logp,
+                      const double* linv_t, uint64_t seed, uint64_t iter, double* qw, double* pw, double* gw, double* h0,
+                      void* stream) {
+  PROLOGUE(h, C);
+  if (!q17 || !grad17 || !logp || !linv_t || !qw || !pw || !gw || !h0) return fail(ABD_ERR_INVALID, "NULL argument");
+  k_hmc_begin<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, q17, grad17, logp, linv_t, seed, iter, qw, pw, gw, h0);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
+int abd_hmc_end_dev(abd_handle* h, int C, double* q17, double* grad17, double* logp, const double* qw, const double* pw,
+                    const double* gw, const double* lpw, const double* inv_mass, const double* h0, uint64_t seed,
+                    uint64_t iter, double* accept_out, double* da, double* eps, int adapt, double target_accept,
+                    void* stream) {
+  PROLOGUE(h, C);
+  if (!q17 || !grad17 || !logp || !qw || !pw || !gw || !lpw || !inv_mass || !h0 || !accept_out)
+    return fail(ABD_ERR_INVALID, "NULL argument");
+  if (adapt && (!da || !eps)) return fail(ABD_ERR_INVALID, "adapt needs the dual-averaging state and eps");
+  k_hmc_end<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, q17, grad17, logp, qw, pw, gw, lpw, inv_mass, h0, seed, iter,
+                                                            accept_out, da, eps, adapt, target_accept);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
 }
 
 int abd_xch_alloc(abd_handle* h, int world, int rank, int max_chains, void* out_ipc_handle) {

@@ -64,18 +64,53 @@ class AbdTarget:
                                  eps.data_ptr(), inv_mass.data_ptr(), self.d_i, self.d_w, self._stream())
         return q, p, lp, grad
 
+    # ---- fused transition (device-resident; no host synchronisation per iteration) -------------
+    def logp_dlogp_into(self, q, logp, grad):
+        self.engine.logp_dlogp_dev(self.C, q.data_ptr(), self.d_i, self.d_w, logp.data_ptr(), grad.data_ptr(), self._stream())
+
+    def leapfrog_inplace(self, q, p, grad, logp, eps, inv_mass, n_steps):
+        self.engine.leapfrog_dev(self.C, n_steps, q.data_ptr(), p.data_ptr(), grad.data_ptr(), logp.data_ptr(),
+                                 eps.data_ptr(), inv_mass.data_ptr(), self.d_i, self.d_w, self._stream())
+
+    def hmc_begin(self, q, grad, logp, linv_t, it, qw, pw, gw, h0):
+        self.engine.hmc_begin_dev(self.C, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), linv_t.data_ptr(), self.seed, it,
+                                  qw.data_ptr(), pw.data_ptr(), gw.data_ptr(), h0.data_ptr(), self._stream())
+
+    def hmc_end(self, q, grad, logp, qw, pw, gw, lpw, inv_mass, h0, it, acc, da, eps, adapt, target_accept):
+        self.engine.hmc_end_dev(self.C, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), qw.data_ptr(), pw.data_ptr(),
+                                gw.data_ptr(), lpw.data_ptr(), inv_mass.data_ptr(), h0.data_ptr(), self.seed, it,
+                                acc.data_ptr(), da.data_ptr(), eps.data_ptr(), adapt, target_accept, self._stream())
+
     def gibbs(self, q, sweep):
         q = q.contiguous()
         self.engine.gibbs_sweep_dev(self.C, q.data_ptr(), 1, None, None, self.d_i, self.d_w, self.seed, sweep,
                                     mode=self.gibbs_mode, transit_p=self.transit_p, stream=self._stream())
 
+    def fits_persistent(self):
+        """Whether a whole trajectory fits one resident grid (abd_leapfrog_dev): try one step."""
+        z = torch.zeros(self.C, 17, dtype=torch.float64, device=self.device)
+        one = torch.full((self.C,), 1e-9, dtype=torch.float64, device=self.device)
+        eye = torch.eye(17, dtype=torch.float64, device=self.device)
+        try:
+            self.leapfrog_inplace(z.clone(), z.clone(), z.clone(), one.clone(), one, eye, 1)
+            torch.cuda.synchronize(self.device)
+            return True
+        except Exception:
+            return False
+
     def deterministics(self, q):
-        """(i, ab_n_mu, ab_s_mu) of the current state, device tensors (C, G, N)."""
+        """(i, ab_n_mu, ab_s_mu) of the current state, device tensors (C, G, N).  No host round
+        trip: the back-transform of q runs on the device, the output buffers are reused."""
         G, N, C = self.engine.G, self.engine.N, self.C
-        th = torch.from_numpy(backward(q.cpu().numpy())[:, Q_OF_THETA].copy()).to(self.device)
-        oi = torch.empty(C, G, N, dtype=torch.int8, device=self.device)
-        mn = torch.empty(C, G, N, dtype=torch.float64, device=self.device)
-        ms = torch.empty(C, G, N, dtype=torch.float64, device=self.device)
+        if not hasattr(self, "_det"):
+            kinds = torch.tensor([{None: 0, "log": 1, "logodds": 2}[Q17_RV[j][1]] for j in Q_OF_THETA], device=self.device)
+            self._det = (kinds, torch.tensor(Q_OF_THETA, device=self.device),
+                         torch.empty(C, G, N, dtype=torch.int8, device=self.device),
+                         torch.empty(C, G, N, dtype=torch.float64, device=self.device),
+                         torch.empty(C, G, N, dtype=torch.float64, device=self.device))
+        kinds, idx, oi, mn, ms = self._det
+        y = q.index_select(1, idx)
+        th = torch.where(kinds == 1, torch.exp(y), torch.where(kinds == 2, torch.sigmoid(y), y)).contiguous()
         self.engine.deterministics_dev(C, th.data_ptr(), self.d_i, self.d_w, oi.data_ptr(), mn.data_ptr(), ms.data_ptr(),
                                        self._stream())
         return oi, mn, ms
@@ -152,8 +187,85 @@ def _windows(tune):
     return ends
 
 
+def _sample_fused(target, q0, cfg, progress):
+    """The same iteration as ``sample`` with the whole transition on the device: five launches per
+    iteration (abd_hmc_begin_dev, abd_leapfrog_dev, abd_hmc_end_dev, abd_gibbs_sweep_dev,
+    abd_logp_dlogp_dev), no host synchronisation; the host only picks the trajectory length and,
+    at the end of a warm-up window, re-estimates the metric."""
+    dev = q0.device
+    C, D = q0.shape
+    f64 = dict(dtype=torch.float64, device=dev)
+    rng = np.random.default_rng(cfg.seed)
+    q = q0.clone().to(torch.float64).contiguous()
+    logp, grad = torch.empty(C, **f64), torch.empty(C, D, **f64)
+    target.logp_dlogp_into(q, logp, grad)
+    inv_mass = torch.eye(D, **f64)
+    linv_t = torch.eye(D, **f64)        # (chol^T)^-1 with inv_mass = chol chol^T
+    eps = torch.full((C,), cfg.init_step, **f64)
+    da = torch.zeros(C, 4, **f64)       # mu, hbar, log_avg, t
+    da[:, 0] = torch.log(10.0 * eps)
+    qw, pw, gw = torch.empty(C, D, **f64), torch.empty(C, D, **f64), torch.empty(C, D, **f64)
+    lpw, h0, acc = torch.empty(C, **f64), torch.empty(C, **f64), torch.empty(C, **f64)
+    ends = _windows(cfg.tune)
+    win_start = 75 if cfg.tune >= 150 else 0
+    win_draws = []
+    total = cfg.tune + cfg.draws
+    out_q = torch.empty(cfg.draws, C, D, **f64)
+    out_lp, out_acc = torch.empty(cfg.draws, C, **f64), torch.empty(cfg.draws, C, **f64)
+    means, n_means, n_grad = {}, 0, 0
+    t0 = time.perf_counter()
+    for it in range(total):
+        L = max(1, int(round(cfg.n_leapfrog * (0.6 + 0.8 * rng.random()))))
+        target.hmc_begin(q, grad, logp, linv_t, it, qw, pw, gw, h0)
+        target.leapfrog_inplace(qw, pw, gw, lpw, eps, inv_mass, L)
+        target.hmc_end(q, grad, logp, qw, pw, gw, lpw, inv_mass, h0, it, acc, da, eps, it < cfg.tune, cfg.target_accept)
+        target.gibbs(q, it)
+        target.logp_dlogp_into(q, logp, grad)
+        n_grad += L + 1
+        if it < cfg.tune:
+            if ends and win_start <= it:
+                win_draws.append(q.clone())
+            if ends and it + 1 == ends[0]:
+                x = torch.stack(win_draws).reshape(-1, D)
+                n = x.shape[0]
+                cov = torch.cov(x.T)
+                inv_mass = ((n / (n + 5.0)) * cov + 1e-3 * (5.0 / (n + 5.0)) * torch.eye(D, **f64)).contiguous()
+                chol = torch.linalg.cholesky(inv_mass)  # Stan's shrinkage keeps it positive definite
+                linv_t = torch.linalg.solve_triangular(chol.T.contiguous(), torch.eye(D, **f64), upper=True).contiguous()
+                win_draws, win_start = [], ends.pop(0)
+                # restart step-size adaptation under the new metric from the averaged step
+                eps = torch.exp(da[:, 2]).contiguous()
+                da.zero_()
+                da[:, 0] = torch.log(10.0 * eps)
+            if it + 1 == cfg.tune:
+                eps = torch.where(da[:, 3] > 0, torch.exp(da[:, 2]), eps).contiguous()
+        else:
+            k = it - cfg.tune
+            out_q[k].copy_(q)
+            out_lp[k].copy_(logp)
+            out_acc[k].copy_(acc)
+            every = cfg.record_deterministics_every
+            if every and hasattr(target, "deterministics") and k % every == 0:
+                oi, mn, ms = target.deterministics(q)
+                for name, v in (("i", oi.to(torch.float64)), ("ab_n_mu", mn), ("ab_s_mu", ms)):
+                    means[name] = v.mean(dim=0) if name not in means else means[name] + v.mean(dim=0)
+                n_means += 1
+        if progress and (it + 1) % progress == 0:
+            print(f"  iter {it + 1}/{total}  step {eps.mean().item():.4f}  accept {acc.mean().item():.2f}", flush=True)
+    torch.cuda.synchronize(dev)
+    target.engine.leapfrog_status(C)
+    wall = time.perf_counter() - t0
+    return SamplerResult(
+        q=out_q.permute(1, 0, 2).cpu().numpy(), logp=out_lp.T.cpu().numpy(), accept=out_acc.T.cpu().numpy(),
+        step_size=eps.cpu().numpy(), inv_mass=inv_mass.cpu().numpy(), wall_s=wall, n_grad_evals=n_grad,
+        means={k: (v / n_means).cpu().numpy() for k, v in means.items()},
+    )
+
+
 def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> SamplerResult:
     """Run tune + draws iterations of [HMC on q | binaries] then [Gibbs on binaries | q]."""
+    if cfg.persistent_trajectories and hasattr(target, "hmc_begin") and target.fits_persistent():
+        return _sample_fused(target, q0, cfg, progress)
     dev = q0.device
     C, D = q0.shape
     gen = torch.Generator(device=dev)

@@ -338,6 +338,31 @@ def run_gpu(args):
     torch.cuda.synchronize()
     ms_l2 = e0.elapsed_time(e1)
 
+    # ---- inside one persistent trajectory launch (abd_leapfrog_dev): L dependent leapfrog steps, each
+    #      one full logp+grad evaluation at a new position; no launch / re-staging between them ----
+    traj = None
+    try:
+        L = 64
+        tq2, tp2, tg2 = tq.clone(), torch.zeros_like(tq), outg.clone()
+        teps = torch.full((C,), 1e-4, dtype=torch.float64, device=dev)
+        tmass = torch.eye(17, dtype=torch.float64, device=dev)
+        with torch.cuda.stream(side):
+            for _ in range(W):
+                eng0.leapfrog_dev(C, L, tq2.data_ptr(), tp2.data_ptr(), tg2.data_ptr(), out.data_ptr(), teps.data_ptr(),
+                                  tmass.data_ptr(), states[0][0], states[0][1], side.cuda_stream)
+            e0.record()
+            for _ in range(K):
+                eng0.leapfrog_dev(C, L, tq2.data_ptr(), tp2.data_ptr(), tg2.data_ptr(), out.data_ptr(), teps.data_ptr(),
+                                  tmass.data_ptr(), states[0][0], states[0][1], side.cuda_stream)
+            e1.record()
+        side.synchronize()
+        eng0.leapfrog_status(C)
+        ms_traj = e0.elapsed_time(e1)
+        traj = {"value": world * C * L * K / (ms_traj / 1e3), "unit": "evals/s", "us_per_step": ms_traj / (K * L) * 1e3,
+                "note": f"abd_leapfrog_dev: {L} dependent leapfrog steps per persistent launch, binary state staged once"}
+    except Exception as ex:  # the grid does not fit at once on this device
+        traj = {"unavailable": str(ex)[:200]}
+
     # ---- e2e: host-pointer C-ABI call, pinned host buffers, all inputs copied every call ----
     hq = torch.from_numpy(q).pin_memory()
     hi = torch.from_numpy(i_raw).pin_memory()
@@ -422,6 +447,26 @@ def run_gpu(args):
                    "collective": "torch.distributed all_reduce(SUM) of 4 x 16 float64 per evaluation (NCCL)",
                    "logp_chain0": float(lp_sh[0].item())}
         se.close()
+        # the same with the all-reduce fused into the kernel over NVLink peer memory (one launch per evaluation)
+        sf = ShardedEngine(big, splits=SPLITS, device_index=local, rank=rank, world=world, fused=True, max_chains=C)
+        sf.upload_state(ib, wb)
+        for _ in range(10):
+            sf.logp_dlogp(tqs)
+        barrier()
+        e0.record()
+        for _ in range(n_sh):
+            lp_f, _ = sf.logp_dlogp(tqs)
+        e1.record()
+        barrier()
+        sf.engine.xch_status()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sharded["fused_peer_allreduce"] = {
+            "value": C * n_sh / (float(t.item()) / 1e3), "unit": "evals/s", "ms_per_eval_batch": float(t.item()) / n_sh,
+            "collective": "none: the finishing CTA of each rank stores its 16 sums into every peer's buffer (NVLink), "
+                          "waits for theirs and finalises in the same launch",
+            "bitwise_equal_to_nccl_path": bool(torch.equal(lp_f, lp_sh))}
+        sf.close()
 
     # ---- ESS/s of the built-in HMC + GPU-Gibbs sampler on the same cohort (bounded run) ----
     ess = None
@@ -429,17 +474,35 @@ def run_gpu(args):
         from abdpymc_b200 import diagnostics as dg
         from abdpymc_b200.sampler import AbdTarget, SamplerConfig, sample
 
+        from abdpymc_b200.engine import forward
+
+        tune_n, draws_n = 1000, 1000
         tgt = AbdTarget(eng0, C, np.zeros_like(i_raw), np.zeros_like(w), seed=1)
-        cfg = SamplerConfig(tune=300, draws=300, seed=1)
-        res = sample(tgt, torch.from_numpy(q).to(dev), cfg)
+        cfg = SamplerConfig(tune=tune_n, draws=draws_n, seed=1)
+        # PyMC-like initial point: prior means on the constrained scale, jittered in q space (abd.infer_builtin)
+        x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
+        q0 = forward(x0)[None, :] + np.random.default_rng(1).uniform(-1, 1, size=(C, 17))
+        res = sample(tgt, torch.from_numpy(q0).to(dev), cfg)
         summ = dg.summary(res.posterior())
         vals_ess = sorted(v["ess_bulk"] for v in summ.values())
+        # Gibbs sweeps on the chains' states at the end of the run (the stationary regime: few accepted flips)
+        tq_end = torch.from_numpy(res.q[:, -1, :].copy()).to(dev)
+        torch.cuda.synchronize()
+        e0.record()
+        for k in range(50):
+            tgt.gibbs(tq_end, 10_000 + k)
+        e1.record()
+        torch.cuda.synchronize()
         # wall time of the whole run (tune + draws) is charged to the draws kept
-        ess = {"sampler": "built-in batched HMC (dense metric) + GPU Metropolised-Gibbs sweep, 4 chains x (300 tune + 300 draws)",
-               "wall_s": res.wall_s, "min_bulk_ess_per_s": vals_ess[0] / res.wall_s,
+        ess = {"sampler": f"built-in batched HMC (dense metric) + GPU Metropolised-Gibbs sweep, device-resident transitions, "
+                          f"{C} chains x ({tune_n} tune + {draws_n} draws)",
+               "wall_s": res.wall_s, "iterations_per_s": (tune_n + draws_n) / res.wall_s,
+               "min_bulk_ess_per_s": vals_ess[0] / res.wall_s,
                "median_bulk_ess_per_s": vals_ess[len(vals_ess) // 2] / res.wall_s,
                "max_rhat": max(v["rhat"] for v in summ.values()), "grad_evals": res.n_grad_evals,
-               "note": "PyMC is not installable offline, so there is no PyMC-CPU ESS/s beside it"}
+               "gibbs_sweeps_per_s_stationary": C * 50 / (e0.elapsed_time(e1) / 1e3),
+               "note": "PyMC is not installable offline, so there is no PyMC-CPU ESS/s beside it; the slowest-mixing "
+                       "parameters are those coupled to the latent infection indicators (data-augmentation Gibbs)"}
 
     if rank != 0:
         if dist:
@@ -473,8 +536,10 @@ def run_gpu(args):
         "l2_resident": {"value": world * C * n_launch / (ms_l2 / 1e3), "unit": "evals/s",
                         "avg_launch_us": ms_l2 / n_launch * 1e3,
                         "note": "same cohort re-evaluated back to back (the access pattern of consecutive NUTS leapfrogs)"},
+        "persistent_trajectory": traj,
         "gibbs": {"metric": "Gibbs sweeps/s (all G*N+N binary variables of one chain)", "value": world * C * n_sw / (ms_gibbs / 1e3),
                   "unit": "sweeps/s", "avg_launch_us": t_sweep * 1e6,
+                  "regime": "states drawn at random (4 % infections, 50 % waners): the burn-in regime, many accepted flips",
                   "roofline": {"bound": "hbm", "achieved": ach_g, "peak": peak, "unit": "GB/s", "frac": ach_g / peak,
                                "traffic": ncu_traffic("k_gibbs"), "kernel": "k_gibbs", "algorithmic_bytes_per_launch": a_gibbs},
                   "e2e": {"value": world * C * n_sw_e2e / dt_gibbs_e2e, "unit": "sweeps/s",

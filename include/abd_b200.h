@@ -198,6 +198,27 @@ int abd_leapfrog_dev(abd_handle* h, int n_chains, int n_steps, double* q17, doub
                      const int8_t* i_raw, const int8_t* waner, void* stream);
 int abd_leapfrog_status(abd_handle* h, int n_chains);
 
+/* The two ends of one HMC transition over q17 for C chains, on the device (what PyMC's HMC / NUTS
+ * step does on the host around its leapfrogs in pm.sample, abd.py:922): momentum refresh and
+ * Metropolis accept, with per-chain step-size adaptation by dual averaging (Hoffman & Gelman 2014,
+ * the scheme PyMC uses).  A host-driven sampler then runs an iteration as five launches and no
+ * device synchronisation: hmc_begin, leapfrog, hmc_end, gibbs_sweep, logp_dlogp.
+ *   abd_hmc_begin_dev: z ~ N(0, I) (Philox4x32-10 keyed by (seed; iter, chain, component)),
+ *     p = linv_t z with linv_t = (L^T)^-1, inv_mass = L L^T (17 x 17 row-major), so p ~ N(0, M);
+ *     writes the work copies qw = q, gw = grad, pw = p and h0 = -logp + z.z / 2.
+ *   abd_hmc_end_dev: h1 = -lpw + pw' inv_mass pw / 2; accept with probability min(1, exp(h0 - h1))
+ *     (not finite => reject): q, grad, logp take the work copies; accept_out[c] = that probability.
+ *     da (C x 4: mu, hbar, log_avg, t) is the dual-averaging state; when adapt != 0 it is advanced
+ *     with accept_out[c] against target_accept and eps[c] = exp(log_eps) is written.          */
+int abd_hmc_begin_dev(abd_handle* h, int n_chains, const double* q17, const double* grad17,
+                      const double* logp, const double* linv_t, uint64_t seed, uint64_t iter,
+                      double* qw, double* pw, double* gw, double* h0, void* stream);
+int abd_hmc_end_dev(abd_handle* h, int n_chains, double* q17, double* grad17, double* logp,
+                    const double* qw, const double* pw, const double* gw, const double* lpw,
+                    const double* inv_mass, const double* h0, uint64_t seed, uint64_t iter,
+                    double* accept_out, double* da, double* eps, int adapt, double target_accept,
+                    void* stream);
+
 /* Individual sharding over the GPUs of one node WITHOUT a separate collective: the all-reduce of
  * the C x 16 raw sums is fused into the kernel through NVLink peer memory (each rank's finishing
  * CTA stores its sums into every peer's buffer, waits for the peers' flags, adds in rank order,
