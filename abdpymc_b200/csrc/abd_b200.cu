@@ -26,6 +26,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -532,54 +533,66 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
 
     // ---- phase 2: one thread per OD row; everything comes from shared memory, no divergence.
     //      P (ever exposed) travels in the sign bit of dT ----
-    const bool direct = kFX && s_direct;
-    {
-      const double b = s_th[N_B], d = s_th[N_D];
+    //      The loops exist twice: `direct` (a chain whose |b| x is too large to factor, or the
+    //      fallback kernel) evaluates one exponential per row, the common case only a product ----
+    auto rows = [&](auto direct_tag) {
+      constexpr bool kDirect = decltype(direct_tag)::value;
+      {
+        const double b = s_th[N_B], d = s_th[N_D];
+        const uint32_t* rcp = s_rc_n - qn0;
+        const double* odp = s_od_n - an0;
+        const CellVal* cvp = s_cv_n - cn0;
 #pragma unroll 2
-      for (int r = rn0 + tid; r < rn1 && tid < nwork; r += nwork) {
-        double s, res, q, xm;
-        const uint32_t rc = s_rc_n[r - qn0];
-        const CellVal cv = s_cv_n[(kFX ? (rc >> 5) : rc) - cn0];
-        if constexpr (kFX) {
-          const double2 xe = s_xe[0][rc & 31];
-          xm = xe.x - cv.m;
-          if (direct) row_eval(xe.x, s_od_n[r - an0], cv.m, b, d, s_tab, s, res, q, xm);
-          else row_eval_E(xe.y * cv.Em, s_od_n[r - an0], d, s, res, q);
-        } else {
-          row_eval(s_x_n[r - an0], s_od_n[r - an0], cv.m, b, d, s_tab, s, res, q, xm);
+        for (int r = rn0 + tid; r < rn1 && tid < nwork; r += nwork) {
+          double sg, res, q, xm;
+          const uint32_t rc = rcp[r];
+          const CellVal cv = cvp[kFX ? (rc >> 5) : rc];
+          if constexpr (kFX) {
+            const double2 xe = s_xe[0][rc & 31];
+            xm = xe.x - cv.m;
+            if constexpr (kDirect) row_eval(xe.x, odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
+            else row_eval_E(xe.y * cv.Em, odp[r], d, sg, res, q);
+          } else {
+            row_eval((s_x_n - an0)[r], odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
+          }
+          acc[SN_0] = fma(res, res, acc[SN_0]);
+          acc[SN_1] = fma(res, sg, acc[SN_1]);
+          acc[SN_2] = fma(q, xm, acc[SN_2]);
+          acc[SN_QINIT] += q;
+          acc[SN_QPERM] += (__double2hiint(cv.dT) < 0) ? 0.0 : q;
+          acc[SN_QTEMP] = fma(q, cv.T, acc[SN_QTEMP]);
+          acc[SN_QRHO] = fma(q, cv.dT, acc[SN_QRHO]);
         }
-        acc[SN_0] = fma(res, res, acc[SN_0]);
-        acc[SN_1] = fma(res, s, acc[SN_1]);
-        acc[SN_2] = fma(q, xm, acc[SN_2]);
-        acc[SN_QINIT] += q;
-        acc[SN_QPERM] += (__double2hiint(cv.dT) < 0) ? 0.0 : q;
-        acc[SN_QTEMP] = fma(q, cv.T, acc[SN_QTEMP]);
-        acc[SN_QRHO] = fma(q, cv.dT, acc[SN_QRHO]);
       }
-    }
-    {
-      const double b = s_th[S_B], d = s_th[S_D];
+      {
+        const double b = s_th[S_B], d = s_th[S_D];
+        const uint32_t* rcp = s_rc_s - qs0;
+        const double* odp = s_od_s - as0;
+        const CellVal* cvp = s_cv_s - cs0;
 #pragma unroll 2
-      for (int r = rs0 + tid; r < rs1 && tid < nwork; r += nwork) {
-        double s, res, q, xm;
-        const uint32_t rc = s_rc_s[r - qs0];
-        const CellVal cv = s_cv_s[(kFX ? (rc >> 5) : rc) - cs0];
-        if constexpr (kFX) {
-          const double2 xe = s_xe[1][rc & 31];
-          xm = xe.x - cv.m;
-          if (direct) row_eval(xe.x, s_od_s[r - as0], cv.m, b, d, s_tab, s, res, q, xm);
-          else row_eval_E(xe.y * cv.Em, s_od_s[r - as0], d, s, res, q);
-        } else {
-          row_eval(s_x_s[r - as0], s_od_s[r - as0], cv.m, b, d, s_tab, s, res, q, xm);
+        for (int r = rs0 + tid; r < rs1 && tid < nwork; r += nwork) {
+          double sg, res, q, xm;
+          const uint32_t rc = rcp[r];
+          const CellVal cv = cvp[kFX ? (rc >> 5) : rc];
+          if constexpr (kFX) {
+            const double2 xe = s_xe[1][rc & 31];
+            xm = xe.x - cv.m;
+            if constexpr (kDirect) row_eval(xe.x, odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
+            else row_eval_E(xe.y * cv.Em, odp[r], d, sg, res, q);
+          } else {
+            row_eval((s_x_s - as0)[r], odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
+          }
+          acc[SS_0] = fma(res, res, acc[SS_0]);
+          acc[SS_1] = fma(res, sg, acc[SS_1]);
+          acc[SS_2] = fma(q, xm, acc[SS_2]);
+          acc[SS_QINIT] += q;
+          acc[SS_QPERM] += (__double2hiint(cv.dT) < 0) ? 0.0 : q;
+          acc[SS_QRHO] = fma(q, cv.dT, acc[SS_QRHO]);
         }
-        acc[SS_0] = fma(res, res, acc[SS_0]);
-        acc[SS_1] = fma(res, s, acc[SS_1]);
-        acc[SS_2] = fma(q, xm, acc[SS_2]);
-        acc[SS_QINIT] += q;
-        acc[SS_QPERM] += (__double2hiint(cv.dT) < 0) ? 0.0 : q;
-        acc[SS_QRHO] = fma(q, cv.dT, acc[SS_QRHO]);
       }
-    }
+    };
+    if (!kFX || s_direct) rows(std::true_type{});
+    else rows(std::false_type{});
 
     PHASE(5);
     // ---- block reduction: butterfly inside a warp, shared memory across warps ----
@@ -1527,11 +1540,25 @@ void plan_grid(const abd_handle* h, int C, int ctas_per_sm, int* want_tiles, int
   *chains_per_cta = cpc;
 }
 
-template <typename M, typename XT>
-cudaError_t sums_occupancy(size_t smem, int* occ) {
-  cudaError_t e = cudaFuncSetAttribute(k_sums<M, XT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024));
+// The dynamic shared-memory limit of a kernel is a per-device function attribute shared by every
+// handle of the process: only ever raise it (a small cohort must not lower it under a large one).
+template <typename M, typename XT, bool TRAJ>
+cudaError_t sums_smem_attr(int device, size_t smem) {
+  static size_t configured[64] = {};
+  const int d = (device >= 0 && device < 64) ? device : 0;
+  const size_t want = std::max<size_t>(smem, 48 * 1024);
+  if (want <= configured[d]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(k_sums<M, XT, TRAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_sums<M, XT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(k_sums<M, XT, TRAJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  configured[d] = want;
+  return cudaSuccess;
+}
+
+template <typename M, typename XT>
+cudaError_t sums_occupancy(int device, size_t smem, int* occ) {
+  cudaError_t e = sums_smem_attr<M, XT, false>(device, smem);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sums<M, XT, false>, kSumsBlock, smem);
 }
@@ -1545,19 +1572,9 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
     std::fprintf(stderr, "[abd_b200] k_sums grid (%u, %u) dyn smem %zu B, occupancy %d CTAs/SM, caps rows %d/%d cells %d/%d\n",
                  grid.x, grid.y, tl.smem, occ, tl.cap_n, tl.cap_s, tl.capk_n, tl.capk_s);
   }
-  static thread_local size_t configured[2] = {0, 0};
   const int tj = traj.n_steps > 0 ? 1 : 0;
-  if (tl.smem > configured[tj]) {
-    const int want = (int)std::max<size_t>(tl.smem, 48 * 1024);
-    if (tj) {
-      CU(cudaFuncSetAttribute(k_sums<M, XT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-      CU(cudaFuncSetAttribute(k_sums<M, XT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    } else {
-      CU(cudaFuncSetAttribute(k_sums<M, XT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-      CU(cudaFuncSetAttribute(k_sums<M, XT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
-    configured[tj] = (size_t)want;
-  }
+  if (tj) CU((sums_smem_attr<M, XT, true>(h->device, tl.smem)));
+  else CU((sums_smem_attr<M, XT, false>(h->device, tl.smem)));
   cudaLaunchConfig_t lc{};
   lc.gridDim = grid;
   lc.blockDim = dim3(kSumsBlock);
@@ -1609,9 +1626,9 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
       int o = 0;
       cudaError_t e;
       if (h->wide)
-        e = h->fx ? sums_occupancy<uint64_t, uint8_t>(tl->smem, &o) : sums_occupancy<uint64_t, double>(tl->smem, &o);
+        e = h->fx ? sums_occupancy<uint64_t, uint8_t>(h->device, tl->smem, &o) : sums_occupancy<uint64_t, double>(h->device, tl->smem, &o);
       else
-        e = h->fx ? sums_occupancy<uint32_t, uint8_t>(tl->smem, &o) : sums_occupancy<uint32_t, double>(tl->smem, &o);
+        e = h->fx ? sums_occupancy<uint32_t, uint8_t>(h->device, tl->smem, &o) : sums_occupancy<uint32_t, double>(h->device, tl->smem, &o);
       CU(e);
       tl->occ = std::max(o, 1);
     }

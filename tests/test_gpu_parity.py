@@ -480,6 +480,29 @@ def test_gibbs_properties_10k(Engine):
     assert np.array_equal(s_i, a_i[:, :, lo:hi]) and np.array_equal(s_w, a_w[:, lo:hi])
 
 
+def test_small_cohort_between_evaluations_of_a_large_one(Engine, cohorts):
+    """The kernels' dynamic shared-memory limit is a per-process function attribute: creating and
+    using an engine for a small cohort must not break an engine of a large one (regression)."""
+    from abdpymc_b200.cohort import synthetic_cohort
+
+    big = synthetic_cohort(10_000)
+    rng = np.random.default_rng(12)
+    q, i_raw, w = draw_points(rng, big.n_gaps, big.n_inds, 2)
+    qs, i_s, w_s = draw_points(rng, 26, 10, 2)
+    with Engine(big, splits=(14, 20)) as eb:
+        lp0, g0 = eb.logp_dlogp(q, i_raw, w)
+        with Engine(cohorts["test_cohort"], splits=(14, 20)) as es:
+            es.logp_dlogp(qs, i_s, w_s)
+            es.set_tuning(100, 1)
+            es.logp_dlogp(qs, i_s, w_s)
+        lp1, g1 = eb.logp_dlogp(q, i_raw, w)
+        eb.set_tuning(1100, 2)
+        eb.logp_dlogp(q, i_raw, w)
+        eb.set_tuning(0, 0)
+        lp2, g2 = eb.logp_dlogp(q, i_raw, w)
+    assert np.array_equal(lp0, lp1) and np.array_equal(g0, g1) and np.array_equal(lp0, lp2) and np.array_equal(g0, g2)
+
+
 def test_fast_math(Engine):
     """The kernels' table-based exp and Newton reciprocal against libm: <= 2 ulp over the whole
     range the OD-row code can produce (z is capped at 700 by the caller)."""
