@@ -561,7 +561,8 @@ def run_gpu(args):
         "cpu_baseline": cpu,
         "e2e": {"value": world * C * n_e2e / dt_e2e, "unit": "evals/s",
                 "h2d_bytes_per_step": int(C * (17 * 8 + G * N + N)), "d2h_bytes_per_step": int(C * 18 * 8),
-                "call": "abd_logp_dlogp(q17, i_raw, waner) with pinned host buffers, one call per step"},
+                "call": "abd_logp_dlogp(q17, i_raw, waner) with pinned host buffers, one call per step (the library pulls pinned "
+                        "chain state with an SM copy kernel over PCIe instead of the copy engine; q17 / results by cudaMemcpyAsync)"},
         "e2e_resident_state": {"value": world * C * n_e2e / dt_res, "unit": "evals/s",
                                "h2d_bytes_per_step": int(C * 17 * 8), "d2h_bytes_per_step": int(C * 18 * 8),
                                "call": "abd_logp_dlogp(q17, NULL, NULL): chain state left on the device by the Gibbs sweep"},

@@ -503,6 +503,31 @@ def test_small_cohort_between_evaluations_of_a_large_one(Engine, cohorts):
     assert np.array_equal(lp0, lp1) and np.array_equal(g0, g1) and np.array_equal(lp0, lp2) and np.array_equal(g0, g2)
 
 
+def test_pinned_state_is_pulled_by_the_sms(Engine):
+    """Chain state handed over in pinned host memory is fetched by a kernel (16-byte loads over
+    PCIe) instead of the copy engine; pageable memory takes cudaMemcpyAsync.  Same bytes on the
+    device either way (sizes that are not multiples of 16 included)."""
+    import torch
+
+    from abdpymc_b200.cohort import synthetic_cohort
+
+    co = synthetic_cohort(1000)
+    rng = np.random.default_rng(3)
+    for C in (3, 4):
+        q, i_raw, w = draw_points(rng, co.n_gaps, co.n_inds, C)
+        assert (C * co.n_gaps * co.n_inds) % 16 == (8 if C == 3 else 0)
+        pi, pw = torch.from_numpy(i_raw).pin_memory(), torch.from_numpy(w).pin_memory()
+        with Engine(co, splits=(14, 20)) as eng:
+            lp_a, g_a = eng.logp_dlogp(q, i_raw, w)                  # pageable
+            back_i, back_w = eng.download_state(C)
+            assert np.array_equal(back_i, i_raw) and np.array_equal(back_w, w)
+            eng.upload_state(np.zeros_like(i_raw), np.zeros_like(w))
+            lp_b, g_b = eng.logp_dlogp(q, pi.numpy(), pw.numpy())    # pinned: pulled
+            back_i, back_w = eng.download_state(C)
+            assert np.array_equal(back_i, i_raw) and np.array_equal(back_w, w)
+        assert np.array_equal(lp_a, lp_b) and np.array_equal(g_a, g_b)
+
+
 def test_fast_math(Engine):
     """The kernels' table-based exp and Newton reciprocal against libm: <= 2 ulp over the whole
     range the OD-row code can produce (z is capped at 700 by the caller)."""
