@@ -1302,6 +1302,7 @@ struct abd_handle {
   double* d_partial = nullptr;
   size_t cap_partial = 0;
   double* h_pin = nullptr;     // pinned staging [C][40]
+  double* h_pin_dev = nullptr; // the same buffer as the device sees it
 };
 
 namespace {
@@ -1525,6 +1526,12 @@ int ensure_chains(abd_handle* h, int C) {
   if ((rc = dev_alloc(h, &h->d_stats, (size_t)C * 2, false))) return rc;
   CU(cudaMemset(h->d_ticket, 0, (size_t)C * sizeof(unsigned)));
   CU(cudaMallocHost((void**)&h->h_pin, (size_t)C * 40 * sizeof(double)));
+  h->h_pin_dev = nullptr;
+  {
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, h->h_pin, 0) == cudaSuccess) h->h_pin_dev = (double*)dp;
+    else cudaGetLastError();
+  }
   h->cap_chains = C;
   return ABD_OK;
 }
@@ -1994,12 +2001,20 @@ int abd_logp_dlogp(abd_handle* h, int C, const double* q17, const int8_t* i_raw,
   // (Letting the kernel read the 17 scalars and write its results in place in the pinned staging
   // buffer over PCIe was measured: 81 us per call instead of 41 -- every CTA pays sysmem latency for
   // its parameter loads.  Small copy-engine transfers on both sides of the launch it is.)
+  // The RESULTS, however, are written by the finishing warps straight into the pinned staging
+  // buffer (posted PCIe writes cost the kernel nothing): no device -> host copy after the launch.
   double* ho = h->h_pin + (size_t)C * 17;
   std::memcpy(h->h_pin, q17, (size_t)C * 17 * sizeof(double));
   CU(cudaMemcpyAsync(h->d_theta, h->h_pin, (size_t)C * 17 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  FinalizeCfg fin{2, h->tot, h->d_out, h->d_out + C};
-  if ((rc = launch_sums(h, C, h->d_theta, 1, h->d_iraw, h->d_waner, h->d_sums, fin, h->stream))) return rc;
-  CU(cudaMemcpyAsync(ho, h->d_out, (size_t)C * 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (h->h_pin_dev && h->use_pull) {
+    double* dout = h->h_pin_dev + (size_t)C * 17;
+    FinalizeCfg fin{2, h->tot, dout, dout + C};
+    if ((rc = launch_sums(h, C, h->d_theta, 1, h->d_iraw, h->d_waner, h->d_sums, fin, h->stream))) return rc;
+  } else {
+    FinalizeCfg fin{2, h->tot, h->d_out, h->d_out + C};
+    if ((rc = launch_sums(h, C, h->d_theta, 1, h->d_iraw, h->d_waner, h->d_sums, fin, h->stream))) return rc;
+    CU(cudaMemcpyAsync(ho, h->d_out, (size_t)C * 18 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
   CU(cudaStreamSynchronize(h->stream));
   std::memcpy(out_logp, ho, (size_t)C * sizeof(double));
   if (out_dlogp) std::memcpy(out_dlogp, ho + C, (size_t)C * 17 * sizeof(double));
