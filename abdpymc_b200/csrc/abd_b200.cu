@@ -1738,6 +1738,26 @@ int copy_state_h2d(abd_handle* h, void* dst, const void* src, size_t bytes) {
   return ABD_OK;
 }
 
+// Device -> host copy of a chain-state array: pinned, 16-byte aligned destinations are written by
+// the SMs (posted PCIe writes), anything else by the copy engine.
+int copy_state_d2h(abd_handle* h, void* dst, const void* src, size_t bytes) {
+  if (bytes >= (4u << 10) && h->use_pull && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      const size_t n16 = bytes / 16, rem = bytes - n16 * 16;
+      const int grid = (int)std::min<size_t>((size_t)h->n_sms * 4, (n16 + 255) / 256);
+      k_pull<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(at.devicePointer), n16,
+                                          rem);
+      CU(cudaGetLastError());
+      h->launches++;
+      return ABD_OK;
+    }
+    cudaGetLastError();
+  }
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  return ABD_OK;
+}
+
 int stage_state(abd_handle* h, int C, const int8_t* i_raw, const int8_t* waner) {
   const size_t gn = (size_t)h->G * h->N;
   int rc;
@@ -1953,8 +1973,9 @@ int abd_upload_state(abd_handle* h, int C, const int8_t* i_raw, const int8_t* wa
 int abd_download_state(abd_handle* h, int C, int8_t* i_raw, int8_t* waner) {
   PROLOGUE(h, C);
   const size_t gn = (size_t)h->G * h->N;
-  if (i_raw) CU(cudaMemcpyAsync(i_raw, h->d_iraw, (size_t)C * gn, cudaMemcpyDeviceToHost, h->stream));
-  if (waner) CU(cudaMemcpyAsync(waner, h->d_waner, (size_t)C * h->N, cudaMemcpyDeviceToHost, h->stream));
+  int rc;
+  if (i_raw && (rc = copy_state_d2h(h, i_raw, h->d_iraw, (size_t)C * gn))) return rc;
+  if (waner && (rc = copy_state_d2h(h, waner, h->d_waner, (size_t)C * h->N))) return rc;
   CU(cudaStreamSynchronize(h->stream));
   return ABD_OK;
 }
@@ -2077,8 +2098,8 @@ int abd_gibbs_sweep(abd_handle* h, int C, const double* theta13, const double* p
   if ((rc = launch_gibbs(h, C, h->d_theta, 0, h->d_p, h->d_p + C, h->d_iraw, h->d_waner, cfg, h->stream)))
     return rc;
   const size_t gn = (size_t)h->G * h->N;
-  if (i_raw) CU(cudaMemcpyAsync(i_raw, h->d_iraw, (size_t)C * gn, cudaMemcpyDeviceToHost, h->stream));
-  if (waner) CU(cudaMemcpyAsync(waner, h->d_waner, (size_t)C * h->N, cudaMemcpyDeviceToHost, h->stream));
+  if (i_raw && (rc = copy_state_d2h(h, i_raw, h->d_iraw, (size_t)C * gn))) return rc;
+  if (waner && (rc = copy_state_d2h(h, waner, h->d_waner, (size_t)C * h->N))) return rc;
   if (out_stats)
     CU(cudaMemcpyAsync(h->h_pin, h->d_stats, (size_t)C * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                        h->stream));

@@ -225,16 +225,24 @@ class AbdEngine:
         return (oi[0], ow[0]) if single else (oi, ow)
 
     def gibbs_sweep(self, theta13, p, p_w, i_raw=None, waner=None, seed=0, sweep=0,
-                    mode=_lib.GIBBS_METROPOLIS, transit_p=0.8, download=True):
+                    mode=_lib.GIBBS_METROPOLIS, transit_p=0.8, download=True, inplace=False):
         """Returns (i_raw, waner, stats) -- updated copies (or (None, None, stats) when
-        ``download=False``: the new state stays resident on the device)."""
+        ``download=False``: the new state stays resident on the device).  ``inplace=True``: the
+        int8 arrays passed in are updated in place in ONE call (abd_gibbs_sweep's in/out
+        contract); with pinned arrays both directions then go over PCIe by SM copy kernels."""
         C_, single = self._chains(theta13, 13)
         th = _f64(theta13, (C_, 13))
         pp, pw = _f64(p, (C_,)), _f64(p_w, (C_,))
         i8, w8 = self._state(C_, i_raw, waner)
+        st = np.zeros((C_, 2), np.int64)
+        if inplace:
+            if i8 is None or not (i8.flags.writeable and w8.flags.writeable and np.may_share_memory(i8, np.asarray(i_raw))):
+                raise ValueError("inplace=True needs writable, contiguous one-byte i_raw / waner arrays")
+            check(self._lib.abd_gibbs_sweep(self._h, C_, _ptr(th), _ptr(pp), _ptr(pw), _ptr(i8), _ptr(w8),
+                                            int(seed), int(sweep), int(mode), float(transit_p), _ptr(st)))
+            return i_raw, waner, (st[0] if single else st)
         if i8 is not None:
             check(self._lib.abd_upload_state(self._h, C_, _ptr(i8), _ptr(w8)))
-        st = np.zeros((C_, 2), np.int64)
         check(self._lib.abd_gibbs_sweep(self._h, C_, _ptr(th), _ptr(pp), _ptr(pw), None, None,
                                         int(seed), int(sweep), int(mode), float(transit_p), _ptr(st)))
         if not download:

@@ -433,7 +433,7 @@ def run_gpu(args):
     n_sw_e2e = max(5, min(50, K))
     t0 = time.perf_counter()
     for k in range(n_sw_e2e):
-        engines[k % n_rep].gibbs_sweep(th13, p, pw, hi.numpy(), hw.numpy(), seed=1, sweep=k)
+        engines[k % n_rep].gibbs_sweep(th13, p, pw, hi.numpy(), hw.numpy(), seed=1, sweep=k, inplace=True)
     dt_gibbs_e2e = time.perf_counter() - t0
     if dist:
         t = torch.tensor([ms_gibbs, dt_gibbs_e2e], dtype=torch.float64, device=dev)

@@ -526,6 +526,18 @@ def test_pinned_state_is_pulled_by_the_sms(Engine):
             back_i, back_w = eng.download_state(C)
             assert np.array_equal(back_i, i_raw) and np.array_equal(back_w, w)
         assert np.array_equal(lp_a, lp_b) and np.array_equal(g_a, g_b)
+        # the in/out Gibbs call: pinned arrays are pulled, swept and pushed back in place
+        vals = np.array([[ora.backward(q[k])[0][n] for n in ora.THETA13] for k in range(C)])
+        p = np.array([ora.backward(q[k])[0]["p"] for k in range(C)])
+        p_w = np.array([ora.backward(q[k])[0]["ab_s_p_waner"] for k in range(C)])
+        with Engine(co, splits=(14, 20)) as eng:
+            ri, rw, rst = eng.gibbs_sweep(vals, p, p_w, i_raw, w, seed=5, sweep=2)
+            pi2, pw2 = pi.clone(), pw.clone()
+            _, _, st = eng.gibbs_sweep(vals, p, p_w, pi2.numpy(), pw2.numpy(), seed=5, sweep=2, inplace=True)
+            pg_i, pg_w = i_raw.copy(), w.copy()
+            eng.gibbs_sweep(vals, p, p_w, pg_i, pg_w, seed=5, sweep=2, inplace=True)   # pageable, in place
+        assert np.array_equal(pi2.numpy(), ri) and np.array_equal(pw2.numpy(), rw) and np.array_equal(st, rst)
+        assert np.array_equal(pg_i, ri) and np.array_equal(pg_w, rw) and not np.array_equal(ri, i_raw)
 
 
 def test_fast_math(Engine):
