@@ -10,7 +10,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 SRC = PKG / "csrc" / "abd_b200.cu"
-DEPS = [SRC, PKG / "csrc" / "abd_device.cuh", PKG.parent / "include" / "abd_b200.h"]
+DEPS = [SRC, *sorted((PKG / "csrc").glob("*.cuh")), PKG.parent / "include" / "abd_b200.h"]
 OUT = PKG / "libabd_b200.so"
 
 

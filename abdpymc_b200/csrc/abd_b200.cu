@@ -7,18 +7,15 @@
 //                               meta_a[R_a] u32 = individual << 6 | gap
 //   per chain (resident state): i_raw[C][G][N] int8, waner[C][N] int8  (the reference layout)
 //
-// Kernels
-//   k_sums      one CTA per (tile of individuals, chain): int8 columns -> bit masks ->
-//               constrained infections in shared memory; one thread per OD row evaluates the
-//               titer in closed form from the masks (power tables in shared memory), the
-//               logistic curve and the 13 gradient accumulators; warp-shuffle + block
-//               reduction; the last CTA of each chain (atomic ticket) reduces the tiles in a
-//               fixed order and applies priors / transforms (single launch, deterministic).
-//   k_finalize  the same finalisation as a separate launch (after an all-reduce when
-//               individuals are sharded across GPUs).
-//   k_gibbs     one warp per (individual, chain), lanes over that individual's OD rows; G+1
-//               sequential single-bit updates, both states evaluated, Philox4x32-10.
-//   k_determ    one thread per (individual, chain): i, ab_n_mu, ab_s_mu for a recorded draw.
+// Files
+//   abd_device.cuh          per-individual building blocks (constraints, trajectories, row likelihood,
+//                           finaliser, Philox, fast exp / reciprocal, mbarrier + bulk-copy wrappers)
+//   abd_kernels_common.cuh  device view of the cohort, launch configurations
+//   k_sums.cuh              k_sums (joint logp + gradient sums, fused finaliser, persistent trajectory
+//                           mode, fused peer all-reduce), k_finalize
+//   k_gibbs.cuh             k_gibbs (Gibbs sweep, conditional log-odds)
+//   k_misc.cuh              k_hmc_begin / k_hmc_end, k_determ, k_pull, k_debug_fast_math
+//   abd_b200.cu (this file) host side: cohort preprocessing, tilings and grid plans, the C ABI
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -52,1197 +49,13 @@ int fail(int code, const std::string& msg) {
       return fail(ABD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
   } while (0)
 
-// ------------------------------------------------------------------------------------------
-// device-side view of the cohort
-// ------------------------------------------------------------------------------------------
-struct DevCohort {
-  int G, N;
-  unsigned ind_offset;       // global index of this shard's first individual (RNG streams)
-  const void* pcr;
-  const void* vac;
-  const int* rp[2];          // [0] = N antigen, [1] = S antigen
-  const double* od[2];
-  const double* x[2];
-  // factored mode (the cohort has <= 32 distinct log_dilution values, the usual case):
-  const uint32_t* rcx[2];      // per row: cell index << 5 | index of its dilution in xlev
-  const double* xlev;          // [32] the distinct dilutions, ascending (padded with 0)
-  int n_xlev;                  // 0: not available (k_sums stages the dilutions as doubles)
-  const uint32_t* meta[2];     // per row: individual << 6 | gap
-  const uint32_t* rowcell[2];  // per row: index of its (individual, gap) cell
-  const uint32_t* cmeta[2];    // per cell: individual << 6 | gap
-  Chunks ch;
-};
-
-constexpr int kSumsBlock = 256;
-constexpr int kSumsWarps = kSumsBlock / 32;
-constexpr int kAuxDoubles = 128;  // 17 x PriorPre (7) + LikPre (6), padded
-constexpr int kTileMaxInds = 128;
-constexpr int kGibbsWarps = 8;
-
-// per-individual state staged in shared memory: constrained infections, vaccinations, waner
-// (packed in the top bit of the vaccination mask; usable gaps <= width - 1)
-template <typename M>
-struct IndState {
-  M inf, vacw;
-};
-template <typename M>
-__device__ __forceinline__ M top_bit() { return (M)1 << (sizeof(M) * 8 - 1); }
-
-__device__ __forceinline__ double load_param(const double* theta, int theta_is_q, int c, int k13) {
-  if (theta_is_q) {
-    const int j = kQOfTheta[k13];
-    return backward(theta[(size_t)c * 17 + j], kQTransform[j]);
-  }
-  return theta[(size_t)c * 13 + k13];
-}
-
-// One warp: pw[k] = rho^k and (optionally) dpw[k] = k rho^(k-1) for k < G by a shuffle scan.
-__device__ __forceinline__ void fill_pow_warp(double rho, int G, int lane, double* pw, double* dpw) {
-  double v = rho;  // inclusive prefix product: rho^(lane+1)
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const double u = __shfl_up_sync(0xffffffffu, v, off);
-    if (lane >= off) v *= u;
-  }
-  const double r32 = __shfl_sync(0xffffffffu, v, 31);  // rho^32
-  double prev = __shfl_up_sync(0xffffffffu, v, 1);      // rho^lane
-  if (lane == 0) prev = 1.0;
-  if (lane == 0) {
-    pw[0] = 1.0;
-    if (dpw) dpw[0] = 0.0;
-  }
-  for (int blk = 0; blk * 32 < G; ++blk) {
-    const int k = blk * 32 + lane + 1;
-    const double scale = blk ? r32 : 1.0;  // G <= 63: at most two blocks
-    if (k < G) {
-      pw[k] = v * scale;
-      if (dpw) dpw[k] = (double)k * prev * scale;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_sums
-// ------------------------------------------------------------------------------------------
-struct FinalizeCfg {
-  int mode;        // 0: write raw sums only; 1: loglik + grad13; 2: joint logp + dlogp17
-  Totals tot;
-  double* out_val;   // [C]
-  double* out_grad;  // [C][13] or [C][17] (may be null)
-};
-
-struct SumsCfg {
-  int ntiles;
-  int cap_n, cap_s;      // staged doubles per antigen (even)
-  int capr_n, capr_s;    // staged row->cell words per antigen (multiple of 4)
-  int capk_n, capk_s;    // staged cell-meta words per antigen (multiple of 4)
-  int chains_per_cta;
-  int C;
-};
-
-// Fused all-reduce over NVLink peer memory (individuals sharded over `world` GPUs of one node):
-// the CTA that finishes a chain last on each rank stores its 16 raw sums straight into every
-// peer's exchange buffer, raises a per-(rank, chain) flag there, waits for the flags the peers
-// raise in ITS buffer, adds the `world` contributions in rank order (bitwise the same result on
-// every rank) and finalises -- compute, exchange and finalisation in one launch, no NCCL call.
-// Buffers are double-buffered on the parity of a per-chain sequence number kept on the device.
-constexpr int kMaxPeers = 8;
-constexpr unsigned long long kXchTimeoutNs = 10ull * 1000 * 1000 * 1000;  // a peer that is 10 s late is declared lost
-struct XchCfg {
-  int world, rank, cmax;                 // world == 0: not sharded
-  double* data[kMaxPeers];               // peer r's buffer: [2][world][cmax][16] doubles ...
-  unsigned long long* flag[kMaxPeers];   // ... followed by [2][world][cmax] flags
-  unsigned* seq;                         // [cmax] local sequence numbers
-  unsigned* err;
-};
-
-// Trajectory mode (n_steps > 0): the kernel stays resident for n_steps leapfrog steps of
-// Hamiltonian dynamics over q17 with the binary state fixed.  Per step every CTA evaluates its
-// tile at the current position; the CTA that finishes a chain last finalises logp / gradient,
-// advances (q, p) and publishes them with a per-chain generation counter the other CTAs of that
-// chain wait on -- no kernel launch, no re-staging of the cohort between evaluations.
-struct TrajCfg {
-  int n_steps;             // 0 = plain evaluation
-  double* q;               // [C][17] in: start position, out: end position
-  double* p;               // [C][17] in/out momentum
-  double* grad;            // [C][17] in: gradient at q, out: gradient at the end position
-  double* logp;            // [C]     out: logp at the end position
-  const double* eps;       // [C] step sizes
-  const double* inv_mass;  // [17][17] (symmetric) inverse mass matrix, shared by all chains
-  double* state;           // [C][34] scratch: position and half-step momentum of the current step
-  unsigned* gen;           // [C] generation counters (zeroed before the launch)
-  unsigned* err;           // set to 1 if a wait timed out
-};
-
-// tile descriptor (48 bytes, three 16-byte loads): individuals [i0, i1); per antigen the OD rows
-// [r0, r1) and the (individual, gap) cells [c0, c1) of those individuals
-struct __align__(16) TileDesc {
-  int i0, i1, rn0, rn1;
-  int rs0, rs1, cn0, cn1;
-  int cs0, cs1, pad0, pad1;
-};
-
-// trajectory of one cell: titer m, decaying part T (or U) and its rho-derivative; in factored mode
-// also Em = exp(b m) (capped so that exp(-b x) * Em <= e^700)
-template <bool FX>
-struct CellValT {
-  double m, T, dT;
-};
-template <>
-struct __align__(16) CellValT<true> {
-  double m, T, dT, Em;
-};
-constexpr int kMaxXLevels = 32;
-
-#ifdef ABD_PHASE_TIMING
-__device__ unsigned long long g_phase[4096][16];
-__device__ unsigned long long g_span[256][2];  // per launch: first CTA start, last CTA end
-__device__ unsigned g_span_idx, g_span_done;
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t_;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
-  return t_;
-}
-#define SPAN_BEGIN()                                                                      \
-  unsigned span_slot_ = 0;                                                                \
-  if (threadIdx.x == 0) {                                                                 \
-    span_slot_ = *(volatile unsigned*)&g_span_idx & 255u;                                 \
-    atomicMin(&g_span[span_slot_][0], gtime());                                           \
-  }
-#define SPAN_END()                                                                        \
-  if (threadIdx.x == 0) {                                                                 \
-    atomicMax(&g_span[span_slot_][1], gtime());                                           \
-    if (atomicAdd(&g_span_done, 1u) == gridDim.x * gridDim.y - 1) {                       \
-      g_span_done = 0;                                                                    \
-      __threadfence();                                                                    \
-      atomicAdd(&g_span_idx, 1u);                                                         \
-    }                                                                                     \
-  }
-#define PHASE(i)                                                                         \
-  do {                                                                                   \
-    if (tid == 0 && blockIdx.y * gridDim.x + blockIdx.x < 4096) {                        \
-      unsigned long long t_;                                                             \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
-      g_phase[blockIdx.y * gridDim.x + blockIdx.x][i] = t_;                              \
-    }                                                                                    \
-  } while (0)
-#define PHASEW(i, cond)                                                                  \
-  do {                                                                                   \
-    if ((cond) && blockIdx.y * gridDim.x + blockIdx.x < 4096) {                          \
-      unsigned long long t_;                                                             \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                             \
-      g_phase[blockIdx.y * gridDim.x + blockIdx.x][i] = t_;                              \
-    }                                                                                    \
-  } while (0)
-#else
-#define PHASE(i)
-#define PHASEW(i, cond)
-#define SPAN_BEGIN()
-#define SPAN_END()
-#endif
-
-#ifndef ABD_SUMS_MINB
-#define ABD_SUMS_MINB 3
-#endif
-// XT: how the dilutions reach the row loop.  uint8_t = factored mode: a row carries the index of
-// its dilution (packed with its cell index), exp(-b (x - m)) = exp(-b x) * exp(b m) costs one exp
-// per CELL plus a per-chain table over the distinct dilutions; double = general fallback, the
-// dilutions themselves are staged and every row evaluates its own exp.
-template <typename M, typename XT, bool TRAJ>
-__global__ void __launch_bounds__(kSumsBlock, ABD_SUMS_MINB)
-k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg,
-       const double* __restrict__ theta, const int theta_is_q,
-       const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
-       double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ sums,
-       const FinalizeCfg fin, const Priors* __restrict__ priors, double* __restrict__ aux, const TrajCfg traj,
-       const XchCfg xch) {
-  const int tile = blockIdx.x, tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int G = dc.G, N = dc.N, ntiles = cfg.ntiles;
-
-  // dynamic shared memory: staged rows (od, x, row->cell), staged cell meta, per-cell values
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  constexpr bool kFX = sizeof(XT) == 1;
-  using CellVal = CellValT<kFX>;
-  double* s_od_n = reinterpret_cast<double*>(dyn_smem);
-  double* s_od_s = s_od_n + cfg.cap_n;
-  CellVal* s_cv_n = reinterpret_cast<CellVal*>(s_od_s + cfg.cap_s);
-  CellVal* s_cv_s = s_cv_n + cfg.capk_n;
-  double* s_x_n = reinterpret_cast<double*>(s_cv_s + cfg.capk_s);   // cap_n doubles (not in factored mode)
-  double* s_x_s = s_x_n + (kFX ? 0 : cfg.cap_n);
-  uint32_t* s_rc_n = reinterpret_cast<uint32_t*>(s_x_s + (kFX ? 0 : cfg.cap_s));
-  uint32_t* s_rc_s = s_rc_n + cfg.capr_n;
-  uint32_t* s_cm_n = s_rc_s + cfg.capr_s;
-  uint32_t* s_cm_s = s_cm_n + cfg.capk_n;
-
-  __shared__ double s_th[16];
-  __shared__ double s_pw[4][kMaxGaps];  // rho_n^k, d/drho; rho_s^k, d/drho
-  __shared__ double s_tab[kExpTab];
-  __shared__ IndState<M> s_ind[kTileMaxInds];
-  __shared__ double s_red[kSumsWarps][kNSums];
-  __shared__ double s_fin[kSumsBlock / 16][kNSums];
-  __shared__ int s_last;
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ PriorPre s_pre[17];
-  __shared__ LikPre s_lik;
-  __shared__ double s_q[17], s_ph[17], s_out[18];  // trajectory mode: position, half-step momentum, logp + gradient
-  __shared__ double s_im[TRAJ ? 17 * 17 : 1];       // trajectory mode: inverse mass matrix
-  __shared__ double2 s_xe[kFX ? 2 : 1][kMaxXLevels];  // factored mode: {x_j, exp(-b x_j)} per antigen
-  __shared__ double s_zmax[2];                      // cap on b m so that exp(-b x) exp(b m) <= e^700
-  __shared__ int s_direct;                          // |b| x too large to factor: rows take their own exp
-
-  PHASE(0);
-  SPAN_BEGIN();
-  griddep_launch_dependents();
-  const int4 d0 = reinterpret_cast<const int4*>(tiles + tile)[0];
-  const int4 d1 = reinterpret_cast<const int4*>(tiles + tile)[1];
-  const int2 d2 = reinterpret_cast<const int2*>(tiles + tile)[4];
-  const int i0 = d0.x, ni = d0.y - d0.x;
-  const int rn0 = d0.z, rn1 = d0.w, rs0 = d1.x, rs1 = d1.y;
-  const int cn0 = d1.z, cn1 = d1.w, cs0 = d2.x, cs1 = d2.y;
-
-  // ---- stage this tile's rows and cell table in shared memory: one thread, bulk async copies ----
-  const int an0 = rn0 & ~1, as0 = rs0 & ~1;      // 16-byte aligned starts (doubles)
-  const int qn0 = rn0 & ~3, qs0 = rs0 & ~3;      // (32-bit words)
-  const int kn0 = cn0 & ~3, ks0 = cs0 & ~3;
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    const uint32_t bn = (uint32_t)(((rn1 + 1) & ~1) - an0) * 8u, bs = (uint32_t)(((rs1 + 1) & ~1) - as0) * 8u;
-    const uint32_t bqn = (uint32_t)(((rn1 + 3) & ~3) - qn0) * 4u, bqs = (uint32_t)(((rs1 + 3) & ~3) - qs0) * 4u;
-    const uint32_t bkn = (uint32_t)(((cn1 + 3) & ~3) - kn0) * 4u, bks = (uint32_t)(((cs1 + 3) & ~3) - ks0) * 4u;
-    mbar_expect_tx(&s_bar, (kFX ? bn + bs : 2 * bn + 2 * bs) + bqn + bqs + bkn + bks);
-    if (bkn) bulk_g2s(s_cm_n, dc.cmeta[0] + kn0, bkn, &s_bar);
-    if (bks) bulk_g2s(s_cm_s, dc.cmeta[1] + ks0, bks, &s_bar);
-    if (bn) {
-      bulk_g2s(s_od_n, dc.od[0] + an0, bn, &s_bar);
-      if (!kFX) bulk_g2s(s_x_n, dc.x[0] + an0, bn, &s_bar);
-    }
-    if (bs) {
-      bulk_g2s(s_od_s, dc.od[1] + as0, bs, &s_bar);
-      if (!kFX) bulk_g2s(s_x_s, dc.x[1] + as0, bs, &s_bar);
-    }
-    if (bqn) bulk_g2s(s_rc_n, (kFX ? dc.rcx[0] : dc.rowcell[0]) + qn0, bqn, &s_bar);
-    if (bqs) bulk_g2s(s_rc_s, (kFX ? dc.rcx[1] : dc.rowcell[1]) + qs0, bqs, &s_bar);
-  }
-  fill_exp_table(s_tab, tid, kSumsBlock);
-  // the immutable PCR+ / vaccination masks of this thread's individual (read before the wait)
-  M my_pcr = 0, my_vac = 0;
-  if (tid < ni) {
-    my_pcr = reinterpret_cast<const M*>(dc.pcr)[i0 + tid];
-    my_vac = reinterpret_cast<const M*>(dc.vac)[i0 + tid];
-  }
-  double x_lev = 0.0;  // factored mode, last warp: lane j holds the j-th distinct dilution
-  if (kFX && warp == kSumsWarps - 1) x_lev = dc.xlev[lane];
-  __syncthreads();  // the exp table is usable from here on (still before the dependency wait)
-  // everything above reads only the immutable cohort; parameters, chain state and the reduction
-  // scratch may be written by the previous kernel in the stream
-  griddep_wait();
-  if (TRAJ) {
-    for (int k = tid; k < 17 * 17; k += kSumsBlock) s_im[k] = traj.inv_mass[k];
-    __syncthreads();
-  }
-  PHASE(1);
-
-  for (int cc = 0; cc < cfg.chains_per_cta; ++cc) {
-    const int c = blockIdx.y * cfg.chains_per_cta + cc;
-    if (c >= cfg.C) break;
-
-    const int nsteps = TRAJ ? traj.n_steps : 1;
-    double cnt_i = 0.0, cnt_w = 0.0;  // this thread's individual: sum(i_raw), waner
-    for (int step = 0; step < nsteps; ++step) {
-    double acc[kNSums];
-#pragma unroll
-    for (int k = 0; k < kNSums; ++k) acc[k] = 0.0;
-    acc[S_KI] = cnt_i;
-    acc[S_KW] = cnt_w;
-
-    // trajectory mode: this step's position.  Step 0: every warp that needs it advances the
-    // start point itself (p_half = p + eps/2 g, q' = q + eps Sigma p_half: 17 FMAs per lane);
-    // later steps: wait for the chain's previous finaliser to publish (q', p_half).
-    double q_lane = 0.0, ph_lane = 0.0;  // lane k < 17: component k
-    if (TRAJ) {
-      if (step > 0) {
-        if (tid == 0) {
-          unsigned seen, polls = 0;
-          do {
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(traj.gen + c) : "memory");
-          } while (seen < (unsigned)step && ++polls < (1u << 26));
-          if (seen < (unsigned)step) *traj.err = 1u;  // watchdog: never hang the GPU
-        }
-        __syncthreads();
-        if (lane < 17) {
-          q_lane = __ldcg(traj.state + (size_t)c * 34 + lane);
-          ph_lane = __ldcg(traj.state + (size_t)c * 34 + 17 + lane);
-        }
-      } else if (warp >= 4) {
-        const double e = traj.eps[c];
-        double mine = 0.0;
-        if (lane < 17) mine = fma(0.5 * e, traj.grad[(size_t)c * 17 + lane], traj.p[(size_t)c * 17 + lane]);
-        double dot = 0.0;
-        for (int j = 0; j < 17; ++j) {
-          const double pj = __shfl_sync(0xffffffffu, mine, j);
-          if (lane < 17) dot = fma(s_im[lane * 17 + j], pj, dot);
-        }
-        ph_lane = mine;
-        if (lane < 17) q_lane = fma(e, dot, traj.q[(size_t)c * 17 + lane]);
-      }
-    }
-    // parameter k13 of this chain for the calling warp (uniform over the warp)
-    auto param13 = [&](int k13) -> double {
-      if (TRAJ) {
-        const int j = kQOfTheta[k13];
-        return backward(__shfl_sync(0xffffffffu, q_lane, j), kQTransform[j]);
-      }
-      return load_param(theta, theta_is_q, c, k13);
-    };
-
-    // ---- phase 0: warps 0-3: one thread per individual reads its int8 column (every load of
-    //      the warp is one coalesced 32-byte segment) and applies the infection constraints;
-    //      warps 4-7: parameters, power tables, dilution table.  (Fetching the block as aligned
-    //      32-bit words + shared-memory atomics / ballots was measured: slower, the transposition
-    //      costs more than the byte loads save.) ----
-    if (tid < kTileMaxInds) {
-      if (tid < ni && step == 0) {
-        const int8_t* col = i_raw + (size_t)c * G * N + i0 + tid;
-        int8_t bytes[sizeof(M) * 8];
-#pragma unroll
-        for (int t = 0; t < (int)sizeof(M) * 8; ++t) {
-          bytes[t] = (t < G) ? __ldg(col) : (int8_t)0;
-          col += N;
-        }
-        M raw = 0;
-#pragma unroll
-        for (int t = 0; t < (int)sizeof(M) * 8; ++t) raw |= (M)(bytes[t] != 0) << t;
-        const int w = waner[(size_t)c * N + i0 + tid] != 0;
-        IndState<M> st;
-        st.inf = constrain<M>(raw, my_pcr, dc.ch);
-        st.vacw = my_vac | (w ? top_bit<M>() : (M)0);
-        s_ind[tid] = st;
-        acc[S_KI] = cnt_i = (double)popc(raw);
-        acc[S_KW] = cnt_w = (double)w;
-      }
-      PHASEW(12, tid == 0);
-    } else if (warp == 4) {
-      fill_pow_warp(param13(N_RHO), G, lane, s_pw[0], s_pw[1]);
-      PHASEW(13, lane == 0);
-    } else if (warp == 5) {
-      fill_pow_warp(param13(S_RHO), G, lane, s_pw[2], s_pw[3]);
-    } else if (warp == 6) {
-      if (TRAJ) {
-        const int j = kQOfTheta[lane < 13 ? lane : 0];
-        const double v = backward(__shfl_sync(0xffffffffu, q_lane, j), kQTransform[j]);
-        if (lane < 13) s_th[lane] = v;
-      } else if (lane < 13) {
-        s_th[lane] = load_param(theta, theta_is_q, c, lane);
-      }
-      PHASEW(14, lane == 0);
-    } else if (warp == kSumsWarps - 1) {
-      if (kFX) {
-        // per-chain table {x_j, exp(-b x_j)} over the distinct dilutions, both antigens, and the
-        // cap on b m that keeps the product <= e^700 (b is not transformed: read it directly)
-        const double zn = -param13(N_B) * x_lev, zs = -param13(S_B) * x_lev;
-        double mn = (lane < dc.n_xlev) ? fabs(zn) : 0.0, ms = (lane < dc.n_xlev) ? fabs(zs) : 0.0;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          mn = fmax(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-          ms = fmax(ms, __shfl_xor_sync(0xffffffffu, ms, off));
-        }
-        // NaN / huge |b| x: every row evaluates its own exponential (same arithmetic as the fallback)
-        const bool direct = !(mn < 300.0 && ms < 300.0);
-        s_xe[0][lane] = make_double2(x_lev, direct ? 0.0 : fast_exp(zn, s_tab));
-        s_xe[kFX ? 1 : 0][lane] = make_double2(x_lev, direct ? 0.0 : fast_exp(zs, s_tab));
-        if (lane == 0) {
-          s_zmax[0] = 700.0 - mn;
-          s_zmax[1] = 700.0 - ms;
-          s_direct = direct;
-        }
-      }
-      if (TRAJ && lane < 17) {  // keeps (q, p_half) for the finaliser
-        s_q[lane] = q_lane;
-        s_ph[lane] = ph_lane;
-      }
-      PHASEW(15, lane == 0);
-    }
-    __syncthreads();
-    PHASE(2);
-    // The finaliser's parameter-only part (priors, transforms, logs: ~2 us of cold libm code) is
-    // taken off the critical path: warp 7 of the chain's first tile computes it now, instead of
-    // processing cells / rows, and parks it in global memory for whichever CTA finishes last.
-    // (the row -> thread assignment must not depend on fin.mode: abd_sums_dev + abd_finalize_* has
-    // to reproduce the fused launch bit for bit)
-    const bool aux_cta = (tile == 0);
-    const int nwork = aux_cta ? kSumsBlock - 32 : kSumsBlock;
-    if (aux_cta && fin.mode != 0 && warp == kSumsWarps - 1) {
-      double* a = aux + (size_t)c * kAuxDoubles;
-      if (fin.mode == 2 && lane < 17) {
-        const PriorPre pp = prior_pre(lane, TRAJ ? s_q[lane] : theta[(size_t)c * 17 + lane], priors->v[lane]);
-        double* o = a + lane * 7;
-        o[0] = pp.lpA, o[1] = pp.dA, o[2] = pp.f, o[3] = pp.lx, o[4] = pp.l1mx, o[5] = pp.x, o[6] = pp.omx;
-      }
-      if (lane == 17) {
-        const LikPre lk = lik_pre(s_th[N_SIGMA], s_th[S_SIGMA]);
-        double* o = a + 17 * 7;
-        o[0] = lk.lsn, o[1] = lk.lss, o[2] = lk.ivn, o[3] = lk.ivs, o[4] = lk.isn, o[5] = lk.iss;
-      }
-    }
-    if (cc == 0 && step == 0) mbar_wait(&s_bar, 0);
-    PHASE(3);
-
-    // ---- phase 1: one thread per (individual, gap) cell: titer in closed form from the masks ----
-    {
-      const double init = s_th[N_INIT], perm = s_th[N_PERM], temp = s_th[N_TEMP];
-      const double bn_fx = s_th[N_B], zmax_n = s_zmax[0];
-      for (int k = cn0 + tid; k < cn1 && tid < nwork; k += nwork) {
-        const uint32_t mt = s_cm_n[k - kn0];
-        const int t = mt & 63, li = (int)(mt >> 6) - i0;
-        double P, T, dT;
-        traj_n<M>(s_ind[li].inf, t, s_pw[0], s_pw[1], P, T, dT);
-        CellVal cv;
-        cv.m = init + perm * P + temp * T;
-        cv.T = T;
-        cv.dT = (P != 0.0) ? dT : -0.0;  // sign bit of dT carries "never exposed" (P = 0)
-        if constexpr (kFX) {
-          const double z = bn_fx * cv.m;
-          cv.Em = fast_exp((z > zmax_n) ? zmax_n : z, s_tab);  // NaN stays NaN
-        }
-        s_cv_n[k - cn0] = cv;
-      }
-    }
-    {
-      const double init = s_th[S_INIT], perm = s_th[S_PERM];
-      const double bs_fx = s_th[S_B], zmax_s = s_zmax[1];
-      for (int k = cs0 + tid; k < cs1 && tid < nwork; k += nwork) {
-        const uint32_t mt = s_cm_s[k - ks0];
-        const int t = mt & 63, li = (int)(mt >> 6) - i0;
-        const IndState<M> st = s_ind[li];
-        double P, U, dU;
-        traj_s<M>(st.inf, st.vacw & ~top_bit<M>(), (st.vacw & top_bit<M>()) != 0, t, s_pw[2], s_pw[3], P, U, dU);
-        CellVal cv;
-        cv.m = init + perm * P + U;
-        cv.T = U;
-        cv.dT = (P != 0.0) ? dU : -0.0;
-        if constexpr (kFX) {
-          const double z = bs_fx * cv.m;
-          cv.Em = fast_exp((z > zmax_s) ? zmax_s : z, s_tab);
-        }
-        s_cv_s[k - cs0] = cv;
-      }
-    }
-    __syncthreads();
-    PHASE(4);
-
-    // ---- phase 2: one thread per OD row; everything comes from shared memory, no divergence.
-    //      P (ever exposed) travels in the sign bit of dT ----
-    //      The loops exist twice: `direct` (a chain whose |b| x is too large to factor, or the
-    //      fallback kernel) evaluates one exponential per row, the common case only a product ----
-    auto rows = [&](auto direct_tag) {
-      constexpr bool kDirect = decltype(direct_tag)::value;
-      {
-        const double b = s_th[N_B], d = s_th[N_D];
-        const uint32_t* rcp = s_rc_n - qn0;
-        const double* odp = s_od_n - an0;
-        const CellVal* cvp = s_cv_n - cn0;
-#pragma unroll 2
-        for (int r = rn0 + tid; r < rn1 && tid < nwork; r += nwork) {
-          double sg, res, q, xm;
-          const uint32_t rc = rcp[r];
-          const CellVal cv = cvp[kFX ? (rc >> 5) : rc];
-          if constexpr (kFX) {
-            const double2 xe = s_xe[0][rc & 31];
-            xm = xe.x - cv.m;
-            if constexpr (kDirect) row_eval(xe.x, odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
-            else row_eval_E(xe.y * cv.Em, odp[r], d, sg, res, q);
-          } else {
-            row_eval((s_x_n - an0)[r], odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
-          }
-          acc[SN_0] = fma(res, res, acc[SN_0]);
-          acc[SN_1] = fma(res, sg, acc[SN_1]);
-          acc[SN_2] = fma(q, xm, acc[SN_2]);
-          acc[SN_QINIT] += q;
-          acc[SN_QPERM] += (__double2hiint(cv.dT) < 0) ? 0.0 : q;
-          acc[SN_QTEMP] = fma(q, cv.T, acc[SN_QTEMP]);
-          acc[SN_QRHO] = fma(q, cv.dT, acc[SN_QRHO]);
-        }
-      }
-      {
-        const double b = s_th[S_B], d = s_th[S_D];
-        const uint32_t* rcp = s_rc_s - qs0;
-        const double* odp = s_od_s - as0;
-        const CellVal* cvp = s_cv_s - cs0;
-#pragma unroll 2
-        for (int r = rs0 + tid; r < rs1 && tid < nwork; r += nwork) {
-          double sg, res, q, xm;
-          const uint32_t rc = rcp[r];
-          const CellVal cv = cvp[kFX ? (rc >> 5) : rc];
-          if constexpr (kFX) {
-            const double2 xe = s_xe[1][rc & 31];
-            xm = xe.x - cv.m;
-            if constexpr (kDirect) row_eval(xe.x, odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
-            else row_eval_E(xe.y * cv.Em, odp[r], d, sg, res, q);
-          } else {
-            row_eval((s_x_s - as0)[r], odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
-          }
-          acc[SS_0] = fma(res, res, acc[SS_0]);
-          acc[SS_1] = fma(res, sg, acc[SS_1]);
-          acc[SS_2] = fma(q, xm, acc[SS_2]);
-          acc[SS_QINIT] += q;
-          acc[SS_QPERM] += (__double2hiint(cv.dT) < 0) ? 0.0 : q;
-          acc[SS_QRHO] = fma(q, cv.dT, acc[SS_QRHO]);
-        }
-      }
-    };
-    if (!kFX || s_direct) rows(std::true_type{});
-    else rows(std::false_type{});
-
-    PHASE(5);
-    // ---- block reduction: butterfly inside a warp, shared memory across warps ----
-    {
-      const double tot = warp_reduce16(acc, lane);
-      if ((lane & 1) == 0) s_red[warp][warp_reduce16_index(lane)] = tot;
-    }
-    __syncthreads();
-    if (tid < kNSums) {
-      double v = 0.0;
-#pragma unroll
-      for (int wv = 0; wv < kSumsWarps; ++wv) v += s_red[wv][tid];
-      partial[((size_t)c * ntiles + tile) * kNSums + tid] = v;
-    }
-
-    PHASE(6);
-    // ---- last CTA of this chain: ordered reduction over tiles, then finalise.  One thread
-    //      releases the CTA's partials (barrier, then fence + ticket) and acquires the others'
-    //      (then barrier): the grid-sync idiom with ONE acq_rel atomic per CTA instead of a pair of
-    //      sequentially consistent fences around a relaxed one ----
-    __syncthreads();
-    if (tid == 0) {
-      unsigned prev;
-      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ticket + c) : "memory");
-      s_last = (prev == (unsigned)(ntiles - 1));
-    }
-    __syncthreads();
-    PHASE(7);
-    if (s_last) {
-      // the parameter-only part of the finaliser was parked in `aux` by the chain's first tile
-      if (fin.mode && tid < kAuxDoubles) {
-        const double v = __ldcg(aux + (size_t)c * kAuxDoubles + tid);
-        if (tid < 17 * 7) reinterpret_cast<double*>(s_pre)[tid] = v;
-        else if (tid < 17 * 7 + 6) reinterpret_cast<double*>(&s_lik)[tid - 17 * 7] = v;
-      }
-      const int k = tid & 15, g = tid >> 4;  // 16 groups of 16 values
-      double v = 0.0;
-      const double* src = partial + (size_t)c * ntiles * kNSums + k;
-      for (int tl = g; tl < ntiles; tl += 8 * (kSumsBlock / 16)) {  // 8 loads in flight, fixed order
-        double ld[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int tt = tl + u * (kSumsBlock / 16);
-          ld[u] = (tt < ntiles) ? __ldcg(src + (size_t)tt * kNSums) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v += ld[u];
-      }
-      s_fin[g][k] = v;
-      PHASE(9);
-      __syncthreads();
-      if (tid < kNSums) {
-        double tot = 0.0;
-#pragma unroll
-        for (int gg = 0; gg < kSumsBlock / 16; ++gg) tot += s_fin[gg][tid];
-        s_red[0][tid] = tot;
-        if (sums) sums[(size_t)c * kNSums + tid] = tot;
-      }
-      __syncthreads();
-      if (!TRAJ && xch.world > 1) {
-        __shared__ unsigned s_seq;
-        if (tid == 0) s_seq = xch.seq[c] + 1u;
-        __syncthreads();
-        const unsigned seq = s_seq, par = seq & 1u;
-        const size_t slot = ((size_t)par * xch.world + xch.rank) * xch.cmax + c;  // my slot in a peer's buffer
-        if (tid < kNSums * xch.world) {
-          const int r = tid >> 4, k = tid & 15;
-          xch.data[r][slot * kNSums + k] = s_red[0][k];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < xch.world) {
-          unsigned long long* f = xch.flag[tid] + slot;
-          asm volatile("st.release.sys.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)seq) : "memory");
-          // wait for peer `tid`'s contribution to arrive in MY buffer
-          const unsigned long long* mine = xch.flag[xch.rank] + ((size_t)par * xch.world + tid) * xch.cmax + c;
-          unsigned long long seen, t_start, t_now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-          do {
-            asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-          } while (seen != (unsigned long long)seq && t_now - t_start < kXchTimeoutNs);
-          if (seen != (unsigned long long)seq) *xch.err = 1u;  // watchdog: never hang the GPU
-        }
-        __syncthreads();
-        if (tid < kNSums) {
-          double tot = 0.0;
-          for (int r = 0; r < xch.world; ++r)
-            tot += __ldcg(xch.data[xch.rank] + (((size_t)par * xch.world + r) * xch.cmax + c) * kNSums + tid);
-          s_red[0][tid] = tot;
-          if (sums) sums[(size_t)c * kNSums + tid] = tot;
-        }
-        if (tid == 0) xch.seq[c] = seq;
-        __syncthreads();
-      }
-      PHASE(10);
-      if (tid == 0) ticket[c] = 0;  // re-arm for the next launch
-      if (warp == 0) {
-        if (fin.mode == 1) {
-          if (lane == 0)
-            finalize_loglik_post(s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
-                                 fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
-        } else if (fin.mode == 2 && !TRAJ) {
-          finalize_logp_post(lane, s_pre, s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
-                             fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
-        } else if (TRAJ && fin.mode == 2) {
-          // trajectory mode: finish this leapfrog step and either publish the next position or
-          // write the end point
-          finalize_logp_post(lane, s_pre, s_th, s_lik, s_red[0], fin.tot, &s_out[0], &s_out[1]);
-          __syncwarp();
-          const double e = traj.eps[c];
-          const double g = lane < 17 ? s_out[1 + lane] : 0.0;
-          const double ph = lane < 17 ? s_ph[lane] : 0.0;
-          if (step == nsteps - 1) {
-            if (lane < 17) {
-              traj.q[(size_t)c * 17 + lane] = s_q[lane];
-              traj.p[(size_t)c * 17 + lane] = fma(0.5 * e, g, ph);
-              traj.grad[(size_t)c * 17 + lane] = g;
-            }
-            if (lane == 0) traj.logp[c] = s_out[0];
-          } else {
-            const double ph2 = fma(e, g, ph);  // two half steps: end of this step + start of the next
-            double dot = 0.0;
-            for (int j = 0; j < 17; ++j) {
-              const double pj = __shfl_sync(0xffffffffu, ph2, j);
-              if (lane < 17) dot = fma(s_im[lane * 17 + j], pj, dot);
-            }
-            if (lane < 17) {
-              traj.state[(size_t)c * 34 + lane] = fma(e, dot, s_q[lane]);
-              traj.state[(size_t)c * 34 + 17 + lane] = ph2;
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-              const unsigned nxt = (unsigned)step + 1u;
-              asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(traj.gen + c), "r"(nxt) : "memory");
-            }
-          }
-        }
-      }
-    }
-    if (s_last) PHASE(11);
-    PHASE(8);
-    __syncthreads();  // shared memory is reused by the next step / chain
-    }  // step
-  }
-  SPAN_END();
-}
-
-// one warp per chain
-__global__ void k_finalize(const int C, const double* __restrict__ theta,
-                           const double* __restrict__ sums, const FinalizeCfg fin,
-                           const Priors* __restrict__ priors) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= C) return;
-  if (fin.mode == 1) {
-    if (lane == 0)
-      finalize_loglik(&theta[(size_t)c * 13], &sums[(size_t)c * kNSums], fin.tot, &fin.out_val[c],
-                      fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
-  } else {
-    __shared__ double s_th[4][16];  // 128 threads = 4 chains per CTA
-    __shared__ PriorPre s_pre[4][17];
-    const int wv = threadIdx.x >> 5;
-    if (lane < 13) s_th[wv][lane] = load_param(theta, 1, c, lane);
-    if (lane < 17) s_pre[wv][lane] = prior_pre(lane, theta[(size_t)c * 17 + lane], priors->v[lane]);
-    __syncwarp();
-    finalize_logp_post(lane, s_pre[wv], s_th[wv], lik_pre(s_th[wv][N_SIGMA], s_th[wv][S_SIGMA]),
-                       &sums[(size_t)c * kNSums], fin.tot, &fin.out_val[c],
-                       fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_gibbs
-// ------------------------------------------------------------------------------------------
-struct GibbsCfg {
-  uint64_t seed, sweep;
-  int mode;          // ABD_GIBBS_*; -1 = conditional log-odds only (no update, no RNG)
-  double transit_p;
-  double* out_i;     // [C][G][N] (mode -1)
-  double* out_w;     // [C][N]
-  unsigned long long* stats;  // [C][2] proposals, accepted flips (may be null)
-};
-
-// One OD row of one individual under a candidate state (value only, times -1/(2 sigma^2)).
-// N and S rows share one code path: lanes differ only in their per-lane parameters.
-struct RowPar {
-  double init, perm, tfac, b, d, nh;
-};
-template <typename M>
-__device__ __forceinline__ double gibbs_row(double x, double od, int t, bool is_s, M inf, M vac, int w,
-                                            const RowPar& rp, const double (*s_pw)[kMaxGaps],
-                                            const double* __restrict__ s_tab) {
-  const M lm = low_mask<M>(t);
-  M e = inf & lm, v = is_s ? (vac & lm) : (M)0;
-  const double P = (e | v) ? rp.perm : 0.0;
-  const double* pw = is_s ? (w ? s_pw[1] : s_pw[2]) : s_pw[0];  // s_pw[2] = all ones (rho_ind = 1)
-  double T = 0.0;
-  while (e) {
-    T += pw[t - ctz(e)];
-    e &= e - 1;
-  }
-  while (v) {
-    T += pw[t - ctz(v)];
-    v &= v - 1;
-  }
-  return rp.nh * row_resid2(x, od, fma(rp.tfac, T, rp.init + P), rp.b, rp.d, s_tab);
-}
-
-// Persistent warps: every warp repeatedly claims the next (chain, individual) from a global
-// counter.  Items are ordered chain-major and, inside a chain, by decreasing OD-row count
-// (longest job first), so the tail at the end of the launch is one short job.
-template <typename M>
-__global__ void __launch_bounds__(kGibbsWarps * 32, 3)
-k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
-        const double* __restrict__ theta, const int theta_is_q,
-        const double* __restrict__ p_arr, const double* __restrict__ pw_arr,
-        int8_t* __restrict__ i_raw, int8_t* __restrict__ waner, unsigned* __restrict__ queue,
-        const GibbsCfg cfg) {
-  constexpr int NSLOT = sizeof(M) / 4;  // proposals owned per lane
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int G = dc.G, N = dc.N;
-
-  __shared__ double s_tab[kExpTab];
-  __shared__ double s_th_all[kGibbsWarps][20];            // theta13, -1/(2 sigma^2) x 2, logit p / p_w, p / p_w
-  __shared__ double s_pw_all[kGibbsWarps][3][kMaxGaps];   // rho_n^k, rho_s^k, ones
-  __shared__ unsigned char s_ord[kGibbsWarps][kMaxGaps];
-  double* s_th = s_th_all[warp];
-  const double (*s_pw)[kMaxGaps] = s_pw_all[warp];
-
-  fill_exp_table(s_tab, tid, kGibbsWarps * 32);
-  for (int k = lane; k < kMaxGaps; k += 32) s_pw_all[warp][2][k] = 1.0;
-  __syncthreads();
-
-  const int nprop = G + 1;  // proposal j < G flips i_raw[j, n]; j == G flips waner[n]
-  const unsigned n_items = (unsigned)C * (unsigned)N;
-  unsigned n_prop = 0, n_acc = 0;
-  int cur_c = -1;
-
-  while (true) {
-    unsigned item = 0;
-    if (lane == 0) item = atomicAdd(queue, 1u);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= n_items) break;
-    const int c = (int)(item / (unsigned)N);
-    const int n = order[item - (unsigned)c * (unsigned)N];
-
-    if (c != cur_c) {  // (re)load this chain's parameters into the warp's shared-memory slot
-      if (cur_c >= 0 && cfg.stats && lane == 0) {
-        atomicAdd(&cfg.stats[(size_t)cur_c * 2], (unsigned long long)n_prop);
-        atomicAdd(&cfg.stats[(size_t)cur_c * 2 + 1], (unsigned long long)n_acc);
-      }
-      n_prop = n_acc = 0;
-      cur_c = c;
-      __syncwarp();
-      fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw_all[warp][0], nullptr);
-      fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw_all[warp][1], nullptr);
-      if (lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
-      if (lane == 13 || lane == 14) {
-        const double sg = load_param(theta, theta_is_q, c, lane == 13 ? N_SIGMA : S_SIGMA);
-        s_th[lane] = -0.5 / (sg * sg);
-      }
-      if (lane == 15 || lane == 16) {
-        const int which = lane - 15;
-        double lo;
-        if (theta_is_q) {  // logit of a logodds-transformed value is the value itself
-          lo = theta[(size_t)c * 17 + (which ? kQ_PW : kQ_P)];
-        } else {
-          const double p = which ? pw_arr[c] : p_arr[c];
-          lo = log(p) - log1p(-p);
-        }
-        s_th[lane] = lo;
-        s_th[lane + 2] = 1.0 / (1.0 + exp(-lo));
-      }
-      __syncwarp();
-    }
-
-    // ---- this individual's column of i_raw (lane t reads gap t), waner, masks, rows ----
-    int8_t* col = i_raw + (size_t)c * G * N + n;
-    M raw = 0;
-#pragma unroll
-    for (int sl = 0; sl < NSLOT; ++sl) {
-      const int t = lane + 32 * sl;
-      const int8_t b = (t < G) ? col[(size_t)t * N] : (int8_t)0;
-      raw |= (M)__ballot_sync(0xffffffffu, b != 0) << (32 * sl);
-    }
-    const M raw_in = raw;
-    int w = waner[(size_t)c * N + n] != 0;
-    const int w_in = w;
-    const M pcr = reinterpret_cast<const M*>(dc.pcr)[n];
-    const M vac = reinterpret_cast<const M*>(dc.vac)[n];
-    const int rn0 = dc.rp[0][n], cnt_n = dc.rp[0][n + 1] - rn0;
-    const int rs0 = dc.rp[1][n], cnt_s = dc.rp[1][n + 1] - rs0;
-    const int nrows = cnt_n + cnt_s;
-
-    // rows of this individual, one per lane (N rows first, then S rows); kept in registers
-    auto load_row = [&](int l, double& x, double& od, int& t, bool& is_s) {
-      is_s = l >= cnt_n;
-      const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
-      if (l < nrows) {
-        x = (is_s ? dc.x[1] : dc.x[0])[r];
-        od = (is_s ? dc.od[1] : dc.od[0])[r];
-        t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
-      } else {
-        x = 0.0;
-        od = 0.0;
-        t = -1;
-      }
-    };
-    auto row_par = [&](bool is_s) {
-      RowPar rp;
-      rp.init = s_th[is_s ? S_INIT : N_INIT];
-      rp.perm = s_th[is_s ? S_PERM : N_PERM];
-      rp.tfac = is_s ? 1.0 : s_th[N_TEMP];
-      rp.b = s_th[is_s ? S_B : N_B];
-      rp.d = s_th[is_s ? S_D : N_D];
-      rp.nh = s_th[is_s ? 14 : 13];
-      return rp;
-    };
-    double x0, od0;
-    int t0;
-    bool s0;
-    load_row(lane, x0, od0, t0, s0);
-    const RowPar rp0 = row_par(s0);
-    // latest sampled gap of either antigen / of the S antigen (rows are sorted by gap)
-    int t_last = t0, t_last_s = s0 ? t0 : -1;
-    for (int l = lane + 32; l < nrows; l += 32) {
-      const bool is_s = l >= cnt_n;
-      const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
-      const int t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
-      t_last = max(t_last, t);
-      if (is_s) t_last_s = max(t_last_s, t);
-    }
-    t_last = __reduce_max_sync(0xffffffffu, t_last);
-    t_last_s = __reduce_max_sync(0xffffffffu, t_last_s);
-
-    auto indiv_ll = [&](M inf_, int w_) {
-      double a = (t0 >= 0) ? gibbs_row<M>(x0, od0, t0, s0, inf_, vac, w_, rp0, s_pw, s_tab) : 0.0;
-      for (int l = lane + 32; l < nrows; l += 32) {  // individuals with more than 32 rows
-        double x, od;
-        int t;
-        bool is_s;
-        load_row(l, x, od, t, is_s);
-        a += gibbs_row<M>(x, od, t, is_s, inf_, vac, w_, row_par(is_s), s_pw, s_tab);
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-      return a;
-    };
-
-    M inf = constrain<M>(raw, pcr, dc.ch);
-    double ll = indiv_ll(inf, w);
-
-    // ---- lane-owned proposals: Philox key (visiting order), transit / accept uniforms ----
-    M act = 0;              // steps that are not skipped
-    int jp_step[NSLOT];     // lane k (+32 sl): proposal visited at step k
-    double acc_u[NSLOT];    // log(u) (Metropolis) or u (heat bath) of the proposals this lane owns
-#pragma unroll
-    for (int sl = 0; sl < NSLOT; ++sl) acc_u[sl] = 0.0;
-    if (cfg.mode >= 0) {
-      uint32_t key[NSLOT];
-      int rank[NSLOT];
-      bool skip[NSLOT];
-#pragma unroll
-      for (int sl = 0; sl < NSLOT; ++sl) {
-        const uint4 r = philox4x32_10(
-            make_uint4((uint32_t)(lane + 32 * sl), (uint32_t)n + dc.ind_offset, (uint32_t)c, (uint32_t)cfg.sweep),
-            make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32) ^ (uint32_t)(cfg.sweep >> 32)));
-        key[sl] = r.x;
-        const double u_t = u01(r.y), u_a = u01(r.z);
-        skip[sl] = (cfg.mode == ABD_GIBBS_METROPOLIS) && !(u_t <= cfg.transit_p);
-        acc_u[sl] = (cfg.mode == ABD_GIBBS_METROPOLIS) ? log(u_a) : u_a;
-        rank[sl] = 0;
-      }
-      for (int jj = 0; jj < nprop; ++jj) {
-        const uint32_t kj = __shfl_sync(0xffffffffu, key[jj >> 5], jj & 31);
-#pragma unroll
-        for (int sl = 0; sl < NSLOT; ++sl) {
-          const int me = lane + 32 * sl;
-          rank[sl] += (kj < key[sl]) || (kj == key[sl] && jj < me);
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int sl = 0; sl < NSLOT; ++sl) {
-        const int me = lane + 32 * sl;
-        if (me < nprop) s_ord[warp][rank[sl]] = (unsigned char)me;
-      }
-      __syncwarp();
-      // the proposal visited at the step this lane stands for; skipped steps drop out of `act`
-#pragma unroll
-      for (int sl = 0; sl < NSLOT; ++sl) {
-        const int step = lane + 32 * sl;
-        const int jp = (step < nprop) ? (int)s_ord[warp][step] : 0;
-        jp_step[sl] = jp;
-        bool sk = __shfl_sync(0xffffffffu, (int)skip[0], jp & 31);
-        if (NSLOT > 1) {
-          const bool sk1 = __shfl_sync(0xffffffffu, (int)skip[NSLOT - 1], jp & 31);
-          if (jp >> 5) sk = sk1;
-        }
-        act |= (M)__ballot_sync(0xffffffffu, step < nprop && !sk) << (32 * sl);
-      }
-    } else {
-#pragma unroll
-      for (int sl = 0; sl < NSLOT; ++sl) jp_step[sl] = lane + 32 * sl;
-      act = low_mask<M>(G);  // every proposal 0..G, in order
-    }
-
-    // Everything about a proposal that depends only on the current state lives in the lane that
-    // owns it and is refreshed (lane-parallel) after an accepted flip of an infection bit:
-    //   inf2  constrained infections if the flip were accepted
-    //   code  2: the data term changes, the individual's likelihood must be evaluated;
-    //         1 / 0: it cannot change (the constrained infections differ only after the last
-    //         sampled gap, or -- waner bit -- there is no S sample after the first exposure), so
-    //         logp(prop) - logp(cur) = +-logit(p) and the flip decision (1 / 0) is already known
-    M inf2_own[NSLOT];
-    int code_own[NSLOT];
-    auto refresh = [&]() {
-#pragma unroll
-      for (int sl = 0; sl < NSLOT; ++sl) {
-        const int me = lane + 32 * sl;
-        const bool is_w = (me == G);
-        const M i2 = (me < G) ? constrain<M>(raw ^ ((M)1 << me), pcr, dc.ch) : inf;
-        inf2_own[sl] = i2;
-        const int cur_bit = is_w ? w : (int)((raw >> (me < G ? me : 0)) & 1);
-        bool affected;
-        if (is_w) {
-          const M ex = inf | vac;
-          affected = ex != 0 && ctz(ex | top_bit<M>()) < t_last_s;
-        } else {
-          const M diff = inf ^ i2;
-          affected = diff != 0 && ctz(diff | top_bit<M>()) <= t_last;
-        }
-        bool flip0;
-        if (cfg.mode == ABD_GIBBS_METROPOLIS) {
-          const double lo = s_th[is_w ? 16 : 15];
-          const double delta = cur_bit ? -lo : lo;
-          flip0 = isfinite(delta) && (acc_u[sl] < delta);
-        } else {
-          flip0 = ((acc_u[sl] <= s_th[is_w ? 18 : 17]) ? 1 : 0) != cur_bit;  // s_th[17 / 18] = sigmoid(logit)
-        }
-        code_own[sl] = affected ? 2 : (flip0 ? 1 : 0);
-      }
-    };
-    refresh();
-
-    while (act) {
-      const int step = ctz(act);
-      act &= act - 1;
-      int jp = jp_step[0];
-      if (NSLOT > 1 && (step >> 5)) jp = jp_step[NSLOT - 1];
-      jp = __shfl_sync(0xffffffffu, jp, step & 31);
-      const int owner = jp & 31;
-      const bool hi = NSLOT > 1 && (jp >> 5);
-      const int code = __shfl_sync(0xffffffffu, hi ? code_own[NSLOT - 1] : code_own[0], owner);
-      const bool is_w = (jp == G);
-      if (cfg.mode >= 0) {
-        ++n_prop;
-        if (code == 0) continue;
-      }
-      const M inf2 = __shfl_sync(0xffffffffu, hi ? inf2_own[NSLOT - 1] : inf2_own[0], owner);
-      const int w2 = is_w ? (w ^ 1) : w;
-      double ll2 = ll;
-      bool flip = true;
-      if (code == 2 || cfg.mode < 0) {
-        const int cur_bit = is_w ? w : (int)((raw >> jp) & 1);
-        if (code == 2) ll2 = indiv_ll(inf2, w2);
-        const double lo = s_th[is_w ? 16 : 15];
-        const double d10 = cur_bit ? (ll - ll2 + lo) : (ll2 - ll + lo);  // log-odds of 1 versus 0
-        if (cfg.mode < 0) {
-          if (lane == 0) {
-            if (is_w) cfg.out_w[(size_t)c * N + n] = d10;
-            else cfg.out_i[((size_t)c * G + jp) * N + n] = d10;
-          }
-          continue;
-        }
-        const double au = __shfl_sync(0xffffffffu, hi ? acc_u[NSLOT - 1] : acc_u[0], owner);
-        if (cfg.mode == ABD_GIBBS_METROPOLIS) {
-          const double delta = cur_bit ? -d10 : d10;  // logp(proposed) - logp(current)
-          flip = isfinite(delta) && (au < delta);
-        } else {
-          const double p1 = 1.0 / (1.0 + exp(-d10));
-          flip = ((au <= p1) ? 1 : 0) != cur_bit;
-        }
-      }
-      if (flip) {
-        ++n_acc;
-        ll = ll2;
-        if (is_w) {
-          w = w2;
-        } else {
-          raw ^= (M)1 << jp;
-          inf = inf2;
-          refresh();
-        }
-      }
-    }
-
-    if (cfg.mode >= 0) {  // write back only what changed
-      const M changed = raw ^ raw_in;
-#pragma unroll
-      for (int sl = 0; sl < NSLOT; ++sl) {
-        const int t = lane + 32 * sl;
-        if (t < G && ((changed >> t) & 1)) col[(size_t)t * N] = (int8_t)((raw >> t) & 1);
-      }
-      if (lane == 0 && w != w_in) waner[(size_t)c * N + n] = (int8_t)w;
-    }
-  }
-  if (cfg.mode >= 0 && cfg.stats && lane == 0 && cur_c >= 0) {
-    atomicAdd(&cfg.stats[(size_t)cur_c * 2], (unsigned long long)n_prop);
-    atomicAdd(&cfg.stats[(size_t)cur_c * 2 + 1], (unsigned long long)n_acc);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_hmc_begin / k_hmc_end -- the two ends of an HMC transition, one warp per chain
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_hmc_begin(const int C, const double* __restrict__ q, const double* __restrict__ grad, const double* __restrict__ logp,
-            const double* __restrict__ linv_t, const uint64_t seed, const uint64_t iter, double* __restrict__ qw,
-            double* __restrict__ pw, double* __restrict__ gw, double* __restrict__ h0) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= C) return;
-  double z = 0.0;
-  if (lane < 17) {  // Box-Muller on two of the four Philox words
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)lane, (uint32_t)c, (uint32_t)iter, 0x484d4331u),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iter >> 32)));
-    z = sqrt(-2.0 * log(u01(r.x))) * cospi(2.0 * u01(r.y));
-  }
-  double p = 0.0, kin = z * z;
-  for (int j = 0; j < 17; ++j) {
-    const double zj = __shfl_sync(0xffffffffu, z, j);
-    if (lane < 17) p = fma(linv_t[lane * 17 + j], zj, p);
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) kin += __shfl_xor_sync(0xffffffffu, kin, off);
-  if (lane < 17) {
-    qw[(size_t)c * 17 + lane] = q[(size_t)c * 17 + lane];
-    gw[(size_t)c * 17 + lane] = grad[(size_t)c * 17 + lane];
-    pw[(size_t)c * 17 + lane] = p;
-  }
-  if (lane == 0) h0[c] = -logp[c] + 0.5 * kin;
-}
-
-__global__ void __launch_bounds__(128)
-k_hmc_end(const int C, double* __restrict__ q, double* __restrict__ grad, double* __restrict__ logp,
-          const double* __restrict__ qw, const double* __restrict__ pw, const double* __restrict__ gw,
-          const double* __restrict__ lpw, const double* __restrict__ inv_mass, const double* __restrict__ h0,
-          const uint64_t seed, const uint64_t iter, double* __restrict__ accept_out, double* __restrict__ da,
-          double* __restrict__ eps, const int adapt, const double target) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= C) return;
-  const double p = lane < 17 ? pw[(size_t)c * 17 + lane] : 0.0;
-  double v = 0.0;
-  for (int j = 0; j < 17; ++j) {
-    const double pj = __shfl_sync(0xffffffffu, p, j);
-    if (lane < 17) v = fma(inv_mass[lane * 17 + j], pj, v);
-  }
-  double kin = p * v;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) kin += __shfl_xor_sync(0xffffffffu, kin, off);
-  const double h1 = -lpw[c] + 0.5 * kin;
-  double dh = h0[c] - h1;
-  if (!isfinite(dh)) dh = -INFINITY;
-  const double acc = exp(fmin(dh, 0.0));
-  const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)c, (uint32_t)iter, 0x41434331u),
-                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iter >> 32)));
-  const bool take = (u01(r.x) - 2.3283064365386963e-10) < acc;  // u in [0, 1)
-  if (take && lane < 17) {
-    q[(size_t)c * 17 + lane] = qw[(size_t)c * 17 + lane];
-    grad[(size_t)c * 17 + lane] = gw[(size_t)c * 17 + lane];
-  }
-  if (lane == 0) {
-    if (take) logp[c] = lpw[c];
-    accept_out[c] = acc;
-    if (adapt) {  // Nesterov dual averaging of log(step size): gamma 0.05, t0 10, kappa 0.75
-      double* s = da + (size_t)c * 4;
-      const double t = s[3] + 1.0, eta = 1.0 / (t + 10.0);
-      const double hbar = (1.0 - eta) * s[1] + eta * (target - acc);
-      const double log_eps = s[0] - sqrt(t) / 0.05 * hbar;
-      const double w = pow(t, -0.75);
-      s[1] = hbar;
-      s[2] = w * log_eps + (1.0 - w) * s[2];
-      s[3] = t;
-      eps[c] = exp(log_eps);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// k_determ
-// ------------------------------------------------------------------------------------------
-template <typename M>
-__global__ void __launch_bounds__(128)
-k_determ(const DevCohort dc, const double* __restrict__ theta13, const int8_t* __restrict__ i_raw,
-         const int8_t* __restrict__ waner, int8_t* __restrict__ out_i, double* __restrict__ out_mu_n,
-         double* __restrict__ out_mu_s) {
-  const int c = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int G = dc.G, N = dc.N;
-  __shared__ double s_th[16];
-  if (threadIdx.x < 13) s_th[threadIdx.x] = theta13[(size_t)c * 13 + threadIdx.x];
-  __syncthreads();
-  if (n >= N) return;
-  M raw = 0;
-  const int8_t* col = i_raw + (size_t)c * G * N + n;
-  for (int t = 0; t < G; ++t) raw |= (M)(col[(size_t)t * N] != 0) << t;
-  const int w = waner[(size_t)c * N + n] != 0;
-  const M inf = constrain<M>(raw, reinterpret_cast<const M*>(dc.pcr)[n], dc.ch);
-  const M vac = reinterpret_cast<const M*>(dc.vac)[n];
-  const double rho_n = s_th[N_RHO], rho_s = w ? s_th[S_RHO] : 1.0;
-  double T = 0.0, U = 0.0, Pn = 0.0, Ps = 0.0;
-  for (int t = 0; t < G; ++t) {  // the recurrence of abd.py:277-293
-    const int it = (int)((inf >> t) & 1), vt = (int)((vac >> t) & 1);
-    T = T * rho_n + it;
-    U = U * rho_s + (it + vt);
-    if (it) Pn = 1.0;
-    if (it | vt) Ps = 1.0;
-    const size_t o = ((size_t)c * G + t) * N + n;
-    if (out_i) out_i[o] = (int8_t)it;
-    if (out_mu_n) out_mu_n[o] = s_th[N_PERM] * Pn + s_th[N_TEMP] * T + s_th[N_INIT];
-    if (out_mu_s) out_mu_s[o] = s_th[S_PERM] * Ps + U + s_th[S_INIT];
-  }
-}
-
-// pinned host memory -> device memory by the SMs (see copy_state_h2d); n16 16-byte words + rem bytes
-__global__ void __launch_bounds__(256)
-k_pull(const uint4* __restrict__ src, uint4* __restrict__ dst, const size_t n16, const size_t rem) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < n16; i += 4 * stride) {  // four independent loads in flight per thread
-    const uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
-    dst[i] = a, dst[i + stride] = b, dst[i + 2 * stride] = c, dst[i + 3 * stride] = d;
-  }
-  for (; i < n16; i += stride) dst[i] = src[i];
-  if (blockIdx.x == 0 && threadIdx.x < rem)
-    reinterpret_cast<uint8_t*>(dst + n16)[threadIdx.x] = reinterpret_cast<const uint8_t*>(src + n16)[threadIdx.x];
-}
-
-__global__ void k_debug_fast_math(const long long n, const double* __restrict__ z, double* __restrict__ out_exp,
-                                  double* __restrict__ out_rcp) {
-  __shared__ double s_tab[kExpTab];
-  fill_exp_table(s_tab, threadIdx.x, blockDim.x);
-  __syncthreads();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    out_exp[i] = fast_exp(z[i], s_tab);
-    out_rcp[i] = fast_rcp(1.0 + fabs(z[i]));
-  }
-}
-
 }  // namespace
+
+#include "abd_kernels_common.cuh"
+#include "k_sums.cuh"
+#include "k_gibbs.cuh"
+#include "k_misc.cuh"
+
 
 // ------------------------------------------------------------------------------------------
 // host side
