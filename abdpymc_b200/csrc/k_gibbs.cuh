@@ -45,8 +45,11 @@ __device__ __forceinline__ double gibbs_row(double x, double od, int t, bool is_
 // Persistent warps: every warp repeatedly claims the next (chain, individual) from a global
 // counter.  Items are ordered chain-major and, inside a chain, by decreasing OD-row count
 // (longest job first), so the tail at the end of the launch is one short job.
+// 4 CTAs/SM (64 registers, a few spills) is 3 % faster than 3 x 80 registers; 5 is slower.  Also
+// measured and dropped: patching each row's decaying response for a candidate instead of summing
+// it again (no gain: the extra live registers cost what the shorter loops save).
 template <typename M>
-__global__ void __launch_bounds__(kGibbsWarps * 32, 3)
+__global__ void __launch_bounds__(kGibbsWarps * 32, 4)
 k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
         const double* __restrict__ theta, const int theta_is_q,
         const double* __restrict__ p_arr, const double* __restrict__ pw_arr,

@@ -124,7 +124,9 @@ class AbdTarget:
 class SamplerConfig:
     tune: int = 500
     draws: int = 500
-    n_leapfrog: int = 12           # mean trajectory length in steps (jittered uniformly in [0.6, 1.4] x)
+    n_leapfrog: int = 5            # mean trajectory length in steps (tools/sampler_sweep.py: on the 10k cohort 4-5 steps
+                                   # give 2-3 x the ESS/s of 12: the Gibbs <-> HMC alternation rate is what mixes)
+    jitter: tuple = (0.6, 1.4)     # each trajectory: n_leapfrog x Uniform(jitter)
     target_accept: float = 0.8
     init_step: float = 0.05
     record_deterministics_every: int = 0   # 0 = never; k = accumulate means every k-th draw
@@ -215,7 +217,7 @@ def _sample_fused(target, q0, cfg, progress):
     means, n_means, n_grad = {}, 0, 0
     t0 = time.perf_counter()
     for it in range(total):
-        L = max(1, int(round(cfg.n_leapfrog * (0.6 + 0.8 * rng.random()))))
+        L = max(1, int(round(cfg.n_leapfrog * (cfg.jitter[0] + (cfg.jitter[1] - cfg.jitter[0]) * rng.random()))))
         target.hmc_begin(q, grad, logp, linv_t, it, qw, pw, gw, h0)
         target.leapfrog_inplace(qw, pw, gw, lpw, eps, inv_mass, L)
         target.hmc_end(q, grad, logp, qw, pw, gw, lpw, inv_mass, h0, it, acc, da, eps, it < cfg.tune, cfg.target_accept)
@@ -293,7 +295,7 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
         z = torch.randn(C, D, dtype=torch.float64, device=dev, generator=gen)
         p = torch.linalg.solve_triangular(chol.T, z.T, upper=True).T
         h0 = -logp + 0.5 * (z * z).sum(dim=1)
-        jitter = 0.6 + 0.8 * torch.rand((), device=dev, generator=gen).item()
+        jitter = cfg.jitter[0] + (cfg.jitter[1] - cfg.jitter[0]) * torch.rand((), device=dev, generator=gen).item()
         L = max(1, int(round(cfg.n_leapfrog * jitter)))
         if use_traj:
             try:
