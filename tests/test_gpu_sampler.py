@@ -66,3 +66,72 @@ def test_cli_without_pymc_writes_posterior(gpu, tmp_path):
     assert z["mean_i"].shape == (26, 10) and z["mean_ab_n_mu"].shape == (26, 10)  # dims ("gap", "ind")
     assert z["last_i_raw"].shape == (2, 26, 10)
     assert np.all((z["ab_n_rho"] > 0) & (z["ab_n_rho"] < 1)) and np.all(z["it_n_sigma"] > 0)
+
+
+def test_hmc_transition_kernels_against_host_formulas(gpu):
+    """abd_hmc_begin_dev / abd_hmc_end_dev (momentum refresh, energy, accept, dual averaging) against
+    the same formulas in torch / the sampler's host-side _DualAveraging."""
+    import torch
+
+    from abdpymc_b200.cohort import CohortArrays
+    from abdpymc_b200.engine import AbdEngine
+    from abdpymc_b200.sampler import _DualAveraging
+
+    C, D = 4096, 17
+    f64 = dict(dtype=torch.float64, device=gpu)
+    g = torch.Generator(device=gpu).manual_seed(0)
+    a = torch.randn(D, D, generator=g, **f64)
+    inv_mass = (a @ a.T / D + torch.eye(D, **f64)).contiguous()          # Sigma
+    chol = torch.linalg.cholesky(inv_mass)
+    linv_t = torch.linalg.solve_triangular(chol.T.contiguous(), torch.eye(D, **f64), upper=True).contiguous()
+    q, grad = torch.randn(C, D, generator=g, **f64), torch.randn(C, D, generator=g, **f64)
+    logp = torch.randn(C, generator=g, **f64) * 10
+    qw, pw, gw, h0 = torch.empty(C, D, **f64), torch.empty(C, D, **f64), torch.empty(C, D, **f64), torch.empty(C, **f64)
+    with AbdEngine(CohortArrays.load("test_cohort"), splits=(14, 20)) as eng:
+        eng.hmc_begin_dev(C, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), linv_t.data_ptr(), 7, 3, qw.data_ptr(), pw.data_ptr(),
+                          gw.data_ptr(), h0.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(qw, q) and torch.equal(gw, grad)
+        kin = 0.5 * ((pw @ inv_mass) * pw).sum(dim=1)                    # p' Sigma p / 2 == z.z / 2
+        assert torch.allclose(h0, -logp + kin, rtol=1e-12, atol=1e-12)
+        # p ~ N(0, Sigma^-1): sample covariance over 4096 chains
+        cov = (pw.T @ pw) / C
+        want = torch.linalg.inv(inv_mass)
+        assert (cov - want).abs().max() < 6 * want.diagonal().max() / C**0.5
+        assert pw.mean(dim=0).abs().max() < 5 * want.diagonal().max().sqrt() / C**0.5
+        # a different iteration / seed gives different momenta, the same one the same
+        pw2 = torch.empty_like(pw)
+        eng.hmc_begin_dev(C, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), linv_t.data_ptr(), 7, 4, qw.data_ptr(), pw2.data_ptr(),
+                          gw.data_ptr(), h0.data_ptr())
+        torch.cuda.synchronize()
+        assert not torch.equal(pw, pw2)
+
+        # end of the transition: proposals with a known energy change
+        dh = torch.linspace(-3, 3, C, **f64)                              # h0 - h1
+        dh[::97] = float("nan")
+        q_new, g_new = q + 1.0, grad - 1.0
+        lpw = -(h0 - dh) + kin_of(pw2, inv_mass)                          # so that h1 = h0 - dh
+        acc, eps = torch.empty(C, **f64), torch.full((C,), 0.1, **f64)
+        da = torch.zeros(C, 4, **f64)
+        da[:, 0] = torch.log(10 * eps)
+        ref = _DualAveraging(eps.clone(), 0.8, gpu)
+        qc, gc, lc = q.clone(), grad.clone(), logp.clone()
+        for it in range(3):
+            eng.hmc_end_dev(C, qc.data_ptr(), gc.data_ptr(), lc.data_ptr(), q_new.data_ptr(), pw2.data_ptr(), g_new.data_ptr(),
+                            lpw.data_ptr(), inv_mass.data_ptr(), h0.data_ptr(), 7, 10 + it, acc.data_ptr(), da.data_ptr(),
+                            eps.data_ptr(), 1, 0.8)
+            torch.cuda.synchronize()
+            want_acc = torch.exp(torch.clamp(torch.nan_to_num(dh, nan=-float("inf")), max=0.0))
+            assert torch.allclose(acc, want_acc, rtol=1e-10, atol=1e-300)
+            assert torch.allclose(eps, ref.update(want_acc), rtol=1e-12)
+        assert torch.allclose(torch.exp(da[:, 2]), ref.final(), rtol=1e-12)
+        taken = (qc == q_new).all(dim=1)
+        assert torch.equal(taken, (gc == g_new).all(dim=1)) and torch.equal(lc[taken], lpw[taken])
+        assert not taken[::97].any()                                      # non-finite energy: rejected
+        assert taken[dh >= 0].all()                                       # never reject a downhill move
+        frac = taken[(dh < 0) & torch.isfinite(dh)].double().mean().item()
+        assert 0.50 < frac < 0.62                                         # E[1 - (1 - e^dh)^3] over dh in (-3, 0) = 0.562
+
+
+def kin_of(p, inv_mass):
+    return 0.5 * ((p @ inv_mass) * p).sum(dim=1)
