@@ -285,7 +285,8 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     //      the warp is one coalesced 32-byte segment) and applies the infection constraints;
     //      warps 4-7: parameters, power tables, dilution table.  (Fetching the block as aligned
     //      32-bit words + shared-memory atomics / ballots was measured: slower, the transposition
-    //      costs more than the byte loads save.) ----
+    //      costs more than the byte loads save; two lanes per individual (even / odd gaps, one
+    //      shuffle) was measured too: 12.2 -> 13.4 us per launch.) ----
     if (tid < kTileMaxInds) {
       if (tid < ni && step == 0) {
         const int8_t* col = i_raw + (size_t)c * G * N + i0 + tid;
