@@ -11,7 +11,8 @@ Same names, argument meaning and error behaviour as the reference for this path:
   ``main()``          ``abdpymc-infer`` with the reference's flags (abd.py:885-924).
 
 PyMC / PyTensor / ArviZ are import-guarded: they are not installable in the offline build image,
-so everything PyMC-facing here is written against the PyMC 5 API and exercised only where PyMC
+so everything PyMC-facing here is written against the PyMC 5 API, executed against a protocol
+stand-in in tests/test_gpu_pymc_glue.py (tests/fake_pymc.py) and against PyMC itself where it
 exists (tests/test_pymc_parity.py, skipped otherwise).  Without PyMC, ``main()`` drives the
 built-in sampler (abdpymc_b200.sampler) on the same model terms and writes the same variable
 names to an .npz (or NetCDF when ArviZ is importable).  There is no CPU fallback for the
@@ -215,6 +216,7 @@ def point_to_q17(point) -> np.ndarray:
 
 if HAVE_PYMC:  # pragma: no cover
     from pymc.step_methods.arraystep import BlockedStep
+    from pymc.step_methods.compound import Competence
 
     class GpuBinaryGibbs(BlockedStep):
         """Drop-in for BinaryGibbsMetropolis over ``i_raw`` and ``ab_s_waner``:
@@ -254,8 +256,6 @@ if HAVE_PYMC:  # pragma: no cover
 
         @staticmethod
         def competence(var, has_grad):
-            from pymc.step_methods.compound import Competence
-
             return Competence.COMPATIBLE if var.name in ("i_raw", "ab_s_waner") else Competence.INCOMPATIBLE
 
 
