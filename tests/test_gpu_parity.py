@@ -605,3 +605,22 @@ def test_persistent_leapfrog_matches_stepwise(Engine, n_inds, C, L):
             np.testing.assert_allclose(tp.cpu().numpy(), pr, rtol=1e-9, atol=1e-7)
             np.testing.assert_allclose(tl.cpu().numpy(), lpr, rtol=1e-11)
             assert grad_ok(tg.cpu().numpy(), gr, 1e-9)
+
+
+def test_randomised_cohorts_against_the_oracle():
+    """tools/fuzz_parity.py as a test: 40 random small cohorts (G in 2..63, ragged / empty rows,
+    0-2 random splits, PCR+ ignored or not, integer and continuous dilutions), logp + gradient,
+    Deterministics, conditional log-odds and one bit-exact Gibbs sweep each."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    root = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, str(root / "tools" / "fuzz_parity.py"), "40", "7"], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
+    assert "40 of 40" in res.stdout
