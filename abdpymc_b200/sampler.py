@@ -228,12 +228,15 @@ def _sample_fused(target, q0, cfg, progress):
             if ends and win_start <= it:
                 win_draws.append(q.clone())
             if ends and it + 1 == ends[0]:
-                x = torch.stack(win_draws).reshape(-1, D)
+                # 17 x 17 linear algebra on the host (a handful of times per run; the first cuSOLVER
+                # call alone would cost more than all of them)
+                x = torch.stack(win_draws).reshape(-1, D).cpu().numpy()
                 n = x.shape[0]
-                cov = torch.cov(x.T)
-                inv_mass = ((n / (n + 5.0)) * cov + 1e-3 * (5.0 / (n + 5.0)) * torch.eye(D, **f64)).contiguous()
-                chol = torch.linalg.cholesky(inv_mass)  # Stan's shrinkage keeps it positive definite
-                linv_t = torch.linalg.solve_triangular(chol.T.contiguous(), torch.eye(D, **f64), upper=True).contiguous()
+                cov = np.cov(x.T)
+                im = (n / (n + 5.0)) * cov + 1e-3 * (5.0 / (n + 5.0)) * np.eye(D)  # Stan's shrinkage keeps it positive definite
+                chol = np.linalg.cholesky(im)
+                inv_mass = torch.from_numpy(np.ascontiguousarray(im)).to(dev)
+                linv_t = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(chol.T))).to(dev)
                 win_draws, win_start = [], ends.pop(0)
                 # restart step-size adaptation under the new metric from the averaged step
                 eps = torch.exp(da[:, 2]).contiguous()
