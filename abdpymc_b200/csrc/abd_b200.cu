@@ -338,6 +338,7 @@ int ensure_chains(abd_handle* h, int C) {
   if ((rc = dev_alloc(h, &h->d_gen, (size_t)C + 1, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_stats, (size_t)C * 2, false))) return rc;
   CU(cudaMemset(h->d_ticket, 0, (size_t)C * sizeof(unsigned)));
+  CU(cudaMemset(h->d_gen, 0, ((size_t)C + 1) * sizeof(unsigned)));
   CU(cudaMallocHost((void**)&h->h_pin, (size_t)C * 40 * sizeof(double)));
   h->h_pin_dev = nullptr;
   {
@@ -418,15 +419,21 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
   cudaLaunchAttribute attr[1];
   const TileDesc* tiles = reinterpret_cast<const TileDesc*>(tl.d_tiles);
   const Priors* pri = h->d_priors;
-  if (tj) {  // CTAs wait on one another: they must all be resident
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sums<M, XT, true>, kSumsBlock, tl.smem));
-    if ((long)grid.x * grid.y > (long)occ * h->n_sms)
-      return fail(ABD_ERR_INVALID, "abd_leapfrog_dev: the grid does not fit on the device at once");
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
+  if (tj) {
+    if (traj.n_steps > 1) {  // CTAs wait on one another: they must all be resident
+      int occ = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sums<M, XT, true>, kSumsBlock, tl.smem));
+      if ((long)grid.x * grid.y > (long)occ * h->n_sms)
+        return fail(ABD_ERR_INVALID, "abd_leapfrog_dev: the grid does not fit on the device at once");
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      lc.numAttrs = 1;
+    } else {  // a single step waits on nothing inside the grid: ordinary launch, overlapped like k_sums
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.numAttrs = h->use_pdl ? 1 : 0;
+    }
     lc.attrs = attr;
-    lc.numAttrs = 1;
     CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, true>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, h->d_partial,
                           h->d_ticket, sums, fin, pri, h->d_aux, traj, XchCfg{}));
   } else {
@@ -1039,7 +1046,7 @@ int abd_leapfrog_dev(abd_handle* h, int C, int n_steps, double* q17, double* p17
   if (!q17 || !p17 || !grad17 || !logp || !eps || !inv_mass || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
   if (n_steps < 1 || n_steps > 4096) return fail(ABD_ERR_INVALID, "n_steps must be in [1, 4096]");
   cudaStream_t st = (cudaStream_t)stream;
-  CU(cudaMemsetAsync(h->d_gen, 0, ((size_t)C + 1) * sizeof(unsigned), st));
+  if (n_steps > 1) CU(cudaMemsetAsync(h->d_gen, 0, ((size_t)C + 1) * sizeof(unsigned), st));
   TrajCfg traj{n_steps, q17, p17, grad17, logp, eps, inv_mass, h->d_traj, h->d_gen, h->d_gen + C};
   FinalizeCfg fin{2, h->tot, nullptr, nullptr};
   return launch_sums(h, C, q17, 1, i_raw, waner, nullptr, fin, st, &traj);

@@ -51,6 +51,12 @@ parts = {
     "gibbs": lambda it: tgt.gibbs(tq, 100 + it),
     "logp_dlogp": lambda it: tgt.logp_dlogp_into(tq, logp, grad),
 }
+def single_steps(it):
+    for _ in range(L):
+        tgt.leapfrog_inplace(qw, pw, gw, lpw, eps, eye, 1)
+
+
+print(f"{'leapfrog as ' + str(L) + ' x 1-step launches':28s} {timed(single_steps):8.1f} us")
 tot = 0.0
 for name, fn in parts.items():
     t = timed(fn)
