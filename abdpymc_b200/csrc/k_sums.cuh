@@ -240,19 +240,22 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     //      the compiler hoisted and spilled the 31 column addresses of the trajectory variant, and
     //      the spills serialised the loads: 4.9 us instead of 1.9) ----
     if (tid < ni) {
+      // Unpredicated loads: gaps beyond G - 1 re-read the last row and are masked off afterwards.
+      // (A load guarded by `t < G` needs a predicate register each, and there are only seven: the
+      // compiler then keeps ~6 loads in flight and the column costs 5 memory round trips.)
       const int8_t* col = i_raw + (size_t)c * G * N + i0 + tid;
+      // (The address walks down the column and stops at the last row: a chain of adds, so that the
+      // compiler cannot precompute -- and spill -- 32 / 64 independent 64-bit addresses.)
+      int8_t bytes[sizeof(M) * 8];
+#pragma unroll
+      for (int t = 0; t < (int)sizeof(M) * 8; ++t) {
+        bytes[t] = __ldg(col);
+        col += (t + 1 < G) ? (size_t)N : (size_t)0;
+      }
       M raw = 0;
 #pragma unroll
-      for (int t0 = 0; t0 < (int)sizeof(M) * 8; t0 += 16) {
-        int8_t bytes[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          bytes[u] = (t0 + u < G) ? __ldg(col) : (int8_t)0;
-          col += N;
-        }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) raw |= (M)(bytes[u] != 0) << (t0 + u);
-      }
+      for (int t = 0; t < (int)sizeof(M) * 8; ++t) raw |= (M)(bytes[t] != 0) << t;
+      raw &= low_mask<M>(G - 1);
       const int w = waner[(size_t)c * N + i0 + tid] != 0;
       IndState<M> st;
       st.inf = constrain<M>(raw, my_pcr, dc.ch);
@@ -527,12 +530,12 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
       for (int tl = g; tl < ntiles; tl += 8 * (kSumsBlock / 16)) {  // 8 loads in flight, fixed order
         double ld[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 8; ++u) {  // unpredicated (clamped) loads, masked afterwards: all in flight
           const int tt = tl + u * (kSumsBlock / 16);
-          ld[u] = (tt < ntiles) ? __ldcg(src + (size_t)tt * kNSums) : 0.0;
+          ld[u] = __ldcg(src + (size_t)min(tt, ntiles - 1) * kNSums);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v += ld[u];
+        for (int u = 0; u < 8; ++u) v += (tl + u * (kSumsBlock / 16) < ntiles) ? ld[u] : 0.0;
       }
       s_fin[g][k] = v;
       PHASE(9);
