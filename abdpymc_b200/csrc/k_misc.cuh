@@ -95,9 +95,18 @@ k_determ(const DevCohort dc, const double* __restrict__ theta13, const int8_t* _
   if (threadIdx.x < 13) s_th[threadIdx.x] = theta13[(size_t)c * 13 + threadIdx.x];
   __syncthreads();
   if (n >= N) return;
+  // unpredicated loads along an address chain, masked afterwards: all in flight (see k_sums)
   M raw = 0;
   const int8_t* col = i_raw + (size_t)c * G * N + n;
-  for (int t = 0; t < G; ++t) raw |= (M)(col[(size_t)t * N] != 0) << t;
+  int8_t bytes[sizeof(M) * 8];
+#pragma unroll
+  for (int t = 0; t < (int)sizeof(M) * 8; ++t) {
+    bytes[t] = __ldg(col);
+    col += (t + 1 < G) ? (size_t)N : (size_t)0;
+  }
+#pragma unroll
+  for (int t = 0; t < (int)sizeof(M) * 8; ++t) raw |= (M)(bytes[t] != 0) << t;
+  raw &= low_mask<M>(G - 1);
   const int w = waner[(size_t)c * N + n] != 0;
   const M inf = constrain<M>(raw, reinterpret_cast<const M*>(dc.pcr)[n], dc.ch);
   const M vac = reinterpret_cast<const M*>(dc.vac)[n];
