@@ -624,3 +624,56 @@ def test_randomised_cohorts_against_the_oracle():
                          timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
     assert "40 of 40" in res.stdout
+
+
+def test_full_size_properties_100k(Engine):
+    """BASELINE configs[3] size (100k individuals, several waves of CTAs per launch): the raw sums of 8
+    shards of individuals add up to the whole cohort's, finalising them on any shard reproduces the
+    unsharded logp / gradient, chains are independent of how they are batched, and a Gibbs sweep of
+    a shard equals the same individuals' part of the unsharded sweep."""
+    import torch
+
+    from abdpymc_b200.cohort import shard_bounds, synthetic_cohort
+
+    co = synthetic_cohort(100_000)
+    rng = np.random.default_rng(18)
+    C, splits, world = 3, (14, 20), 8
+    q, i_raw, w = draw_points(rng, co.n_gaps, co.n_inds, C)
+    dev = torch.device("cuda:0")
+    tq = torch.from_numpy(q).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    with Engine(co, splits=splits) as eng:
+        lp, g = eng.logp_dlogp(q, i_raw, w)
+        lp1, g1 = eng.logp_dlogp(q[1], i_raw[1], w[1])          # one chain on its own
+        assert np.isfinite(lp).all() and np.isfinite(g).all()
+        assert abs(lp1 - lp[1]) <= 1e-12 * abs(lp[1]) and grad_ok(g1, g[1], 1e-11)
+        eng.upload_state(i_raw, w)
+        vals = np.array([[ora.backward(q[k])[0][n] for n in ora.THETA13] for k in range(C)])
+        p = np.array([ora.backward(q[k])[0]["p"] for k in range(C)])
+        pw = np.array([ora.backward(q[k])[0]["ab_s_p_waner"] for k in range(C)])
+        gi, gw, gst = eng.gibbs_sweep(vals, p, pw, seed=3, sweep=1)
+    totals = (co.n_inds, int((co.antigen == 1).sum()), int((co.antigen == 0).sum()))
+    acc = np.zeros((C, 16))
+    out = torch.zeros(C, dtype=torch.float64, device=dev)
+    outg = torch.zeros(C, 17, dtype=torch.float64, device=dev)
+    flips = 0
+    for r in range(world):
+        lo, hi = shard_bounds(co.n_inds, r, world)
+        with Engine(co.shard(r, world), splits=splits, totals=totals, ind_offset=lo) as eng:
+            tis = torch.from_numpy(np.ascontiguousarray(i_raw[:, :, lo:hi])).to(dev)
+            tws = torch.from_numpy(np.ascontiguousarray(w[:, lo:hi])).to(dev)
+            s = torch.zeros(C, 16, dtype=torch.float64, device=dev)
+            eng.sums_dev(C, tq.data_ptr(), 1, tis.data_ptr(), tws.data_ptr(), s.data_ptr(), st)
+            torch.cuda.synchronize()
+            acc += s.cpu().numpy()
+            if r in (0, world - 1):   # the sweep of a shard is the shard of the sweep (RNG keyed by global individual)
+                si, sw, sst = eng.gibbs_sweep(vals, p, pw, i_raw[:, :, lo:hi], w[:, lo:hi], seed=3, sweep=1)
+                assert np.array_equal(si, gi[:, :, lo:hi]) and np.array_equal(sw, gw[:, lo:hi])
+                flips += int(sst[:, 1].sum())
+            if r == world - 1:
+                ts = torch.from_numpy(acc).to(dev)
+                eng.finalize_logp_dev(C, tq.data_ptr(), ts.data_ptr(), out.data_ptr(), outg.data_ptr(), st)
+                torch.cuda.synchronize()
+    assert np.all(np.abs(out.cpu().numpy() - lp) <= 1e-12 * np.abs(lp))
+    assert grad_ok(outg.cpu().numpy(), g, 1e-11)
+    assert 0 < flips < int(gst[:, 1].sum())
