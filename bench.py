@@ -496,20 +496,35 @@ def run_gpu(args):
 
     # ---- ESS/s of the built-in HMC + GPU-Gibbs sampler on the same cohort (bounded run) ----
     ess = None
-    if world == 1 and not args.no_ess:
+    if not args.no_ess:
         from abdpymc_b200 import diagnostics as dg
         from abdpymc_b200.sampler import AbdTarget, SamplerConfig, sample
 
         from abdpymc_b200.engine import forward
 
         tune_n, draws_n = 1000, 1000
-        tgt = AbdTarget(eng0, C, np.zeros_like(i_raw), np.zeros_like(w), seed=1)
-        cfg = SamplerConfig(tune=tune_n, draws=draws_n, seed=1)
+        # every rank samples its own C chains (chain sharding: no collective), seeds differ by rank
+        tgt = AbdTarget(eng0, C, np.zeros_like(i_raw), np.zeros_like(w), seed=1 + rank)
+        cfg = SamplerConfig(tune=tune_n, draws=draws_n, seed=1 + rank)
         # PyMC-like initial point: prior means on the constrained scale, jittered in q space (abd.infer_builtin)
         x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
-        q0 = forward(x0)[None, :] + np.random.default_rng(1).uniform(-1, 1, size=(C, 17))
+        q0 = forward(x0)[None, :] + np.random.default_rng(1 + rank).uniform(-1, 1, size=(C, 17))
+        barrier()
         res = sample(tgt, torch.from_numpy(q0).to(dev), cfg)
-        summ = dg.summary(res.posterior())
+        draws_q, wall = res.q, res.wall_s
+        if dist:  # gather every rank's draws on all ranks: diagnostics over world x C chains, slowest rank's wall time
+            tdraw = torch.from_numpy(np.ascontiguousarray(res.q)).to(dev)
+            parts = [torch.empty_like(tdraw) for _ in range(world)]
+            dist.all_gather(parts, tdraw)
+            draws_q = torch.cat(parts, dim=0).cpu().numpy()
+            tw = torch.tensor([res.wall_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            wall = float(tw.item())
+        from abdpymc_b200.engine import Q17_RV, backward as _bw
+
+        xq = _bw(draws_q)
+        summ = dg.summary({name: xq[:, :, k] for k, (name, _) in enumerate(Q17_RV)})
+        res.wall_s = wall
         vals_ess = sorted(v["ess_bulk"] for v in summ.values())
         # Gibbs sweeps on the chains' states at the end of the run (the stationary regime: few accepted flips)
         tq_end = torch.from_numpy(res.q[:, -1, :].copy()).to(dev)
@@ -521,12 +536,12 @@ def run_gpu(args):
         torch.cuda.synchronize()
         # wall time of the whole run (tune + draws) is charged to the draws kept
         ess = {"sampler": f"built-in batched HMC (dense metric) + GPU Metropolised-Gibbs sweep, device-resident transitions, "
-                          f"{C} chains x ({tune_n} tune + {draws_n} draws)",
-               "wall_s": res.wall_s, "iterations_per_s": (tune_n + draws_n) / res.wall_s,
+                          f"{world * C} chains x ({tune_n} tune + {draws_n} draws)" + (f" on {world} GPUs" if world > 1 else ""),
+               "chains": world * C, "wall_s": res.wall_s, "iterations_per_s": (tune_n + draws_n) / res.wall_s,
                "min_bulk_ess_per_s": vals_ess[0] / res.wall_s,
                "median_bulk_ess_per_s": vals_ess[len(vals_ess) // 2] / res.wall_s,
                "max_rhat": max(v["rhat"] for v in summ.values()), "grad_evals": res.n_grad_evals,
-               "gibbs_sweeps_per_s_stationary": C * 50 / (e0.elapsed_time(e1) / 1e3),
+               "gibbs_sweeps_per_s_stationary": world * C * 50 / (e0.elapsed_time(e1) / 1e3),
                "note": "PyMC is not installable offline, so there is no PyMC-CPU ESS/s beside it; the slowest-mixing "
                        "parameters are those coupled to the latent infection indicators (data-augmentation Gibbs)"}
 
