@@ -39,6 +39,11 @@ N_INDS = 10_000
 N_CHAINS = 4
 SPLITS = (14, 20)
 EVALS_PER_STEP = 256
+# what the benchmark cohort was simulated with (cohort.SimParams; simulation.py defaults).  The S
+# response of the model has no temp factor (abd.py:263-274), so ab_s_temp* have no counterpart.
+SIM_TRUTH = {"ab_n_perm": 2.0, "ab_n_temp": 1.5, "ab_n_rho": 0.95, "ab_n_init": -2.0, "ab_s_perm": 2.0, "ab_s_rho": 0.95,
+             "ab_s_init": -2.0, "it_n_b": -2.2, "it_n_d": 1.6, "it_n_sigma": 0.1, "it_s_b": -2.2, "it_s_d": 1.6,
+             "it_s_sigma": 0.1}
 L2_BYTES = 126e6
 METRIC = "logp+grad evals/s (10k individuals, joint logp + 17-dim gradient, per chain)"
 
@@ -158,18 +163,27 @@ def _cpu_eval(k):
     return time.perf_counter() - t
 
 
-def cpu_throughput(n_sub, dense, cores, steps, warmup):
+def _cpu_eval_value(k):
+    """Value only (no gradient): what one BinaryGibbsMetropolis proposal costs the reference."""
+    c = k % N_CHAINS
+    t = time.perf_counter()
+    _CPU["o"].logp(_CPU["q"][c], _CPU["i_raw"][c], _CPU["w"][c])
+    return time.perf_counter() - t
+
+
+def cpu_throughput(n_sub, dense, cores, steps, warmup, fn=None):
     """steps x (one logp+grad evaluation on n_sub individuals on each of `cores` processes).
     Returns (chain-evals/s extrapolated linearly to N_INDS individuals, seconds per step)."""
     import multiprocessing as mp
 
+    fn = fn or _cpu_eval
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_cpu_init, initargs=(n_sub, dense)) as pool:
         for _ in range(warmup):
-            pool.map(_cpu_eval, range(cores), chunksize=1)
+            pool.map(fn, range(cores), chunksize=1)
         t0 = time.perf_counter()
         for _ in range(steps):
-            pool.map(_cpu_eval, range(cores), chunksize=1)
+            pool.map(fn, range(cores), chunksize=1)
         dt = time.perf_counter() - t0
     evals = steps * cores * (n_sub / N_INDS)
     return evals / dt, dt / steps
@@ -182,7 +196,18 @@ def cpu_baseline():
     n_sub, steps = 5000, 20
     v_dense, _ = cpu_throughput(n_sub, True, cores, steps, 1)
     v_scan, _ = cpu_throughput(N_INDS, False, cores, steps, 1)
+    # Gibbs on the CPU: the reference's BinaryGibbsMetropolis evaluates the WHOLE model's logp (value
+    # only) once per proposed flip, 0.8 (G N + N) proposals per sweep and chain; one
+    # sweep at 10k individuals takes hours, so it is extrapolated from timed value-only evaluations
+    v_val, _ = cpu_throughput(n_sub, True, cores, 8, 1, fn=_cpu_eval_value)
+    co = workload()[0]
+    proposals = 0.8 * (co.n_gaps * co.n_inds + co.n_inds)
     return {"value": v_dense, "unit": "evals/s", "cores": cores, "kind": "port",
+            "gibbs": {"value": v_val / proposals, "unit": "sweeps/s", "logp_value_evals_per_s": v_val,
+                      "proposals_per_sweep": proposals,
+                      "sample": f"extrapolated: {cores} processes x 8 value-only dense-formulation logp evaluations on the "
+                                f"first {n_sub} individuals (scaled to {N_INDS}), one evaluation per proposed flip, "
+                                f"0.8 (G N + N) proposals per sweep (BinaryGibbsMetropolis, transit_p = 0.8)"},
             "sample": (f"{steps} steps x {cores} processes x 1 dense-formulation logp+grad evaluation on the first {n_sub} of "
                        f"{N_INDS} individuals, scaled by {n_sub}/{N_INDS}; PyMC is not installable offline, so this is "
                        "the NumPy restatement of the reference graph (oracle/abd_oracle.py)"),
@@ -337,6 +362,50 @@ def run_gpu(args):
     e1.record()
     torch.cuda.synchronize()
     ms_l2 = e0.elapsed_time(e1)
+
+    # ---- the same block issued over S streams (independent evaluation requests: what S PyMC worker
+    #      processes -- pm.sample(cores=S), one chain group each -- present to one GPU).  A single
+    #      stream leaves the SMs idle while a launch's last CTA finalises and the next one starts;
+    #      independent streams fill those gaps.  HBM-cold replicas as in the headline region. ----
+    concurrent = {}
+    for S in (2, 4):
+        if n_rep < 2 * S:
+            continue
+        streams = [torch.cuda.Stream(device=dev) for _ in range(S - 1)]
+        outs = [(torch.zeros_like(out), torch.zeros_like(outg)) for _ in range(S)]
+        gS = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gS, stream=side):
+            fork = torch.cuda.Event()
+            fork.record(side)
+            for st in streams:
+                st.wait_event(fork)
+            m = n_rep - n_rep % S  # engine j always runs on stream j % S: its scratch is never shared by two streams
+            for k in range(EVALS_PER_STEP):
+                j, sidx = k % m, k % S
+                stream = side if sidx == 0 else streams[sidx - 1]
+                o, og = outs[sidx]
+                engines[j].logp_dlogp_dev(C, tq.data_ptr(), states[j][0], states[j][1], o.data_ptr(), og.data_ptr(),
+                                          stream.cuda_stream)
+            for st in streams:
+                join = torch.cuda.Event()
+                join.record(st)
+                side.wait_event(join)
+        for _ in range(W):
+            gS.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(K):
+            gS.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_S = e0.elapsed_time(e1)
+        assert all(np.array_equal(o.cpu().numpy(), check_lp) for o, _ in outs), "concurrent streams changed the result"
+        concurrent[f"{S}_streams"] = {"value": world * C * n_launch / (ms_S / 1e3), "unit": "evals/s",
+                                      "avg_us_per_launch": ms_S / n_launch * 1e3,
+                                      "hbm_frac": a_logp / (ms_S / 1e3 / n_launch) / 1e9 / measured_peak_gbs()[0]}
+        del gS
+    concurrent["note"] = ("the headline block issued round-robin over S streams inside one CUDA graph (independent evaluation "
+                          "requests, e.g. S PyMC worker processes sharing the GPU); `value` stays the single-stream number")
 
     # ---- inside one persistent trajectory launch (abd_leapfrog_dev): L dependent leapfrog steps, each
     #      one full logp+grad evaluation at a new position; no launch / re-staging between them ----
@@ -502,7 +571,7 @@ def run_gpu(args):
 
         from abdpymc_b200.engine import forward
 
-        tune_n, draws_n = 1000, 1000
+        tune_n, draws_n = args.ess_tune, args.ess_draws
         # every rank samples its own C chains (chain sharding: no collective), seeds differ by rank
         tgt = AbdTarget(eng0, C, np.zeros_like(i_raw), np.zeros_like(w), seed=1 + rank)
         cfg = SamplerConfig(tune=tune_n, draws=draws_n, seed=1 + rank)
@@ -542,8 +611,23 @@ def run_gpu(args):
                "median_bulk_ess_per_s": vals_ess[len(vals_ess) // 2] / res.wall_s,
                "max_rhat": max(v["rhat"] for v in summ.values()), "grad_evals": res.n_grad_evals,
                "gibbs_sweeps_per_s_stationary": world * C * 50 / (e0.elapsed_time(e1) / 1e3),
-               "note": "PyMC is not installable offline, so there is no PyMC-CPU ESS/s beside it; the slowest-mixing "
+               "posterior": {name: {"mean": float(np.mean(xq[:, :, k])), "sd": float(np.std(xq[:, :, k])),
+                                    "ess_bulk": float(summ[name]["ess_bulk"]), "rhat": float(summ[name]["rhat"]),
+                                    "simulated_with": SIM_TRUTH.get(name)}
+                             for k, (name, _) in enumerate(Q17_RV)},
+               "note": "PyMC is not installable offline, so there is no measured PyMC-CPU ESS/s beside it (cpu_extrapolation "
+                       "scales this run's ESS per iteration by the CPU cost of one iteration); the slowest-mixing "
                        "parameters are those coupled to the latent infection indicators (data-augmentation Gibbs)"}
+        if cpu and cpu.get("gibbs"):
+            # one iteration of the reference's compound step = one NUTS draw (>= the 5 leapfrogs used here) + one
+            # BinaryGibbsMetropolis sweep; its chains run one per core.  Same ESS per iteration assumed.
+            t_iter = 1.0 / (cpu["gibbs"]["value"] / cpu["cores"]) + cfg.n_leapfrog / (cpu["value"] / cpu["cores"])
+            ess_per_iter = vals_ess[0] / (tune_n + draws_n)
+            ess["cpu_extrapolation"] = {
+                "seconds_per_iteration_per_chain": t_iter, "min_bulk_ess_per_s": ess_per_iter / t_iter,
+                "how": f"this run's min bulk ESS per iteration ({world * C} chains) / CPU seconds per iteration of one chain on "
+                       f"one core (1 Gibbs sweep + {cfg.n_leapfrog} logp+grad evaluations of the restated reference, "
+                       "cpu_baseline), chains in parallel on separate cores"}
 
     if rank != 0:
         if dist:
@@ -584,6 +668,7 @@ def run_gpu(args):
         "l2_resident": {"value": world * C * n_launch / (ms_l2 / 1e3), "unit": "evals/s",
                         "avg_launch_us": ms_l2 / n_launch * 1e3,
                         "note": "same cohort re-evaluated back to back (the access pattern of consecutive NUTS leapfrogs)"},
+        "concurrent_streams": concurrent,
         "persistent_trajectory": traj,
         "batched_128_chains": batched,
         "gibbs": {"metric": "Gibbs sweeps/s (all G*N+N binary variables of one chain)", "value": world * C * n_sw / (ms_gibbs / 1e3),
@@ -609,6 +694,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
+    ap.add_argument("--ess-tune", type=int, default=2000)
+    ap.add_argument("--ess-draws", type=int, default=6000)
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: a few un-captured logp+grad launches and Gibbs sweeps, no JSON line")
     args = ap.parse_args()
