@@ -54,6 +54,7 @@ int fail(int code, const std::string& msg) {
 #include "abd_kernels_common.cuh"
 #include "k_sums.cuh"
 #include "k_gibbs.cuh"
+#include "k_gibbs_blk.cuh"
 #include "k_misc.cuh"
 
 
@@ -89,6 +90,7 @@ struct abd_handle {
   int* d_order = nullptr;       // individuals by decreasing OD-row count (Gibbs work queue)
   unsigned* d_queue = nullptr;  // Gibbs work-queue counter
   int gibbs_ctas = 0;
+  int gibbs_blk_ctas = 0;
   // peer exchange (individual sharding over NVLink)
   XchCfg xch{};
   void* xch_local = nullptr;
@@ -507,6 +509,27 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
 
 int launch_gibbs(abd_handle* h, int C, const double* theta, int theta_is_q, const double* p,
                  const double* pw, int8_t* i_raw, int8_t* waner, const GibbsCfg& cfg, cudaStream_t st) {
+  if (cfg.mode == ABD_GIBBS_BLOCKED) {
+    if (h->wide || h->dc.ch.n < 2) {
+      // no "first raw 1 of the chunk" structure (one chunk) or more options than lanes (wide masks):
+      // single-site exact conditionals instead
+      GibbsCfg c2 = cfg;
+      c2.mode = ABD_GIBBS_HEATBATH;
+      return launch_gibbs(h, C, theta, theta_is_q, p, pw, i_raw, waner, c2, st);
+    }
+    if (!h->gibbs_blk_ctas) {
+      int occ = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gibbs_blk, kGibbsWarps * 32, 0));
+      h->gibbs_blk_ctas = h->n_sms * std::max(occ, 1);
+    }
+    const long items = (long)C * h->N;
+    const int grid = (int)std::min<long>(h->gibbs_blk_ctas, (items + kGibbsWarps - 1) / kGibbsWarps);
+    CU(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
+    k_gibbs_blk<<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, h->d_order, C, theta, theta_is_q, p, pw, i_raw, waner, h->d_queue, cfg);
+    CU(cudaGetLastError());
+    h->launches++;
+    return ABD_OK;
+  }
   if (!h->gibbs_ctas) {
     int occ = 0;
     if (h->wide)
@@ -908,7 +931,8 @@ int abd_gibbs_sweep(abd_handle* h, int C, const double* theta13, const double* p
                     double transit_p, int64_t* out_stats) {
   PROLOGUE(h, C);
   if (!theta13 || !p || !p_w) return fail(ABD_ERR_INVALID, "NULL argument");
-  if (mode != ABD_GIBBS_METROPOLIS && mode != ABD_GIBBS_HEATBATH) return fail(ABD_ERR_INVALID, "bad mode");
+  if (mode != ABD_GIBBS_METROPOLIS && mode != ABD_GIBBS_HEATBATH && mode != ABD_GIBBS_BLOCKED)
+    return fail(ABD_ERR_INVALID, "bad mode");
   if (!(transit_p >= 0.0 && transit_p <= 1.0)) return fail(ABD_ERR_INVALID, "transit_p must be in [0, 1]");
   int rc = stage_state(h, C, i_raw, waner);
   if (rc) return rc;
@@ -1021,7 +1045,8 @@ int abd_gibbs_sweep_dev(abd_handle* h, int C, const double* theta, int theta_is_
   PROLOGUE(h, C);
   if (!theta || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
   if (!theta_is_q17 && (!p || !p_w)) return fail(ABD_ERR_INVALID, "p / p_w required with theta13");
-  if (mode != ABD_GIBBS_METROPOLIS && mode != ABD_GIBBS_HEATBATH) return fail(ABD_ERR_INVALID, "bad mode");
+  if (mode != ABD_GIBBS_METROPOLIS && mode != ABD_GIBBS_HEATBATH && mode != ABD_GIBBS_BLOCKED)
+    return fail(ABD_ERR_INVALID, "bad mode");
   GibbsCfg cfg{seed, sweep_idx, mode, transit_p, nullptr, nullptr, stats};
   return launch_gibbs(h, C, theta, theta_is_q17, p, p_w, i_raw, waner, cfg, (cudaStream_t)stream);
 }

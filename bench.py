@@ -497,6 +497,20 @@ def run_gpu(args):
         e1.record()
     barrier()
     ms_gibbs = e0.elapsed_time(e1)
+    # the other two update rules on the same states (ABD_GIBBS_HEATBATH, ABD_GIBBS_BLOCKED)
+    ms_modes = {}
+    for mode_name, mode_id in (("heatbath", 1), ("blocked", 2)):
+        with torch.cuda.stream(side):
+            engines[0].gibbs_sweep_dev(C, tth.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), states[0][0], states[0][1], 1, 0,
+                                       mode=mode_id, stream=side.cuda_stream)
+            e0.record()
+            for k in range(n_sw):
+                j = k % n_rep
+                engines[j].gibbs_sweep_dev(C, tth.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), states[j][0], states[j][1],
+                                           1, 500 + k, mode=mode_id, stream=side.cuda_stream)
+            e1.record()
+        barrier()
+        ms_modes[mode_name] = e0.elapsed_time(e1)
     for e in engines:
         e.upload_state(i_raw, w)
     n_sw_e2e = max(5, min(50, K))
@@ -674,6 +688,7 @@ def run_gpu(args):
         "gibbs": {"metric": "Gibbs sweeps/s (all G*N+N binary variables of one chain)", "value": world * C * n_sw / (ms_gibbs / 1e3),
                   "unit": "sweeps/s", "avg_launch_us": t_sweep * 1e6,
                   "regime": "states drawn at random (4 % infections, 50 % waners): the burn-in regime, many accepted flips",
+                  "other_update_rules": {name: {"value": world * C * n_sw / (v / 1e3), "unit": "sweeps/s"} for name, v in ms_modes.items()},
                   "roofline": {"bound": "hbm", "achieved": ach_g, "peak": peak, "unit": "GB/s", "frac": ach_g / peak,
                                "traffic": ncu_traffic("k_gibbs"), "kernel": "k_gibbs", "algorithmic_bytes_per_launch": a_gibbs},
                   "e2e": {"value": world * C * n_sw_e2e / dt_gibbs_e2e, "unit": "sweeps/s",

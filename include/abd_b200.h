@@ -57,6 +57,15 @@ extern "C" {
 #define ABD_GIBBS_METROPOLIS 0 /* PyMC BinaryGibbsMetropolis semantics: propose the flip w.p.
                                   transit_p, accept w.p. min(1, exp(delta)); random order   */
 #define ABD_GIBBS_HEATBATH 1   /* draw every bit from its exact full conditional            */
+#define ABD_GIBBS_BLOCKED 2    /* per time chunk, redraw the chunk's raw bits TOGETHER from their
+                                  exact full conditional (the position of the chunk's first raw 1
+                                  is a categorical over len + 1 options; bits behind it, and all
+                                  bits of a chunk overridden by PCR+, only have their Bernoulli(p)
+                                  prior), then ab_s_waner as HEATBATH.  Same stationary
+                                  distribution as the two single-site modes, far fewer sweeps to
+                                  move an infection in time.  Needs time chunks (splits) and
+                                  G <= 31; otherwise it runs as HEATBATH.  transit_p is ignored;
+                                  stats = {block draws, blocks whose first 1 / waner changed}   */
 
 typedef struct abd_handle abd_handle;
 

@@ -502,6 +502,55 @@ def _u01(r):
     return (float(r) + 1.0) * 2.0**-32
 
 
+def _blocked_individual(sub, ll, col, wn, cur, G, splits, p, lo_w, n_global, chain, sweep, key):
+    """ABD_GIBBS_BLOCKED for one individual (include/abd_b200.h): per time chunk, the chunk's raw
+    bits are redrawn together from their exact full conditional -- a categorical over the position
+    of the chunk's first raw 1 (or none), prior p (1-p)^o / (1-p)^len, the bits behind the first 1
+    (and every bit of a chunk overridden by PCR+) fresh Bernoulli(p) draws -- then the waner bit
+    from its exact conditional.  Random numbers: Philox counter (j, individual, chain, sweep), word
+    0 = fresh bit of gap j, word 1 = categorical uniform of chunk j, word 2 (j = 0) = waner."""
+    rnd = [philox4x32_10((j, n_global, chain, sweep & _M32), key) for j in range(32)]
+    fresh = np.array([1 if _u01(rnd[t][0]) <= p else 0 for t in range(G)], dtype=col.dtype)
+    lp1, lp0 = np.log(p), np.log1p(-p)
+    pcr = sub.pcr[:, 0]
+    n_prop = n_acc = 0
+    for k, (a, b) in enumerate(chunk_bounds(G, splits)):
+        if a == b:
+            continue
+        n_prop += 1
+        if pcr[a:b].any():
+            col[a:b] = fresh[a:b]
+            continue
+        length = b - a
+        lls = np.empty(length + 1)
+        for o in range(length + 1):
+            cand = col.copy()
+            cand[a:b] = 0
+            if o < length:
+                cand[a + o] = 1
+            lls[o] = ll(cand, wn)
+        lw = lls + np.concatenate([np.arange(length) * lp0 + lp1, [length * lp0]])
+        lw = np.where(np.isnan(lw), -np.inf, lw)
+        old_first = int(np.argmax(col[a:b])) if col[a:b].any() else length
+        if not np.isfinite(lw.max()):
+            pick = length
+        else:
+            cum = np.cumsum(np.exp(lw - lw.max()))
+            pick = int((cum[:length] < _u01(rnd[k][1]) * cum[length]).sum())
+        col[a:b] = 0
+        if pick < length:
+            col[a + pick] = 1
+            col[a + pick + 1:b] = fresh[a + pick + 1:b]
+        n_acc += pick != old_first
+        cur = lls[pick]
+    n_prop += 1
+    new = ll(col, 1 - wn)
+    d10 = lo_w + ((cur - new) if wn else (new - cur))
+    w_new = 1 if _u01(rnd[0][2]) <= 1.0 / (1.0 + np.exp(-d10)) else 0
+    n_acc += w_new != wn
+    return col, w_new, (n_prop, n_acc)
+
+
 def device_gibbs_sweep(cohort, splits, ignore_pcrpos, theta13, p, p_w, i_raw, w, seed, sweep, chain,
                        mode=0, transit_p=0.8, ind_offset=0):
     """One sweep of one chain exactly as the CUDA kernel schedules it: for every individual n,
@@ -521,10 +570,16 @@ def device_gibbs_sweep(cohort, splits, ignore_pcrpos, theta13, p, p_w, i_raw, w,
         def ll(col, wn):
             return sub.loglik(theta13, col.reshape(G, 1), np.array([wn]))
 
-        rnd = [philox4x32_10((j, n + ind_offset, chain, sweep & _M32), key) for j in range(G + 1)]
-        order = sorted(range(G + 1), key=lambda j: (rnd[j][0], j))
         col, wn = i_raw[:, n].copy(), int(w[n])
         cur = ll(col, wn)
+        if mode == 2:
+            col, wn, st = _blocked_individual(sub, ll, col, wn, cur, G, splits, p, lo_w, n + ind_offset, chain, sweep, key)
+            n_prop += st[0]
+            n_flip += st[1]
+            i_raw[:, n], w[n] = col, wn
+            continue
+        rnd = [philox4x32_10((j, n + ind_offset, chain, sweep & _M32), key) for j in range(G + 1)]
+        order = sorted(range(G + 1), key=lambda j: (rnd[j][0], j))
         for j in order:
             u_t, u_a = _u01(rnd[j][1]), _u01(rnd[j][2])
             if mode == 0 and not (u_t <= transit_p):

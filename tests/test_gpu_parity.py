@@ -292,11 +292,13 @@ def test_error_behaviour(Engine, cohorts):
 
 
 # ------------------------------------------------------------------------------ Gibbs
-@pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("splits", [(), (14, 20)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("splits", [(), (14, 20), (9,)])
 def test_gibbs_sweep_bit_exact_vs_restated_device_sweep(Engine, cohorts, mode, splits):
     """Same Philox stream, same visiting order, same accept rule on the CPU: the states after
-    three consecutive sweeps must be identical bit for bit."""
+    three consecutive sweeps must be identical bit for bit.  (Mode 2, the per-chunk block draw,
+    needs time chunks: without splits the library runs it as mode 1.)"""
+    omode = 1 if (mode == 2 and not splits) else mode
     co = cohorts["test_cohort"]
     rng = np.random.default_rng(11 + mode)
     C = 3
@@ -314,7 +316,7 @@ def test_gibbs_sweep_bit_exact_vs_restated_device_sweep(Engine, cohorts, mode, s
             gi, gw, st = eng.gibbs_sweep(th, p, pw, gi, gw, seed=seed, sweep=sweep, mode=mode, transit_p=0.8)
             for c in range(C):
                 ri[c], rw[c], rst = ora.device_gibbs_sweep(co, splits, False, th[c], p[c], pw[c], ri[c], rw[c],
-                                                           seed, sweep, c, mode=mode, transit_p=0.8)
+                                                           seed, sweep, c, mode=omode, transit_p=0.8)
                 assert list(st[c]) == rst, (sweep, c, st[c], rst)
             assert np.array_equal(gi, ri) and np.array_equal(gw, rw), sweep
         assert not np.array_equal(gi, i_raw)  # something moved
@@ -333,8 +335,9 @@ def test_gibbs_sweep_wide_mask_bit_exact(Engine):
     assert np.array_equal(gi, ri) and np.array_equal(gw, rw) and list(st) == rst
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_gibbs_stationary_distribution_small_model(Engine, mode):
+@pytest.mark.parametrize("with_pcr", [False, True])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_gibbs_stationary_distribution_small_model(Engine, mode, with_pcr):
     """Statistical parity: on a G = 5 cohort every individual has 2^6 binary states, so the exact
     conditional posterior given theta is enumerable with the oracle.  Both update rules must
     leave it invariant: compare empirical state frequencies over many sweeps x chains."""
@@ -343,7 +346,10 @@ def test_gibbs_stationary_distribution_small_model(Engine, mode):
     rng = np.random.default_rng(2024)
     G, N, C, sweeps = 5, 6, 256, 400
     co = random_cohort(rng, G, N, rows_per_ind=5, p_empty=0.0)
-    co = CohortArrays(vacs=co.vacs, pcrpos=np.zeros((N, G)), ind=co.ind, gap=co.gap, antigen=co.antigen, x=co.x,
+    pcrpos = np.zeros((N, G))
+    if with_pcr:  # a PCR+ month overrides its whole chunk: the chunk's raw bits are then prior-only
+        pcrpos[0, 1] = pcrpos[1, 3] = pcrpos[2, 0] = pcrpos[2, 4] = 1
+    co = CohortArrays(vacs=co.vacs, pcrpos=pcrpos, ind=co.ind, gap=co.gap, antigen=co.antigen, x=co.x,
                       od=rng.normal(0.9, 0.4, size=co.n_rows))
     v = ora.sample_prior(rng, G)
     v.update(it_n_sigma=0.8, it_s_sigma=0.8, p=0.3, ab_s_p_waner=0.4)

@@ -133,3 +133,45 @@ def test_gibbs_sweep_restatement_keeps_shapes(cohorts):
     i2, w2 = ora.binary_gibbs_metropolis_sweep(o, th, 0.04, 0.5, i_raw, w, rng)
     assert i2.shape == (o.G, o.N) and w2.shape == (o.N,)
     assert set(np.unique(i2)) <= {0, 1} and set(np.unique(w2)) <= {0, 1}
+
+
+def test_restated_blocked_sweep_leaves_exact_conditional_invariant():
+    """ABD_GIBBS_BLOCKED as the oracle restates it (the checker of the CUDA kernel) is a valid Gibbs
+    kernel: on a G = 5 individual with two time chunks (one of them PCR+ for the second individual)
+    the long-run state frequencies match the enumerated conditional posterior."""
+    from abdpymc_b200.cohort import CohortArrays
+
+    rng = np.random.default_rng(7)
+    G, N, sweeps = 5, 2, 4000
+    r = 8
+    pcrpos = np.zeros((N, G))
+    pcrpos[1, 3] = 1
+    co = CohortArrays(vacs=rng.random((N, G)) < 0.2, pcrpos=pcrpos, ind=np.repeat(np.arange(N), r // N),
+                      gap=rng.integers(0, G, size=r), antigen=rng.integers(0, 2, size=r),
+                      x=rng.integers(0, 8, size=r).astype(float), od=rng.normal(0.9, 0.4, size=r))
+    v = ora.sample_prior(rng, G)
+    v.update(it_n_sigma=0.8, it_s_sigma=0.8, p=0.3, ab_s_p_waner=0.4)
+    th = np.array([v[n] for n in ora.THETA13])
+    splits = (2,)
+    states = [(np.array([(s >> t) & 1 for t in range(G)]), (s >> G) & 1) for s in range(2 ** (G + 1))]
+    exact = np.empty((N, len(states)))
+    for n in range(N):
+        sub = ora.Oracle(co.take(np.array([n])), splits=splits, dense=False)
+        for s, (col, wn) in enumerate(states):
+            k = col.sum()
+            exact[n, s] = (sub.loglik(th, col.reshape(G, 1), np.array([wn])) + k * np.log(v["p"])
+                           + (G - k) * np.log1p(-v["p"]) + (np.log(v["ab_s_p_waner"]) if wn else np.log1p(-v["ab_s_p_waner"])))
+    exact = np.exp(exact - exact.max(axis=1, keepdims=True))
+    exact /= exact.sum(axis=1, keepdims=True)
+    counts = np.zeros_like(exact)
+    i_raw, w = np.zeros((G, N), np.int8), np.zeros(N, np.int8)
+    weights = 1 << np.arange(G)
+    for sweep in range(sweeps + 20):
+        i_raw, w, st = ora.device_gibbs_sweep(co, splits, False, th, v["p"], v["ab_s_p_waner"], i_raw, w, 5, sweep, 0, mode=2)
+        assert st[0] == N * 3
+        if sweep >= 20:
+            code = (i_raw.astype(np.int64) * weights[:, None]).sum(axis=0) + (w.astype(np.int64) << G)
+            for n in range(N):
+                counts[n, code[n]] += 1
+    tv = 0.5 * np.abs(counts / sweeps - exact).sum(axis=1)
+    assert np.all(tv < 0.06), tv
