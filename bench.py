@@ -399,6 +399,10 @@ def run_gpu(args):
         e1.record()
         torch.cuda.synchronize()
         ms_S = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms_S], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_S = float(t.item())
         assert all(np.array_equal(o.cpu().numpy(), check_lp) for o, _ in outs), "concurrent streams changed the result"
         concurrent[f"{S}_streams"] = {"value": world * C * n_launch / (ms_S / 1e3), "unit": "evals/s",
                                       "avg_us_per_launch": ms_S / n_launch * 1e3,
@@ -511,6 +515,10 @@ def run_gpu(args):
             e1.record()
         barrier()
         ms_modes[mode_name] = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms_modes[mode_name]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_modes[mode_name] = float(t.item())
     for e in engines:
         e.upload_state(i_raw, w)
     n_sw_e2e = max(5, min(50, K))
