@@ -91,6 +91,7 @@ struct abd_handle {
   unsigned* d_queue = nullptr;  // Gibbs work-queue counter
   int gibbs_ctas = 0;
   int gibbs_blk_ctas = 0;
+  ThetaInline thin{};           // parameters passed by value with the next k_sums launch (n = 0: none)
   // peer exchange (individual sharding over NVLink)
   XchCfg xch{};
   void* xch_local = nullptr;
@@ -100,6 +101,7 @@ struct abd_handle {
   bool fx = false;              // factored mode: rows carry (cell, dilution index), see k_sums
   bool use_pdl = true;          // programmatic dependent launch (ABD_B200_NO_PDL=1 disables)
   bool use_pull = true;         // SM-driven upload of pinned chain state (ABD_B200_NO_PULL=1 disables)
+  bool use_inline = true;       // <= 8 chains: parameters by value in the launch (ABD_B200_NO_INLINE=1 disables)
 
   // per-chain scratch
   int cap_chains = 0;
@@ -404,7 +406,7 @@ cudaError_t sums_occupancy(int device, size_t smem, int* occ) {
 template <typename M, typename XT>
 int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cfg, dim3 grid, const double* theta,
                   int theta_is_q, const int8_t* i_raw, const int8_t* waner, double* sums, const FinalizeCfg& fin,
-                  const TrajCfg& traj, cudaStream_t st) {
+                  const TrajCfg& traj, cudaStream_t st, const ThetaInline& thin) {
   if (std::getenv("ABD_B200_VERBOSE")) {
     const int occ = tl.occ;
     std::fprintf(stderr, "[abd_b200] k_sums grid (%u, %u) dyn smem %zu B, occupancy %d CTAs/SM, caps rows %d/%d cells %d/%d\n",
@@ -437,14 +439,14 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
     }
     lc.attrs = attr;
     CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, true>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, h->d_partial,
-                          h->d_ticket, sums, fin, pri, h->d_aux, traj, XchCfg{}));
+                          h->d_ticket, sums, fin, pri, h->d_aux, traj, XchCfg{}, ThetaInline{}));
   } else {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = h->use_pdl ? 1 : 0;
     CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, false>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, h->d_partial,
-                          h->d_ticket, sums, fin, pri, h->d_aux, traj, h->xch_active ? h->xch : XchCfg{}));
+                          h->d_ticket, sums, fin, pri, h->d_aux, traj, h->xch_active ? h->xch : XchCfg{}, thin));
   }
   return ABD_OK;
 }
@@ -454,6 +456,8 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
                 const TrajCfg* traj_in = nullptr) {
   TrajCfg traj{};
   if (traj_in) traj = *traj_in;
+  const ThetaInline thin = h->thin;  // consumed by this call whatever happens below
+  h->thin.n = 0;
   // plan for the kernel's register-limited occupancy first; if the tiles that plan needs do not
   // fit that many CTAs per SM (shared memory), plan again for what actually fits
   int want, cpc, rc;
@@ -496,11 +500,11 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
   SumsCfg cfg{tl->ntiles, tl->cap_n, tl->cap_s, tl->capr_n, tl->capr_s, tl->capk_n, tl->capk_s, cpc, C};
   dim3 grid(tl->ntiles, (C + cpc - 1) / cpc);
   if (h->wide)
-    rc = h->fx ? launch_sums_t<uint64_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st)
-               : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st);
+    rc = h->fx ? launch_sums_t<uint64_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st, thin)
+               : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st, thin);
   else
-    rc = h->fx ? launch_sums_t<uint32_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st)
-               : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st);
+    rc = h->fx ? launch_sums_t<uint32_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st, thin)
+               : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st, thin);
   if (rc) return rc;
   CU(cudaGetLastError());
   h->launches++;
@@ -652,6 +656,7 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
   h->device = device;
   if (const char* e = std::getenv("ABD_B200_NO_PDL")) h->use_pdl = !(e[0] == '1');
   if (const char* e = std::getenv("ABD_B200_NO_PULL")) h->use_pull = !(e[0] == '1');
+  if (const char* e = std::getenv("ABD_B200_NO_INLINE")) h->use_inline = !(e[0] == '1');
   {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->n_sms = v;
@@ -836,8 +841,13 @@ int abd_loglik_grad(abd_handle* h, int C, const double* theta13, const int8_t* i
   if (!theta13 || !out_loglik) return fail(ABD_ERR_INVALID, "NULL argument");
   int rc = stage_state(h, C, i_raw, waner);
   if (rc) return rc;
-  std::memcpy(h->h_pin, theta13, (size_t)C * 13 * sizeof(double));
-  CU(cudaMemcpyAsync(h->d_theta, h->h_pin, (size_t)C * 13 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (C <= kInlineChains && h->use_inline) {  // by value, inside the launch (no host -> device copy)
+    h->thin.n = C * 13;
+    std::memcpy(h->thin.v, theta13, (size_t)C * 13 * sizeof(double));
+  } else {
+    std::memcpy(h->h_pin, theta13, (size_t)C * 13 * sizeof(double));
+    CU(cudaMemcpyAsync(h->d_theta, h->h_pin, (size_t)C * 13 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
   FinalizeCfg fin{1, h->tot, h->d_out, h->d_out + C};
   if ((rc = launch_sums(h, C, h->d_theta, 0, h->d_iraw, h->d_waner, h->d_sums, fin, h->stream))) return rc;
   double* hp = h->h_pin;
@@ -868,8 +878,13 @@ int abd_logp_dlogp(abd_handle* h, int C, const double* q17, const int8_t* i_raw,
   // The RESULTS, however, are written by the finishing warps straight into the pinned staging
   // buffer (posted PCIe writes cost the kernel nothing): no device -> host copy after the launch.
   double* ho = h->h_pin + (size_t)C * 17;
-  std::memcpy(h->h_pin, q17, (size_t)C * 17 * sizeof(double));
-  CU(cudaMemcpyAsync(h->d_theta, h->h_pin, (size_t)C * 17 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (C <= kInlineChains && h->use_inline) {  // by value, inside the launch (no host -> device copy)
+    h->thin.n = C * 17;
+    std::memcpy(h->thin.v, q17, (size_t)C * 17 * sizeof(double));
+  } else {
+    std::memcpy(h->h_pin, q17, (size_t)C * 17 * sizeof(double));
+    CU(cudaMemcpyAsync(h->d_theta, h->h_pin, (size_t)C * 17 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
   if (h->h_pin_dev && h->use_pull) {
     double* dout = h->h_pin_dev + (size_t)C * 17;
     FinalizeCfg fin{2, h->tot, dout, dout + C};

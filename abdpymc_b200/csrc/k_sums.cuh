@@ -9,6 +9,15 @@ using namespace abd;
 // ------------------------------------------------------------------------------------------
 // k_sums
 // ------------------------------------------------------------------------------------------
+// Parameters of a few chains handed over by value, inside the kernel's parameter space (constant
+// bank): the host-pointer calls (abd_logp_dlogp, abd_loglik_grad) then need no host -> device copy
+// of q17 / theta13 before the launch.  n = 0: read the `theta` pointer instead.
+constexpr int kInlineChains = 8;
+struct ThetaInline {
+  int n;
+  double v[kInlineChains * 17];
+};
+
 struct FinalizeCfg {
   int mode;        // 0: write raw sums only; 1: loglik + grad13; 2: joint logp + dlogp17
   Totals tot;
@@ -143,11 +152,12 @@ constexpr int kRowUnroll = ABD_ROW_UNROLL, kCellUnroll = ABD_CELL_UNROLL;
 template <typename M, typename XT, bool TRAJ>
 __global__ void __launch_bounds__(kSumsBlock, ABD_SUMS_MINB)
 k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg,
-       const double* __restrict__ theta, const int theta_is_q,
+       const double* __restrict__ theta_ptr, const int theta_is_q,
        const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
        double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ sums,
        const FinalizeCfg fin, const Priors* __restrict__ priors, double* __restrict__ aux, const TrajCfg traj,
-       const XchCfg xch) {
+       const XchCfg xch, const __grid_constant__ ThetaInline thin) {
+  const double* theta = thin.n ? thin.v : theta_ptr;
   const int tile = blockIdx.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int G = dc.G, N = dc.N, ntiles = cfg.ntiles;
