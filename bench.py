@@ -293,6 +293,10 @@ def run_gpu(args):
         for k in range(max(K, 1)):
             j = k % n_rep
             engines[j].gibbs_sweep_dev(C, tth.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), states[j][0], states[j][1], 1, k)
+        for k in range(max(K, 1)):  # the per-chunk block draw (k_gibbs_blk)
+            j = k % n_rep
+            engines[j].gibbs_sweep_dev(C, tth.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), states[j][0], states[j][1], 1,
+                                       100 + k, mode=2)
         torch.cuda.synchronize()
         print("profile run done:", o1.cpu().numpy())
         return
