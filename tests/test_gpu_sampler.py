@@ -135,3 +135,52 @@ def test_hmc_transition_kernels_against_host_formulas(gpu):
 
 def kin_of(p, inv_mass):
     return 0.5 * ((p @ inv_mass) * p).sum(dim=1)
+
+
+@pytest.mark.parametrize("gibbs_mode", [0, 2])
+def test_sampler_recovers_the_priors_on_a_cohort_without_data(gpu, gibbs_mode):
+    """Statistical check of the whole transition (priors, transforms + Jacobians, HMC on the device,
+    Gibbs over the indicators) against distributions known in closed form: without OD rows the
+    posterior of the 17 scalars IS their prior (scipy.stats moments), and the indicators are
+    Bernoulli(p) / Bernoulli(p_waner) given those."""
+    import torch
+    from scipy import stats
+
+    from abdpymc_b200 import diagnostics as dg
+    from abdpymc_b200.cohort import CohortArrays
+    from abdpymc_b200.engine import Q17_RV, AbdEngine, backward, forward
+    from abdpymc_b200.sampler import AbdTarget, SamplerConfig, sample
+
+    rng = np.random.default_rng(1)
+    G, N, C = 10, 6, 8
+    empty = np.zeros(0)
+    co = CohortArrays(vacs=rng.random((N, G)) < 0.1, pcrpos=np.zeros((N, G)), ind=empty.astype(int), gap=empty.astype(int),
+                      antigen=empty.astype(int), x=empty, od=empty)
+
+    def gam(mu, sigma):
+        return stats.gamma(a=mu * mu / sigma**2, scale=sigma**2 / mu)
+
+    prior = {"p": stats.beta(1, G - 1), "ab_n_perm": gam(2, .5), "ab_n_temp": gam(1, .5), "ab_n_rho": stats.beta(10, 1),
+             "ab_n_init": stats.norm(-2, 1), "ab_s_perm": gam(2, .5), "ab_s_rho": stats.beta(10, 1),
+             "ab_s_p_waner": stats.beta(1, 1), "ab_s_tempinf": gam(1, .5), "ab_s_tempvac": gam(1, .5),
+             "ab_s_init": stats.norm(-2, 1), "it_n_b": stats.norm(-1, .5), "it_n_d": stats.norm(2, .5),
+             "it_n_sigma": stats.expon(), "it_s_b": stats.norm(-1, .5), "it_s_d": stats.norm(2, .5), "it_s_sigma": stats.expon()}
+    with AbdEngine(co, splits=(4,)) as eng:
+        tgt = AbdTarget(eng, C, np.zeros((C, G, N), np.int8), np.zeros((C, N), np.int8), seed=3, gibbs_mode=gibbs_mode)
+        x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
+        q0 = forward(x0)[None, :] + rng.uniform(-1, 1, size=(C, 17))
+        res = sample(tgt, torch.from_numpy(q0).to(gpu), SamplerConfig(tune=1000, draws=6000, seed=3))
+        i_raw, waner = tgt.state()
+    x = backward(res.q)
+    summ = dg.summary({name: x[:, :, k] for k, (name, _) in enumerate(Q17_RV)})
+    for name, dist in prior.items():
+        v = summ[name]
+        se = dist.std() / np.sqrt(max(v["ess_bulk"], 50.0))
+        assert v["rhat"] < 1.05, (name, v)
+        assert abs(v["mean"] - dist.mean()) < 5 * se + 0.01 * dist.std(), (name, v, dist.mean())
+        assert abs(v["sd"] / dist.std() - 1.0) < 0.15, (name, v, dist.std())
+        # a few quantiles of the pooled draws against the prior's
+        draws = x[:, :, [k for k, (n_, _) in enumerate(Q17_RV) if n_ == name][0]].ravel()
+        for qq in (0.1, 0.5, 0.9):
+            assert abs((draws < dist.ppf(qq)).mean() - qq) < 0.05, (name, qq)
+    assert set(np.unique(i_raw)) <= {0, 1} and set(np.unique(waner)) <= {0, 1}

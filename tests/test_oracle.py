@@ -175,3 +175,72 @@ def test_restated_blocked_sweep_leaves_exact_conditional_invariant():
                 counts[n, code[n]] += 1
     tv = 0.5 * np.abs(counts / sweeps - exact).sum(axis=1)
     assert np.all(tv < 0.06), tv
+
+
+def _scipy_priors(n_gaps):
+    """The 17 priors as scipy.stats frozen distributions, from the reference's declarations
+    (abd.py:424, 329-340, 367-388, 464-467) and PyMC's (mu, sigma) Gamma parametrisation
+    alpha = mu^2 / sigma^2, beta = mu / sigma^2."""
+    from scipy import stats
+
+    def gam(mu, sigma):
+        return stats.gamma(a=mu * mu / sigma**2, scale=sigma**2 / mu)
+
+    return {
+        "p": stats.beta(1, n_gaps - 1), "ab_n_perm": gam(2, 0.5), "ab_n_temp": gam(1, 0.5), "ab_n_rho": stats.beta(10, 1),
+        "ab_n_init": stats.norm(-2, 1), "ab_s_perm": gam(2, 0.5), "ab_s_rho": stats.beta(10, 1),
+        "ab_s_p_waner": stats.beta(1, 1), "ab_s_tempinf": gam(1, 0.5), "ab_s_tempvac": gam(1, 0.5),
+        "ab_s_init": stats.norm(-2, 1), "it_n_b": stats.norm(-1, 0.5), "it_n_d": stats.norm(2, 0.5),
+        "it_n_sigma": stats.expon(scale=1.0), "it_s_b": stats.norm(-1, 0.5), "it_s_d": stats.norm(2, 0.5),
+        "it_s_sigma": stats.expon(scale=1.0),
+    }
+
+
+def test_prior_log_densities_against_scipy():
+    """The restated PyMC log-densities (the part no live PyMC pins here) against an independent
+    implementation: scipy.stats logpdf of the same distributions, and the gamma means / sds the
+    reference declares (mu = 2 or 1, sigma = 0.5)."""
+    rng = np.random.default_rng(3)
+    for G in (5, 26, 31):
+        pri = _scipy_priors(G)
+        assert np.isclose(pri["ab_n_perm"].mean(), 2.0) and np.isclose(pri["ab_n_perm"].std(), 0.5)
+        assert np.isclose(pri["ab_n_temp"].mean(), 1.0) and np.isclose(pri["ab_s_tempvac"].std(), 0.5)
+        for _ in range(20):
+            vals = ora.sample_prior(rng, G)
+            lp, dlp = ora.prior_logp(vals, G)
+            for name, dist in pri.items():
+                assert np.isclose(lp[name], dist.logpdf(vals[name]), rtol=1e-12, atol=1e-12), name
+                h = 1e-6 * max(1.0, abs(vals[name]))
+                fd = (dist.logpdf(vals[name] + h) - dist.logpdf(vals[name] - h)) / (2 * h)
+                assert np.isclose(dlp[name], fd, rtol=1e-5, atol=1e-6), name
+
+
+def test_joint_logp_without_data_is_priors_plus_jacobians_plus_bernoulli():
+    """On a cohort without OD rows the joint logp is the sum of the scipy prior log-densities, the
+    log / logodds Jacobians and the Bernoulli terms of i_raw and ab_s_waner -- assembled here from
+    scratch, independently of the oracle's own bookkeeping."""
+    from abdpymc_b200.cohort import CohortArrays
+
+    rng = np.random.default_rng(5)
+    G, N = 7, 9
+    empty = np.zeros(0)
+    co = CohortArrays(vacs=rng.random((N, G)) < 0.1, pcrpos=np.zeros((N, G)), ind=empty.astype(int), gap=empty.astype(int),
+                      antigen=empty.astype(int), x=empty, od=empty)
+    o = ora.Oracle(co, splits=(3,), dense=False)
+    pri = _scipy_priors(G)
+    for _ in range(10):
+        vals = ora.sample_prior(rng, G)
+        q = ora.forward(vals)
+        i_raw = (rng.random((G, N)) < 0.2).astype(np.int8)
+        w = (rng.random(N) < 0.5).astype(np.int8)
+        want = sum(d.logpdf(vals[k]) for k, d in pri.items())
+        for (name, tr), y in zip(ora.VALUE_VARS, q):
+            if tr == "log":
+                want += y
+            elif tr == "logodds":
+                want += -np.logaddexp(0, -y) - np.logaddexp(0, y)  # log sigmoid(y) + log(1 - sigmoid(y))
+        k = i_raw.sum()
+        want += k * np.log(vals["p"]) + (G * N - k) * np.log1p(-vals["p"])
+        kw = w.sum()
+        want += kw * np.log(vals["ab_s_p_waner"]) + (N - kw) * np.log1p(-vals["ab_s_p_waner"])
+        assert np.isclose(o.logp(q, i_raw, w), want, rtol=1e-12)
