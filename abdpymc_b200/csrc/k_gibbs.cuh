@@ -42,6 +42,116 @@ __device__ __forceinline__ double gibbs_row(double x, double od, int t, bool is_
   return rp.nh * row_resid2(x, od, fma(rp.tfac, T, rp.init + P), rp.b, rp.d, s_tab);
 }
 
+// One chain's parameters into a warp's shared-memory slot (all 32 lanes call it):
+//   s_th[0..12] theta13, [13], [14] -1/(2 sigma^2) of N / S, [15], [16] logit p / p_waner,
+//   [17], [18] sigmoid of those, [19], [20], [21] log p, log(1 - p), p; s_pw[0] = rho_n^k, s_pw[1] = rho_s^k.
+__device__ __forceinline__ void gibbs_load_chain(const double* __restrict__ theta, int theta_is_q,
+                                                 const double* __restrict__ p_arr, const double* __restrict__ pw_arr,
+                                                 int c, int G, int lane, double* s_th, double (*s_pw)[kMaxGaps]) {
+  __syncwarp();
+  fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw[0], nullptr);
+  fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw[1], nullptr);
+  if (lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
+  if (lane == 13 || lane == 14) {
+    const double sg = load_param(theta, theta_is_q, c, lane == 13 ? N_SIGMA : S_SIGMA);
+    s_th[lane] = -0.5 / (sg * sg);
+  }
+  if (lane == 15 || lane == 16) {
+    const int which = lane - 15;
+    double lo, pv;
+    if (theta_is_q) {  // logit of a logodds-transformed value is the value itself
+      lo = theta[(size_t)c * 17 + (which ? kQ_PW : kQ_P)];
+      pv = 1.0 / (1.0 + exp(-lo));
+    } else {
+      pv = which ? pw_arr[c] : p_arr[c];
+      lo = log(pv) - log1p(-pv);
+    }
+    s_th[lane] = lo;
+    s_th[lane + 2] = 1.0 / (1.0 + exp(-lo));  // the heat-bath threshold of a prior-only bit: sigmoid(logit)
+    if (!which) {
+      s_th[19] = log(pv);
+      s_th[20] = log1p(-pv);
+      s_th[21] = pv;
+    }
+  }
+  __syncwarp();
+}
+
+// The OD rows of one individual as a warp holds them: lane l keeps row l (N rows first, then S
+// rows) in registers, rows beyond 32 are read again in every pass; ll() is the individual's
+// log-likelihood under a candidate state (butterfly sum: every lane gets the total).
+template <typename M>
+struct GibbsRows {
+  const DevCohort& dc;
+  const double* s_th;
+  const double (*s_pw)[kMaxGaps];
+  const double* s_tab;
+  int lane, rn0, cnt_n, rs0, cnt_s, nrows;
+  double x0, od0;
+  int t0;
+  bool s0;
+  RowPar rp0;
+  int t_last, t_last_s;  // latest sampled gap of either antigen / of the S antigen (rows are sorted by gap)
+
+  __device__ __forceinline__ GibbsRows(const DevCohort& dc_, int n, int lane_, const double* s_th_,
+                                       const double (*s_pw_)[kMaxGaps], const double* s_tab_)
+      : dc(dc_), s_th(s_th_), s_pw(s_pw_), s_tab(s_tab_), lane(lane_) {
+    rn0 = dc.rp[0][n], cnt_n = dc.rp[0][n + 1] - rn0;
+    rs0 = dc.rp[1][n], cnt_s = dc.rp[1][n + 1] - rs0;
+    nrows = cnt_n + cnt_s;
+    load_row(lane, x0, od0, t0, s0);
+    rp0 = row_par(s0);
+    t_last = t0, t_last_s = s0 ? t0 : -1;
+    for (int l = lane + 32; l < nrows; l += 32) {
+      const bool is_s = l >= cnt_n;
+      const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
+      const int t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
+      t_last = max(t_last, t);
+      if (is_s) t_last_s = max(t_last_s, t);
+    }
+    t_last = __reduce_max_sync(0xffffffffu, t_last);
+    t_last_s = __reduce_max_sync(0xffffffffu, t_last_s);
+  }
+  __device__ __forceinline__ void load_row(int l, double& x, double& od, int& t, bool& is_s) const {
+    is_s = l >= cnt_n;
+    const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
+    if (l < nrows) {
+      x = (is_s ? dc.x[1] : dc.x[0])[r];
+      od = (is_s ? dc.od[1] : dc.od[0])[r];
+      t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
+    } else {
+      x = 0.0;
+      od = 0.0;
+      t = -1;
+    }
+  }
+  __device__ __forceinline__ RowPar row_par(bool is_s) const {
+    RowPar rp;
+    rp.init = s_th[is_s ? S_INIT : N_INIT];
+    rp.perm = s_th[is_s ? S_PERM : N_PERM];
+    rp.tfac = is_s ? 1.0 : s_th[N_TEMP];
+    rp.b = s_th[is_s ? S_B : N_B];
+    rp.d = s_th[is_s ? S_D : N_D];
+    rp.nh = s_th[is_s ? 14 : 13];
+    return rp;
+  }
+  __device__ __forceinline__ double ll(M inf_, M vac, int w_) const {
+    double a = (t0 >= 0) ? gibbs_row<M>(x0, od0, t0, s0, inf_, vac, w_, rp0, s_pw, s_tab) : 0.0;
+    for (int l = lane + 32; l < nrows; l += 32) {  // individuals with more than 32 rows
+      double x, od;
+      int t;
+      bool is_s;
+      load_row(l, x, od, t, is_s);
+      a += gibbs_row<M>(x, od, t, is_s, inf_, vac, w_, row_par(is_s), s_pw, s_tab);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    return a;
+  }
+};
+
+// (k_gibbs below keeps its own hand-inlined copy of these two: going through the helpers costs it
+// 4 % -- 274 instead of 264 us per sweep, a few more spilled registers under its 64-register cap.)
 // Persistent warps: every warp repeatedly claims the next (chain, individual) from a global
 // counter.  Items are ordered chain-major and, inside a chain, by decreasing OD-row count
 // (longest job first), so the tail at the end of the launch is one short job.

@@ -36,7 +36,7 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
   const int G = dc.G, N = dc.N;
 
   __shared__ double s_tab[kExpTab];
-  __shared__ double s_th_all[kGibbsWarps][24];            // theta13, -1/(2 sigma^2) x 2, logit p / p_w, p / p_w, log p, log(1-p)
+  __shared__ double s_th_all[kGibbsWarps][24];            // see gibbs_load_chain
   __shared__ double s_pw_all[kGibbsWarps][3][kMaxGaps];   // rho_n^k, rho_s^k, ones
   double* s_th = s_th_all[warp];
   const double (*s_pw)[kMaxGaps] = s_pw_all[warp];
@@ -64,32 +64,7 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
       }
       n_prop = n_acc = 0;
       cur_c = c;
-      __syncwarp();
-      fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw_all[warp][0], nullptr);
-      fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw_all[warp][1], nullptr);
-      if (lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
-      if (lane == 13 || lane == 14) {
-        const double sg = load_param(theta, theta_is_q, c, lane == 13 ? N_SIGMA : S_SIGMA);
-        s_th[lane] = -0.5 / (sg * sg);
-      }
-      if (lane == 15 || lane == 16) {
-        const int which = lane - 15;
-        double lo, pv;
-        if (theta_is_q) {  // logit of a logodds-transformed value is the value itself
-          lo = theta[(size_t)c * 17 + (which ? kQ_PW : kQ_P)];
-          pv = 1.0 / (1.0 + exp(-lo));
-        } else {
-          pv = which ? pw_arr[c] : p_arr[c];
-          lo = log(pv) - log1p(-pv);
-        }
-        s_th[lane] = lo;
-        s_th[lane + 2] = pv;
-        if (!which) {
-          s_th[19] = log(pv);
-          s_th[20] = log1p(-pv);
-        }
-      }
-      __syncwarp();
+      gibbs_load_chain(theta, theta_is_q, p_arr, pw_arr, c, G, lane, s_th, s_pw_all[warp]);
     }
 
     // ---- this individual's column of i_raw (lane t reads gap t), waner, masks, rows ----
@@ -101,62 +76,9 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
     const int w_in = w;
     const M pcr = reinterpret_cast<const M*>(dc.pcr)[n];
     const M vac = reinterpret_cast<const M*>(dc.vac)[n];
-    const int rn0 = dc.rp[0][n], cnt_n = dc.rp[0][n + 1] - rn0;
-    const int rs0 = dc.rp[1][n], cnt_s = dc.rp[1][n + 1] - rs0;
-    const int nrows = cnt_n + cnt_s;
-
-    auto load_row = [&](int l, double& x, double& od, int& t, bool& is_s) {
-      is_s = l >= cnt_n;
-      const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
-      if (l < nrows) {
-        x = (is_s ? dc.x[1] : dc.x[0])[r];
-        od = (is_s ? dc.od[1] : dc.od[0])[r];
-        t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
-      } else {
-        x = 0.0;
-        od = 0.0;
-        t = -1;
-      }
-    };
-    auto row_par = [&](bool is_s) {
-      RowPar rp;
-      rp.init = s_th[is_s ? S_INIT : N_INIT];
-      rp.perm = s_th[is_s ? S_PERM : N_PERM];
-      rp.tfac = is_s ? 1.0 : s_th[N_TEMP];
-      rp.b = s_th[is_s ? S_B : N_B];
-      rp.d = s_th[is_s ? S_D : N_D];
-      rp.nh = s_th[is_s ? 14 : 13];
-      return rp;
-    };
-    double x0, od0;
-    int t0;
-    bool s0;
-    load_row(lane, x0, od0, t0, s0);
-    const RowPar rp0 = row_par(s0);
-    int t_last = t0, t_last_s = s0 ? t0 : -1;  // latest sampled gap of either antigen / of the S antigen
-    for (int l = lane + 32; l < nrows; l += 32) {
-      const bool is_s = l >= cnt_n;
-      const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
-      const int t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
-      t_last = max(t_last, t);
-      if (is_s) t_last_s = max(t_last_s, t);
-    }
-    t_last = __reduce_max_sync(FULL, t_last);
-    t_last_s = __reduce_max_sync(FULL, t_last_s);
-
-    auto indiv_ll = [&](M inf_, int w_) {
-      double a = (t0 >= 0) ? gibbs_row<M>(x0, od0, t0, s0, inf_, vac, w_, rp0, s_pw, s_tab) : 0.0;
-      for (int l = lane + 32; l < nrows; l += 32) {  // individuals with more than 32 rows
-        double x, od;
-        int t;
-        bool is_s;
-        load_row(l, x, od, t, is_s);
-        a += gibbs_row<M>(x, od, t, is_s, inf_, vac, w_, row_par(is_s), s_pw, s_tab);
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(FULL, a, off);
-      return a;
-    };
+    const GibbsRows<M> rows(dc, n, lane, s_th, s_pw, s_tab);
+    const int t_last = rows.t_last, t_last_s = rows.t_last_s;
+    auto indiv_ll = [&](M inf_, int w_) { return rows.ll(inf_, vac, w_); };
 
     M inf = constrain<M>(raw, pcr, dc.ch);
     double ll = indiv_ll(inf, w);
@@ -166,7 +88,7 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
     const uint4 rnd = philox4x32_10(
         make_uint4((uint32_t)lane, (uint32_t)n + dc.ind_offset, (uint32_t)c, (uint32_t)cfg.sweep),
         make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32) ^ (uint32_t)(cfg.sweep >> 32)));
-    const double pv = s_th[17], lp1 = s_th[19], lp0 = s_th[20];
+    const double pv = s_th[21], lp1 = s_th[19], lp0 = s_th[20];
     const M fresh = __ballot_sync(FULL, lane < G && u01(rnd.x) <= pv);
     const double u_cat = u01(rnd.y);
 
