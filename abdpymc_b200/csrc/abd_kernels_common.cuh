@@ -31,7 +31,13 @@ constexpr int kSumsBlock = 256;
 constexpr int kSumsWarps = kSumsBlock / 32;
 constexpr int kAuxDoubles = 128;  // 17 x PriorPre (7) + LikPre (6), padded
 constexpr int kTileMaxInds = 128;
-constexpr int kGibbsWarps = 8;
+#ifndef ABD_GIBBS_WARPS
+#define ABD_GIBBS_WARPS 8
+#endif
+#ifndef ABD_GIBBS_MINB
+#define ABD_GIBBS_MINB 4
+#endif
+constexpr int kGibbsWarps = ABD_GIBBS_WARPS;  // warps per CTA of the Gibbs kernels; ABD_GIBBS_MINB CTAs per SM
 
 // per-individual state staged in shared memory: constrained infections, vaccinations, waner
 // (packed in the top bit of the vaccination mask; usable gaps <= width - 1)

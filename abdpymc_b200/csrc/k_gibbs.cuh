@@ -159,7 +159,7 @@ struct GibbsRows {
 // measured and dropped: patching each row's decaying response for a candidate instead of summing
 // it again (no gain: the extra live registers cost what the shorter loops save).
 template <typename M>
-__global__ void __launch_bounds__(kGibbsWarps * 32, 4)
+__global__ void __launch_bounds__(kGibbsWarps * 32, ABD_GIBBS_MINB)
 k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
         const double* __restrict__ theta, const int theta_is_q,
         const double* __restrict__ p_arr, const double* __restrict__ pw_arr,

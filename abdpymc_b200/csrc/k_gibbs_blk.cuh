@@ -24,7 +24,7 @@
 namespace {
 using namespace abd;
 
-__global__ void __launch_bounds__(kGibbsWarps * 32, 4)
+__global__ void __launch_bounds__(kGibbsWarps * 32, ABD_GIBBS_MINB)
 k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
             const double* __restrict__ theta, const int theta_is_q,
             const double* __restrict__ p_arr, const double* __restrict__ pw_arr,
