@@ -262,7 +262,7 @@ if HAVE_PYMC:  # pragma: no cover
 # ------------------------------------------------------------------------------------------
 # abdpymc-infer
 # ------------------------------------------------------------------------------------------
-def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0, seed=0, progress=None):
+def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0, seed=0, progress=None, gibbs_mode=0):
     """tune + draws iterations of the built-in HMC + GPU-Gibbs sampler.  Returns (result,
     {name: array (chain, draw, ...)}) with the reference's posterior variable names."""
     import torch
@@ -275,7 +275,8 @@ def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0
     # PyMC-like initial point: prior means on the constrained scale, jittered in q space
     x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
     q0 = forward(x0)[None, :] + rng.uniform(-1, 1, size=(chains, 17))
-    target = AbdTarget(engine, chains, np.zeros((chains, G, N), np.int8), np.zeros((chains, N), np.int8), seed=seed)
+    target = AbdTarget(engine, chains, np.zeros((chains, G, N), np.int8), np.zeros((chains, N), np.int8), seed=seed,
+                       gibbs_mode=gibbs_mode)
     cfg = SamplerConfig(tune=tune, draws=draws, seed=seed, record_deterministics_every=1)
     res = sample(target, torch.from_numpy(q0).to(target.device), cfg, progress=progress)
     post = res.posterior()
@@ -297,6 +298,9 @@ def main(argv=None):
     parser.add_argument("--netcdf", help="Path of netCDF file to save.")
     parser.add_argument("--chains", type=int, default=4, help="(extension) chains batched on the GPU")
     parser.add_argument("--device", type=int, default=0, help="(extension) CUDA device")
+    parser.add_argument("--gibbs_mode", type=int, default=0, choices=[0, 1, 2],
+                        help="(extension) update rule of the indicator sweep: 0 BinaryGibbsMetropolis semantics, "
+                             "1 single-site exact conditionals, 2 per-chunk block draw (include/abd_b200.h)")
     args = parser.parse_args(argv)
 
     data = CohortArrays.from_disk(args.ititers_data)
@@ -307,14 +311,15 @@ def main(argv=None):
         import arviz as az
 
         with model(data, splits=splits, ignore_pcrpos=args.ignore_pcrpos, device=args.device) as m:
-            step = GpuBinaryGibbs([m["i_raw"], m["ab_s_waner"]], model=m)
+            step = GpuBinaryGibbs([m["i_raw"], m["ab_s_waner"]], model=m, mode=args.gibbs_mode)
             # chains run in this process: CUDA contexts do not survive pm.sample's fork
             idata = pm.sample(tune=args.tune, draws=args.draws, cores=1, chains=args.chains, step=[step])
         az.to_netcdf(idata, args.netcdf)
         return idata
 
     res, post, last = infer_builtin(data, splits, args.ignore_pcrpos, args.tune, args.draws, chains=args.chains,
-                                    device=args.device, progress=max(1, (args.tune + args.draws) // 10))
+                                    device=args.device, progress=max(1, (args.tune + args.draws) // 10),
+                                    gibbs_mode=args.gibbs_mode)
     out = args.netcdf or "abd_posterior.npz"
     np.savez_compressed(out if out.endswith(".npz") else out + ".npz", **post, **{f"mean_{k}": v for k, v in res.means.items()},
                         **{f"last_{k}": v for k, v in last.items()}, step_size=res.step_size, wall_s=res.wall_s)

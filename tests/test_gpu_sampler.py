@@ -66,6 +66,12 @@ def test_cli_without_pymc_writes_posterior(gpu, tmp_path):
     assert z["mean_i"].shape == (26, 10) and z["mean_ab_n_mu"].shape == (26, 10)  # dims ("gap", "ind")
     assert z["last_i_raw"].shape == (2, 26, 10)
     assert np.all((z["ab_n_rho"] > 0) & (z["ab_n_rho"] < 1)) and np.all(z["it_n_sigma"] > 0)
+    # the block-draw update rule through the same front end
+    out2 = tmp_path / "post2.npz"
+    abd.main(["--tune", "40", "--draws", "20", "--ititers_data", str(tmp_path / "cohort_data"), "--split_delta",
+              "--split_omicron", "--netcdf", str(out2), "--chains", "2", "--gibbs_mode", "2"])
+    z2 = np.load(out2)
+    assert z2["p"].shape == (2, 20) and set(np.unique(z2["last_i_raw"])) <= {0, 1}
 
 
 def test_hmc_transition_kernels_against_host_formulas(gpu):
