@@ -1071,10 +1071,15 @@ int abd_deterministics_dev(abd_handle* h, int C, const double* theta13, const in
   PROLOGUE(h, C);
   if (!theta13 || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
   dim3 grid((h->N + 127) / 128, C);
-  if (h->wide)
-    k_determ<uint64_t><<<grid, 128, 0, (cudaStream_t)stream>>>(h->dc, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s);
-  else
-    k_determ<uint32_t><<<grid, 128, 0, (cudaStream_t)stream>>>(h->dc, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s);
+  const cudaStream_t st = (cudaStream_t)stream;
+  const bool big = (size_t)C * 17 * h->G * h->N > ((size_t)64 << 20);  // outputs beyond half the L2: stream them
+  if (h->wide) {
+    if (big) k_determ<uint64_t, true><<<grid, 128, 0, st>>>(h->dc, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s);
+    else k_determ<uint64_t, false><<<grid, 128, 0, st>>>(h->dc, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s);
+  } else {
+    if (big) k_determ<uint32_t, true><<<grid, 128, 0, st>>>(h->dc, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s);
+    else k_determ<uint32_t, false><<<grid, 128, 0, st>>>(h->dc, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s);
+  }
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;

@@ -84,7 +84,10 @@ k_hmc_end(const int C, double* __restrict__ q, double* __restrict__ grad, double
 // ------------------------------------------------------------------------------------------
 // k_determ
 // ------------------------------------------------------------------------------------------
-template <typename M>
+// STREAM: streaming (evict-first) stores.  Outputs larger than the L2 go straight to HBM (72 -> 84 %
+// of the copy peak at 32 chains x 10k individuals); small outputs stay ordinary stores so that the
+// consumer (the sampler's running means) finds them in L2 (8.4 us instead of 10.4 at 4 chains).
+template <typename M, bool STREAM>
 __global__ void __launch_bounds__(128)
 k_determ(const DevCohort dc, const double* __restrict__ theta13, const int8_t* __restrict__ i_raw,
          const int8_t* __restrict__ waner, int8_t* __restrict__ out_i, double* __restrict__ out_mu_n,
@@ -119,9 +122,17 @@ k_determ(const DevCohort dc, const double* __restrict__ theta13, const int8_t* _
     if (it) Pn = 1.0;
     if (it | vt) Ps = 1.0;
     const size_t o = ((size_t)c * G + t) * N + n;
-    if (out_i) out_i[o] = (int8_t)it;
-    if (out_mu_n) out_mu_n[o] = s_th[N_PERM] * Pn + s_th[N_TEMP] * T + s_th[N_INIT];
-    if (out_mu_s) out_mu_s[o] = s_th[S_PERM] * Ps + U + s_th[S_INIT];
+    const double mn = s_th[N_PERM] * Pn + s_th[N_TEMP] * T + s_th[N_INIT];
+    const double ms = s_th[S_PERM] * Ps + U + s_th[S_INIT];
+    if constexpr (STREAM) {
+      if (out_i) __stcs(reinterpret_cast<signed char*>(out_i) + o, (signed char)it);
+      if (out_mu_n) __stcs(out_mu_n + o, mn);
+      if (out_mu_s) __stcs(out_mu_s + o, ms);
+    } else {
+      if (out_i) out_i[o] = (int8_t)it;
+      if (out_mu_n) out_mu_n[o] = mn;
+      if (out_mu_s) out_mu_s[o] = ms;
+    }
   }
 }
 

@@ -466,6 +466,39 @@ def run_gpu(args):
     eng_b.close()
     del tqb, outb, outgb
 
+    # ---- Deterministics (i, ab_n_mu, ab_s_mu of every (gap, individual): what a recorded draw costs):
+    #      k_determ is the write-bound kernel of the path, 17 G N bytes out + G N + N bytes in per chain ----
+    determ = {}
+    for CD in (C, 128):
+        cod, _, vd, idd, wdd = workload(n_chains=CD, chain_offset=rank * CD)
+        eng_d = AbdEngine(co, splits=SPLITS, device=local)
+        eng_d.upload_state(idd, wdd)
+        sd = eng_d.state_dev(CD)
+        thd = torch.from_numpy(vd[:, [1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14, 15, 16]].copy()).to(dev)
+        oi = torch.empty(CD, G, N, dtype=torch.int8, device=dev)
+        omn = torch.empty(CD, G, N, dtype=torch.float64, device=dev)
+        oms = torch.empty(CD, G, N, dtype=torch.float64, device=dev)
+        with torch.cuda.stream(side):
+            for _ in range(W):
+                eng_d.deterministics_dev(CD, thd.data_ptr(), sd[0], sd[1], oi.data_ptr(), omn.data_ptr(), oms.data_ptr(),
+                                         side.cuda_stream)
+            e0.record()
+            n_d = 20
+            for _ in range(n_d):
+                eng_d.deterministics_dev(CD, thd.data_ptr(), sd[0], sd[1], oi.data_ptr(), omn.data_ptr(), oms.data_ptr(),
+                                         side.cuda_stream)
+            e1.record()
+        side.synchronize()
+        t_d = e0.elapsed_time(e1) / n_d / 1e3
+        a_d = CD * (18 * G * N + N)
+        determ[f"{CD}_chains"] = {"avg_launch_us": t_d * 1e6, "algorithmic_bytes_per_launch": a_d, "achieved_gbs": a_d / t_d / 1e9,
+                                  "hbm_frac": a_d / t_d / 1e9 / measured_peak_gbs()[0],
+                                  "outputs_larger_than_l2": bool(CD * 17 * G * N > L2_BYTES)}
+        eng_d.close()
+        del oi, omn, oms
+    determ["note"] = ("abd_deterministics_dev (k_determ), the bandwidth-bound kernel of the path: one thread per (individual, chain) "
+                      "runs the recurrence and writes int8 i and f64 ab_n_mu / ab_s_mu coalesced over individuals")
+
     # ---- e2e: host-pointer C-ABI call, pinned host buffers, all inputs copied every call ----
     hq = torch.from_numpy(q).pin_memory()
     hi = torch.from_numpy(i_raw).pin_memory()
@@ -697,6 +730,7 @@ def run_gpu(args):
         "concurrent_streams": concurrent,
         "persistent_trajectory": traj,
         "batched_128_chains": batched,
+        "deterministics": determ,
         "gibbs": {"metric": "Gibbs sweeps/s (all G*N+N binary variables of one chain)", "value": world * C * n_sw / (ms_gibbs / 1e3),
                   "unit": "sweeps/s", "avg_launch_us": t_sweep * 1e6,
                   "regime": "states drawn at random (4 % infections, 50 % waners): the burn-in regime, many accepted flips",
