@@ -1085,6 +1085,21 @@ int abd_deterministics_dev(abd_handle* h, int C, const double* theta13, const in
   return ABD_OK;
 }
 
+int abd_deterministics_accum_dev(abd_handle* h, int C, const double* theta, int theta_is_q17, const int8_t* i_raw,
+                                 const int8_t* waner, double* sum_i, double* sum_mu_n, double* sum_mu_s, void* stream) {
+  PROLOGUE(h, C);
+  if (!theta || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
+  const int grid = (h->N + 127) / 128;
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (h->wide)
+    k_determ_accum<uint64_t><<<grid, 128, 0, st>>>(h->dc, C, theta, theta_is_q17, i_raw, waner, sum_i, sum_mu_n, sum_mu_s);
+  else
+    k_determ_accum<uint32_t><<<grid, 128, 0, st>>>(h->dc, C, theta, theta_is_q17, i_raw, waner, sum_i, sum_mu_n, sum_mu_s);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
 int abd_leapfrog_dev(abd_handle* h, int C, int n_steps, double* q17, double* p17, double* grad17, double* logp,
                      const double* eps, const double* inv_mass, const int8_t* i_raw, const int8_t* waner, void* stream) {
   PROLOGUE(h, C);

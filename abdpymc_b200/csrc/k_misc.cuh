@@ -136,6 +136,72 @@ k_determ(const DevCohort dc, const double* __restrict__ theta13, const int8_t* _
   }
 }
 
+// Streaming posterior summaries: the same recurrence, but instead of writing every
+// chain's (G, N) arrays the kernel ADDS the sum over the C chains to running totals sum_i, sum_mu_n,
+// sum_mu_s (G, N) -- what the consumers of the InferenceData need are posterior means
+// (survival.py:68-69, timelines.py:274).  One thread per individual, chains in order (the result
+// does not depend on the launch geometry); 3 x 8 G N bytes added to per 8 chains instead of 17 G N
+// written per chain and then reduced by a dozen framework kernels.
+template <typename M>
+__global__ void __launch_bounds__(128)
+k_determ_accum(const DevCohort dc, const int C, const double* __restrict__ theta, const int theta_is_q,
+               const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner, double* __restrict__ sum_i,
+               double* __restrict__ sum_mu_n, double* __restrict__ sum_mu_s) {
+  constexpr int KC = 8;  // chains advanced together: their sum is formed in registers, in chain order
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = dc.G, N = dc.N;
+  __shared__ double s_th[KC][13];
+  M pcr = 0, vac = 0;
+  if (n < N) {
+    pcr = reinterpret_cast<const M*>(dc.pcr)[n];
+    vac = reinterpret_cast<const M*>(dc.vac)[n];
+  }
+  for (int c0 = 0; c0 < C; c0 += KC) {
+    const int nc = min(KC, C - c0);
+    __syncthreads();
+    if ((int)threadIdx.x < nc * 13) s_th[threadIdx.x / 13][threadIdx.x % 13] = load_param(theta, theta_is_q, c0 + threadIdx.x / 13, threadIdx.x % 13);
+    __syncthreads();
+    if (n >= N) continue;
+    M inf[KC];
+    double T[KC], U[KC], rho_s[KC];
+    unsigned pn = 0, ps = 0;  // bit k: chain k has been exposed (N: infection; S: infection or vaccination)
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      inf[k] = 0, T[k] = 0.0, U[k] = 0.0, rho_s[k] = 1.0;
+      if (k < nc) {
+        const int8_t* col = i_raw + (size_t)(c0 + k) * G * N + n;
+        M raw = 0;
+        for (int t = 0; t < G; ++t) raw |= (M)(__ldg(col + (size_t)t * N) != 0) << t;
+        inf[k] = constrain<M>(raw, pcr, dc.ch);
+        if (waner[(size_t)(c0 + k) * N + n] != 0) rho_s[k] = s_th[k][S_RHO];
+      }
+    }
+    for (int t = 0; t < G; ++t) {
+      const int vt = (int)((vac >> t) & 1);
+      double si = 0.0, sn = 0.0, ss = 0.0;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        if (k < nc) {
+          const int it = (int)((inf[k] >> t) & 1);
+          T[k] = T[k] * s_th[k][N_RHO] + it;
+          U[k] = U[k] * rho_s[k] + (it + vt);
+          if (it) pn |= 1u << k;
+          if (it | vt) ps |= 1u << k;
+          si += it;
+          sn += s_th[k][N_PERM] * (double)((pn >> k) & 1u) + s_th[k][N_TEMP] * T[k] + s_th[k][N_INIT];
+          ss += s_th[k][S_PERM] * (double)((ps >> k) & 1u) + U[k] + s_th[k][S_INIT];
+        }
+      }
+      // one reduction-add per element and launch (no other thread touches (t, n)): fire and forget,
+      // and the totals do not depend on any ordering between threads
+      const size_t o = (size_t)t * N + n;
+      if (sum_i && si != 0.0) atomicAdd(sum_i + o, si);
+      if (sum_mu_n) atomicAdd(sum_mu_n + o, sn);
+      if (sum_mu_s) atomicAdd(sum_mu_s + o, ss);
+    }
+  }
+}
+
 // pinned host memory -> device memory by the SMs (see copy_state_h2d); n16 16-byte words + rem bytes
 __global__ void __launch_bounds__(256)
 k_pull(const uint4* __restrict__ src, uint4* __restrict__ dst, const size_t n16, const size_t rem) {

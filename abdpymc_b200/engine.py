@@ -319,3 +319,8 @@ class AbdEngine:
 
     def deterministics_dev(self, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream=0):
         check(self._lib.abd_deterministics_dev(self._h, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream))
+
+    def deterministics_accum_dev(self, C_, theta, theta_is_q17, i_raw, waner, sum_i, sum_mu_n, sum_mu_s, stream=0):
+        """Adds the sum over chains of i, ab_n_mu, ab_s_mu (G, N) to the running totals (device pointers)."""
+        check(self._lib.abd_deterministics_accum_dev(self._h, C_, theta, int(theta_is_q17), i_raw, waner, sum_i, sum_mu_n,
+                                                     sum_mu_s, stream))

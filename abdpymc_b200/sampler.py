@@ -115,6 +115,18 @@ class AbdTarget:
                                        self._stream())
         return oi, mn, ms
 
+    def accumulate_deterministics(self, q, sums):
+        """Streaming posterior summaries: adds this state's i, ab_n_mu, ab_s_mu, summed over the chains,
+        to ``sums`` (a dict of (G, N) float64 device tensors, created on first use) in ONE launch --
+        no per-chain (C, G, N) arrays, no framework reductions."""
+        G, N = self.engine.G, self.engine.N
+        for name in ("i", "ab_n_mu", "ab_s_mu"):
+            if name not in sums:
+                sums[name] = torch.zeros(G, N, dtype=torch.float64, device=self.device)
+        q = q.contiguous()
+        self.engine.deterministics_accum_dev(self.C, q.data_ptr(), 1, self.d_i, self.d_w, sums["i"].data_ptr(),
+                                             sums["ab_n_mu"].data_ptr(), sums["ab_s_mu"].data_ptr(), self._stream())
+
     def state(self):
         torch.cuda.synchronize(self.device)
         return self.engine.download_state(self.C)
@@ -255,11 +267,15 @@ def _sample_fused(target, q0, cfg, progress):
             out_lp[k].copy_(logp)
             out_acc[k].copy_(acc)
             every = cfg.record_deterministics_every
-            if every and hasattr(target, "deterministics") and k % every == 0:
-                oi, mn, ms = target.deterministics(q)
-                for name, v in (("i", oi.to(torch.float64)), ("ab_n_mu", mn), ("ab_s_mu", ms)):
-                    means[name] = v.mean(dim=0) if name not in means else means[name] + v.mean(dim=0)
-                n_means += 1
+            if every and k % every == 0:
+                if hasattr(target, "accumulate_deterministics"):
+                    target.accumulate_deterministics(q, means)   # sums over chains; divided once at the end
+                    n_means += C
+                elif hasattr(target, "deterministics"):
+                    oi, mn, ms = target.deterministics(q)
+                    for name, v in (("i", oi.to(torch.float64)), ("ab_n_mu", mn), ("ab_s_mu", ms)):
+                        means[name] = v.sum(dim=0) if name not in means else means[name] + v.sum(dim=0)
+                    n_means += C
         if progress and (it + 1) % progress == 0:
             print(f"  iter {it + 1}/{total}  step {eps.mean().item():.4f}  accept {acc.mean().item():.2f}", flush=True)
     torch.cuda.synchronize(dev)
@@ -352,11 +368,15 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
             k = it - cfg.tune
             out_q[k], out_lp[k], out_acc[k] = q, logp, acc_p
             every = cfg.record_deterministics_every
-            if every and hasattr(target, "deterministics") and k % every == 0:
-                oi, mn, ms = target.deterministics(q)
-                for name, v in (("i", oi.to(torch.float64)), ("ab_n_mu", mn), ("ab_s_mu", ms)):
-                    means[name] = v.mean(dim=0) if name not in means else means[name] + v.mean(dim=0)
-                n_means += 1
+            if every and k % every == 0:
+                if hasattr(target, "accumulate_deterministics"):
+                    target.accumulate_deterministics(q, means)   # sums over chains; divided once at the end
+                    n_means += C
+                elif hasattr(target, "deterministics"):
+                    oi, mn, ms = target.deterministics(q)
+                    for name, v in (("i", oi.to(torch.float64)), ("ab_n_mu", mn), ("ab_s_mu", ms)):
+                        means[name] = v.sum(dim=0) if name not in means else means[name] + v.sum(dim=0)
+                    n_means += C
         if progress and (it + 1) % progress == 0:
             print(f"  iter {it + 1}/{total}  step {eps.mean().item():.4f}  accept {acc_p.mean().item():.2f}", flush=True)
     if dev.type == "cuda":

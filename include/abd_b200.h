@@ -194,6 +194,13 @@ int abd_gibbs_sweep_dev(abd_handle* h, int n_chains, const double* theta, int th
 int abd_deterministics_dev(abd_handle* h, int n_chains, const double* theta13,
                            const int8_t* i_raw, const int8_t* waner, int8_t* out_i,
                            double* out_mu_n, double* out_mu_s, void* stream);
+/* Streaming posterior summaries: ADD the sum over the chains of i, ab_n_mu, ab_s_mu (each (G, N),
+ * float64, gap-major like the Deterministics' dims ("gap", "ind"), abd.py:341,389-391,649,667) to
+ * the caller's running totals; any of the three may be NULL.  Divide by chains x recorded draws for
+ * the posterior means survival.py:68-69 / timelines.py:274 read.  theta_is_q17 as above.      */
+int abd_deterministics_accum_dev(abd_handle* h, int n_chains, const double* theta, int theta_is_q17,
+                                 const int8_t* i_raw, const int8_t* waner, double* sum_i,
+                                 double* sum_mu_n, double* sum_mu_s, void* stream);
 /* n_steps leapfrog steps of Hamiltonian dynamics over q17 for C chains with the binary state
  * fixed, in ONE persistent launch (what a NUTS / HMC trajectory of pm.sample, abd.py:922, costs
  * n_steps calls of logp_dlogp_function for).  Per step: p += eps/2 grad; q += eps inv_mass p;

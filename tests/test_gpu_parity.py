@@ -221,6 +221,38 @@ def random_cohort(rng, G, N, rows_per_ind=6, p_empty=0.2):
     )
 
 
+@pytest.mark.parametrize("G,N,splits", [(26, 300, (14, 20)), (45, 70, (20,)), (5, 3, ())])
+def test_streaming_posterior_sums_match_the_per_chain_deterministics(Engine, G, N, splits):
+    """abd_deterministics_accum_dev adds, in one launch and straight from q17, the sum over chains of
+    the three Deterministics to running totals: two calls on two states must equal the oracle's
+    Deterministics summed over all chains of both states (i exactly, the titers to 1e-12)."""
+    import torch
+
+    rng = np.random.default_rng(G + N)
+    co = random_cohort(rng, G, N)
+    C = 5
+    o = ora.Oracle(co, splits=splits, dense=False)
+    want = [np.zeros((G, N)) for _ in range(3)]
+    with Engine(co, splits=splits) as eng:
+        sums = [torch.zeros(G, N, dtype=torch.float64, device="cuda") for _ in range(3)]
+        for rep in range(2):
+            q, i_raw, w = draw_points(rng, G, N, C)
+            eng.upload_state(i_raw, w)
+            di, dw = eng.state_dev(C)
+            tq = torch.from_numpy(q).cuda()
+            eng.deterministics_accum_dev(C, tq.data_ptr(), 1, di, dw, sums[0].data_ptr(), sums[1].data_ptr(), sums[2].data_ptr())
+            torch.cuda.synchronize()
+            for c in range(C):
+                vals = ora.backward(q[c])[0]
+                th = np.array([vals[n] for n in ora.THETA13])
+                for acc, v in zip(want, o.deterministics(th, i_raw[c], w[c])):
+                    acc += v
+        got = [t.cpu().numpy() for t in sums]
+    assert np.array_equal(got[0], want[0])
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(got[2], want[2], rtol=1e-12, atol=1e-12)
+
+
 @pytest.mark.parametrize("G,N,splits", [(40, 70, (14, 20)), (63, 33, (30,)), (31, 1, (14, 20)), (2, 5, ()),
                                         (32, 64, (0, 32)), (12, 300, (5, 5 + 3))])
 def test_ragged_and_wide_cohorts(Engine, G, N, splits):
