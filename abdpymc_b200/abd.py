@@ -262,7 +262,8 @@ if HAVE_PYMC:  # pragma: no cover
 # ------------------------------------------------------------------------------------------
 # abdpymc-infer
 # ------------------------------------------------------------------------------------------
-def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0, seed=0, progress=None, gibbs_mode=0):
+def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0, seed=0, progress=None, gibbs_mode=0,
+                  thinned=0):
     """tune + draws iterations of the built-in HMC + GPU-Gibbs sampler.  Returns (result,
     {name: array (chain, draw, ...)}) with the reference's posterior variable names."""
     import torch
@@ -277,7 +278,7 @@ def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0
     q0 = forward(x0)[None, :] + rng.uniform(-1, 1, size=(chains, 17))
     target = AbdTarget(engine, chains, np.zeros((chains, G, N), np.int8), np.zeros((chains, N), np.int8), seed=seed,
                        gibbs_mode=gibbs_mode)
-    cfg = SamplerConfig(tune=tune, draws=draws, seed=seed, record_deterministics_every=1)
+    cfg = SamplerConfig(tune=tune, draws=draws, seed=seed, record_deterministics_every=1, thinned_deterministics=thinned)
     res = sample(target, torch.from_numpy(q0).to(target.device), cfg, progress=progress)
     post = res.posterior()
     i_raw, waner = target.state()
@@ -298,6 +299,9 @@ def main(argv=None):
     parser.add_argument("--netcdf", help="Path of netCDF file to save.")
     parser.add_argument("--chains", type=int, default=4, help="(extension) chains batched on the GPU")
     parser.add_argument("--device", type=int, default=0, help="(extension) CUDA device")
+    parser.add_argument("--thinned", type=int, default=250,
+                        help="(extension, PyMC-free driver) evenly spaced draws of i / ab_n_mu / ab_s_mu kept per chain "
+                             "(the downstream code uses <= 250: survival.py:109-114)")
     parser.add_argument("--gibbs_mode", type=int, default=0, choices=[0, 1, 2],
                         help="(extension) update rule of the indicator sweep: 0 BinaryGibbsMetropolis semantics, "
                              "1 single-site exact conditionals, 2 per-chunk block draw (include/abd_b200.h)")
@@ -319,10 +323,11 @@ def main(argv=None):
 
     res, post, last = infer_builtin(data, splits, args.ignore_pcrpos, args.tune, args.draws, chains=args.chains,
                                     device=args.device, progress=max(1, (args.tune + args.draws) // 10),
-                                    gibbs_mode=args.gibbs_mode)
+                                    gibbs_mode=args.gibbs_mode, thinned=args.thinned)
     out = args.netcdf or "abd_posterior.npz"
     np.savez_compressed(out if out.endswith(".npz") else out + ".npz", **post, **{f"mean_{k}": v for k, v in res.means.items()},
-                        **{f"last_{k}": v for k, v in last.items()}, step_size=res.step_size, wall_s=res.wall_s)
+                        **{f"last_{k}": v for k, v in last.items()}, step_size=res.step_size, wall_s=res.wall_s,
+                        **{("thinned_draw" if k == "draw" else k): v for k, v in res.thinned.items()})
     print(f"PyMC not installed: sampled with the built-in HMC+Gibbs driver in {res.wall_s:.1f} s; wrote {out}", file=sys.stderr)
     return res
 

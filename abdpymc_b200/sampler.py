@@ -142,6 +142,8 @@ class SamplerConfig:
     target_accept: float = 0.8
     init_step: float = 0.05
     record_deterministics_every: int = 0   # 0 = never; k = accumulate means every k-th draw
+    thinned_deterministics: int = 0        # keep this many evenly spaced draws of i / ab_n_mu / ab_s_mu per chain (the
+                                           # consumers use <= 250: survival.py:109-114, timelines.py:289-301); 0 = none
     persistent_trajectories: bool = True   # leapfrog integration inside the library (abd_leapfrog_dev) when it fits
     single_step_launches: bool = True      # ... as one launch per step rather than one persistent launch per trajectory
     seed: int = 0
@@ -157,6 +159,7 @@ class SamplerResult:
     wall_s: float
     n_grad_evals: int
     means: dict = field(default_factory=dict)   # posterior means of i, ab_n_mu, ab_s_mu (G, N)
+    thinned: dict = field(default_factory=dict)  # i (int8), ab_n_mu, ab_s_mu (float32): (chains, kept draws, G, N); "draw" = their indexes
 
     def posterior(self):
         """{RV name: (chains, draws)} on the constrained scale, named as abd.model names them."""
@@ -202,6 +205,38 @@ def _windows(tune):
     return ends
 
 
+class _Thinned:
+    """Evenly spaced draws of the three Deterministics, kept on the device until the end of the run
+    (int8 i, float32 titers: 9 G N bytes per chain and kept draw)."""
+
+    def __init__(self, target, cfg):
+        n_keep = 0
+        if cfg.thinned_deterministics and hasattr(target, "deterministics"):
+            per_draw = 9 * target.C * target.engine.G * target.engine.N           # bytes per kept draw
+            n_keep = int(min(cfg.thinned_deterministics, cfg.draws, max(1, (4 << 30) // per_draw)))  # at most 4 GiB
+        self.keep = sorted(set(np.linspace(0, cfg.draws - 1, n_keep).round().astype(int).tolist())) if n_keep else []
+        self.pos = {k: j for j, k in enumerate(self.keep)}
+        if self.keep:
+            G, N, C, dev = target.engine.G, target.engine.N, target.C, target.device
+            self.i = torch.empty(len(self.keep), C, G, N, dtype=torch.int8, device=dev)
+            self.mn = torch.empty(len(self.keep), C, G, N, dtype=torch.float32, device=dev)
+            self.ms = torch.empty(len(self.keep), C, G, N, dtype=torch.float32, device=dev)
+
+    def record(self, target, k, q):
+        j = self.pos.get(k)
+        if j is not None:
+            oi, mn, ms = target.deterministics(q)
+            self.i[j].copy_(oi)
+            self.mn[j].copy_(mn)
+            self.ms[j].copy_(ms)
+
+    def result(self):
+        if not self.keep:
+            return {}
+        return {"draw": np.array(self.keep), "i": self.i.permute(1, 0, 2, 3).cpu().numpy(),
+                "ab_n_mu": self.mn.permute(1, 0, 2, 3).cpu().numpy(), "ab_s_mu": self.ms.permute(1, 0, 2, 3).cpu().numpy()}
+
+
 def _sample_fused(target, q0, cfg, progress):
     """The same iteration as ``sample`` with the whole transition on the device: abd_hmc_begin_dev,
     abd_leapfrog_dev (one launch per step, or one persistent launch), abd_hmc_end_dev,
@@ -228,6 +263,7 @@ def _sample_fused(target, q0, cfg, progress):
     out_q = torch.empty(cfg.draws, C, D, **f64)
     out_lp, out_acc = torch.empty(cfg.draws, C, **f64), torch.empty(cfg.draws, C, **f64)
     means, n_means, n_grad = {}, 0, 0
+    thin = _Thinned(target, cfg)
     t0 = time.perf_counter()
     for it in range(total):
         L = max(1, int(round(cfg.n_leapfrog * (cfg.jitter[0] + (cfg.jitter[1] - cfg.jitter[0]) * rng.random()))))
@@ -266,6 +302,7 @@ def _sample_fused(target, q0, cfg, progress):
             out_q[k].copy_(q)
             out_lp[k].copy_(logp)
             out_acc[k].copy_(acc)
+            thin.record(target, k, q)
             every = cfg.record_deterministics_every
             if every and k % every == 0:
                 if hasattr(target, "accumulate_deterministics"):
@@ -284,7 +321,7 @@ def _sample_fused(target, q0, cfg, progress):
     return SamplerResult(
         q=out_q.permute(1, 0, 2).cpu().numpy(), logp=out_lp.T.cpu().numpy(), accept=out_acc.T.cpu().numpy(),
         step_size=eps.cpu().numpy(), inv_mass=inv_mass.cpu().numpy(), wall_s=wall, n_grad_evals=n_grad,
-        means={k: (v / n_means).cpu().numpy() for k, v in means.items()},
+        means={k: (v / n_means).cpu().numpy() for k, v in means.items()}, thinned=thin.result(),
     )
 
 
@@ -310,6 +347,7 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     out_lp = torch.empty(cfg.draws, C, dtype=torch.float64, device=dev)
     out_acc = torch.empty(cfg.draws, C, dtype=torch.float64, device=dev)
     means, n_means, n_grad = {}, 0, 0
+    thin = _Thinned(target, cfg)
     has_gibbs = hasattr(target, "gibbs")
     use_traj = hasattr(target, "leapfrog") and cfg.persistent_trajectories
     t0 = time.perf_counter()
@@ -367,6 +405,7 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
         else:
             k = it - cfg.tune
             out_q[k], out_lp[k], out_acc[k] = q, logp, acc_p
+            thin.record(target, k, q)
             every = cfg.record_deterministics_every
             if every and k % every == 0:
                 if hasattr(target, "accumulate_deterministics"):
@@ -385,5 +424,5 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     return SamplerResult(
         q=out_q.permute(1, 0, 2).cpu().numpy(), logp=out_lp.T.cpu().numpy(), accept=out_acc.T.cpu().numpy(),
         step_size=eps.cpu().numpy(), inv_mass=inv_mass.cpu().numpy(), wall_s=wall, n_grad_evals=n_grad,
-        means={k: (v / n_means).cpu().numpy() for k, v in means.items()},
+        means={k: (v / n_means).cpu().numpy() for k, v in means.items()}, thinned=thin.result(),
     )

@@ -65,6 +65,11 @@ def test_cli_without_pymc_writes_posterior(gpu, tmp_path):
     assert z["p"].shape == (2, 40) and z["ab_s_rho"].shape == (2, 40)
     assert z["mean_i"].shape == (26, 10) and z["mean_ab_n_mu"].shape == (26, 10)  # dims ("gap", "ind")
     assert z["last_i_raw"].shape == (2, 26, 10)
+    # thinned draws of the Deterministics, dims (chain, draw, gap, ind) as in the InferenceData
+    assert z["i"].shape == (2, 40, 26, 10) and z["i"].dtype == np.int8 and set(np.unique(z["i"])) <= {0, 1}
+    assert z["ab_n_mu"].shape == z["ab_s_mu"].shape == (2, 40, 26, 10) and list(z["thinned_draw"]) == list(range(40))
+    np.testing.assert_allclose(z["i"].mean(axis=(0, 1)), z["mean_i"], atol=1e-12)
+    np.testing.assert_allclose(z["ab_n_mu"].mean(axis=(0, 1)), z["mean_ab_n_mu"], rtol=1e-5, atol=1e-5)
     assert np.all((z["ab_n_rho"] > 0) & (z["ab_n_rho"] < 1)) and np.all(z["it_n_sigma"] > 0)
     # the block-draw update rule through the same front end
     out2 = tmp_path / "post2.npz"
