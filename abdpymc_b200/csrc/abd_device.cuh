@@ -106,44 +106,42 @@ __device__ __forceinline__ double ipow(double r, int k) {
 }
 
 // N antigen at gap t: P = 1[any infection <= t], T = sum_{s in inf, s<=t} rho^(t-s),
-// dT = dT/drho.  pw[k] = rho^k, dpw[k] = k rho^(k-1).
+// dT = dT/drho.  pwd[k] = {rho^k, k rho^(k-1)} (one 16-byte shared-memory load per event).
 template <typename M>
-__device__ __forceinline__ void traj_n(M inf, int t, const double* pw, const double* dpw,
-                                       double& P, double& T, double& dT) {
+__device__ __forceinline__ void traj_n(M inf, int t, const double2* pwd, double& P, double& T, double& dT) {
   M e = inf & low_mask<M>(t);
   P = e ? 1.0 : 0.0;
   T = 0.0;
   dT = 0.0;
   while (e) {
-    const int k = t - ctz(e);
+    const double2 v = pwd[t - ctz(e)];
     e &= e - 1;
-    T += pw[k];
-    dT += dpw[k];
+    T += v.x;
+    dT += v.y;
   }
 }
 
 // S antigen: exposure = i + v (a month with both counts twice, abd.py:378-386).
 // w == 0 => rho_ind = 1 (abd.py:374): U = number of exposures so far, dU/drho_s = 0.
+// One loop over the months with any exposure (its trip count in a warp is the largest number of
+// exposed months, not the largest number of infections plus the largest number of vaccinations).
 template <typename M>
-__device__ __forceinline__ void traj_s(M inf, M vac, int w, int t, const double* pw,
-                                       const double* dpw, double& P, double& U, double& dU) {
+__device__ __forceinline__ void traj_s(M inf, M vac, int w, int t, const double2* pwd, double& P, double& U, double& dU) {
   const M lm = low_mask<M>(t);
-  M e = inf & lm, v = vac & lm;
-  P = (e | v) ? 1.0 : 0.0;
+  const M e = inf & lm, v = vac & lm;
+  M u = e | v;
+  const M both = e & v;
+  P = u ? 1.0 : 0.0;
   U = 0.0;
   dU = 0.0;
   if (w) {
-    while (e) {
-      const int k = t - ctz(e);
-      e &= e - 1;
-      U += pw[k];
-      dU += dpw[k];
-    }
-    while (v) {
-      const int k = t - ctz(v);
-      v &= v - 1;
-      U += pw[k];
-      dU += dpw[k];
+    while (u) {
+      const int s = ctz(u);
+      const double2 p = pwd[t - s];
+      const double cnt = ((both >> s) & 1) ? 2.0 : 1.0;
+      u &= u - 1;
+      U = fma(cnt, p.x, U);
+      dU = fma(cnt, p.y, dU);
     }
   } else {
     U = (double)(popc(e) + popc(v));

@@ -81,4 +81,25 @@ __device__ __forceinline__ void fill_pow_warp(double rho, int G, int lane, doubl
   }
 }
 
+// The same, interleaved: tab[k] = {rho^k, k rho^(k-1)}.
+__device__ __forceinline__ void fill_pow2_warp(double rho, int G, int lane, double2* tab) {
+  double v = rho;  // inclusive prefix product: rho^(lane+1)
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double u = __shfl_up_sync(0xffffffffu, v, off);
+    if (lane >= off) v *= u;
+  }
+  const double r32 = __shfl_sync(0xffffffffu, v, 31);  // rho^32
+  double prev = __shfl_up_sync(0xffffffffu, v, 1);      // rho^lane
+  if (lane == 0) {
+    prev = 1.0;
+    tab[0] = make_double2(1.0, 0.0);
+  }
+  for (int blk = 0; blk * 32 < G; ++blk) {
+    const int k = blk * 32 + lane + 1;
+    const double scale = blk ? r32 : 1.0;  // G <= 63: at most two blocks
+    if (k < G) tab[k] = make_double2(v * scale, (double)k * prev * scale);
+  }
+}
+
 }  // namespace

@@ -178,7 +178,7 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
   uint32_t* s_cm_s = s_cm_n + cfg.capk_n;
 
   __shared__ double s_th[16];
-  __shared__ double s_pw[4][kMaxGaps];  // rho_n^k, d/drho; rho_s^k, d/drho
+  __shared__ double2 s_pw[2][kMaxGaps];  // {rho^k, k rho^(k-1)} for rho_n, rho_s
   __shared__ double s_tab[kExpTab];
   __shared__ IndState<M> s_ind[kTileMaxInds];
   __shared__ double s_red[kSumsWarps][kNSums];
@@ -336,10 +336,10 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     if (tid < kTileMaxInds) {
       PHASEW(12, tid == 0);
     } else if (warp == 4) {
-      fill_pow_warp(param13(N_RHO), G, lane, s_pw[0], s_pw[1]);
+      fill_pow2_warp(param13(N_RHO), G, lane, s_pw[0]);
       PHASEW(13, lane == 0);
     } else if (warp == 5) {
-      fill_pow_warp(param13(S_RHO), G, lane, s_pw[2], s_pw[3]);
+      fill_pow2_warp(param13(S_RHO), G, lane, s_pw[1]);
     } else if (warp == 6) {
       if (TRAJ) {
         const int j = kQOfTheta[lane < 13 ? lane : 0];
@@ -410,7 +410,7 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         const uint32_t mt = s_cm_n[k - kn0];
         const int t = mt & 63, li = (int)(mt >> 6) - i0;
         double P, T, dT;
-        traj_n<M>(s_ind[li].inf, t, s_pw[0], s_pw[1], P, T, dT);
+        traj_n<M>(s_ind[li].inf, t, s_pw[0], P, T, dT);
         CellVal cv;
         cv.m = init + perm * P + temp * T;
         cv.T = T;
@@ -431,7 +431,7 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         const int t = mt & 63, li = (int)(mt >> 6) - i0;
         const IndState<M> st = s_ind[li];
         double P, U, dU;
-        traj_s<M>(st.inf, st.vacw & ~top_bit<M>(), (st.vacw & top_bit<M>()) != 0, t, s_pw[2], s_pw[3], P, U, dU);
+        traj_s<M>(st.inf, st.vacw & ~top_bit<M>(), (st.vacw & top_bit<M>()) != 0, t, s_pw[1], P, U, dU);
         CellVal cv;
         cv.m = init + perm * P + U;
         cv.T = U;
