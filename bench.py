@@ -452,13 +452,17 @@ def run_gpu(args):
     with torch.cuda.stream(side):
         for _ in range(W):
             eng_b.logp_dlogp_dev(CB, tqb.data_ptr(), sb[0], sb[1], outb.data_ptr(), outgb.data_ptr(), side.cuda_stream)
-        e0.record()
-        n_b = max(8, min(64, K))
-        for _ in range(n_b):
-            eng_b.logp_dlogp_dev(CB, tqb.data_ptr(), sb[0], sb[1], outb.data_ptr(), outgb.data_ptr(), side.cuda_stream)
-        e1.record()
-    side.synchronize()
-    ms_b = e0.elapsed_time(e1)
+    n_b = max(8, min(64, K))
+    reps_b = []
+    for _ in range(3):  # median of three repeats (a single block of ~40 launches is at the mercy of one hiccup)
+        with torch.cuda.stream(side):
+            e0.record()
+            for _ in range(n_b):
+                eng_b.logp_dlogp_dev(CB, tqb.data_ptr(), sb[0], sb[1], outb.data_ptr(), outgb.data_ptr(), side.cuda_stream)
+            e1.record()
+        side.synchronize()
+        reps_b.append(e0.elapsed_time(e1))
+    ms_b = sorted(reps_b)[1]
     a_b = eng_b.algorithmic_bytes_logp(CB)
     batched = {"chains": CB, "value": world * CB * n_b / (ms_b / 1e3), "unit": "evals/s", "avg_launch_us": ms_b / n_b * 1e3,
                "algorithmic_bytes_per_launch": a_b, "hbm_frac": a_b / (ms_b / n_b / 1e3) / 1e9 / measured_peak_gbs()[0],
