@@ -71,6 +71,12 @@ def test_cli_without_pymc_writes_posterior(gpu, tmp_path):
     np.testing.assert_allclose(z["i"].mean(axis=(0, 1)), z["mean_i"], atol=1e-12)
     np.testing.assert_allclose(z["ab_n_mu"].mean(axis=(0, 1)), z["mean_ab_n_mu"], rtol=1e-5, atol=1e-5)
     assert np.all((z["ab_n_rho"] > 0) & (z["ab_n_rho"] < 1)) and np.all(z["it_n_sigma"] > 0)
+    # no split flags: the OneTimeChunk model (abd.py:640-649), SURVEY 8d config 1 "splits (14, 20) and none"
+    out1 = tmp_path / "post1.npz"
+    abd.main(["--tune", "40", "--draws", "20", "--ititers_data", str(tmp_path / "cohort_data"), "--netcdf", str(out1),
+              "--chains", "2", "--thinned", "5"])
+    z1 = np.load(out1)
+    assert z1["p"].shape == (2, 20) and z1["i"].shape == (2, 5, 26, 10) and np.isfinite(z1["ab_s_rho"]).all()
     # the block-draw update rule through the same front end
     out2 = tmp_path / "post2.npz"
     abd.main(["--tune", "40", "--draws", "20", "--ititers_data", str(tmp_path / "cohort_data"), "--split_delta",
