@@ -263,7 +263,7 @@ if HAVE_PYMC:  # pragma: no cover
 # abdpymc-infer
 # ------------------------------------------------------------------------------------------
 def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0, seed=0, progress=None, gibbs_mode=0,
-                  thinned=0):
+                  thinned=0, kernel="hmc"):
     """tune + draws iterations of the built-in HMC + GPU-Gibbs sampler.  Returns (result,
     {name: array (chain, draw, ...)}) with the reference's posterior variable names."""
     import torch
@@ -278,7 +278,8 @@ def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0
     q0 = forward(x0)[None, :] + rng.uniform(-1, 1, size=(chains, 17))
     target = AbdTarget(engine, chains, np.zeros((chains, G, N), np.int8), np.zeros((chains, N), np.int8), seed=seed,
                        gibbs_mode=gibbs_mode)
-    cfg = SamplerConfig(tune=tune, draws=draws, seed=seed, record_deterministics_every=1, thinned_deterministics=thinned)
+    cfg = SamplerConfig(tune=tune, draws=draws, seed=seed, record_deterministics_every=1, thinned_deterministics=thinned,
+                        kernel=kernel)
     res = sample(target, torch.from_numpy(q0).to(target.device), cfg, progress=progress)
     post = res.posterior()
     i_raw, waner = target.state()
@@ -302,6 +303,9 @@ def main(argv=None):
     parser.add_argument("--thinned", type=int, default=250,
                         help="(extension, PyMC-free driver) evenly spaced draws of i / ab_n_mu / ab_s_mu kept per chain "
                              "(the downstream code uses <= 250: survival.py:109-114)")
+    parser.add_argument("--kernel", default="hmc", choices=["hmc", "nuts"],
+                        help="(extension, PyMC-free driver) transition for the 17 scalars: fused device-resident HMC "
+                             "(default, fastest) or batched No-U-Turn trajectories")
     parser.add_argument("--gibbs_mode", type=int, default=0, choices=[0, 1, 2],
                         help="(extension) update rule of the indicator sweep: 0 BinaryGibbsMetropolis semantics, "
                              "1 single-site exact conditionals, 2 per-chunk block draw (include/abd_b200.h)")
@@ -323,7 +327,7 @@ def main(argv=None):
 
     res, post, last = infer_builtin(data, splits, args.ignore_pcrpos, args.tune, args.draws, chains=args.chains,
                                     device=args.device, progress=max(1, (args.tune + args.draws) // 10),
-                                    gibbs_mode=args.gibbs_mode, thinned=args.thinned)
+                                    gibbs_mode=args.gibbs_mode, thinned=args.thinned, kernel=args.kernel)
     out = args.netcdf or "abd_posterior.npz"
     if not out.endswith(".npz"):
         try:  # pragma: no cover - ArviZ is absent from the build image

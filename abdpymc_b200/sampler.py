@@ -147,6 +147,10 @@ class SamplerConfig:
     persistent_trajectories: bool = True   # leapfrog integration inside the library (abd_leapfrog_dev) when it fits
     single_step_launches: bool = True      # ... as one launch per step rather than one persistent launch per trajectory
     seed: int = 0
+    kernel: str = "hmc"                    # "hmc": jittered fixed-length trajectories (the fused device loop when it fits);
+                                           # "nuts": batched multinomial No-U-Turn trajectories (what pm.sample runs for
+                                           # the 17 scalars, abd.py:922), chains doubling in lockstep, host-driven
+    max_treedepth: int = 8
 
 
 @dataclass
@@ -325,9 +329,104 @@ def _sample_fused(target, q0, cfg, progress):
     )
 
 
+def _nuts_transition(target, q, logp, grad, eps, inv_mass, chol, gen, max_depth):
+    """One No-U-Turn transition for a batch of chains (multinomial sampling inside sub-trees, biased
+    progressive sampling between them, the generalised U-turn criterion on every balanced sub-tree:
+    Betancourt 2017, as in Stan / PyMC).  The chains double in lockstep -- one batched logp + gradient
+    evaluation per leaf serves them all -- and a chain that has terminated is masked.  Sub-tree U-turn
+    checks use O(depth) momentum checkpoints per chain instead of recursion.
+    Returns (q, logp, grad, mean acceptance statistic, tree depth, diverged, leaves evaluated)."""
+    B, D = q.shape
+    dev, f64 = q.device, torch.float64
+    z = torch.randn(B, D, dtype=f64, device=dev, generator=gen)
+    p0 = torch.linalg.solve_triangular(chol.T, z.T, upper=True).T          # p ~ N(0, M), M = Sigma^-1
+    h0 = -logp + 0.5 * (z * z).sum(dim=1)
+    e = eps[:, None]
+
+    def turning(p_a, p_b, rho):  # either end of the span still moving against the span's momentum sum
+        adj = rho - 0.5 * (p_a + p_b)
+        return (((p_a @ inv_mass) * adj).sum(dim=1) <= 0) | (((p_b @ inv_mass) * adj).sum(dim=1) <= 0)
+
+    q_l, p_l, g_l = q.clone(), p0.clone(), grad.clone()
+    q_r, p_r, g_r = q.clone(), p0.clone(), grad.clone()
+    q_prop, lp_prop, g_prop = q.clone(), logp.clone(), grad.clone()
+    log_w = torch.zeros(B, dtype=f64, device=dev)          # log sum of exp(h0 - h) over the tree (start point: 0)
+    rho = p0.clone()
+    active = torch.ones(B, dtype=torch.bool, device=dev)
+    depth = torch.zeros(B, dtype=torch.long, device=dev)
+    diverged = torch.zeros(B, dtype=torch.bool, device=dev)
+    sum_acc = torch.zeros(B, dtype=f64, device=dev)
+    n_acc = torch.zeros(B, dtype=f64, device=dev)
+    n_leaves = 0
+    neg_inf = torch.full((B,), -float("inf"), dtype=f64, device=dev)
+    for j in range(max_depth):
+        if not bool(active.any()):
+            break
+        fwd = torch.rand(B, device=dev, generator=gen) < 0.5
+        v = torch.where(fwd, 1.0, -1.0).to(f64)[:, None]
+        fw = fwd[:, None]
+        q_e, p_e, g_e = torch.where(fw, q_r, q_l), torch.where(fw, p_r, p_l), torch.where(fw, g_r, g_l)
+        s_q, s_lp, s_g = q_e.clone(), lp_prop.clone(), g_e.clone()
+        s_log_w, s_rho = neg_inf.clone(), torch.zeros(B, D, dtype=f64, device=dev)
+        s_stop = ~active                                     # turned inside the sub-tree, diverged, or not running
+        p_ck = torch.zeros(B, max(j, 1), D, dtype=f64, device=dev)
+        rho_ck = torch.zeros(B, max(j, 1), D, dtype=f64, device=dev)
+        for n in range(1 << j):
+            run = ~s_stop
+            if not bool(run.any()):
+                break
+            ph = p_e + 0.5 * v * e * g_e
+            qn = q_e + v * e * (ph @ inv_mass)
+            lpn, gn = target.logp_dlogp(qn)
+            n_leaves += 1
+            pn = ph + 0.5 * v * e * gn
+            dh = h0 - (-lpn + 0.5 * ((pn @ inv_mass) * pn).sum(dim=1))
+            dh = torch.where(torch.isfinite(dh), dh, neg_inf)
+            div = run & (dh < -1000.0)
+            ok = run & ~div
+            r2 = run[:, None]
+            q_e, p_e, g_e = torch.where(r2, qn, q_e), torch.where(r2, pn, p_e), torch.where(r2, gn, g_e)
+            sum_acc = sum_acc + torch.where(run, torch.exp(torch.clamp(dh, max=0.0)), torch.zeros_like(dh))
+            n_acc = n_acc + run.to(f64)
+            new_w = torch.logaddexp(s_log_w, dh)
+            take = ok & (torch.rand(B, dtype=f64, device=dev, generator=gen) < torch.exp(dh - new_w))
+            t2 = take[:, None]
+            s_q, s_lp, s_g = torch.where(t2, qn, s_q), torch.where(take, lpn, s_lp), torch.where(t2, gn, s_g)
+            s_log_w = torch.where(ok, new_w, s_log_w)
+            s_rho = s_rho + torch.where(ok[:, None], pn, torch.zeros_like(pn))
+            diverged |= div
+            s_stop = s_stop | div
+            if j > 0:
+                # checkpoints: leaf n closes the balanced sub-trees that start at the leaves whose
+                # checkpoints sit at idx_min .. idx_max (n odd); an even leaf opens one at idx_max
+                idx_max = bin(n >> 1).count("1")
+                if n % 2 == 0:
+                    p_ck[:, idx_max] = torch.where(ok[:, None], pn, p_ck[:, idx_max])
+                    rho_ck[:, idx_max] = torch.where(ok[:, None], s_rho, rho_ck[:, idx_max])
+                else:
+                    trailing = (n ^ (n + 1)).bit_length() - 1          # number of trailing one bits of n
+                    idx_min = idx_max - trailing + 1
+                    for i in range(idx_max, idx_min - 1, -1):
+                        span = s_rho - rho_ck[:, i] + p_ck[:, i]
+                        s_stop = s_stop | (ok & turning(p_ck[:, i], pn, span))
+        # merge the finished sub-tree (chains that neither turned inside it nor diverged)
+        good = active & ~s_stop
+        take = good & (torch.rand(B, dtype=f64, device=dev, generator=gen) < torch.exp(torch.clamp(s_log_w - log_w, max=0.0)))
+        t2 = take[:, None]
+        q_prop, lp_prop, g_prop = torch.where(t2, s_q, q_prop), torch.where(take, s_lp, lp_prop), torch.where(t2, s_g, g_prop)
+        log_w = torch.where(good, torch.logaddexp(log_w, s_log_w), log_w)
+        rho = rho + torch.where(good[:, None], s_rho, torch.zeros_like(s_rho))
+        gr, gl = (good & fwd)[:, None], (good & ~fwd)[:, None]
+        q_r, p_r, g_r = torch.where(gr, q_e, q_r), torch.where(gr, p_e, p_r), torch.where(gr, g_e, g_r)
+        q_l, p_l, g_l = torch.where(gl, q_e, q_l), torch.where(gl, p_e, p_l), torch.where(gl, g_e, g_l)
+        depth = depth + active.to(torch.long)
+        active = good & ~turning(p_l, p_r, rho)
+    return q_prop, lp_prop, g_prop, sum_acc / torch.clamp(n_acc, min=1.0), depth, diverged, n_leaves
+
+
 def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> SamplerResult:
     """Run tune + draws iterations of [HMC on q | binaries] then [Gibbs on binaries | q]."""
-    if cfg.persistent_trajectories and hasattr(target, "hmc_begin") and target.fits_persistent():
+    if cfg.kernel == "hmc" and cfg.persistent_trajectories and hasattr(target, "hmc_begin") and target.fits_persistent():
         return _sample_fused(target, q0, cfg, progress)
     dev = q0.device
     C, D = q0.shape
@@ -352,35 +451,41 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     use_traj = hasattr(target, "leapfrog") and cfg.persistent_trajectories
     t0 = time.perf_counter()
     for it in range(total):
-        # ---- HMC over q given the binaries -------------------------------------------------
-        # p ~ N(0, M) with M = Sigma^-1:  p = chol^-T z
-        z = torch.randn(C, D, dtype=torch.float64, device=dev, generator=gen)
-        p = torch.linalg.solve_triangular(chol.T, z.T, upper=True).T
-        h0 = -logp + 0.5 * (z * z).sum(dim=1)
-        jitter = cfg.jitter[0] + (cfg.jitter[1] - cfg.jitter[0]) * torch.rand((), device=dev, generator=gen).item()
-        L = max(1, int(round(cfg.n_leapfrog * jitter)))
-        if use_traj:
-            try:
-                qn, pn, lpn, gn = target.leapfrog(q, p, grad, eps, inv_mass, L)
-            except Exception:  # too many chains for one resident grid: per-step launches
-                use_traj = False
-        if not use_traj:
-            qn, pn, gn, lpn = q, p, grad, logp
-            e = eps[:, None]
-            for _ in range(L):
-                pn = pn + 0.5 * e * gn
-                qn = qn + e * (pn @ inv_mass)
-                lpn, gn = target.logp_dlogp(qn)
-                pn = pn + 0.5 * e * gn
-        n_grad += L
-        h1 = -lpn + 0.5 * ((pn @ inv_mass) * pn).sum(dim=1)
-        dh = h0 - h1
-        dh = torch.where(torch.isfinite(dh), dh, torch.full_like(dh, -float("inf")))
-        acc_p = torch.exp(torch.clamp(dh, max=0.0))
-        take = torch.rand(C, dtype=torch.float64, device=dev, generator=gen) < acc_p
-        q = torch.where(take[:, None], qn, q)
-        grad = torch.where(take[:, None], gn, grad)
-        logp = torch.where(take, lpn, logp)
+        if cfg.kernel == "nuts":
+            # ---- NUTS over q given the binaries (abd.py:922 runs PyMC's) ------------------------
+            q, logp, grad, acc_p, _, _, n_leaf = _nuts_transition(target, q, logp, grad, eps, inv_mass, chol, gen,
+                                                                  cfg.max_treedepth)
+            n_grad += n_leaf
+        else:
+            # ---- HMC over q given the binaries ---------------------------------------------
+            # p ~ N(0, M) with M = Sigma^-1:  p = chol^-T z
+            z = torch.randn(C, D, dtype=torch.float64, device=dev, generator=gen)
+            p = torch.linalg.solve_triangular(chol.T, z.T, upper=True).T
+            h0 = -logp + 0.5 * (z * z).sum(dim=1)
+            jitter = cfg.jitter[0] + (cfg.jitter[1] - cfg.jitter[0]) * torch.rand((), device=dev, generator=gen).item()
+            L = max(1, int(round(cfg.n_leapfrog * jitter)))
+            if use_traj:
+                try:
+                    qn, pn, lpn, gn = target.leapfrog(q, p, grad, eps, inv_mass, L)
+                except Exception:  # too many chains for one resident grid: per-step launches
+                    use_traj = False
+            if not use_traj:
+                qn, pn, gn, lpn = q, p, grad, logp
+                e = eps[:, None]
+                for _ in range(L):
+                    pn = pn + 0.5 * e * gn
+                    qn = qn + e * (pn @ inv_mass)
+                    lpn, gn = target.logp_dlogp(qn)
+                    pn = pn + 0.5 * e * gn
+            n_grad += L
+            h1 = -lpn + 0.5 * ((pn @ inv_mass) * pn).sum(dim=1)
+            dh = h0 - h1
+            dh = torch.where(torch.isfinite(dh), dh, torch.full_like(dh, -float("inf")))
+            acc_p = torch.exp(torch.clamp(dh, max=0.0))
+            take = torch.rand(C, dtype=torch.float64, device=dev, generator=gen) < acc_p
+            q = torch.where(take[:, None], qn, q)
+            grad = torch.where(take[:, None], gn, grad)
+            logp = torch.where(take, lpn, logp)
         # ---- Gibbs over the binaries given q (then logp / grad at the new state) -------------
         if has_gibbs:
             target.gibbs(q, it)

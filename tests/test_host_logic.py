@@ -127,6 +127,35 @@ def test_sampler_recovers_gaussian_moments():
         assert dg.ess_bulk(res.q[:, :, k]) > 400
 
 
+def test_nuts_kernel_recovers_gaussian_moments():
+    """The batched No-U-Turn transition (SamplerConfig(kernel="nuts")): moments of a badly scaled and
+    of a strongly correlated Gaussian, tails, and the antithetic behaviour NUTS shows on Gaussians
+    (bulk ESS above the number of draws)."""
+    from abdpymc_b200.sampler import SamplerConfig, sample
+
+    tgt = GaussianTarget()
+    res = sample(tgt, torch.zeros(6, 5, dtype=torch.float64), SamplerConfig(tune=300, draws=400, seed=3, kernel="nuts"))
+    x = res.q.reshape(-1, 5)
+    assert np.all(np.abs(x.mean(axis=0) - tgt.mu.numpy()) < 0.15 * tgt.sd.numpy())
+    assert np.all(np.abs(x.std(axis=0) / tgt.sd.numpy() - 1) < 0.1)
+    assert 0.6 < res.accept.mean() < 0.97
+    for k in range(5):
+        assert dg.rhat(res.q[:, :, k]) < 1.03 and dg.ess_bulk(res.q[:, :, k]) > 1500
+
+    class Correlated:  # rho = 0.95, scales 1 and 2
+        cov = torch.tensor([[1.0, 1.9], [1.9, 4.0]], dtype=torch.float64)
+        prec = torch.linalg.inv(cov)
+
+        def logp_dlogp(self, q):
+            g = -(q @ self.prec)
+            return 0.5 * (q * g).sum(dim=1), g
+
+    res = sample(Correlated(), torch.zeros(6, 2, dtype=torch.float64), SamplerConfig(tune=200, draws=700, seed=5, kernel="nuts"))
+    x = res.q.reshape(-1, 2)
+    np.testing.assert_allclose(np.cov(x.T), Correlated.cov.numpy(), rtol=0.12, atol=0.12)
+    assert abs((np.abs(x[:, 0]) > 2).mean() - 0.0455) < 0.015
+
+
 # ------------------------------------------------------------------------------ gloo, world_size 2
 def _free_port():
     with socket.socket() as s:
