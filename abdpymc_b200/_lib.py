@@ -81,6 +81,8 @@ SIGNATURES = {
     "abd_logp_dlogp_sharded_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 6),
     "abd_xch_status": (C.c_int, [H]),
     "abd_state_dev": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "abd_state_touch": (C.c_int, [H]),
+    "abd_set_chain_offset": (C.c_int, [H, C.c_int64]),
     "abd_set_tuning": (C.c_int, [H, C.c_int, C.c_int]),
     "abd_debug_fast_math": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }  # fmt: skip

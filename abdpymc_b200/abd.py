@@ -87,17 +87,56 @@ def make_engine(data, splits=None, ignore_pcrpos=False, device=0, **kw) -> AbdEn
 # PyTensor Ops
 # ------------------------------------------------------------------------------------------
 class _Cache:
-    """Value and gradient come out of one kernel launch; NUTS asks for both at the same point."""
+    """Shared by the Ops of one model and its ``GpuBinaryGibbs`` step.
 
-    def __init__(self, engine):
-        self.engine, self.key, self.val = engine, None, None
+    * Value and gradient come out of one kernel launch; NUTS asks for both at the same point.
+    * The binaries (``i_raw`` 2.5 MB of int64 at 10k individuals, ``ab_s_waner``) only change once per
+      Gibbs sweep, NUTS evaluates dozens of leapfrogs in between: they travel to the GPU only when they
+      changed.  "Unchanged" is decided without touching their bytes on the hot path: PyTensor hands
+      ``perform`` the SAME ndarray objects (the storage of the shared "extra values") until PyMC sets new
+      ones, so object identity with the arrays seen last time is the test; when the objects are new
+      (once per sweep) their contents are compared once with the host copy of what the sweep left on the
+      device, and only a real difference (a new chain's initial point, a user evaluating some other
+      point) costs an upload.  Inputs are assumed not to be mutated in place between calls (PyTensor /
+      PyMC never do); ``strict=True`` compares contents on every call instead.
+    """
+
+    def __init__(self, engine, strict=False):
+        self.engine, self.strict = engine, strict
+        self.key, self.val = None, None
+        self._seen = None   # (i_raw, waner) objects known to equal the resident state
+        self._host = None   # one-byte copies of the resident state
+        self.uploads = 0
+
+    def note_resident(self, i8, w8):
+        """The device state is now (i8, w8): called by the Gibbs step after a sweep."""
+        self._host, self._seen, self.key = (i8, w8), None, None
+
+    def binaries_resident(self, i_raw, waner) -> bool:
+        if not self.strict and self._seen is not None and self._seen[0] is i_raw and self._seen[1] is waner:
+            return True
+        h = self._host
+        if h is not None and h[0].shape == np.shape(i_raw) and np.array_equal(h[0], i_raw) and np.array_equal(h[1], waner):
+            self._seen = (i_raw, waner)
+            return True
+        return False
+
+    def ensure_resident(self, i_raw, waner):
+        i_raw, waner = np.asarray(i_raw), np.asarray(waner)
+        if self.binaries_resident(i_raw, waner):
+            return
+        i8 = np.ascontiguousarray(i_raw != 0, dtype=np.int8)
+        w8 = np.ascontiguousarray(waner != 0, dtype=np.int8)
+        self.engine.upload_state(i8, w8)
+        self.uploads += 1
+        self._host, self._seen, self.key = (i8, w8), (i_raw, waner), None
 
     def get(self, inputs):
         th = np.array([float(v) for v in inputs[:13]], dtype=np.float64)
-        i_raw, waner = np.asarray(inputs[13]), np.asarray(inputs[14])
-        key = (th.tobytes(), i_raw.tobytes(), waner.tobytes())
+        self.ensure_resident(inputs[13], inputs[14])
+        key = th.tobytes()
         if key != self.key:
-            ll, g, _ = self.engine.loglik_grad(th, i_raw, waner)
+            ll, g, _ = self.engine.loglik_grad(th)   # chain state resident: 13 scalars in, 14 out
             self.key, self.val = key, (float(ll), np.asarray(g, dtype=np.float64))
         return self.val
 
@@ -154,8 +193,8 @@ class AbdDeterministics(Op):
 
     __props__ = ()
 
-    def __init__(self, engine):
-        self.engine = engine
+    def __init__(self, engine, cache=None):
+        self.engine, self.cache = engine, cache
 
     def make_node(self, *inputs):
         inputs = [pt.as_tensor_variable(v) for v in inputs]
@@ -163,7 +202,11 @@ class AbdDeterministics(Op):
 
     def perform(self, node, inputs, output_storage):
         th = np.array([float(v) for v in inputs[:13]], dtype=np.float64)
-        i, mn, ms = self.engine.deterministics(th, inputs[13], inputs[14])
+        if self.cache is not None:
+            self.cache.ensure_resident(inputs[13], inputs[14])
+            i, mn, ms = self.engine.deterministics(th)
+        else:
+            i, mn, ms = self.engine.deterministics(th, inputs[13], inputs[14])
         output_storage[0][0], output_storage[1][0], output_storage[2][0] = i, mn, ms
 
 
@@ -197,12 +240,13 @@ def model(data, splits=None, ignore_pcrpos=False, device=0):
         s_b, s_d = pm.Normal("it_s_b", -1, 0.5), pm.Normal("it_s_d", 2, 0.5)
         s_sigma = pm.Exponential("it_s_sigma", 1)
         theta = [n_perm, n_temp, n_rho, n_init, s_perm, s_rho, s_init, n_b, n_d, n_sigma, s_b, s_d, s_sigma]
-        pm.Potential("loglik", AbdLogLik(engine)(*theta, i_raw, waner))
-        i, mu_n, mu_s = AbdDeterministics(engine)(*theta, i_raw, waner)
+        cache = _Cache(engine)
+        pm.Potential("loglik", AbdLogLik(engine, cache)(*theta, i_raw, waner))
+        i, mu_n, mu_s = AbdDeterministics(engine, cache)(*theta, i_raw, waner)
         pm.Deterministic("i", i, dims=GAP_IND)
         pm.Deterministic("ab_n_mu", mu_n, dims=GAP_IND)
         pm.Deterministic("ab_s_mu", mu_s, dims=GAP_IND)
-    m.abd_engine = engine
+    m.abd_engine, m.abd_cache = engine, cache
     return m
 
 
@@ -229,11 +273,19 @@ if HAVE_PYMC:  # pragma: no cover
         stats_dtypes_shapes = {"p_jump": (float, []), "tune": (bool, [])}
         stats_dtypes = [{"p_jump": float, "tune": bool}]  # PyMC < 5.7 spelling
 
+        def __new__(cls, vars=None, model=None, **kwargs):
+            # BlockedStep.__new__ needs `vars`: fill in the model's two binary RVs when they are not given
+            model = pm.modelcontext(model)
+            if vars is None:
+                vars = [model["i_raw"], model["ab_s_waner"]]
+            return super().__new__(cls, vars=vars, model=model, **kwargs)
+
         def __init__(self, vars=None, model=None, transit_p=0.8, mode=0, seed=None, **kwargs):
             model = pm.modelcontext(model)
             vars = vars or [model["i_raw"], model["ab_s_waner"]]
             self.vars = [model.rvs_to_values.get(v, v) for v in vars]
             self.engine = model.abd_engine
+            self.cache = getattr(model, "abd_cache", None)
             self.transit_p, self.mode = transit_p, mode
             self.seed = int(np.random.SeedSequence(seed).generate_state(1, dtype=np.uint64)[0])
             self.sweep, self.tune = 0, True
@@ -242,9 +294,17 @@ if HAVE_PYMC:  # pragma: no cover
         def step(self, point):
             q = point_to_q17(point)
             x = backward(q)
-            i_raw, waner, st = self.engine.gibbs_sweep(x[Q_OF_THETA], x[Q_P], x[Q_PW], point["i_raw"],
-                                                       point["ab_s_waner"], seed=self.seed, sweep=self.sweep,
-                                                       mode=self.mode, transit_p=self.transit_p)
+            if self.cache is not None:
+                # the binaries NUTS has just been evaluating are already on the device: sweep them there,
+                # and tell the Ops what the device holds afterwards (no upload on the next leapfrog)
+                self.cache.ensure_resident(point["i_raw"], point["ab_s_waner"])
+                i_raw, waner, st = self.engine.gibbs_sweep(x[Q_OF_THETA], x[Q_P], x[Q_PW], seed=self.seed, sweep=self.sweep,
+                                                           mode=self.mode, transit_p=self.transit_p)
+                self.cache.note_resident(i_raw, waner)
+            else:
+                i_raw, waner, st = self.engine.gibbs_sweep(x[Q_OF_THETA], x[Q_P], x[Q_PW], point["i_raw"],
+                                                           point["ab_s_waner"], seed=self.seed, sweep=self.sweep,
+                                                           mode=self.mode, transit_p=self.transit_p)
             self.sweep += 1
             new = dict(point)
             new["i_raw"] = i_raw.astype(np.asarray(point["i_raw"]).dtype)
@@ -310,6 +370,9 @@ def main(argv=None):
                         help="(extension) update rule of the indicator sweep: 0 BinaryGibbsMetropolis semantics, "
                              "1 single-site exact conditionals, 2 per-chunk block draw (include/abd_b200.h)")
     args = parser.parse_args(argv)
+    if args.cores not in (None, 1):
+        print(f"abdpymc-infer: --cores {args.cores} ignored -- the chains of a run are batched on the GPU(s) of this process "
+              "(a CUDA context does not survive pm.sample's fork); use --chains / --devices", file=sys.stderr)
 
     data = CohortArrays.from_disk(args.ititers_data)
     splits = (None if (not args.split_delta) and (not args.split_omicron)

@@ -41,6 +41,13 @@ class CohortArrays:
     truth: dict = field(default_factory=dict)  # simulated ground truth, if any
 
     def __post_init__(self):
+        # The reference uses vacs / pcrpos NUMERICALLY (exposure = i + v, abd.py:368,384; i_raw + pcrpos, abd.py:643);
+        # the device layout is one bit per (individual, gap), so anything but 0 / 1 would silently change the titers.
+        for name in ("vacs", "pcrpos"):
+            a = np.asarray(getattr(self, name))
+            if a.size and not np.isin(a, (0, 1)).all():
+                raise ValueError(f"{name} must hold only 0 / 1 (found values outside {{0, 1}}); "
+                                 "several doses or positives in one gap are not supported by the bit-mask layout")
         self.vacs = np.ascontiguousarray(self.vacs, dtype=np.uint8)
         self.pcrpos = np.ascontiguousarray(self.pcrpos, dtype=np.uint8)
         if self.vacs.shape != self.pcrpos.shape:

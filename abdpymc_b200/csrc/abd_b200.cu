@@ -107,6 +107,10 @@ struct abd_handle {
   int cap_chains = 0;
   int8_t* d_iraw = nullptr;
   int8_t* d_waner = nullptr;
+  void* d_pack = nullptr;      // PackedState<M>[C][N] beside the int8 state (see abd_kernels_common.cuh)
+  int pack_valid = 0;          // leading chains whose packed entries mirror d_iraw / d_waner
+  bool lazy_pack = true;       // a launch on the resident state may (re)build the packed copy first
+  bool use_pack = true;        // ABD_B200_NO_PACK=1: always read the int8 arrays
   double* d_theta = nullptr;   // [C][17]
   double* d_p = nullptr;       // [C][2]
   double* d_sums = nullptr;    // [C][16]
@@ -326,12 +330,19 @@ int ensure_chains(abd_handle* h, int C) {
     CU(cudaMemcpy(ni, old_i, (size_t)oldC * gn, cudaMemcpyDeviceToDevice));
     CU(cudaMemcpy(nw, old_w, (size_t)oldC * h->N, cudaMemcpyDeviceToDevice));
   }
-  for (void* p : {(void*)old_i, (void*)old_w, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
+  for (void* p : {(void*)old_i, (void*)old_w, h->d_pack, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
                   (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_aux, (void*)h->d_traj, (void*)h->d_gen})
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   h->d_iraw = ni;
   h->d_waner = nw;
+  h->d_pack = nullptr;
+  h->pack_valid = 0;
+  {
+    char* pk = nullptr;
+    if ((rc = dev_alloc(h, &pk, (size_t)C * h->N * (h->wide ? 16 : 8), false))) return rc;
+    h->d_pack = pk;
+  }
   if ((rc = dev_alloc(h, &h->d_theta, (size_t)C * 17, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_p, (size_t)C * 2, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_sums, (size_t)C * kNSums, false))) return rc;
@@ -403,10 +414,30 @@ cudaError_t sums_occupancy(int device, size_t smem, int* occ) {
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sums<M, XT, false>, kSumsBlock, smem);
 }
 
+// The packed copy of the resident chain state for a launch that reads (i_raw, waner): non-null only
+// when those ARE the handle's resident buffers.  If the copy is stale it is rebuilt first (one small
+// launch on the same stream) unless the caller has just staged fresh host state for a single use.
+int resident_pack(abd_handle* h, int C, const int8_t* i_raw, const int8_t* waner, cudaStream_t st, void** out) {
+  *out = nullptr;
+  if (!h->use_pack || i_raw != h->d_iraw || waner != h->d_waner || !h->d_pack) return ABD_OK;
+  if (h->pack_valid < C) {
+    if (!h->lazy_pack) return ABD_OK;
+    dim3 grid((h->N + 127) / 128, C);
+    if (h->wide) k_pack<uint64_t><<<grid, 128, 0, st>>>(h->dc, h->d_iraw, h->d_waner, (PackedState<uint64_t>*)h->d_pack);
+    else k_pack<uint32_t><<<grid, 128, 0, st>>>(h->dc, h->d_iraw, h->d_waner, (PackedState<uint32_t>*)h->d_pack);
+    CU(cudaGetLastError());
+    h->launches++;
+    h->pack_valid = C;
+  }
+  *out = h->d_pack;
+  return ABD_OK;
+}
+
 template <typename M, typename XT>
 int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cfg, dim3 grid, const double* theta,
-                  int theta_is_q, const int8_t* i_raw, const int8_t* waner, double* sums, const FinalizeCfg& fin,
-                  const TrajCfg& traj, cudaStream_t st, const ThetaInline& thin) {
+                  int theta_is_q, const int8_t* i_raw, const int8_t* waner, const void* pack_v, double* sums,
+                  const FinalizeCfg& fin, const TrajCfg& traj, cudaStream_t st, const ThetaInline& thin) {
+  const PackedState<M>* pack = reinterpret_cast<const PackedState<M>*>(pack_v);
   if (std::getenv("ABD_B200_VERBOSE")) {
     const int occ = tl.occ;
     std::fprintf(stderr, "[abd_b200] k_sums grid (%u, %u) dyn smem %zu B, occupancy %d CTAs/SM, caps rows %d/%d cells %d/%d\n",
@@ -438,14 +469,14 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
       lc.numAttrs = h->use_pdl ? 1 : 0;
     }
     lc.attrs = attr;
-    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, true>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, h->d_partial,
+    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, true>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, pack, h->d_partial,
                           h->d_ticket, sums, fin, pri, h->d_aux, traj, XchCfg{}, ThetaInline{}));
   } else {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = h->use_pdl ? 1 : 0;
-    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, false>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, h->d_partial,
+    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, false>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, pack, h->d_partial,
                           h->d_ticket, sums, fin, pri, h->d_aux, traj, h->xch_active ? h->xch : XchCfg{}, thin));
   }
   return ABD_OK;
@@ -499,12 +530,14 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
   }
   SumsCfg cfg{tl->ntiles, tl->cap_n, tl->cap_s, tl->capr_n, tl->capr_s, tl->capk_n, tl->capk_s, cpc, C};
   dim3 grid(tl->ntiles, (C + cpc - 1) / cpc);
+  void* pack = nullptr;
+  if ((rc = resident_pack(h, C, i_raw, waner, st, &pack))) return rc;
   if (h->wide)
-    rc = h->fx ? launch_sums_t<uint64_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st, thin)
-               : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st, thin);
+    rc = h->fx ? launch_sums_t<uint64_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, pack, sums, fin, traj, st, thin)
+               : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, pack, sums, fin, traj, st, thin);
   else
-    rc = h->fx ? launch_sums_t<uint32_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st, thin)
-               : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, sums, fin, traj, st, thin);
+    rc = h->fx ? launch_sums_t<uint32_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, pack, sums, fin, traj, st, thin)
+               : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, pack, sums, fin, traj, st, thin);
   if (rc) return rc;
   CU(cudaGetLastError());
   h->launches++;
@@ -529,7 +562,11 @@ int launch_gibbs(abd_handle* h, int C, const double* theta, int theta_is_q, cons
     const long items = (long)C * h->N;
     const int grid = (int)std::min<long>(h->gibbs_blk_ctas, (items + kGibbsWarps - 1) / kGibbsWarps);
     CU(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
-    k_gibbs_blk<<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, h->d_order, C, theta, theta_is_q, p, pw, i_raw, waner, h->d_queue, cfg);
+    void* pack = nullptr;
+    int rcp = resident_pack(h, C, i_raw, waner, st, &pack);
+    if (rcp) return rcp;
+    k_gibbs_blk<<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, h->d_order, C, theta, theta_is_q, p, pw, i_raw, waner,
+                                                   (PackedState<uint32_t>*)pack, h->d_queue, cfg);
     CU(cudaGetLastError());
     h->launches++;
     return ABD_OK;
@@ -545,12 +582,15 @@ int launch_gibbs(abd_handle* h, int C, const double* theta, int theta_is_q, cons
   const long items = (long)C * h->N;
   const int grid = (int)std::min<long>(h->gibbs_ctas, (items + kGibbsWarps - 1) / kGibbsWarps);
   CU(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
+  void* pack = nullptr;
+  int rcp = resident_pack(h, C, i_raw, waner, st, &pack);
+  if (rcp) return rcp;
   if (h->wide)
     k_gibbs<uint64_t><<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, h->d_order, C, theta, theta_is_q, p, pw, i_raw, waner,
-                                                          h->d_queue, cfg);
+                                                          (PackedState<uint64_t>*)pack, h->d_queue, cfg);
   else
     k_gibbs<uint32_t><<<grid, kGibbsWarps * 32, 0, st>>>(h->dc, h->d_order, C, theta, theta_is_q, p, pw, i_raw, waner,
-                                                          h->d_queue, cfg);
+                                                          (PackedState<uint32_t>*)pack, h->d_queue, cfg);
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;
@@ -608,6 +648,10 @@ int copy_state_d2h(abd_handle* h, void* dst, const void* src, size_t bytes) {
 int stage_state(abd_handle* h, int C, const int8_t* i_raw, const int8_t* waner) {
   const size_t gn = (size_t)h->G * h->N;
   int rc;
+  // fresh host state for (usually) a single use: the kernels of this call read the int8 arrays and the
+  // packed copy goes stale; a call on the resident state (NULL pointers) rebuilds it on first use
+  h->lazy_pack = !(i_raw || waner);
+  if (i_raw || waner) h->pack_valid = 0;
   if (i_raw && (rc = copy_state_h2d(h, h->d_iraw, i_raw, (size_t)C * gn))) return rc;
   if (waner && (rc = copy_state_h2d(h, h->d_waner, waner, (size_t)C * h->N))) return rc;
   return ABD_OK;
@@ -657,6 +701,7 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
   if (const char* e = std::getenv("ABD_B200_NO_PDL")) h->use_pdl = !(e[0] == '1');
   if (const char* e = std::getenv("ABD_B200_NO_PULL")) h->use_pull = !(e[0] == '1');
   if (const char* e = std::getenv("ABD_B200_NO_INLINE")) h->use_inline = !(e[0] == '1');
+  if (const char* e = std::getenv("ABD_B200_NO_PACK")) h->use_pack = !(e[0] == '1');
   {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->n_sms = v;
@@ -695,6 +740,7 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
   h->dc.G = G;
   h->dc.N = N;
   h->dc.ind_offset = (unsigned)co->ind_offset;
+  h->dc.chain_offset = 0;
   // time chunks, abd.py:865-882
   h->dc.ch.n = co->n_splits + 1;
   {
@@ -769,7 +815,7 @@ int abd_destroy(abd_handle* h) {
     if (p) cudaIpcCloseMemHandle(p);
   if (h->xch_local) cudaFree(h->xch_local);
   for (void* p : h->owned) cudaFree(p);
-  for (void* p : {(void*)h->d_iraw, (void*)h->d_waner, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
+  for (void* p : {(void*)h->d_iraw, (void*)h->d_waner, h->d_pack, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
                   (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_partial, (void*)h->d_aux, (void*)h->d_traj,
                   (void*)h->d_gen})
     if (p) cudaFree(p);
@@ -814,7 +860,24 @@ int abd_upload_state(abd_handle* h, int C, const int8_t* i_raw, const int8_t* wa
   if (!i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL state");
   int rc = stage_state(h, C, i_raw, waner);
   if (rc) return rc;
+  // state uploaded to stay: build its packed copy now (every later evaluation / sweep reads that)
+  h->lazy_pack = true;
+  void* pk = nullptr;
+  if ((rc = resident_pack(h, C, h->d_iraw, h->d_waner, h->stream, &pk))) return rc;
   CU(cudaStreamSynchronize(h->stream));
+  return ABD_OK;
+}
+
+int abd_state_touch(abd_handle* h) {
+  if (!h) return fail(ABD_ERR_INVALID, "NULL handle");
+  h->pack_valid = 0;
+  return ABD_OK;
+}
+
+int abd_set_chain_offset(abd_handle* h, int64_t chain_offset) {
+  if (!h) return fail(ABD_ERR_INVALID, "NULL handle");
+  if (chain_offset < 0 || chain_offset > 0x7fffffffLL) return fail(ABD_ERR_INVALID, "chain_offset must be in [0, 2^31)");
+  h->dc.chain_offset = (unsigned)chain_offset;
   return ABD_OK;
 }
 
@@ -1011,6 +1074,7 @@ int abd_deterministics(abd_handle* h, int C, const double* theta13, const int8_t
 int abd_sums_dev(abd_handle* h, int C, const double* theta, int theta_is_q17, const int8_t* i_raw,
                  const int8_t* waner, double* sums, void* stream) {
   PROLOGUE(h, C);
+  h->lazy_pack = true;
   if (!theta || !i_raw || !waner || !sums) return fail(ABD_ERR_INVALID, "NULL argument");
   FinalizeCfg fin{0, h->tot, nullptr, nullptr};
   return launch_sums(h, C, theta, theta_is_q17, i_raw, waner, sums, fin, (cudaStream_t)stream);
@@ -1041,6 +1105,7 @@ int abd_finalize_logp_dev(abd_handle* h, int C, const double* q17, const double*
 int abd_loglik_grad_dev(abd_handle* h, int C, const double* theta13, const int8_t* i_raw, const int8_t* waner,
                         double* out_loglik, double* out_grad, void* stream) {
   PROLOGUE(h, C);
+  h->lazy_pack = true;
   if (!theta13 || !i_raw || !waner || !out_loglik) return fail(ABD_ERR_INVALID, "NULL argument");
   FinalizeCfg fin{1, h->tot, out_loglik, out_grad};
   return launch_sums(h, C, theta13, 0, i_raw, waner, h->d_sums, fin, (cudaStream_t)stream);
@@ -1049,6 +1114,7 @@ int abd_loglik_grad_dev(abd_handle* h, int C, const double* theta13, const int8_
 int abd_logp_dlogp_dev(abd_handle* h, int C, const double* q17, const int8_t* i_raw, const int8_t* waner,
                        double* out_logp, double* out_dlogp, void* stream) {
   PROLOGUE(h, C);
+  h->lazy_pack = true;
   if (!q17 || !i_raw || !waner || !out_logp) return fail(ABD_ERR_INVALID, "NULL argument");
   FinalizeCfg fin{2, h->tot, out_logp, out_dlogp};
   return launch_sums(h, C, q17, 1, i_raw, waner, h->d_sums, fin, (cudaStream_t)stream);
@@ -1058,6 +1124,7 @@ int abd_gibbs_sweep_dev(abd_handle* h, int C, const double* theta, int theta_is_
                         const double* p_w, int8_t* i_raw, int8_t* waner, uint64_t seed, uint64_t sweep_idx,
                         int mode, double transit_p, unsigned long long* stats, void* stream) {
   PROLOGUE(h, C);
+  h->lazy_pack = true;
   if (!theta || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
   if (!theta_is_q17 && (!p || !p_w)) return fail(ABD_ERR_INVALID, "p / p_w required with theta13");
   if (mode != ABD_GIBBS_METROPOLIS && mode != ABD_GIBBS_HEATBATH && mode != ABD_GIBBS_BLOCKED)
@@ -1103,6 +1170,7 @@ int abd_deterministics_accum_dev(abd_handle* h, int C, const double* theta, int 
 int abd_leapfrog_dev(abd_handle* h, int C, int n_steps, double* q17, double* p17, double* grad17, double* logp,
                      const double* eps, const double* inv_mass, const int8_t* i_raw, const int8_t* waner, void* stream) {
   PROLOGUE(h, C);
+  h->lazy_pack = true;
   if (!q17 || !p17 || !grad17 || !logp || !eps || !inv_mass || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
   if (n_steps < 1 || n_steps > 4096) return fail(ABD_ERR_INVALID, "n_steps must be in [1, 4096]");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1124,7 +1192,8 @@ int abd_hmc_begin_dev(abd_handle* h, int C, const double* q17, const double* gra
                       void* stream) {
   PROLOGUE(h, C);
   if (!q17 || !grad17 || !logp || !linv_t || !qw || !pw || !gw || !h0) return fail(ABD_ERR_INVALID, "NULL argument");
-  k_hmc_begin<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, q17, grad17, logp, linv_t, seed, iter, qw, pw, gw, h0);
+  k_hmc_begin<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, q17, grad17, logp, linv_t, seed, iter, qw, pw, gw, h0,
+                                                              h->dc.chain_offset);
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;
@@ -1139,7 +1208,7 @@ int abd_hmc_end_dev(abd_handle* h, int C, double* q17, double* grad17, double* l
     return fail(ABD_ERR_INVALID, "NULL argument");
   if (adapt && (!da || !eps)) return fail(ABD_ERR_INVALID, "adapt needs the dual-averaging state and eps");
   k_hmc_end<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, q17, grad17, logp, qw, pw, gw, lpw, inv_mass, h0, seed, iter,
-                                                            accept_out, da, eps, adapt, target_accept);
+                                                            accept_out, da, eps, adapt, target_accept, h->dc.chain_offset);
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;
@@ -1197,6 +1266,7 @@ int abd_xch_connect(abd_handle* h, const void* all_ipc_handles) {
 int abd_logp_dlogp_sharded_dev(abd_handle* h, int C, const double* q17, const int8_t* i_raw, const int8_t* waner,
                                double* out_logp, double* out_dlogp, void* stream) {
   PROLOGUE(h, C);
+  h->lazy_pack = true;
   if (!q17 || !i_raw || !waner || !out_logp) return fail(ABD_ERR_INVALID, "NULL argument");
   if (!h->xch_local || !h->xch.data[h->xch.world - 1] || !h->xch.data[0])
     return fail(ABD_ERR_INVALID, "abd_logp_dlogp_sharded_dev: call abd_xch_alloc and abd_xch_connect first");

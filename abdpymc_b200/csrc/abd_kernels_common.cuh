@@ -12,6 +12,7 @@ using namespace abd;
 struct DevCohort {
   int G, N;
   unsigned ind_offset;       // global index of this shard's first individual (RNG streams)
+  unsigned chain_offset;     // global index of this handle's first chain (RNG streams; abd_set_chain_offset)
   const void* pcr;
   const void* vac;
   const int* rp[2];          // [0] = N antigen, [1] = S antigen
@@ -47,6 +48,17 @@ struct IndState {
 };
 template <typename M>
 __device__ __forceinline__ M top_bit() { return (M)1 << (sizeof(M) * 8 - 1); }
+
+// Packed resident chain state, one entry per (chain, individual), kept beside the int8 boundary
+// arrays by every library call that writes the resident state (abd_upload_state, the Gibbs sweeps):
+//   rw  = the individual's i_raw column as a bit mask over gaps | ab_s_waner in the top bit
+//   inf = constrain(raw, pcr, chunks), the constrained infections (abd.py:640-667)
+// so that an evaluation reads 8 (16) bytes per individual and chain instead of G + 1 strided bytes
+// and does not repeat the integer prologue: the binary state only changes once per Gibbs sweep.
+template <typename M>
+struct __align__(2 * sizeof(M)) PackedState {
+  M rw, inf;
+};
 
 __device__ __forceinline__ double load_param(const double* theta, int theta_is_q, int c, int k13) {
   if (theta_is_q) {

@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(kGibbsWarps * 32, ABD_GIBBS_MINB)
 k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
         const double* __restrict__ theta, const int theta_is_q,
         const double* __restrict__ p_arr, const double* __restrict__ pw_arr,
-        int8_t* __restrict__ i_raw, int8_t* __restrict__ waner, unsigned* __restrict__ queue,
-        const GibbsCfg cfg) {
+        int8_t* __restrict__ i_raw, int8_t* __restrict__ waner, PackedState<M>* __restrict__ pack,
+        unsigned* __restrict__ queue, const GibbsCfg cfg) {
   constexpr int NSLOT = sizeof(M) / 4;  // proposals owned per lane
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = dc.G, N = dc.N;
@@ -225,17 +225,26 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
 
     // ---- this individual's column of i_raw (lane t reads gap t), waner, masks, rows ----
     int8_t* col = i_raw + (size_t)c * G * N + n;
-    M raw = 0;
+    const M pcr = reinterpret_cast<const M*>(dc.pcr)[n];
+    M raw = 0, inf;
+    int w;
+    if (pack) {  // resident state: one broadcast load instead of G strided bytes, constraints already applied
+      const PackedState<M> ps = pack[(size_t)c * N + n];
+      raw = ps.rw & ~top_bit<M>();
+      w = (ps.rw & top_bit<M>()) != 0;
+      inf = ps.inf;
+    } else {
 #pragma unroll
-    for (int sl = 0; sl < NSLOT; ++sl) {
-      const int t = lane + 32 * sl;
-      const int8_t b = (t < G) ? col[(size_t)t * N] : (int8_t)0;
-      raw |= (M)__ballot_sync(0xffffffffu, b != 0) << (32 * sl);
+      for (int sl = 0; sl < NSLOT; ++sl) {
+        const int t = lane + 32 * sl;
+        const int8_t b = (t < G) ? col[(size_t)t * N] : (int8_t)0;
+        raw |= (M)__ballot_sync(0xffffffffu, b != 0) << (32 * sl);
+      }
+      w = waner[(size_t)c * N + n] != 0;
+      inf = constrain<M>(raw, pcr, dc.ch);
     }
     const M raw_in = raw;
-    int w = waner[(size_t)c * N + n] != 0;
     const int w_in = w;
-    const M pcr = reinterpret_cast<const M*>(dc.pcr)[n];
     const M vac = reinterpret_cast<const M*>(dc.vac)[n];
     const int rn0 = dc.rp[0][n], cnt_n = dc.rp[0][n + 1] - rn0;
     const int rs0 = dc.rp[1][n], cnt_s = dc.rp[1][n + 1] - rs0;
@@ -296,7 +305,6 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
       return a;
     };
 
-    M inf = constrain<M>(raw, pcr, dc.ch);
     double ll = indiv_ll(inf, w);
 
     // ---- lane-owned proposals: Philox key (visiting order), transit / accept uniforms ----
@@ -312,7 +320,7 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
 #pragma unroll
       for (int sl = 0; sl < NSLOT; ++sl) {
         const uint4 r = philox4x32_10(
-            make_uint4((uint32_t)(lane + 32 * sl), (uint32_t)n + dc.ind_offset, (uint32_t)c, (uint32_t)cfg.sweep),
+            make_uint4((uint32_t)(lane + 32 * sl), (uint32_t)n + dc.ind_offset, (uint32_t)c + dc.chain_offset, (uint32_t)cfg.sweep),
             make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32) ^ (uint32_t)(cfg.sweep >> 32)));
         key[sl] = r.x;
         const double u_t = u01(r.y), u_a = u01(r.z);
@@ -452,6 +460,12 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
         if (t < G && ((changed >> t) & 1)) col[(size_t)t * N] = (int8_t)((raw >> t) & 1);
       }
       if (lane == 0 && w != w_in) waner[(size_t)c * N + n] = (int8_t)w;
+      if (pack && lane == 0 && (changed != 0 || w != w_in)) {
+        PackedState<M> ps;
+        ps.rw = raw | (w ? top_bit<M>() : (M)0);
+        ps.inf = inf;
+        pack[(size_t)c * N + n] = ps;
+      }
     }
   }
   if (cfg.mode >= 0 && cfg.stats && lane == 0 && cur_c >= 0) {

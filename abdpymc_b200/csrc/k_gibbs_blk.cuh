@@ -28,8 +28,8 @@ __global__ void __launch_bounds__(kGibbsWarps * 32, ABD_GIBBS_MINB)
 k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
             const double* __restrict__ theta, const int theta_is_q,
             const double* __restrict__ p_arr, const double* __restrict__ pw_arr,
-            int8_t* __restrict__ i_raw, int8_t* __restrict__ waner, unsigned* __restrict__ queue,
-            const GibbsCfg cfg) {
+            int8_t* __restrict__ i_raw, int8_t* __restrict__ waner, PackedState<uint32_t>* __restrict__ pack,
+            unsigned* __restrict__ queue, const GibbsCfg cfg) {
   using M = uint32_t;
   constexpr unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -69,24 +69,33 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
 
     // ---- this individual's column of i_raw (lane t reads gap t), waner, masks, rows ----
     int8_t* col = i_raw + (size_t)c * G * N + n;
-    const int8_t b0 = (lane < G) ? col[(size_t)lane * N] : (int8_t)0;
-    M raw = __ballot_sync(FULL, b0 != 0);
-    const M raw_in = raw;
-    int w = waner[(size_t)c * N + n] != 0;
-    const int w_in = w;
     const M pcr = reinterpret_cast<const M*>(dc.pcr)[n];
+    M raw, inf;
+    int w;
+    if (pack) {  // resident state: one broadcast load, constraints already applied
+      const PackedState<M> ps = pack[(size_t)c * N + n];
+      raw = ps.rw & ~top_bit<M>();
+      w = (ps.rw & top_bit<M>()) != 0;
+      inf = ps.inf;
+    } else {
+      const int8_t b0 = (lane < G) ? col[(size_t)lane * N] : (int8_t)0;
+      raw = __ballot_sync(FULL, b0 != 0);
+      w = waner[(size_t)c * N + n] != 0;
+      inf = constrain<M>(raw, pcr, dc.ch);
+    }
+    const M raw_in = raw;
+    const int w_in = w;
     const M vac = reinterpret_cast<const M*>(dc.vac)[n];
     const GibbsRows<M> rows(dc, n, lane, s_th, s_pw, s_tab);
     const int t_last = rows.t_last, t_last_s = rows.t_last_s;
     auto indiv_ll = [&](M inf_, int w_) { return rows.ll(inf_, vac, w_); };
 
-    M inf = constrain<M>(raw, pcr, dc.ch);
     double ll = indiv_ll(inf, w);
 
     // ---- random numbers: lane t: fresh Bernoulli(p) draw for gap t (x), categorical uniform of
     //      chunk t (y), waner uniform (lane 0, z) ----
     const uint4 rnd = philox4x32_10(
-        make_uint4((uint32_t)lane, (uint32_t)n + dc.ind_offset, (uint32_t)c, (uint32_t)cfg.sweep),
+        make_uint4((uint32_t)lane, (uint32_t)n + dc.ind_offset, (uint32_t)c + dc.chain_offset, (uint32_t)cfg.sweep),
         make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32) ^ (uint32_t)(cfg.sweep >> 32)));
     const double pv = s_th[21], lp1 = s_th[19], lp0 = s_th[20];
     const M fresh = __ballot_sync(FULL, lane < G && u01(rnd.x) <= pv);
@@ -165,6 +174,12 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
       const M changed = raw ^ raw_in;
       if (lane < G && ((changed >> lane) & 1)) col[(size_t)lane * N] = (int8_t)((raw >> lane) & 1);
       if (lane == 0 && w != w_in) waner[(size_t)c * N + n] = (int8_t)w;
+      if (pack && lane == 0 && (changed != 0 || w != w_in)) {
+        PackedState<M> ps;
+        ps.rw = raw | (w ? top_bit<M>() : (M)0);
+        ps.inf = inf;
+        pack[(size_t)c * N + n] = ps;
+      }
     }
   }
   if (cfg.stats && lane == 0 && cur_c >= 0) {

@@ -12,12 +12,12 @@ using namespace abd;
 __global__ void __launch_bounds__(128)
 k_hmc_begin(const int C, const double* __restrict__ q, const double* __restrict__ grad, const double* __restrict__ logp,
             const double* __restrict__ linv_t, const uint64_t seed, const uint64_t iter, double* __restrict__ qw,
-            double* __restrict__ pw, double* __restrict__ gw, double* __restrict__ h0) {
+            double* __restrict__ pw, double* __restrict__ gw, double* __restrict__ h0, const unsigned chain_offset) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double z = 0.0;
   if (lane < 17) {  // Box-Muller on two of the four Philox words
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)lane, (uint32_t)c, (uint32_t)iter, 0x484d4331u),
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)lane, (uint32_t)c + chain_offset, (uint32_t)iter, 0x484d4331u),
                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iter >> 32)));
     z = sqrt(-2.0 * log(u01(r.x))) * cospi(2.0 * u01(r.y));
   }
@@ -41,7 +41,7 @@ k_hmc_end(const int C, double* __restrict__ q, double* __restrict__ grad, double
           const double* __restrict__ qw, const double* __restrict__ pw, const double* __restrict__ gw,
           const double* __restrict__ lpw, const double* __restrict__ inv_mass, const double* __restrict__ h0,
           const uint64_t seed, const uint64_t iter, double* __restrict__ accept_out, double* __restrict__ da,
-          double* __restrict__ eps, const int adapt, const double target) {
+          double* __restrict__ eps, const int adapt, const double target, const unsigned chain_offset) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   const double p = lane < 17 ? pw[(size_t)c * 17 + lane] : 0.0;
@@ -57,7 +57,7 @@ k_hmc_end(const int C, double* __restrict__ q, double* __restrict__ grad, double
   double dh = h0[c] - h1;
   if (!isfinite(dh)) dh = -INFINITY;
   const double acc = exp(fmin(dh, 0.0));
-  const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)c, (uint32_t)iter, 0x41434331u),
+  const uint4 r = philox4x32_10(make_uint4(0u, (uint32_t)c + chain_offset, (uint32_t)iter, 0x41434331u),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(iter >> 32)));
   const bool take = (u01(r.x) - 2.3283064365386963e-10) < acc;  // u in [0, 1)
   if (take && lane < 17) {
@@ -200,6 +200,31 @@ k_determ_accum(const DevCohort dc, const int C, const double* __restrict__ theta
       if (sum_mu_s) atomicAdd(sum_mu_s + o, ss);
     }
   }
+}
+
+// int8 boundary state -> packed resident state (see PackedState): one thread per (individual, chain)
+template <typename M>
+__global__ void __launch_bounds__(128)
+k_pack(const DevCohort dc, const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
+       PackedState<M>* __restrict__ pack) {
+  const int c = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = dc.G, N = dc.N;
+  if (n >= N) return;
+  M raw = 0;
+  const int8_t* col = i_raw + (size_t)c * G * N + n;
+  int8_t bytes[sizeof(M) * 8];
+#pragma unroll
+  for (int t = 0; t < (int)sizeof(M) * 8; ++t) {  // unpredicated loads along an address chain (see k_sums)
+    bytes[t] = __ldg(col);
+    col += (t + 1 < G) ? (size_t)N : (size_t)0;
+  }
+#pragma unroll
+  for (int t = 0; t < (int)sizeof(M) * 8; ++t) raw |= (M)(bytes[t] != 0) << t;
+  raw &= low_mask<M>(G - 1);
+  PackedState<M> ps;
+  ps.inf = constrain<M>(raw, reinterpret_cast<const M*>(dc.pcr)[n], dc.ch);
+  ps.rw = raw | (waner[(size_t)c * N + n] != 0 ? top_bit<M>() : (M)0);
+  pack[(size_t)c * N + n] = ps;
 }
 
 // pinned host memory -> device memory by the SMs (see copy_state_h2d); n16 16-byte words + rem bytes

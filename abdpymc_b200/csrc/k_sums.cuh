@@ -153,7 +153,7 @@ template <typename M, typename XT, bool TRAJ>
 __global__ void __launch_bounds__(kSumsBlock, ABD_SUMS_MINB)
 k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg,
        const double* __restrict__ theta_ptr, const int theta_is_q,
-       const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner,
+       const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner, const PackedState<M>* __restrict__ pack,
        double* __restrict__ partial, unsigned* __restrict__ ticket, double* __restrict__ sums,
        const FinalizeCfg fin, const Priors* __restrict__ priors, double* __restrict__ aux, const TrajCfg traj,
        const XchCfg xch, const __grid_constant__ ThetaInline thin) {
@@ -256,7 +256,18 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     //      binary state is fixed over a trajectory, so this sits OUTSIDE the step loop (inside it
     //      the compiler hoisted and spilled the 31 column addresses of the trajectory variant, and
     //      the spills serialised the loads: 4.9 us instead of 1.9) ----
-    if (tid < ni) {
+    if (tid < ni && pack) {
+      // resident state, packed (PackedState): one coalesced 8 / 16-byte load per individual, the
+      // constraints were applied when the state was written
+      const PackedState<M> ps = pack[(size_t)c * N + i0 + tid];
+      const M w = ps.rw & top_bit<M>();
+      IndState<M> st;
+      st.inf = ps.inf;
+      st.vacw = my_vac | w;
+      s_ind[tid] = st;
+      cnt_i = (double)popc(ps.rw & ~top_bit<M>());
+      cnt_w = w ? 1.0 : 0.0;
+    } else if (tid < ni) {
       // Unpredicated loads: gaps beyond G - 1 re-read the last row and are masked off afterwards.
       // (A load guarded by `t < G` needs a predicate register each, and there are only seven: the
       // compiler then keeps ~6 loads in flight and the column costs 5 memory round trips.)

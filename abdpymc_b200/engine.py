@@ -169,6 +169,15 @@ class AbdEngine:
     def launch_count(self):
         return int(self._lib.abd_launch_count(self._h))
 
+    def set_chain_offset(self, chain_offset):
+        """Global index of this engine's first chain: keys the Philox streams of the Gibbs sweeps and of the HMC
+        kernels, so that processes sharding the chains of one run (same seed) never share a stream."""
+        check(self._lib.abd_set_chain_offset(self._h, int(chain_offset)))
+
+    def state_touch(self):
+        """Tell the library that the caller wrote into the resident int8 state (``state_dev`` pointers) itself."""
+        check(self._lib.abd_state_touch(self._h))
+
     def set_tuning(self, rows_per_tile=0, chains_per_cta=0):
         check(self._lib.abd_set_tuning(self._h, int(rows_per_tile), int(chains_per_cta)))
 

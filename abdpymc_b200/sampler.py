@@ -39,11 +39,20 @@ class AbdTarget:
         self.engine, self.C = engine, n_chains
         self.device = torch.device("cuda", engine.device)
         engine.upload_state(i_raw, waner)
-        self.d_i, self.d_w = engine.state_dev(n_chains)
         self.out = torch.zeros(n_chains, dtype=torch.float64, device=self.device)
         self.outg = torch.zeros(n_chains, 17, dtype=torch.float64, device=self.device)
         self.seed, self.gibbs_mode, self.transit_p = seed, gibbs_mode, transit_p
         self.dim = 17
+
+    # the resident state's addresses are asked for on every use: the library reallocates the buffers when a
+    # call with more chains than ever before arrives, and cached pointers would dangle silently
+    @property
+    def d_i(self):
+        return self.engine.state_dev(self.C)[0]
+
+    @property
+    def d_w(self):
+        return self.engine.state_dev(self.C)[1]
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -72,6 +72,12 @@ def workload(n_inds=N_INDS, n_chains=N_CHAINS, seed=0, chain_offset=0):
     return co, q, vals, i_raw, w
 
 
+def workload_name(co, n_chains=N_CHAINS):
+    """config.workload: one string for both arms (the driver compares them)."""
+    return (f"simulated {co.n_inds}-individual cohort (G={co.n_gaps}, {co.n_rows} OD rows), {n_chains} chains per GPU, "
+            f"splits {list(SPLITS)}")
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -128,6 +134,10 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+TRAFFIC_SOURCE = ("static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture "
+                  "of this kernel on this workload (profiles/ncu_traffic.json, profiles/README.md); not re-measured in this run")
 
 
 def ncu_traffic(kernel):
@@ -231,7 +241,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"simulated {N_INDS}-individual cohort, {N_CHAINS} chains, splits {list(SPLITS)}",
+        "config": {"workload": workload_name(workload()[0]),
                    "reference": "NumPy restatement of abd.py's dense formulation (oracle/abd_oracle.py); PyMC unavailable offline"},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -658,6 +668,12 @@ def run_gpu(args):
         summ = dg.summary({name: xq[:, :, k] for k, (name, _) in enumerate(Q17_RV)})
         res.wall_s = wall
         vals_ess = sorted(v["ess_bulk"] for v in summ.values())
+        # R-hat gate: an ESS/s is only quoted for quantities whose chains agree (rank-normalised split R-hat <= 1.05);
+        # if any of the 17 scalars fails it the run as a whole is reported as not converged and min ESS/s is null
+        RHAT_MAX = 1.05
+        bad = sorted(name for name, v in summ.items() if not (v["rhat"] <= RHAT_MAX))
+        ok_ess = sorted(v["ess_bulk"] for v in summ.values() if v["rhat"] <= RHAT_MAX)
+        converged = not bad
         # Gibbs sweeps on the chains' states at the end of the run (the stationary regime: few accepted flips)
         tq_end = torch.from_numpy(res.q[:, -1, :].copy()).to(dev)
         torch.cuda.synchronize()
@@ -670,8 +686,11 @@ def run_gpu(args):
         ess = {"sampler": f"built-in batched HMC (dense metric) + GPU Metropolised-Gibbs sweep, device-resident transitions, "
                           f"{world * C} chains x ({tune_n} tune + {draws_n} draws)" + (f" on {world} GPUs" if world > 1 else ""),
                "chains": world * C, "wall_s": res.wall_s, "iterations_per_s": (tune_n + draws_n) / res.wall_s,
-               "min_bulk_ess_per_s": vals_ess[0] / res.wall_s,
-               "median_bulk_ess_per_s": vals_ess[len(vals_ess) // 2] / res.wall_s,
+               "converged": converged, "rhat_gate": RHAT_MAX, "not_converged": bad,
+               "min_bulk_ess_per_s": (vals_ess[0] / res.wall_s) if converged else None,
+               "median_bulk_ess_per_s": (vals_ess[len(vals_ess) // 2] / res.wall_s) if converged else None,
+               "min_bulk_ess_per_s_over_converged_quantities": (ok_ess[0] / res.wall_s) if ok_ess else None,
+               "n_converged_quantities": len(ok_ess),
                "max_rhat": max(v["rhat"] for v in summ.values()), "grad_evals": res.n_grad_evals,
                "gibbs_sweeps_per_s_stationary": world * C * 50 / (e0.elapsed_time(e1) / 1e3),
                "posterior": {name: {"mean": float(np.mean(xq[:, :, k])), "sd": float(np.std(xq[:, :, k])),
@@ -680,12 +699,13 @@ def run_gpu(args):
                              for k, (name, _) in enumerate(Q17_RV)},
                "note": "PyMC is not installable offline, so there is no measured PyMC-CPU ESS/s beside it (cpu_extrapolation "
                        "scales this run's ESS per iteration by the CPU cost of one iteration); the slowest-mixing "
-                       "parameters are those coupled to the latent infection indicators (data-augmentation Gibbs)"}
+                       "parameters are those coupled to the latent infection indicators (data-augmentation Gibbs); "
+                       "quantities that fail the R-hat gate get no ESS/s"}
         if cpu and cpu.get("gibbs"):
             # one iteration of the reference's compound step = one NUTS draw (>= the 5 leapfrogs used here) + one
             # BinaryGibbsMetropolis sweep; its chains run one per core.  Same ESS per iteration assumed.
             t_iter = 1.0 / (cpu["gibbs"]["value"] / cpu["cores"]) + cfg.n_leapfrog / (cpu["value"] / cpu["cores"])
-            ess_per_iter = vals_ess[0] / (tune_n + draws_n)
+            ess_per_iter = (vals_ess[0] if converged else (ok_ess[0] if ok_ess else float("nan"))) / (tune_n + draws_n)
             ess["cpu_extrapolation"] = {
                 "seconds_per_iteration_per_chain": t_iter, "min_bulk_ess_per_s": ess_per_iter / t_iter,
                 "how": f"this run's min bulk ESS per iteration ({world * C} chains) / CPU seconds per iteration of one chain on "
@@ -707,13 +727,14 @@ def run_gpu(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": f"simulated {N_INDS}-individual cohort (G={G}, {co.n_rows} OD rows), {C} chains per GPU, splits {list(SPLITS)}",
+            "workload": workload_name(co, C),
             "step": f"{EVALS_PER_STEP} consecutive batched logp+grad evaluations (one CUDA graph replay)",
             "l2": f"inputs larger than L2: evaluations rotate over {n_rep} cohort+state replicas ({n_rep * a_logp / 1e6:.0f} MB > 2 x 126 MB L2)",
             "parallelism": "chains sharded across GPUs, cohort replicated, no collective" if world > 1 else "1 GPU",
         },
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": ncu_traffic("k_sums"), "kernel": "k_sums", "algorithmic_bytes_per_launch": a_logp,
+                     "traffic": ncu_traffic("k_sums"), "traffic_source": TRAFFIC_SOURCE, "kernel": "k_sums",
+                     "algorithmic_bytes_per_launch": a_logp,
                      "avg_launch_us": t_kernel * 1e6, "peak_source": peak_src,
                      # the second, honest bound: fp64 work, 60 R + 12 G N flop-equivalents per chain evaluation
                      "fp64": {"flops_per_launch": flops, "achieved_tflops": flops / t_kernel / 1e12,
@@ -740,7 +761,8 @@ def run_gpu(args):
                   "regime": "states drawn at random (4 % infections, 50 % waners): the burn-in regime, many accepted flips",
                   "other_update_rules": {name: {"value": world * C * n_sw / (v / 1e3), "unit": "sweeps/s"} for name, v in ms_modes.items()},
                   "roofline": {"bound": "hbm", "achieved": ach_g, "peak": peak, "unit": "GB/s", "frac": ach_g / peak,
-                               "traffic": ncu_traffic("k_gibbs"), "kernel": "k_gibbs", "algorithmic_bytes_per_launch": a_gibbs},
+                               "traffic": ncu_traffic("k_gibbs"), "traffic_source": TRAFFIC_SOURCE, "kernel": "k_gibbs",
+                               "algorithmic_bytes_per_launch": a_gibbs},
                   "e2e": {"value": world * C * n_sw_e2e / dt_gibbs_e2e, "unit": "sweeps/s",
                           "h2d_bytes_per_step": int(C * (G * N + N + 15 * 8)), "d2h_bytes_per_step": int(C * (G * N + N + 16))}},
         "sharded_100k": sharded, "ess": ess,

@@ -253,8 +253,23 @@ int abd_logp_dlogp_sharded_dev(abd_handle* h, int n_chains, const double* q17, c
                                void* stream);
 int abd_xch_status(abd_handle* h);
 
-/* Pointers to the resident chain state (valid until the next call that changes n_chains).   */
+/* Pointers to the resident chain state (valid until a call with MORE chains than any before: the
+ * buffers are then reallocated -- query again).  Beside these int8 arrays the library keeps a packed
+ * copy of the resident state (per chain and individual: the i_raw column as a bit mask, the waner
+ * bit and the constrained infections, abd.py:640-667) that every evaluation / sweep on the resident
+ * state reads instead; abd_upload_state and the Gibbs sweeps keep both in step.  A caller that
+ * WRITES into the int8 arrays itself must call abd_state_touch afterwards (the packed copy is then
+ * rebuilt on next use).  One stream per handle at a time: the per-handle scratch (partials, tickets,
+ * work queue) is shared by every call on the handle.                                           */
 int abd_state_dev(abd_handle* h, int n_chains, int8_t** i_raw, int8_t** waner);
+int abd_state_touch(abd_handle* h);
+
+/* Global index of this handle's first chain (default 0).  The Philox streams of the Gibbs sweeps
+ * and of abd_hmc_begin_dev / abd_hmc_end_dev are keyed by (seed; sweep | iteration, GLOBAL chain,
+ * GLOBAL individual, ...): processes that shard the CHAINS of one run over several GPUs with one
+ * seed set their rank's first chain here, so that no two chains of the run share a stream
+ * (the reference's chains draw from independent generators, pm.sample abd.py:922).            */
+int abd_set_chain_offset(abd_handle* h, int64_t chain_offset);
 
 /* Tuning knobs of the log-likelihood kernel (0 = automatic): target OD rows per CTA tile and
  * chains looped over inside one CTA (reusing the rows staged in shared memory).             */

@@ -151,7 +151,13 @@ def Deterministic(name, var, dims=None):
 
 
 class BlockedStep:
-    pass
+    """PyMC 5's BlockedStep allocates in __new__ and wants the variables there (pymc/step_methods/compound.py)."""
+
+    def __new__(cls, *args, **kwargs):
+        vars = kwargs.get("vars", args[0] if args else None)
+        if vars is None or len(vars) == 0 or any(v is None for v in vars):
+            raise ValueError("No free random variables to sample.")
+        return super().__new__(cls)
 
 
 class Competence(enum.IntEnum):

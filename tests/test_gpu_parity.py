@@ -354,6 +354,79 @@ def test_gibbs_sweep_bit_exact_vs_restated_device_sweep(Engine, cohorts, mode, s
         assert not np.array_equal(gi, i_raw)  # something moved
 
 
+@pytest.mark.parametrize("G,N,splits", [(26, 10, (14, 20)), (45, 9, (20,)), (31, 257, ())])
+def test_packed_resident_state_matches_the_int8_path(Engine, cohorts, G, N, splits):
+    """The library keeps a packed copy of the resident chain state (bit masks + constrained infections) that
+    evaluations and sweeps on the resident state read instead of the int8 arrays.  Both routes must give
+    bitwise identical results, the sweeps must keep the two representations in step, and a caller that
+    writes into the int8 arrays itself only has to call abd_state_touch."""
+    import torch
+
+    rng = np.random.default_rng(5 + G)
+    co = cohorts["test_cohort"] if (G, N) == (26, 10) else random_cohort(rng, G, N, rows_per_ind=7)
+    C = 3
+    q, i_raw, w = draw_points(rng, G, N, C)
+    vals = [ora.backward(q[k])[0] for k in range(C)]
+    th = np.array([[v[n] for n in ora.THETA13] for v in vals])
+    p = np.array([v["p"] for v in vals])
+    pw = np.array([v["ab_s_p_waner"] for v in vals])
+    with Engine(co, splits=splits) as eng:
+        lp_h, g_h = eng.logp_dlogp(q, i_raw, w)            # host state: staged for one use, int8 route
+        eng.upload_state(i_raw, w)                          # resident: packed route
+        lp_r, g_r = eng.logp_dlogp(q)
+        assert np.array_equal(lp_h, lp_r) and np.array_equal(g_h, g_r)
+        for mode in (0, 1, 2):
+            # in place on host arrays (int8 route) against upload + resident sweep + download (packed route)
+            a_i, a_w = i_raw.copy(), w.copy()
+            _, _, st_a = eng.gibbs_sweep(th, p, pw, a_i, a_w, seed=3, sweep=mode, mode=mode, inplace=True)
+            b_i, b_w, st_b = eng.gibbs_sweep(th, p, pw, i_raw, w, seed=3, sweep=mode, mode=mode)
+            assert np.array_equal(a_i, b_i) and np.array_equal(a_w, b_w) and np.array_equal(st_a, st_b)
+            # the packed copy followed the sweep: evaluating the resident state == evaluating what was downloaded
+            lp_res, g_res = eng.logp_dlogp(q)
+            lp_dl, g_dl = eng.logp_dlogp(q, b_i, b_w)
+            assert np.array_equal(lp_res, lp_dl) and np.array_equal(g_res, g_dl)
+            assert not np.array_equal(b_i, i_raw)
+        # a caller writing into the resident int8 arrays itself: stale until abd_state_touch
+        eng.upload_state(i_raw, w)
+        d_i, d_w = eng.state_dev(C)
+        new_i = (rng.random((C, G, N)) < 0.1).astype(np.int8)
+        ti = torch.from_numpy(new_i).cuda()
+        import ctypes
+
+        cudart = ctypes.CDLL("libcudart.so.12")  # already loaded by torch
+        cudart.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        assert cudart.cudaMemcpy(d_i, ti.data_ptr(), new_i.nbytes, 3) == 0  # device to device
+        torch.cuda.synchronize()
+        eng.state_touch()
+        lp_t, g_t = eng.logp_dlogp(q)
+        lp_n, g_n = eng.logp_dlogp(q, new_i, w)
+        assert np.array_equal(lp_t, lp_n) and np.array_equal(g_t, g_n)
+
+
+def test_chain_offset_keys_the_rng_streams(Engine, cohorts):
+    """abd_set_chain_offset: chain c of an engine whose first chain is global chain k draws from the stream of
+    global chain k + c (what processes that shard the chains of one run rely on)."""
+    co = cohorts["test_cohort"]
+    rng = np.random.default_rng(21)
+    C, splits = 2, (14, 20)
+    vals = [ora.sample_prior(rng, co.n_gaps) for _ in range(C)]
+    th = np.array([[v[n] for n in ora.THETA13] for v in vals])
+    p = np.array([v["p"] for v in vals])
+    pw = np.array([v["ab_s_p_waner"] for v in vals])
+    i_raw = (rng.random((C, co.n_gaps, co.n_inds)) < 0.05).astype(np.int8)
+    w = (rng.random((C, co.n_inds)) < 0.5).astype(np.int8)
+    with Engine(co, splits=splits) as eng:
+        base_i, base_w, _ = eng.gibbs_sweep(th, p, pw, i_raw, w, seed=9, sweep=4)
+        eng.set_chain_offset(5)
+        off_i, off_w, st = eng.gibbs_sweep(th, p, pw, i_raw, w, seed=9, sweep=4)
+        assert not np.array_equal(base_i, off_i)
+        for c in range(C):
+            ri, rw, rst = ora.device_gibbs_sweep(co, splits, False, th[c], p[c], pw[c], i_raw[c], w[c], 9, 4, 5 + c)
+            assert np.array_equal(off_i[c], ri) and np.array_equal(off_w[c], rw) and list(st[c]) == rst
+        with pytest.raises(Exception):
+            eng.set_chain_offset(-1)
+
+
 def test_gibbs_sweep_wide_mask_bit_exact(Engine):
     rng = np.random.default_rng(77)
     co = random_cohort(rng, 45, 9, rows_per_ind=10, p_empty=0.0)
@@ -685,6 +758,9 @@ def test_full_size_properties_100k(Engine):
         lp1, g1 = eng.logp_dlogp(q[1], i_raw[1], w[1])          # one chain on its own
         assert np.isfinite(lp).all() and np.isfinite(g).all()
         assert abs(lp1 - lp[1]) <= 1e-12 * abs(lp[1]) and grad_ok(g1, g[1], 1e-11)
+        # the oracle at this size too (recurrence form, one chain: half a minute of NumPy)
+        rl, rg = ora.Oracle(co, splits=splits, dense=False).logp_dlogp(q[0], i_raw[0], w[0])
+        assert abs(lp[0] - rl) <= RTOL * abs(rl) and grad_ok(g[0], rg)
         eng.upload_state(i_raw, w)
         vals = np.array([[ora.backward(q[k])[0][n] for n in ora.THETA13] for k in range(C)])
         p = np.array([ora.backward(q[k])[0]["p"] for k in range(C)])

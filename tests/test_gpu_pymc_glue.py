@@ -82,11 +82,25 @@ def test_model_ops_and_step_method_against_the_oracle(glue, cohorts):
     assert all(new[name] == pm_point[name] for name in Q17)          # the continuous values pass through
     assert stats == [{"p_jump": want_st[1] / max(want_st[0], 1), "tune": True}]
     step.stop_tuning()
-    _, stats2 = step.step(new)
+    new2, stats2 = step.step(new)
     assert stats2[0]["tune"] is False and step.sweep == 2
     C = abd.Competence
     assert abd.GpuBinaryGibbs.competence(m["i_raw"], False) == C.COMPATIBLE
     assert abd.GpuBinaryGibbs.competence(m["p"], True) == C.INCOMPATIBLE
+
+    # the binaries travel only when they changed: NUTS evaluates many leapfrogs between two sweeps
+    cache = m.abd_cache
+    up0 = cache.uploads
+    for k in range(4):   # new continuous values, the same binaries (what `new2` holds is what the last sweep left on the device)
+        pt_k = {**{name: np.float64(v * (1 + 0.01 * k)) for name, v in vals.items()}, "i_raw": new2["i_raw"],
+                "ab_s_waner": new2["ab_s_waner"]}
+        th_k = np.array([pt_k[n] for n in THETA13])
+        ll_k, _ = o.loglik_grad(th_k, new2["i_raw"], new2["ab_s_waner"])
+        assert abs(float(fake.evaluate(pot, pt_k)) - ll_k) <= 1e-10 * abs(ll_k)
+    assert cache.uploads == up0
+    other = {**point, "i_raw": 1 - i_raw}      # someone evaluates another point: uploaded, and correct
+    ll_o, _ = o.loglik_grad(th, 1 - i_raw, waner)
+    assert abs(float(fake.evaluate(pot, other)) - ll_o) <= 1e-10 * abs(ll_o) and cache.uploads == up0 + 1
 
     # model() validates splits like the reference (abd.py:604-622, :881-882)
     with pytest.raises(ValueError, match="ascending"):
