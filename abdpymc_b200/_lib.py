@@ -80,6 +80,8 @@ SIGNATURES = {
     "abd_xch_connect": (C.c_int, [H, C.c_void_p]),
     "abd_logp_dlogp_sharded_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 6),
     "abd_xch_status": (C.c_int, [H]),
+    "abd_leapfrog_sharded_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 9),
+    "abd_xch_stats": (C.c_int, [H, C.c_void_p, C.c_int]),
     "abd_state_dev": (C.c_int, [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "abd_state_touch": (C.c_int, [H]),
     "abd_set_chain_offset": (C.c_int, [H, C.c_int64]),

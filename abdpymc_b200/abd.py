@@ -323,29 +323,136 @@ if HAVE_PYMC:  # pragma: no cover
 # abdpymc-infer
 # ------------------------------------------------------------------------------------------
 def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0, seed=0, progress=None, gibbs_mode=0,
-                  thinned=0, kernel="hmc"):
+                  thinned=0, kernel="hmc", shard=None, rank=0, world=1):
     """tune + draws iterations of the built-in HMC + GPU-Gibbs sampler.  Returns (result,
-    {name: array (chain, draw, ...)}) with the reference's posterior variable names."""
+    {name: array (chain, draw, ...)}, last binary state) with the reference's posterior variable names.
+
+    ``shard`` (one process per GPU, ``torch.distributed`` initialised, ``world`` ranks):
+      "individuals": the cohort is split into contiguous blocks of individuals, one per rank; the 17 scalars
+          are replicated and every evaluation all-reduces C x 16 sums inside the kernel (NVLink peer memory);
+          every rank returns the same draws, Deterministic means / last state are gathered over the blocks;
+      "chains": every rank holds the whole cohort and chains / world of the chains (no communication until the
+          draws are gathered; RNG streams keyed by global chain)."""
     import torch
 
     from .sampler import AbdTarget, SamplerConfig, sample
 
-    engine = make_engine(cohort, splits=splits, ignore_pcrpos=ignore_pcrpos, device=device)
+    cohort = as_cohort(cohort)
+    G, N = cohort.n_gaps, cohort.n_inds
     rng = np.random.default_rng(seed)
-    G, N = engine.G, engine.N
     # PyMC-like initial point: prior means on the constrained scale, jittered in q space
     x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
     q0 = forward(x0)[None, :] + rng.uniform(-1, 1, size=(chains, 17))
-    target = AbdTarget(engine, chains, np.zeros((chains, G, N), np.int8), np.zeros((chains, N), np.int8), seed=seed,
-                       gibbs_mode=gibbs_mode)
     cfg = SamplerConfig(tune=tune, draws=draws, seed=seed, record_deterministics_every=1, thinned_deterministics=thinned,
                         kernel=kernel)
-    res = sample(target, torch.from_numpy(q0).to(target.device), cfg, progress=progress)
-    post = res.posterior()
+    if world > 1 and shard == "individuals":
+        from .distributed import ShardedEngine, ShardedTarget
+
+        check_splits(splits, cohort)
+        sh = ShardedEngine(cohort, splits=splits, ignore_pcrpos=ignore_pcrpos, device_index=device, rank=rank, world=world,
+                           fused=True, max_chains=chains)
+        target = ShardedTarget(sh, chains, np.zeros((chains, G, N), np.int8), np.zeros((chains, N), np.int8), seed=seed,
+                               gibbs_mode=gibbs_mode)
+        cfg.thinned_deterministics = 0      # (G, N) draws of a sharded cohort are not gathered; the means are
+        cfg.kernel = "hmc"
+        res = sample(target, torch.from_numpy(q0).to(target.device), cfg, progress=progress if rank == 0 else None)
+        li, lw = target.state()
+        post_last = dict(i_raw=target.gather_individuals(li), ab_s_waner=target.gather_individuals(lw))
+        res.means = {k: target.gather_individuals(v) for k, v in res.means.items()}
+        sh.close()
+        return res, res.posterior(), post_last
+    engine = make_engine(cohort, splits=splits, ignore_pcrpos=ignore_pcrpos, device=device)
+    lo, hi = 0, chains
+    if world > 1 and shard == "chains":
+        from .cohort import shard_bounds
+
+        lo, hi = shard_bounds(chains, rank, world)
+        if hi <= lo:
+            raise ValueError("fewer chains than GPUs")
+        engine.set_chain_offset(lo)          # Philox streams keyed by GLOBAL chain: no two ranks share one
+    c_loc = hi - lo
+    target = AbdTarget(engine, c_loc, np.zeros((c_loc, G, N), np.int8), np.zeros((c_loc, N), np.int8), seed=seed,
+                       gibbs_mode=gibbs_mode)
+    res = sample(target, torch.from_numpy(q0[lo:hi]).to(target.device), cfg, progress=progress if rank == 0 else None)
     i_raw, waner = target.state()
     post_last = dict(i_raw=i_raw, ab_s_waner=waner)
     engine.close()
-    return res, post, post_last
+    if world > 1 and shard == "chains":
+        import torch.distributed as dist
+
+        parts = [None] * world
+        dist.all_gather_object(parts, (res.q, res.logp, res.accept, res.step_size, res.means, res.thinned, post_last, c_loc))
+        res.q, res.logp, res.accept = (np.concatenate([p[k] for p in parts], axis=0) for k in range(3))
+        res.step_size = np.concatenate([p[3] for p in parts])
+        tot = sum(p[7] for p in parts)
+        res.means = {k: sum(p[4][k] * p[7] for p in parts) / tot for k in parts[0][4]}
+        if res.thinned:
+            res.thinned = {k: (v if k == "draw" else np.concatenate([p[5][k] for p in parts], axis=0)) for k, v in res.thinned.items()}
+        post_last = {k: np.concatenate([p[6][k] for p in parts], axis=0) for k in post_last}
+    return res, res.posterior(), post_last
+
+
+def _write_builtin(args, data, res, post, last):
+    out = args.netcdf or "abd_posterior.npz"
+    if not out.endswith(".npz"):
+        try:  # pragma: no cover - ArviZ is absent from the build image
+            import arviz as az
+
+            posterior = dict(post)
+            dims = {}
+            if res.thinned:  # the Deterministics only exist for the kept draws: thin everything alike
+                keep = res.thinned["draw"]
+                posterior = {k: v[:, keep] for k, v in posterior.items()}
+                for name in ("i", "ab_n_mu", "ab_s_mu"):
+                    posterior[name] = res.thinned[name]
+                    dims[name] = list(GAP_IND)
+            sample_stats = {"acceptance_rate": res.accept, "lp": res.logp}
+            idata = az.from_dict(posterior=posterior, sample_stats=sample_stats, dims=dims,
+                                 coords={"gap": np.arange(data.n_gaps), "ind": np.arange(data.n_inds)})
+            az.to_netcdf(idata, out)
+            print(f"PyMC not installed: sampled with the built-in HMC+Gibbs driver in {res.wall_s:.1f} s; wrote {out}",
+                  file=sys.stderr)
+            return
+        except ImportError:
+            pass
+    # no ArviZ: the same variables as a compressed .npz (posterior draws (chain, draw), sample_stats_* like the
+    # InferenceData's sample_stats group, the Deterministics as posterior means + thinned draws, the last binary state)
+    np.savez_compressed(out if out.endswith(".npz") else out + ".npz", **post, **{f"mean_{k}": v for k, v in res.means.items()},
+                        **{f"last_{k}": v for k, v in last.items()}, step_size=res.step_size, wall_s=res.wall_s,
+                        sample_stats_acceptance_rate=res.accept, sample_stats_lp=res.logp,
+                        sample_stats_step_size=np.broadcast_to(res.step_size[:, None], res.accept.shape),
+                        **{("thinned_draw" if k == "draw" else k): v for k, v in res.thinned.items()})
+    print(f"PyMC not installed: sampled with the built-in HMC+Gibbs driver in {res.wall_s:.1f} s; wrote {out}", file=sys.stderr)
+
+
+def _builtin_worker(rank, args, devices, port):
+    """One process per GPU of --devices (spawned by main, or started by torchrun)."""
+    import os
+
+    world = len(devices)
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                          MASTER_PORT=str(port))
+        torch.cuda.set_device(devices[rank])
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", devices[rank]))
+    data = CohortArrays.from_disk(args.ititers_data)
+    splits = (None if (not args.split_delta) and (not args.split_omicron)
+              else data.calculate_splits(delta=args.split_delta, omicron=args.split_omicron))
+    res, post, last = infer_builtin(data, splits, args.ignore_pcrpos, args.tune, args.draws, chains=args.chains,
+                                    device=devices[rank], progress=max(1, (args.tune + args.draws) // 10),
+                                    gibbs_mode=args.gibbs_mode, thinned=args.thinned, kernel=args.kernel,
+                                    shard=args.shard if world > 1 else None, rank=rank, world=world)
+    if rank == 0:
+        _write_builtin(args, data, res, post, last)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    return res
 
 
 def main(argv=None):
@@ -360,6 +467,12 @@ def main(argv=None):
     parser.add_argument("--netcdf", help="Path of netCDF file to save.")
     parser.add_argument("--chains", type=int, default=4, help="(extension) chains batched on the GPU")
     parser.add_argument("--device", type=int, default=0, help="(extension) CUDA device")
+    parser.add_argument("--devices", default=None,
+                        help="(extension, PyMC-free driver) comma-separated CUDA devices of this node, one process each, e.g. "
+                             "0,1,2,3,4,5,6,7; see --shard")
+    parser.add_argument("--shard", default="individuals", choices=["individuals", "chains"],
+                        help="(extension) with --devices: split the INDIVIDUALS over the GPUs (large cohorts; one fused "
+                             "NVLink all-reduce of chains x 16 doubles per evaluation) or the CHAINS (no communication)")
     parser.add_argument("--thinned", type=int, default=250,
                         help="(extension, PyMC-free driver) evenly spaced draws of i / ab_n_mu / ab_s_mu kept per chain "
                              "(the downstream code uses <= 250: survival.py:109-114)")
@@ -374,12 +487,12 @@ def main(argv=None):
         print(f"abdpymc-infer: --cores {args.cores} ignored -- the chains of a run are batched on the GPU(s) of this process "
               "(a CUDA context does not survive pm.sample's fork); use --chains / --devices", file=sys.stderr)
 
-    data = CohortArrays.from_disk(args.ititers_data)
-    splits = (None if (not args.split_delta) and (not args.split_omicron)
-              else data.calculate_splits(delta=args.split_delta, omicron=args.split_omicron))
-
     if HAVE_PYMC:  # pragma: no cover
         import arviz as az
+
+        data = CohortArrays.from_disk(args.ititers_data)
+        splits = (None if (not args.split_delta) and (not args.split_omicron)
+                  else data.calculate_splits(delta=args.split_delta, omicron=args.split_omicron))
 
         with model(data, splits=splits, ignore_pcrpos=args.ignore_pcrpos, device=args.device) as m:
             step = GpuBinaryGibbs([m["i_raw"], m["ab_s_waner"]], model=m, mode=args.gibbs_mode)
@@ -388,35 +501,19 @@ def main(argv=None):
         az.to_netcdf(idata, args.netcdf)
         return idata
 
-    res, post, last = infer_builtin(data, splits, args.ignore_pcrpos, args.tune, args.draws, chains=args.chains,
-                                    device=args.device, progress=max(1, (args.tune + args.draws) // 10),
-                                    gibbs_mode=args.gibbs_mode, thinned=args.thinned, kernel=args.kernel)
-    out = args.netcdf or "abd_posterior.npz"
-    if not out.endswith(".npz"):
-        try:  # pragma: no cover - ArviZ is absent from the build image
-            import arviz as az
+    devices = [int(d) for d in args.devices.split(",")] if args.devices else [args.device]
+    if len(devices) == 1:
+        return _builtin_worker(0, args, devices, 0)
+    # several GPUs of this node: one process each (the CUDA context of this process is never created)
+    import socket
 
-            posterior = dict(post)
-            dims = {}
-            if res.thinned:  # the Deterministics only exist for the kept draws: thin everything alike
-                keep = res.thinned["draw"]
-                posterior = {k: v[:, keep] for k, v in posterior.items()}
-                for name in ("i", "ab_n_mu", "ab_s_mu"):
-                    posterior[name] = res.thinned[name]
-                    dims[name] = list(GAP_IND)
-            idata = az.from_dict(posterior=posterior, dims=dims,
-                                 coords={"gap": np.arange(data.n_gaps), "ind": np.arange(data.n_inds)})
-            az.to_netcdf(idata, out)
-            print(f"PyMC not installed: sampled with the built-in HMC+Gibbs driver in {res.wall_s:.1f} s; wrote {out}",
-                  file=sys.stderr)
-            return res
-        except ImportError:
-            pass
-    np.savez_compressed(out if out.endswith(".npz") else out + ".npz", **post, **{f"mean_{k}": v for k, v in res.means.items()},
-                        **{f"last_{k}": v for k, v in last.items()}, step_size=res.step_size, wall_s=res.wall_s,
-                        **{("thinned_draw" if k == "draw" else k): v for k, v in res.thinned.items()})
-    print(f"PyMC not installed: sampled with the built-in HMC+Gibbs driver in {res.wall_s:.1f} s; wrote {out}", file=sys.stderr)
-    return res
+    import torch.multiprocessing as mp
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_builtin_worker, args=(args, devices, port), nprocs=len(devices), join=True)
+    return None
 
 
 if __name__ == "__main__":

@@ -455,6 +455,8 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
   const TileDesc* tiles = reinterpret_cast<const TileDesc*>(tl.d_tiles);
   const Priors* pri = h->d_priors;
   if (tj) {
+    if (traj.n_steps > 1 && h->xch_active)
+      return fail(ABD_ERR_INVALID, "sharded leapfrog: one step per launch");
     if (traj.n_steps > 1) {  // CTAs wait on one another: they must all be resident
       int occ = 0;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sums<M, XT, true>, kSumsBlock, tl.smem));
@@ -470,7 +472,7 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
     }
     lc.attrs = attr;
     CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, true>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, pack, h->d_partial,
-                          h->d_ticket, sums, fin, pri, h->d_aux, traj, XchCfg{}, ThetaInline{}));
+                          h->d_ticket, sums, fin, pri, h->d_aux, traj, h->xch_active ? h->xch : XchCfg{}, ThetaInline{}));
   } else {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1229,12 +1231,16 @@ int abd_xch_alloc(abd_handle* h, int world, int rank, int max_chains, void* out_
   unsigned* seq;
   if ((rc = dev_alloc(h, &seq, (size_t)max_chains + 1))) return rc;
   CU(cudaMemset(seq, 0, ((size_t)max_chains + 1) * sizeof(unsigned)));
+  unsigned long long* stat;
+  if ((rc = dev_alloc(h, &stat, (size_t)kMaxPeers + 1))) return rc;
+  CU(cudaMemset(stat, 0, ((size_t)kMaxPeers + 1) * sizeof(unsigned long long)));
   h->xch = XchCfg{};
   h->xch.world = world;
   h->xch.rank = rank;
   h->xch.cmax = max_chains;
   h->xch.seq = seq;
   h->xch.err = seq + max_chains;
+  h->xch.stat = stat;
   cudaIpcMemHandle_t ipc;
   CU(cudaIpcGetMemHandle(&ipc, h->xch_local));
   static_assert(sizeof(ipc) == ABD_IPC_HANDLE_BYTES, "IPC handle size");
@@ -1276,6 +1282,32 @@ int abd_logp_dlogp_sharded_dev(abd_handle* h, int C, const double* q17, const in
   const int rc = launch_sums(h, C, q17, 1, i_raw, waner, h->d_sums, fin, (cudaStream_t)stream);
   h->xch_active = false;
   return rc;
+}
+
+int abd_leapfrog_sharded_dev(abd_handle* h, int C, double* q17, double* p17, double* grad17, double* logp, const double* eps,
+                             const double* inv_mass, const int8_t* i_raw, const int8_t* waner, void* stream) {
+  PROLOGUE(h, C);
+  h->lazy_pack = true;
+  if (!q17 || !p17 || !grad17 || !logp || !eps || !inv_mass || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
+  if (!h->xch_local || !h->xch.data[h->xch.world - 1] || !h->xch.data[0])
+    return fail(ABD_ERR_INVALID, "abd_leapfrog_sharded_dev: call abd_xch_alloc and abd_xch_connect first");
+  if (C > h->xch.cmax) return fail(ABD_ERR_INVALID, "more chains than abd_xch_alloc reserved");
+  TrajCfg traj{1, q17, p17, grad17, logp, eps, inv_mass, h->d_traj, h->d_gen, h->d_gen + C};
+  FinalizeCfg fin{2, h->tot, nullptr, nullptr};
+  h->xch_active = true;
+  const int rc = launch_sums(h, C, q17, 1, i_raw, waner, nullptr, fin, (cudaStream_t)stream, &traj);
+  h->xch_active = false;
+  return rc;
+}
+
+int abd_xch_stats(abd_handle* h, uint64_t* out, int reset) {
+  if (!h || !h->xch_local || !out) return fail(ABD_ERR_INVALID, "no exchange buffer");
+  int rc = set_device(h);
+  if (rc) return rc;
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+  CU(cudaMemcpy(out, h->xch.stat, (kMaxPeers + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (reset) CU(cudaMemset(h->xch.stat, 0, (kMaxPeers + 1) * sizeof(uint64_t)));
+  return ABD_OK;
 }
 
 int abd_xch_status(abd_handle* h) {

@@ -48,6 +48,7 @@ struct XchCfg {
   unsigned long long* flag[kMaxPeers];   // ... followed by [2][world][cmax] flags
   unsigned* seq;                         // [cmax] local sequence numbers
   unsigned* err;
+  unsigned long long* stat;              // [kMaxPeers + 1]: ns spent waiting for each peer's flag, exchanges done
 };
 
 // Trajectory mode (n_steps > 0): the kernel stays resident for n_steps leapfrog steps of
@@ -578,7 +579,7 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         if (sums) sums[(size_t)c * kNSums + tid] = tot;
       }
       __syncthreads();
-      if (!TRAJ && xch.world > 1) {
+      if (xch.world > 1) {  // (trajectory mode: single-step launches only, the host checks)
         __shared__ unsigned s_seq;
         if (tid == 0) s_seq = xch.seq[c] + 1u;
         __syncthreads();
@@ -602,6 +603,9 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
           } while (seen != (unsigned long long)seq && t_now - t_start < kXchTimeoutNs);
           if (seen != (unsigned long long)seq) *xch.err = 1u;  // watchdog: never hang the GPU
+          // exchange cost, kept apart from compute: how long this rank's finishing CTA sat waiting for peer `tid`
+          atomicAdd(xch.stat + tid, t_now - t_start);
+          if (tid == 0) atomicAdd(xch.stat + kMaxPeers, 1ull);
         }
         __syncthreads();
         if (tid < kNSums) {

@@ -130,13 +130,16 @@ class ShardedEngine:
         return self.engine.upload_state(np.ascontiguousarray(i_raw[..., self.ind_slice]),
                                         np.ascontiguousarray(waner[..., self.ind_slice]))
 
-    def logp_dlogp(self, q17, n_chains=None):
+    def logp_dlogp(self, q17, n_chains=None, out=None, outg=None):
         """``q17``: torch (C, 17) float64 tensor on this rank's device (identical on all ranks).
-        Uses the resident chain state.  Returns (logp (C,), dlogp (C, 17)) device tensors."""
+        Uses the resident chain state.  Returns (logp (C,), dlogp (C, 17)) device tensors (``out`` /
+        ``outg`` when given, otherwise buffers reused by the next call)."""
         import torch
 
         C = q17.shape[0] if n_chains is None else n_chains
-        sums, out, outg = self._buffers(C)
+        sums, out_, outg_ = self._buffers(C)
+        out = out_ if out is None else out
+        outg = outg_ if outg is None else outg
         st = torch.cuda.current_stream(self.device).cuda_stream
         d_i, d_w = self.engine.state_dev(C)
         if self.fused:
@@ -158,5 +161,113 @@ class ShardedEngine:
         self.engine.gibbs_sweep_dev(C, q17.data_ptr(), 1, None, None, d_i, d_w, seed, sweep, mode=mode,
                                     transit_p=transit_p, stream=st)
 
+    def leapfrog_step(self, C, q, p, grad, logp, eps, inv_mass):
+        """One leapfrog step in place (device tensors), the exchange fused into the launch (fused engines only)."""
+        import torch
+
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        d_i, d_w = self.engine.state_dev(C)
+        self.engine.leapfrog_sharded_dev(C, q.data_ptr(), p.data_ptr(), grad.data_ptr(), logp.data_ptr(), eps.data_ptr(),
+                                         inv_mass.data_ptr(), d_i, d_w, st)
+
+    def exchange_wait_us(self, reset=True):
+        """Mean time (us) the finishing CTA of an evaluation spent waiting for its slowest peer's contribution
+        -- launch skew between the ranks plus NVLink latency -- since the last reset (fused engines only)."""
+        ns, n = self.engine.xch_stats(reset=reset)
+        return float(ns.max()) / max(n, 1) / 1e3
+
     def close(self):
         self.engine.close()
+
+
+class ShardedTarget:
+    """The posterior of an INDIVIDUAL-SHARDED cohort as a sampler target (same interface as
+    ``sampler.AbdTarget``): every rank holds a contiguous block of individuals and the matching slice of
+    every chain's binary state; the 17 scalars, their momenta, step sizes and the metric are replicated.
+
+    * logp + gradient / leapfrog steps: local sums, all-reduce of C x 16 doubles fused into the launch
+      over NVLink peer memory (``fused=True``) -- every rank obtains bitwise identical results, so the
+      replicated HMC state never diverges; or ``abd_sums_dev`` -> NCCL / gloo all-reduce ->
+      ``abd_finalize_logp_dev`` (``fused=False``; the sampler then runs its host-driven loop).
+    * momentum refresh / accept (``abd_hmc_begin_dev`` / ``abd_hmc_end_dev``): Philox streams keyed by
+      (seed; iteration, chain) -- the same seed on every rank gives the same momenta and decisions.
+    * Gibbs sweep: local, no communication (individuals are conditionally independent given the
+      scalars; streams keyed by GLOBAL individual, so the draws do not depend on the sharding).
+    What abd.py:922 runs as NUTS + BinaryGibbsMetropolis on one CPU core per chain."""
+
+    def __init__(self, sharded: ShardedEngine, n_chains, i_raw, waner, seed=0, gibbs_mode=0, transit_p=0.8):
+        import torch
+
+        self.sh, self.engine, self.C = sharded, sharded.engine, n_chains
+        self.device = sharded.device
+        sharded.upload_state(i_raw, waner)          # (C, G, N_total) / (C, N_total): this rank keeps its block
+        self.seed, self.gibbs_mode, self.transit_p = seed, gibbs_mode, transit_p
+        self.dim = 17
+        self.out = torch.zeros(n_chains, dtype=torch.float64, device=self.device)
+        self.outg = torch.zeros(n_chains, 17, dtype=torch.float64, device=self.device)
+        if sharded.fused:  # the device-resident transition of sampler._sample_fused
+            self.hmc_begin, self.hmc_end = self._hmc_begin, self._hmc_end
+
+    def _stream(self):
+        import torch
+
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def logp_dlogp(self, q):
+        lp, g = self.sh.logp_dlogp(q.contiguous(), self.C)
+        return lp.clone(), g.clone()
+
+    def logp_dlogp_into(self, q, logp, grad):
+        self.sh.logp_dlogp(q, self.C, out=logp, outg=grad)
+
+    def check_status(self):
+        self.engine.leapfrog_status(self.C)
+        if self.sh.fused:
+            self.engine.xch_status()
+
+    def leapfrog_inplace(self, q, p, grad, logp, eps, inv_mass, n_steps):
+        for _ in range(n_steps):
+            self.sh.leapfrog_step(self.C, q, p, grad, logp, eps, inv_mass)
+
+    def _hmc_begin(self, q, grad, logp, linv_t, it, qw, pw, gw, h0):
+        self.engine.hmc_begin_dev(self.C, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), linv_t.data_ptr(), self.seed, it,
+                                  qw.data_ptr(), pw.data_ptr(), gw.data_ptr(), h0.data_ptr(), self._stream())
+
+    def _hmc_end(self, q, grad, logp, qw, pw, gw, lpw, inv_mass, h0, it, acc, da, eps, adapt, target_accept):
+        self.engine.hmc_end_dev(self.C, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), qw.data_ptr(), pw.data_ptr(),
+                                gw.data_ptr(), lpw.data_ptr(), inv_mass.data_ptr(), h0.data_ptr(), self.seed, it,
+                                acc.data_ptr(), da.data_ptr(), eps.data_ptr(), adapt, target_accept, self._stream())
+
+    def gibbs(self, q, sweep):
+        self.sh.gibbs_sweep(q.contiguous(), self.seed, sweep, mode=self.gibbs_mode, transit_p=self.transit_p)
+
+    def fits_persistent(self):
+        return self.sh.fused
+
+    def accumulate_deterministics(self, q, sums):
+        """Running totals of i, ab_n_mu, ab_s_mu over this rank's individuals: (G, N_local) device tensors."""
+        import torch
+
+        G, N = self.engine.G, self.engine.N
+        for name in ("i", "ab_n_mu", "ab_s_mu"):
+            if name not in sums:
+                sums[name] = torch.zeros(G, N, dtype=torch.float64, device=self.device)
+        q = q.contiguous()
+        d_i, d_w = self.engine.state_dev(self.C)
+        self.engine.deterministics_accum_dev(self.C, q.data_ptr(), 1, d_i, d_w, sums["i"].data_ptr(),
+                                             sums["ab_n_mu"].data_ptr(), sums["ab_s_mu"].data_ptr(), self._stream())
+
+    def state(self):
+        """This rank's block of the binary state: (i_raw (C, G, N_local), waner (C, N_local))."""
+        import torch
+
+        torch.cuda.synchronize(self.device)
+        return self.engine.download_state(self.C)
+
+    def gather_individuals(self, local, axis=-1):
+        """Concatenate per-rank blocks of individuals (NumPy arrays) along ``axis`` on every rank."""
+        import torch.distributed as dist
+
+        parts = [None] * self.sh.world
+        dist.all_gather_object(parts, np.ascontiguousarray(local), group=self.sh.group)
+        return np.concatenate(parts, axis=axis)

@@ -326,6 +326,15 @@ class AbdEngine:
     def xch_status(self):
         check(self._lib.abd_xch_status(self._h))
 
+    def leapfrog_sharded_dev(self, C_, q17, p17, grad17, logp, eps, inv_mass, i_raw, waner, stream=0):
+        check(self._lib.abd_leapfrog_sharded_dev(self._h, C_, q17, p17, grad17, logp, eps, inv_mass, i_raw, waner, stream))
+
+    def xch_stats(self, reset=False):
+        """(ns waited for each peer [8], exchanges done): the fused all-reduce's cost apart from compute."""
+        out = np.zeros(9, np.uint64)
+        check(self._lib.abd_xch_stats(self._h, out.ctypes.data, int(reset)))
+        return out[:8].copy(), int(out[8])
+
     def deterministics_dev(self, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream=0):
         check(self._lib.abd_deterministics_dev(self._h, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream))
 

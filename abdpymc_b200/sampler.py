@@ -95,6 +95,9 @@ class AbdTarget:
         self.engine.gibbs_sweep_dev(self.C, q.data_ptr(), 1, None, None, self.d_i, self.d_w, self.seed, sweep,
                                     mode=self.gibbs_mode, transit_p=self.transit_p, stream=self._stream())
 
+    def check_status(self):
+        self.engine.leapfrog_status(self.C)
+
     def fits_persistent(self):
         """Whether a whole trajectory fits one resident grid (abd_leapfrog_dev): try one step."""
         z = torch.zeros(self.C, 17, dtype=torch.float64, device=self.device)
@@ -329,7 +332,7 @@ def _sample_fused(target, q0, cfg, progress):
         if progress and (it + 1) % progress == 0:
             print(f"  iter {it + 1}/{total}  step {eps.mean().item():.4f}  accept {acc.mean().item():.2f}", flush=True)
     torch.cuda.synchronize(dev)
-    target.engine.leapfrog_status(C)
+    target.check_status()
     wall = time.perf_counter() - t0
     return SamplerResult(
         q=out_q.permute(1, 0, 2).cpu().numpy(), logp=out_lp.T.cpu().numpy(), accept=out_acc.T.cpu().numpy(),

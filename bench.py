@@ -251,6 +251,119 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+def _timed_us(fn, n, dist, dev, warm=5):
+    """Average device time (us) of n calls of fn on the current stream, max over ranks."""
+    import torch
+
+    for _ in range(warm):
+        fn()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / n * 1e3
+
+
+def bench_sharded(dist, rank, world, local, dev, K, n_big=100_000, chain_counts=(4, 32), block=32):
+    """BASELINE configs[3].  One evaluation = joint logp + gradient of all C chains on the 100k cohort.
+    `one_gpu`: the whole cohort on rank 0's GPU (the baseline the speed-ups are quoted against; the other
+    ranks idle).  With world > 1: individuals split into `world` contiguous blocks, the C x 16 sums exchanged
+    per evaluation by NCCL (three launches + a collective, host-driven) or inside the kernel over NVLink peer
+    memory (one launch; host-driven, and as a CUDA graph of `block` evaluations, which removes the launch skew
+    between the ranks' host threads).  Everything here re-evaluates ONE cohort back to back (L2-resident on
+    every side, the access pattern of consecutive leapfrogs)."""
+    import torch
+
+    from abdpymc_b200.cohort import synthetic_cohort
+    from abdpymc_b200.distributed import ShardedEngine
+    from abdpymc_b200.engine import AbdEngine
+
+    big = synthetic_cohort(n_big)
+    out = {"workload": f"simulated {n_big}-individual cohort (G={big.n_gaps}, {big.n_rows} OD rows) sharded by individual over "
+                       f"{world} GPU(s), splits {list(SPLITS)}", "unit": "us per evaluation of all C chains", "by_chains": {}}
+    side = torch.cuda.Stream(device=dev)
+    n_rep = max(3, min(20, K))
+    for Csh in chain_counts:
+        rngb = np.random.default_rng(77)
+        ib = (rngb.random((Csh, big.n_gaps, big.n_inds)) < 0.04).astype(np.int8)
+        wb = (rngb.random((Csh, big.n_inds)) < 0.5).astype(np.int8)
+        tqs = torch.from_numpy(workload(n_inds=1000, n_chains=Csh, chain_offset=0)[1]).to(dev)  # identical q on every rank
+        res = {}
+        # -- baseline: the whole cohort on one GPU (rank 0), a graph of `block` evaluations
+        t1 = torch.zeros(1, dtype=torch.float64, device=dev)
+        lp1 = torch.zeros(Csh, dtype=torch.float64, device=dev)
+        if rank == 0:
+            with AbdEngine(big, splits=SPLITS, device=local) as e1g:
+                e1g.upload_state(ib, wb)
+                di, dw = e1g.state_dev(Csh)
+                o1 = torch.zeros(Csh, dtype=torch.float64, device=dev)
+                o2 = torch.zeros(Csh, 17, dtype=torch.float64, device=dev)
+                with torch.cuda.stream(side):
+                    e1g.logp_dlogp_dev(Csh, tqs.data_ptr(), di, dw, o1.data_ptr(), o2.data_ptr(), side.cuda_stream)
+                side.synchronize()
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1, stream=side):
+                    for _ in range(block):
+                        e1g.logp_dlogp_dev(Csh, tqs.data_ptr(), di, dw, o1.data_ptr(), o2.data_ptr(), side.cuda_stream)
+                t1[0] = _timed_us(g1.replay, n_rep, None, dev, warm=2) / block
+                lp1.copy_(o1)
+                del g1
+        if dist:
+            dist.broadcast(t1, 0)
+            dist.broadcast(lp1, 0)
+        us1 = float(t1.item())
+        res["one_gpu"] = {"us_per_eval": us1, "evals_per_s": Csh / us1 * 1e6}
+        if dist:
+            se = ShardedEngine(big, splits=SPLITS, device_index=local, rank=rank, world=world)
+            se.upload_state(ib, wb)
+            us_nccl = _timed_us(lambda: se.logp_dlogp(tqs), max(50, 10 * n_rep), dist, dev, warm=10)
+            lp_n = se.logp_dlogp(tqs)[0].clone()
+            se.close()
+            sf = ShardedEngine(big, splits=SPLITS, device_index=local, rank=rank, world=world, fused=True, max_chains=Csh)
+            sf.upload_state(ib, wb)
+            us_fused = _timed_us(lambda: sf.logp_dlogp(tqs), max(50, 10 * n_rep), dist, dev, warm=10)
+            lp_f = sf.logp_dlogp(tqs)[0].clone()
+            sf.exchange_wait_us(reset=True)
+            with torch.cuda.stream(side):
+                sf.logp_dlogp(tqs)
+            side.synchronize()
+            dist.barrier()
+            gf = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf, stream=side):
+                for _ in range(block):
+                    sf.logp_dlogp(tqs)
+            sf.exchange_wait_us(reset=True)
+            us_graph = _timed_us(gf.replay, n_rep, dist, dev, warm=2) / block
+            wait_us = sf.exchange_wait_us(reset=True)
+            tw = torch.tensor([wait_us], dtype=torch.float64, device=dev)
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            sf.engine.xch_status()
+            del gf
+            sf.close()
+            rel = float(((lp_f - lp1).abs() / lp1.abs()).max())
+            res["nccl"] = {"us_per_eval": us_nccl, "speedup_vs_1gpu": us1 / us_nccl,
+                           "collective": f"torch.distributed all_reduce(SUM) of {Csh} x 16 float64 per evaluation (NCCL), host-driven"}
+            res["fused_peer_allreduce"] = {
+                "us_per_eval": us_fused, "speedup_vs_1gpu": us1 / us_fused, "host_driven": True,
+                "bitwise_equal_to_nccl_path": bool(torch.equal(lp_f, lp_n)), "rel_err_vs_one_gpu": rel}
+            res["fused_peer_allreduce_graph"] = {
+                "us_per_eval": us_graph, "speedup_vs_1gpu": us1 / us_graph, "evals_per_s": Csh / us_graph * 1e6,
+                "exchange_wait_us_per_eval_max_over_ranks": float(tw.item()),
+                "note": f"CUDA graph of {block} evaluations per rank; exchange_wait = mean time the finishing CTA spent waiting "
+                        "for its slowest peer's sums (launch skew + NVLink latency), measured in the kernel with %globaltimer"}
+        out["by_chains"][str(Csh)] = res
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
 
@@ -585,56 +698,12 @@ def run_gpu(args):
     for e in engines[1:]:
         e.close()
 
-    # ---- individual sharding (BASELINE configs[3]): 100k-individual cohort split over the ranks,
-    #      one all-reduce of C x 16 doubles per evaluation (NCCL), host-driven loop ----
+    # ---- individual sharding (BASELINE configs[3]): the 100k-individual cohort on ONE GPU (baseline, rank 0)
+    #      and split over the ranks, C = 4 and C = 32 chains; NCCL all-reduce against the all-reduce fused into
+    #      the kernel over NVLink peer memory, host-driven and as a CUDA graph ----
     sharded = None
-    if dist:
-        from abdpymc_b200.cohort import synthetic_cohort
-        from abdpymc_b200.distributed import ShardedEngine
-
-        big = synthetic_cohort(100_000)
-        rngb = np.random.default_rng(77)
-        ib = (rngb.random((C, big.n_gaps, big.n_inds)) < 0.04).astype(np.int8)
-        wb = (rngb.random((C, big.n_inds)) < 0.5).astype(np.int8)
-        se = ShardedEngine(big, splits=SPLITS, device_index=local, rank=rank, world=world)
-        se.upload_state(ib, wb)
-        tqs = torch.from_numpy(workload(chain_offset=0)[1]).to(dev)  # identical q on every rank
-        for _ in range(10):
-            se.logp_dlogp(tqs)
-        barrier()
-        n_sh = max(50, min(500, K * 10))
-        e0.record()
-        for _ in range(n_sh):
-            lp_sh, _ = se.logp_dlogp(tqs)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sharded = {"workload": "simulated 100000-individual cohort sharded by individual, 4 chains",
-                   "value": C * n_sh / (float(t.item()) / 1e3), "unit": "evals/s", "ms_per_eval_batch": float(t.item()) / n_sh,
-                   "collective": "torch.distributed all_reduce(SUM) of 4 x 16 float64 per evaluation (NCCL)",
-                   "logp_chain0": float(lp_sh[0].item())}
-        se.close()
-        # the same with the all-reduce fused into the kernel over NVLink peer memory (one launch per evaluation)
-        sf = ShardedEngine(big, splits=SPLITS, device_index=local, rank=rank, world=world, fused=True, max_chains=C)
-        sf.upload_state(ib, wb)
-        for _ in range(10):
-            sf.logp_dlogp(tqs)
-        barrier()
-        e0.record()
-        for _ in range(n_sh):
-            lp_f, _ = sf.logp_dlogp(tqs)
-        e1.record()
-        barrier()
-        sf.engine.xch_status()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        sharded["fused_peer_allreduce"] = {
-            "value": C * n_sh / (float(t.item()) / 1e3), "unit": "evals/s", "ms_per_eval_batch": float(t.item()) / n_sh,
-            "collective": "none: the finishing CTA of each rank stores its 16 sums into every peer's buffer (NVLink), "
-                          "waits for theirs and finalises in the same launch",
-            "bitwise_equal_to_nccl_path": bool(torch.equal(lp_f, lp_sh))}
-        sf.close()
+    if not args.no_sharded:
+        sharded = bench_sharded(dist, rank, world, local, dev, K)
 
     # ---- ESS/s of the built-in HMC + GPU-Gibbs sampler on the same cohort (bounded run) ----
     ess = None
@@ -781,6 +850,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the 100k-individual (individual-sharded) leg")
     ap.add_argument("--ess-tune", type=int, default=2000)
     ap.add_argument("--ess-draws", type=int, default=6000)
     ap.add_argument("--profile", action="store_true",

@@ -252,6 +252,19 @@ int abd_logp_dlogp_sharded_dev(abd_handle* h, int n_chains, const double* q17, c
                                const int8_t* waner, double* out_logp, double* out_dlogp,
                                void* stream);
 int abd_xch_status(abd_handle* h);
+/* One leapfrog step (abd_leapfrog_dev with n_steps = 1) on an individual-sharded cohort, the all-reduce
+ * fused into the launch as in abd_logp_dlogp_sharded_dev: every rank starts from the same (q, p, grad,
+ * eps, inv_mass), evaluates its individuals at the new position, exchanges, and ends with bitwise
+ * identical (q, p, grad, logp).  A COLLECTIVE call.  With abd_hmc_begin_dev / abd_hmc_end_dev (same
+ * seed on every rank) and the local Gibbs sweeps this runs the whole compound sampler of pm.sample
+ * (abd.py:922) on a sharded cohort with no other communication.                                  */
+int abd_leapfrog_sharded_dev(abd_handle* h, int n_chains, double* q17, double* p17, double* grad17,
+                             double* logp, const double* eps, const double* inv_mass,
+                             const int8_t* i_raw, const int8_t* waner, void* stream);
+/* Exchange cost kept apart from compute: out[r] (r < 8) = nanoseconds this rank's finishing CTAs have
+ * spent waiting for peer r's contribution (launch skew + NVLink latency), out[8] = exchanges done
+ * (one per chain and evaluation).  Synchronous; reset != 0 zeroes the counters.                   */
+int abd_xch_stats(abd_handle* h, uint64_t* out, int reset);
 
 /* Pointers to the resident chain state (valid until a call with MORE chains than any before: the
  * buffers are then reallocated -- query again).  Beside these int8 arrays the library keeps a packed

