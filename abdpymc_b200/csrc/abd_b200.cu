@@ -374,6 +374,7 @@ void plan_grid(const abd_handle* h, int C, int ctas_per_sm, int* want_tiles, int
   const int target = h->tile_rows_override > 0 ? h->tile_rows_override : 2200;
   int cpc = h->chains_per_cta_override > 0 ? h->chains_per_cta_override : (C >= 32 ? 4 : 1);
   cpc = std::min(cpc, C);
+  if (h->xch_active) cpc = std::min(cpc, 16);  // a CTA remembers at most 16 chains it finished last (k_sums: s_pend)
   const int groups = (C + cpc - 1) / cpc;
   const int min_tiles = (h->N + kTileMaxInds - 1) / kTileMaxInds;
   const int resident = h->n_sms * ctas_per_sm;
@@ -1224,8 +1225,7 @@ int abd_xch_alloc(abd_handle* h, int world, int rank, int max_chains, void* out_
   int rc = set_device(h);
   if (rc) return rc;
   if (h->xch_local) return fail(ABD_ERR_INVALID, "abd_xch_alloc: already allocated");
-  const size_t nd = (size_t)2 * world * max_chains * kNSums, nf = (size_t)2 * world * max_chains;
-  const size_t bytes = nd * sizeof(double) + nf * sizeof(unsigned long long);
+  const size_t bytes = (size_t)2 * world * max_chains * 32 * sizeof(unsigned long long);
   CU(cudaMalloc(&h->xch_local, bytes));
   CU(cudaMemset(h->xch_local, 0, bytes));
   unsigned* seq;
@@ -1254,7 +1254,6 @@ int abd_xch_connect(abd_handle* h, const void* all_ipc_handles) {
   int rc = set_device(h);
   if (rc) return rc;
   const int world = h->xch.world;
-  const size_t nd = (size_t)2 * world * h->xch.cmax * kNSums;
   for (int r = 0; r < world; ++r) {
     void* base = h->xch_local;
     if (r != h->xch.rank) {
@@ -1263,8 +1262,7 @@ int abd_xch_connect(abd_handle* h, const void* all_ipc_handles) {
       CU(cudaIpcOpenMemHandle(&base, ipc, cudaIpcMemLazyEnablePeerAccess));
       h->xch_peer[r] = base;
     }
-    h->xch.data[r] = (double*)base;
-    h->xch.flag[r] = (unsigned long long*)((double*)base + nd);
+    h->xch.buf[r] = (unsigned long long*)base;
   }
   return ABD_OK;
 }
@@ -1274,7 +1272,7 @@ int abd_logp_dlogp_sharded_dev(abd_handle* h, int C, const double* q17, const in
   PROLOGUE(h, C);
   h->lazy_pack = true;
   if (!q17 || !i_raw || !waner || !out_logp) return fail(ABD_ERR_INVALID, "NULL argument");
-  if (!h->xch_local || !h->xch.data[h->xch.world - 1] || !h->xch.data[0])
+  if (!h->xch_local || !h->xch.buf[h->xch.world - 1] || !h->xch.buf[0])
     return fail(ABD_ERR_INVALID, "abd_logp_dlogp_sharded_dev: call abd_xch_alloc and abd_xch_connect first");
   if (C > h->xch.cmax) return fail(ABD_ERR_INVALID, "more chains than abd_xch_alloc reserved");
   FinalizeCfg fin{2, h->tot, out_logp, out_dlogp};
@@ -1289,7 +1287,7 @@ int abd_leapfrog_sharded_dev(abd_handle* h, int C, double* q17, double* p17, dou
   PROLOGUE(h, C);
   h->lazy_pack = true;
   if (!q17 || !p17 || !grad17 || !logp || !eps || !inv_mass || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
-  if (!h->xch_local || !h->xch.data[h->xch.world - 1] || !h->xch.data[0])
+  if (!h->xch_local || !h->xch.buf[h->xch.world - 1] || !h->xch.buf[0])
     return fail(ABD_ERR_INVALID, "abd_leapfrog_sharded_dev: call abd_xch_alloc and abd_xch_connect first");
   if (C > h->xch.cmax) return fail(ABD_ERR_INVALID, "more chains than abd_xch_alloc reserved");
   TrajCfg traj{1, q17, p17, grad17, logp, eps, inv_mass, h->d_traj, h->d_gen, h->d_gen + C};

@@ -36,16 +36,18 @@ struct SumsCfg {
 
 // Fused all-reduce over NVLink peer memory (individuals sharded over `world` GPUs of one node):
 // the CTA that finishes a chain last on each rank stores its 16 raw sums straight into every
-// peer's exchange buffer, raises a per-(rank, chain) flag there, waits for the flags the peers
-// raise in ITS buffer, adds the `world` contributions in rank order (bitwise the same result on
-// every rank) and finalises -- compute, exchange and finalisation in one launch, no NCCL call.
-// Buffers are double-buffered on the parity of a per-chain sequence number kept on the device.
+// peer's exchange buffer -- as 32 eight-byte words, each half a double plus the 32-bit sequence
+// number of the exchange, so that no fence and no separate flag (a second trip over NVLink) is
+// needed --, later polls the words the peers store in ITS buffer, adds the `world` contributions
+// in rank order (bitwise the same result on every rank) and finalises: compute, exchange and
+// finalisation in one launch, no NCCL call.  Buffers are double-buffered on the parity of a
+// per-chain sequence number kept on the device (a rank can be at most one exchange ahead of a
+// peer: it cannot finish exchange k + 1 before the peer has posted k + 1, i.e. finished k).
 constexpr int kMaxPeers = 8;
 constexpr unsigned long long kXchTimeoutNs = 10ull * 1000 * 1000 * 1000;  // a peer that is 10 s late is declared lost
 struct XchCfg {
   int world, rank, cmax;                 // world == 0: not sharded
-  double* data[kMaxPeers];               // peer r's buffer: [2][world][cmax][16] doubles ...
-  unsigned long long* flag[kMaxPeers];   // ... followed by [2][world][cmax] flags
+  unsigned long long* buf[kMaxPeers];    // peer r's buffer: [2][world][cmax][32] words = 32-bit half | sequence << 32
   unsigned* seq;                         // [cmax] local sequence numbers
   unsigned* err;
   unsigned long long* stat;              // [kMaxPeers + 1]: ns spent waiting for each peer's flag, exchanges done
@@ -245,6 +247,63 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     __syncthreads();
   }
   PHASE(1);
+
+  __shared__ int s_pend[16], s_npend;          // sharded: chains this CTA finished last (posted, not yet collected)
+  __shared__ unsigned s_pend_seq[16];
+  __shared__ unsigned s_xw[kMaxPeers][32];     // sharded: the peers' 16 sums as 32-bit halves
+  if (tid == 0) s_npend = 0;
+  // the parameter-only part of the finaliser, parked in `aux` by the chain's first tile
+  auto load_aux = [&](int c) {
+    if (fin.mode && tid < kAuxDoubles) {
+      const double v = __ldcg(aux + (size_t)c * kAuxDoubles + tid);
+      if (tid < 17 * 7) reinterpret_cast<double*>(s_pre)[tid] = v;
+      else if (tid < 17 * 7 + 6) reinterpret_cast<double*>(&s_lik)[tid - 17 * 7] = v;
+    }
+  };
+  // warp 0: totals in s_red[0] -> loglik / joint logp and gradient (or, trajectory mode, the end of the step)
+  auto finalize_chain = [&](int c, int step, int nsteps) {
+    if (fin.mode == 1) {
+      if (lane == 0)
+        finalize_loglik_post(s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
+                             fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
+    } else if (fin.mode == 2 && !TRAJ) {
+      finalize_logp_post(lane, s_pre, s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
+                         fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
+    } else if (TRAJ && fin.mode == 2) {
+      // trajectory mode: finish this leapfrog step and either publish the next position or
+      // write the end point
+      finalize_logp_post(lane, s_pre, s_th, s_lik, s_red[0], fin.tot, &s_out[0], &s_out[1]);
+      __syncwarp();
+      const double e = traj.eps[c];
+      const double g = lane < 17 ? s_out[1 + lane] : 0.0;
+      const double ph = lane < 17 ? s_ph[lane] : 0.0;
+      if (step == nsteps - 1) {
+        if (lane < 17) {
+          traj.q[(size_t)c * 17 + lane] = s_q[lane];
+          traj.p[(size_t)c * 17 + lane] = fma(0.5 * e, g, ph);
+          traj.grad[(size_t)c * 17 + lane] = g;
+        }
+        if (lane == 0) traj.logp[c] = s_out[0];
+      } else {
+        const double ph2 = fma(e, g, ph);  // two half steps: end of this step + start of the next
+        double dot = 0.0;
+        for (int j = 0; j < 17; ++j) {
+          const double pj = __shfl_sync(0xffffffffu, ph2, j);
+          if (lane < 17) dot = fma(s_im[lane * 17 + j], pj, dot);
+        }
+        if (lane < 17) {
+          traj.state[(size_t)c * 34 + lane] = fma(e, dot, s_q[lane]);
+          traj.state[(size_t)c * 34 + 17 + lane] = ph2;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned nxt = (unsigned)step + 1u;
+          asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(traj.gen + c), "r"(nxt) : "memory");
+        }
+      }
+    }
+  };
 
   for (int cc = 0; cc < cfg.chains_per_cta; ++cc) {
     const int c = blockIdx.y * cfg.chains_per_cta + cc;
@@ -549,12 +608,9 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     __syncthreads();
     PHASE(7);
     if (s_last) {
+      const bool sharded = xch.world > 1;
       // the parameter-only part of the finaliser was parked in `aux` by the chain's first tile
-      if (fin.mode && tid < kAuxDoubles) {
-        const double v = __ldcg(aux + (size_t)c * kAuxDoubles + tid);
-        if (tid < 17 * 7) reinterpret_cast<double*>(s_pre)[tid] = v;
-        else if (tid < 17 * 7 + 6) reinterpret_cast<double*>(&s_lik)[tid - 17 * 7] = v;
-      }
+      if (!sharded) load_aux(c);
       const int k = tid & 15, g = tid >> 4;  // 16 groups of 16 values
       double v = 0.0;
       const double* src = partial + (size_t)c * ntiles * kNSums + k;
@@ -576,98 +632,82 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
 #pragma unroll
         for (int gg = 0; gg < kSumsBlock / 16; ++gg) tot += s_fin[gg][tid];
         s_red[0][tid] = tot;
-        if (sums) sums[(size_t)c * kNSums + tid] = tot;
+        if (sums && !sharded) sums[(size_t)c * kNSums + tid] = tot;
       }
-      __syncthreads();
-      if (xch.world > 1) {  // (trajectory mode: single-step launches only, the host checks)
-        __shared__ unsigned s_seq;
-        if (tid == 0) s_seq = xch.seq[c] + 1u;
-        __syncthreads();
-        const unsigned seq = s_seq, par = seq & 1u;
-        const size_t slot = ((size_t)par * xch.world + xch.rank) * xch.cmax + c;  // my slot in a peer's buffer
-        if (tid < kNSums * xch.world) {
-          const int r = tid >> 4, k = tid & 15;
-          xch.data[r][slot * kNSums + k] = s_red[0][k];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < xch.world) {
-          unsigned long long* f = xch.flag[tid] + slot;
-          asm volatile("st.release.sys.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)seq) : "memory");
-          // wait for peer `tid`'s contribution to arrive in MY buffer
-          const unsigned long long* mine = xch.flag[xch.rank] + ((size_t)par * xch.world + tid) * xch.cmax + c;
-          unsigned long long seen, t_start, t_now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-          do {
-            asm volatile("ld.acquire.sys.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-          } while (seen != (unsigned long long)seq && t_now - t_start < kXchTimeoutNs);
-          if (seen != (unsigned long long)seq) *xch.err = 1u;  // watchdog: never hang the GPU
-          // exchange cost, kept apart from compute: how long this rank's finishing CTA sat waiting for peer `tid`
-          atomicAdd(xch.stat + tid, t_now - t_start);
-          if (tid == 0) atomicAdd(xch.stat + kMaxPeers, 1ull);
-        }
-        __syncthreads();
-        if (tid < kNSums) {
-          double tot = 0.0;
-          for (int r = 0; r < xch.world; ++r)
-            tot += __ldcg(xch.data[xch.rank] + (((size_t)par * xch.world + r) * xch.cmax + c) * kNSums + tid);
-          s_red[0][tid] = tot;
-          if (sums) sums[(size_t)c * kNSums + tid] = tot;
-        }
-        if (tid == 0) xch.seq[c] = seq;
-        __syncthreads();
-      }
-      PHASE(10);
       if (tid == 0) ticket[c] = 0;  // re-arm for the next launch
-      if (warp == 0) {
-        if (fin.mode == 1) {
-          if (lane == 0)
-            finalize_loglik_post(s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
-                                 fin.out_grad ? &fin.out_grad[(size_t)c * 13] : nullptr);
-        } else if (fin.mode == 2 && !TRAJ) {
-          finalize_logp_post(lane, s_pre, s_th, s_lik, s_red[0], fin.tot, &fin.out_val[c],
-                             fin.out_grad ? &fin.out_grad[(size_t)c * 17] : nullptr);
-        } else if (TRAJ && fin.mode == 2) {
-          // trajectory mode: finish this leapfrog step and either publish the next position or
-          // write the end point
-          finalize_logp_post(lane, s_pre, s_th, s_lik, s_red[0], fin.tot, &s_out[0], &s_out[1]);
-          __syncwarp();
-          const double e = traj.eps[c];
-          const double g = lane < 17 ? s_out[1 + lane] : 0.0;
-          const double ph = lane < 17 ? s_ph[lane] : 0.0;
-          if (step == nsteps - 1) {
-            if (lane < 17) {
-              traj.q[(size_t)c * 17 + lane] = s_q[lane];
-              traj.p[(size_t)c * 17 + lane] = fma(0.5 * e, g, ph);
-              traj.grad[(size_t)c * 17 + lane] = g;
-            }
-            if (lane == 0) traj.logp[c] = s_out[0];
-          } else {
-            const double ph2 = fma(e, g, ph);  // two half steps: end of this step + start of the next
-            double dot = 0.0;
-            for (int j = 0; j < 17; ++j) {
-              const double pj = __shfl_sync(0xffffffffu, ph2, j);
-              if (lane < 17) dot = fma(s_im[lane * 17 + j], pj, dot);
-            }
-            if (lane < 17) {
-              traj.state[(size_t)c * 34 + lane] = fma(e, dot, s_q[lane]);
-              traj.state[(size_t)c * 34 + 17 + lane] = ph2;
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-              const unsigned nxt = (unsigned)step + 1u;
-              asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(traj.gen + c), "r"(nxt) : "memory");
-            }
-          }
+      __syncthreads();
+      PHASE(10);
+      if (sharded) {
+        // ---- post this rank's 16 sums into every peer's buffer and move on: the wait for the peers'
+        //      sums and the finalisation happen after the CTA's last chain (a CTA that finished a chain
+        //      last would otherwise sit in the exchange while its remaining chains wait, and so become
+        //      the last CTA of the next chain as well: the exchanges of a chain group would serialise).
+        //      Low-latency protocol: every 8-byte word carries 4 bytes of payload and the 4-byte sequence
+        //      number of this exchange, so the words may arrive in any order and no fence / separate flag
+        //      (a second NVLink round trip) is needed. ----
+        const unsigned seq = xch.seq[c] + 1u;  // every thread reads it before thread 0 writes it back (barrier below)
+        if (tid < 32 * xch.world) {
+          const int r = tid >> 5, j = tid & 31;
+          const double val = s_red[0][j >> 1];
+          const unsigned half = (j & 1) ? (unsigned)__double2hiint(val) : (unsigned)__double2loint(val);
+          const unsigned long long word = ((unsigned long long)seq << 32) | half;
+          unsigned long long* dst = xch.buf[r] + ((((size_t)(seq & 1u) * xch.world + xch.rank) * xch.cmax + c) << 5) + j;
+          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
         }
+        __syncthreads();
+        if (tid == 0) {
+          xch.seq[c] = seq;
+          s_pend[s_npend] = c;
+          s_pend_seq[s_npend] = seq;
+          ++s_npend;
+        }
+      } else if (warp == 0) {
+        finalize_chain(c, step, nsteps);
       }
     }
     if (s_last) PHASE(11);
     PHASE(8);
     __syncthreads();  // shared memory is reused by the next step / chain
     }  // step
+  }
+
+  // ---- sharded: collect the peers' sums of the chains this CTA finished last, add the `world`
+  //      contributions in rank order (bitwise the same total on every rank) and finalise ----
+  if (xch.world > 1) {
+    const int npend = s_npend;
+    for (int pi = 0; pi < npend; ++pi) {
+      const int c = s_pend[pi];
+      const unsigned seq = s_pend_seq[pi];
+      load_aux(c);
+      if (!TRAJ && warp == 0 && lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);  // as warp 6 computed it
+      if (tid < 32 * xch.world) {
+        const int r = tid >> 5, j = tid & 31;
+        const unsigned long long* mine = xch.buf[xch.rank] + ((((size_t)(seq & 1u) * xch.world + r) * xch.cmax + c) << 5) + j;
+        unsigned long long word, t_start, t_now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+        do {
+          asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(mine) : "memory");
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+        } while ((unsigned)(word >> 32) != seq && t_now - t_start < kXchTimeoutNs);
+        if ((unsigned)(word >> 32) != seq) *xch.err = 1u;  // watchdog: never hang the GPU
+        s_xw[r][j] = (unsigned)word;
+        // exchange cost, kept apart from compute: how long this CTA sat waiting for peer r's sums
+        if (j == 0) {
+          atomicAdd(xch.stat + r, t_now - t_start);
+          if (r == 0) atomicAdd(xch.stat + kMaxPeers, 1ull);
+        }
+      }
+      __syncthreads();
+      if (tid < kNSums) {
+        double tot = 0.0;
+        for (int r = 0; r < xch.world; ++r) tot += __hiloint2double((int)s_xw[r][2 * tid + 1], (int)s_xw[r][2 * tid]);
+        s_red[0][tid] = tot;
+        if (sums) sums[(size_t)c * kNSums + tid] = tot;
+      }
+      __syncthreads();
+      if (warp == 0) finalize_chain(c, 0, 1);
+      __syncthreads();
+    }
   }
   SPAN_END();
 }
