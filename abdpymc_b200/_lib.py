@@ -51,6 +51,9 @@ SIGNATURES = {
     "abd_version": (C.c_int, []),
     "abd_create": (C.c_int, [C.POINTER(H), C.POINTER(AbdCohort), C.c_int]),
     "abd_destroy": (C.c_int, [H]),
+    "abd_save_cache": (C.c_int, [H, C.c_char_p]),
+    "abd_create_from_cache": (C.c_int, [C.POINTER(H), C.c_char_p, C.c_int]),
+    "abd_cohort_info": (C.c_int, [H, c_int32_p, c_int32_p, c_int32_p]),
     "abd_sizes": (C.c_int, [H, c_int32_p, c_int32_p, c_int64_p, c_int64_p]),
     "abd_algorithmic_bytes_logp": (C.c_int64, [H, C.c_int]),
     "abd_algorithmic_bytes_gibbs": (C.c_int64, [H, C.c_int]),

@@ -323,7 +323,7 @@ if HAVE_PYMC:  # pragma: no cover
 # abdpymc-infer
 # ------------------------------------------------------------------------------------------
 def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0, seed=0, progress=None, gibbs_mode=0,
-                  thinned=0, kernel="hmc", shard=None, rank=0, world=1):
+                  thinned=0, kernel="hmc", shard=None, rank=0, world=1, engine=None):
     """tune + draws iterations of the built-in HMC + GPU-Gibbs sampler.  Returns (result,
     {name: array (chain, draw, ...)}, last binary state) with the reference's posterior variable names.
 
@@ -337,8 +337,11 @@ def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0
 
     from .sampler import AbdTarget, SamplerConfig, sample
 
-    cohort = as_cohort(cohort)
-    G, N = cohort.n_gaps, cohort.n_inds
+    if engine is None:
+        cohort = as_cohort(cohort)
+        G, N = cohort.n_gaps, cohort.n_inds
+    else:  # a ready engine (AbdEngine.from_cache): the cohort never exists on the host
+        G, N = engine.G, engine.N
     rng = np.random.default_rng(seed)
     # PyMC-like initial point: prior means on the constrained scale, jittered in q space
     x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
@@ -361,7 +364,8 @@ def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0
         res.means = {k: target.gather_individuals(v) for k, v in res.means.items()}
         sh.close()
         return res, res.posterior(), post_last
-    engine = make_engine(cohort, splits=splits, ignore_pcrpos=ignore_pcrpos, device=device)
+    if engine is None:
+        engine = make_engine(cohort, splits=splits, ignore_pcrpos=ignore_pcrpos, device=device)
     lo, hi = 0, chains
     if world > 1 and shard == "chains":
         from .cohort import shard_bounds
@@ -438,13 +442,31 @@ def _builtin_worker(rank, args, devices, port):
                           MASTER_PORT=str(port))
         torch.cuda.set_device(devices[rank])
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", devices[rank]))
-    data = CohortArrays.from_disk(args.ititers_data)
-    splits = (None if (not args.split_delta) and (not args.split_omicron)
-              else data.calculate_splits(delta=args.split_delta, omicron=args.split_omicron))
+    from pathlib import Path
+
+    from .cohort import splits_from_t0
+
+    splits = None
+    if args.split_delta or args.split_omicron:
+        t0 = (Path(args.ititers_data) / "t0.txt").read_text().strip()
+        splits = splits_from_t0(t0, args.split_delta, args.split_omicron)
+    # --cache: the preprocessed cohort as one binary file (no CSV parsing, no sorting); with the individuals
+    # sharded every rank preprocesses its own block instead
+    use_cache = bool(args.cache) and not (world > 1 and args.shard == "individuals")
+    engine = None
+    if use_cache and Path(args.cache).exists():
+        engine = AbdEngine.from_cache(args.cache, device=devices[rank], splits=splits or (), ignore_pcrpos=args.ignore_pcrpos)
+        data = type("Sizes", (), {"n_gaps": engine.G, "n_inds": engine.N})()
+    else:
+        data = CohortArrays.from_disk(args.ititers_data)
+        if use_cache:
+            engine = make_engine(data, splits=splits, ignore_pcrpos=args.ignore_pcrpos, device=devices[rank])
+            if rank == 0:
+                engine.save_cache(args.cache)
     res, post, last = infer_builtin(data, splits, args.ignore_pcrpos, args.tune, args.draws, chains=args.chains,
                                     device=devices[rank], progress=max(1, (args.tune + args.draws) // 10),
                                     gibbs_mode=args.gibbs_mode, thinned=args.thinned, kernel=args.kernel,
-                                    shard=args.shard if world > 1 else None, rank=rank, world=world)
+                                    shard=args.shard if world > 1 else None, rank=rank, world=world, engine=engine)
     if rank == 0:
         _write_builtin(args, data, res, post, last)
     if world > 1:
@@ -473,6 +495,10 @@ def main(argv=None):
     parser.add_argument("--shard", default="individuals", choices=["individuals", "chains"],
                         help="(extension) with --devices: split the INDIVIDUALS over the GPUs (large cohorts; one fused "
                              "NVLink all-reduce of chains x 16 doubles per evaluation) or the CHAINS (no communication)")
+    parser.add_argument("--cache", default=None,
+                        help="(extension, PyMC-free driver) preprocessed-cohort file: read it if it exists (skips parsing "
+                             "df.csv / vacs.txt / pcrpos.txt and the sorts of abd_create), otherwise build from "
+                             "--ititers_data and write it")
     parser.add_argument("--thinned", type=int, default=250,
                         help="(extension, PyMC-free driver) evenly spaced draws of i / ab_n_mu / ab_s_mu kept per chain "
                              "(the downstream code uses <= 250: survival.py:109-114)")

@@ -28,6 +28,17 @@ ANTIGEN_N, ANTIGEN_S = 0, 1
 MEASUREMENT_S, MEASUREMENT_N = "10222020-S", "40588-V08B"
 
 
+def splits_from_t0(t0: str, delta: bool, omicron: bool) -> tuple:
+    """abd.py:204-221: gaps from t0 ("YYYY-MM") to 2021-07 (delta) and 2022-01 (omicron)."""
+    y, m = (int(v) for v in str(t0).split("-")[:2])
+    out = []
+    if delta:
+        out.append((2021 - y) * 12 + (7 - m))
+    if omicron:
+        out.append((2022 - y) * 12 + (1 - m))
+    return tuple(out)
+
+
 @dataclass
 class CohortArrays:
     vacs: np.ndarray  # (N, G) uint8
@@ -148,13 +159,7 @@ class CohortArrays:
 
     def calculate_splits(self, delta: bool, omicron: bool) -> tuple:
         """abd.py:204-221: gaps from t0 to 2021-07 (delta) and 2022-01 (omicron)."""
-        y, m = (int(v) for v in self.t0.split("-")[:2])
-        out = []
-        if delta:
-            out.append((2021 - y) * 12 + (7 - m))
-        if omicron:
-            out.append((2022 - y) * 12 + (1 - m))
-        return tuple(out)
+        return splits_from_t0(self.t0, delta, omicron)
 
     # ---- re-sampling / sharding --------------------------------------------------------
     def take(self, individuals: np.ndarray) -> "CohortArrays":

@@ -111,6 +111,7 @@ struct abd_handle {
   int pack_valid = 0;          // leading chains whose packed entries mirror d_iraw / d_waner
   bool lazy_pack = true;       // a launch on the resident state may (re)build the packed copy first
   bool use_pack = true;        // ABD_B200_NO_PACK=1: always read the int8 arrays
+  bool has_pcr = true;         // built with PCR+ data (false: ignore_pcrpos)
   double* d_theta = nullptr;   // [C][17]
   double* d_p = nullptr;       // [C][2]
   double* d_sums = nullptr;    // [C][16]
@@ -660,6 +661,127 @@ int stage_state(abd_handle* h, int C, const int8_t* i_raw, const int8_t* waner) 
   return ABD_OK;
 }
 
+// A handle with its device facts, stream and environment switches (everything that does not depend on the cohort)
+int new_handle(abd_handle** out, int device, int G, int N) {
+  abd_handle* h = new abd_handle();
+  h->device = device;
+  if (const char* e = std::getenv("ABD_B200_NO_PDL")) h->use_pdl = !(e[0] == '1');
+  if (const char* e = std::getenv("ABD_B200_NO_PULL")) h->use_pull = !(e[0] == '1');
+  if (const char* e = std::getenv("ABD_B200_NO_INLINE")) h->use_inline = !(e[0] == '1');
+  if (const char* e = std::getenv("ABD_B200_NO_PACK")) h->use_pack = !(e[0] == '1');
+  {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->n_sms = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess) h->smem_optin = (size_t)v;
+  }
+  h->G = G;
+  h->N = N;
+  h->wide = G > 31;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    abd_destroy(h);
+    return fail(ABD_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  *out = h;
+  return ABD_OK;
+}
+
+// what every handle needs after its cohort arrays are on the device
+int finish_handle(abd_handle* h) {
+  int rc;
+  if ((rc = dev_alloc(h, &h->d_queue, 1))) return rc;
+  Priors pr = default_priors(h->G);
+  if ((rc = dev_alloc(h, &h->d_priors, 1))) return rc;
+  CU(cudaMemcpy(h->d_priors, &pr, sizeof(pr), cudaMemcpyHostToDevice));
+  return ABD_OK;
+}
+
+// ---- preprocessed-cohort cache file (TiterData -> device upload format) -----------------
+// Everything abd_create derives from the cohort (bit masks, CSR row / cell tables sorted by individual and
+// gap, packed row -> cell / dilution words, the Gibbs work order) as one binary file: a header, then the
+// arrays in a fixed order, each padded to 16 bytes.  Loading it is reading + uploading.
+struct CacheHeader {
+  char magic[8];           // "ABDB200\0"
+  int32_t version, G, N, n_chunks;
+  uint64_t chunk_mask[3];
+  int32_t wide, fx, n_xlev, has_pcr;
+  int64_t R[2], K[2];      // OD rows / (individual, gap) cells per antigen (N, S)
+  double tot[4];
+  uint32_t ind_offset, pad;
+  double xlev[kMaxXLevels];
+};
+constexpr int kCacheVersion = 1;
+
+struct CacheIo {
+  FILE* f = nullptr;
+  bool writing = false, ok = true;
+  ~CacheIo() {
+    if (f) std::fclose(f);
+  }
+  void raw(void* p, size_t bytes) {
+    if (!ok || !bytes) return;
+    ok = writing ? std::fwrite(p, 1, bytes, f) == bytes : std::fread(p, 1, bytes, f) == bytes;
+    const size_t padn = (16 - bytes % 16) % 16;
+    char z[16] = {};
+    if (ok && padn) ok = writing ? std::fwrite(z, 1, padn, f) == padn : std::fread(z, 1, padn, f) == padn;
+  }
+};
+
+// one device array <-> the file (through a host bounce buffer)
+template <typename T>
+int cache_array(abd_handle* h, CacheIo& io, T** dptr, size_t n, std::vector<T>* keep = nullptr) {
+  std::vector<T> host(n);
+  if (io.writing) {
+    if (n) CU(cudaMemcpy(host.data(), *dptr, n * sizeof(T), cudaMemcpyDeviceToHost));
+    io.raw(host.data(), n * sizeof(T));
+  } else {
+    io.raw(host.data(), n * sizeof(T));
+    if (!io.ok) return fail(ABD_ERR_INVALID, "cache file truncated");
+    int rc = upload(h, dptr, host);
+    if (rc) return rc;
+    if (keep) *keep = host;
+  }
+  return io.ok ? ABD_OK : fail(ABD_ERR_INVALID, "cache file I/O error");
+}
+
+// the cohort arrays of a handle, in file order (shared by save and load)
+int cache_body(abd_handle* h, CacheIo& io, const CacheHeader& hd) {
+  int rc;
+  const size_t N = (size_t)hd.N;
+  if (hd.wide) {
+    uint64_t *p = (uint64_t*)h->dc.pcr, *v = (uint64_t*)h->dc.vac;
+    if ((rc = cache_array(h, io, &p, N)) || (rc = cache_array(h, io, &v, N))) return rc;
+    h->dc.pcr = p, h->dc.vac = v;
+  } else {
+    uint32_t *p = (uint32_t*)h->dc.pcr, *v = (uint32_t*)h->dc.vac;
+    if ((rc = cache_array(h, io, &p, N)) || (rc = cache_array(h, io, &v, N))) return rc;
+    h->dc.pcr = p, h->dc.vac = v;
+  }
+  for (int a = 0; a < 2; ++a) {
+    const size_t R = (size_t)hd.R[a], K = (size_t)hd.K[a];
+    int* rp = (int*)h->dc.rp[a];
+    double *x = (double*)h->dc.x[a], *od = (double*)h->dc.od[a];
+    uint32_t *meta = (uint32_t*)h->dc.meta[a], *rowcell = (uint32_t*)h->dc.rowcell[a], *cmeta = (uint32_t*)h->dc.cmeta[a];
+    uint32_t* rcx = (uint32_t*)h->dc.rcx[a];
+    if ((rc = cache_array(h, io, &rp, N + 1, &h->h_rp[a]))) return rc;
+    if ((rc = cache_array(h, io, &x, R + 2)) || (rc = cache_array(h, io, &od, R + 2))) return rc;
+    if ((rc = cache_array(h, io, &meta, R + 4)) || (rc = cache_array(h, io, &rowcell, R + 4))) return rc;
+    if ((rc = cache_array(h, io, &cmeta, K + 4))) return rc;
+    if (hd.fx && (rc = cache_array(h, io, &rcx, R + 4))) return rc;
+    // the cell CSR pointers only live on the host
+    if (io.writing) {
+      io.raw(h->h_cp[a].data(), (N + 1) * sizeof(int));
+    } else {
+      h->h_cp[a].assign(N + 1, 0);
+      io.raw(h->h_cp[a].data(), (N + 1) * sizeof(int));
+    }
+    h->dc.rp[a] = rp, h->dc.x[a] = x, h->dc.od[a] = od, h->dc.meta[a] = meta, h->dc.rowcell[a] = rowcell;
+    h->dc.cmeta[a] = cmeta, h->dc.rcx[a] = hd.fx ? rcx : nullptr;
+    h->R[a] = hd.R[a];
+  }
+  if ((rc = cache_array(h, io, &h->d_order, N))) return rc;
+  return io.ok ? ABD_OK : fail(ABD_ERR_INVALID, "cache file I/O error");
+}
+
 #define PROLOGUE(h, C)                                         \
   if (!(h)) return fail(ABD_ERR_INVALID, "NULL handle");       \
   {                                                            \
@@ -699,26 +821,15 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
   if (device < 0 || device >= ndev) return fail(ABD_ERR_CUDA, "no such CUDA device");
   CU(cudaSetDevice(device));
 
-  abd_handle* h = new abd_handle();
-  h->device = device;
-  if (const char* e = std::getenv("ABD_B200_NO_PDL")) h->use_pdl = !(e[0] == '1');
-  if (const char* e = std::getenv("ABD_B200_NO_PULL")) h->use_pull = !(e[0] == '1');
-  if (const char* e = std::getenv("ABD_B200_NO_INLINE")) h->use_inline = !(e[0] == '1');
-  if (const char* e = std::getenv("ABD_B200_NO_PACK")) h->use_pack = !(e[0] == '1');
+  abd_handle* h = nullptr;
   {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->n_sms = v;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess) h->smem_optin = (size_t)v;
+    int rc0 = new_handle(&h, device, G, N);
+    if (rc0) return rc0;
   }
-  h->G = G;
-  h->N = N;
-  h->wide = G > 31;
   auto bail = [&](int rc) {
     abd_destroy(h);
     return rc;
   };
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
-    return bail(fail(ABD_ERR_CUDA, "cudaStreamCreate failed"));
 
   // bit masks per individual
   std::vector<uint64_t> pcr((size_t)N, 0), vac((size_t)N, 0);
@@ -794,7 +905,6 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
     };
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nrows(a) > nrows(b); });
     if ((rc = upload(h, &h->d_order, order))) return bail(rc);
-    if ((rc = dev_alloc(h, &h->d_queue, 1))) return bail(rc);
   }
   const double tn = co->total_inds > 0 ? (double)co->total_inds : (double)N;
   h->tot.rows_n = co->total_rows_n > 0 ? (double)co->total_rows_n : (double)co->n_rows_n;
@@ -802,11 +912,84 @@ int abd_create(abd_handle** out, const abd_cohort* co, int device) {
   h->tot.bits_i = tn * G;
   h->tot.bits_w = tn;
 
-  Priors pr = default_priors(G);
-  if ((rc = dev_alloc(h, &h->d_priors, 1))) return bail(rc);
-  if (cudaMemcpy(h->d_priors, &pr, sizeof(pr), cudaMemcpyHostToDevice) != cudaSuccess)
-    return bail(fail(ABD_ERR_CUDA, "cudaMemcpy(priors) failed"));
+  h->has_pcr = co->pcrpos != nullptr;
+  if ((rc = finish_handle(h))) return bail(rc);
   *out = h;
+  return ABD_OK;
+}
+
+int abd_save_cache(abd_handle* h, const char* path) {
+  if (!h || !path) return fail(ABD_ERR_INVALID, "NULL argument");
+  int rc = set_device(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  CacheHeader hd{};
+  std::memcpy(hd.magic, "ABDB200", 8);
+  hd.version = kCacheVersion, hd.G = h->G, hd.N = h->N, hd.n_chunks = h->dc.ch.n;
+  for (int k = 0; k < 3; ++k) hd.chunk_mask[k] = h->dc.ch.mask[k];
+  hd.wide = h->wide, hd.fx = h->fx, hd.n_xlev = h->dc.n_xlev, hd.has_pcr = h->has_pcr;
+  for (int a = 0; a < 2; ++a) hd.R[a] = h->R[a], hd.K[a] = h->h_cp[a].empty() ? 0 : h->h_cp[a].back();
+  hd.tot[0] = h->tot.rows_n, hd.tot[1] = h->tot.rows_s, hd.tot[2] = h->tot.bits_i, hd.tot[3] = h->tot.bits_w;
+  hd.ind_offset = h->dc.ind_offset;
+  for (size_t k = 0; k < h->x_levels.size() && k < (size_t)kMaxXLevels; ++k) hd.xlev[k] = h->x_levels[k];
+  CacheIo io;
+  io.writing = true;
+  io.f = std::fopen(path, "wb");
+  if (!io.f) return fail(ABD_ERR_INVALID, std::string("cannot write ") + path);
+  io.raw(&hd, sizeof(hd));
+  if ((rc = cache_body(h, io, hd))) return rc;
+  return io.ok ? ABD_OK : fail(ABD_ERR_INVALID, "cache file I/O error");
+}
+
+int abd_create_from_cache(abd_handle** out, const char* path, int device) {
+  if (!out || !path) return fail(ABD_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  CacheIo io;
+  io.f = std::fopen(path, "rb");
+  if (!io.f) return fail(ABD_ERR_INVALID, std::string("cannot read ") + path);
+  CacheHeader hd{};
+  io.raw(&hd, sizeof(hd));
+  if (!io.ok || std::memcmp(hd.magic, "ABDB200", 8) != 0) return fail(ABD_ERR_INVALID, "not an abd_b200 cache file");
+  if (hd.version != kCacheVersion) return fail(ABD_ERR_INVALID, "cache file of another version: rebuild it");
+  if (hd.G < 1 || hd.G > ABD_MAX_GAPS || hd.N < 1 || hd.N >= (1 << 26) || hd.n_chunks < 1 || hd.n_chunks > 3 ||
+      hd.R[0] < 0 || hd.R[1] < 0 || hd.K[0] < 0 || hd.K[1] < 0 || hd.n_xlev < 0 || hd.n_xlev > kMaxXLevels)
+    return fail(ABD_ERR_INVALID, "corrupt cache header");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(ABD_ERR_CUDA, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  abd_handle* h = nullptr;
+  int rc = new_handle(&h, device, hd.G, hd.N);
+  if (rc) return rc;
+  auto bail = [&](int r) {
+    abd_destroy(h);
+    return r;
+  };
+  h->dc.G = hd.G, h->dc.N = hd.N, h->dc.ind_offset = hd.ind_offset, h->dc.chain_offset = 0;
+  h->dc.ch.n = hd.n_chunks;
+  for (int k = 0; k < 3; ++k) h->dc.ch.mask[k] = hd.chunk_mask[k];
+  h->fx = hd.fx != 0, h->has_pcr = hd.has_pcr != 0;
+  h->x_levels.assign(hd.xlev, hd.xlev + hd.n_xlev);
+  {
+    std::vector<double> padded(hd.xlev, hd.xlev + kMaxXLevels);
+    double* d_lv;
+    if ((rc = upload(h, &d_lv, padded))) return bail(rc);
+    h->dc.xlev = d_lv, h->dc.n_xlev = hd.n_xlev;
+  }
+  h->tot.rows_n = hd.tot[0], h->tot.rows_s = hd.tot[1], h->tot.bits_i = hd.tot[2], h->tot.bits_w = hd.tot[3];
+  if ((rc = cache_body(h, io, hd))) return bail(rc);
+  if ((rc = finish_handle(h))) return bail(rc);
+  *out = h;
+  return ABD_OK;
+}
+
+int abd_cohort_info(const abd_handle* h, int32_t* n_splits, int32_t* splits, int32_t* has_pcrpos) {
+  if (!h) return fail(ABD_ERR_INVALID, "NULL handle");
+  const int ns = h->dc.ch.n - 1;
+  if (n_splits) *n_splits = ns;
+  if (splits)
+    for (int k = 0; k < ns; ++k) splits[k] = h->dc.ch.mask[k + 1] ? __builtin_ctzll(h->dc.ch.mask[k + 1]) : h->G;
+  if (has_pcrpos) *has_pcrpos = h->has_pcr ? 1 : 0;
   return ABD_OK;
 }
 

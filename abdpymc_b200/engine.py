@@ -86,6 +86,7 @@ class AbdEngine:
         self.G, self.N = int(cohort.n_gaps), int(cohort.n_inds)
         self._out17 = {}
         self.splits = splits
+        self.ignore_pcrpos = bool(ignore_pcrpos)
         self.device = device
         keep = []
 
@@ -115,6 +116,35 @@ class AbdEngine:
             d.total_inds, d.total_rows_s, d.total_rows_n = (int(v) for v in totals)
         d.ind_offset = int(ind_offset)
         check(self._lib.abd_create(C.byref(self._h), C.byref(d), int(device)))
+
+    # ------------------------------------------------------------------------------ cache file
+    def save_cache(self, path):
+        """Write the preprocessed cohort (the device upload format) to ``path``; ``AbdEngine.from_cache`` reads it."""
+        check(self._lib.abd_save_cache(self._h, str(path).encode()))
+
+    @classmethod
+    def from_cache(cls, path, device=0, splits=None, ignore_pcrpos=None):
+        """An engine from a file written by ``save_cache``: no CSV parsing, no sorting -- read and upload.
+        ``splits`` / ``ignore_pcrpos``, when given, must be what the cache was built with (ValueError otherwise)."""
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        check(self._lib.abd_create_from_cache(C.byref(self._h), str(path).encode(), int(device)))
+        g, n, rs, rn = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        check(self._lib.abd_sizes(self._h, C.byref(g), C.byref(n), C.byref(rs), C.byref(rn)))
+        self.G, self.N, self.R_s, self.R_n = g.value, n.value, rs.value, rn.value
+        ns, sp, hp = C.c_int32(), (C.c_int32 * 2)(), C.c_int32()
+        check(self._lib.abd_cohort_info(self._h, C.byref(ns), sp, C.byref(hp)))
+        self.splits = tuple(int(sp[k]) for k in range(ns.value))
+        self.ignore_pcrpos = not hp.value
+        self._out17, self.device = {}, device
+        if splits is not None and tuple(splits or ()) != self.splits:
+            self.close()
+            raise ValueError(f"cache built with splits {self.splits}, asked for {tuple(splits or ())}")
+        if ignore_pcrpos is not None and bool(ignore_pcrpos) != self.ignore_pcrpos:
+            self.close()
+            raise ValueError(f"cache built with ignore_pcrpos={self.ignore_pcrpos}")
+        return self
 
     # ------------------------------------------------------------------------------ lifetime
     def close(self):

@@ -272,6 +272,42 @@ def _timed_us(fn, n, dist, dev, warm=5):
     return float(t.item()) / n * 1e3
 
 
+def bench_create(co, device):
+    """how a large cohort reaches the GPU.  Seconds for (a) the reference's route, text files ->
+    arrays (pd.read_csv of df.csv, np.loadtxt of vacs.txt / pcrpos.txt: TiterData.from_disk, abd.py:171-202),
+    (b) abd_create from in-memory arrays (sorts, CSR / cell tables, packing, upload), (c) abd_create_from_cache
+    from the binary cache file abd_save_cache wrote (read + upload)."""
+    import tempfile
+
+    from abdpymc_b200.cohort import CohortArrays
+    from abdpymc_b200.engine import AbdEngine
+
+    res = {"n_inds": co.n_inds, "n_rows": co.n_rows}
+    with tempfile.TemporaryDirectory() as td:
+        t = time.perf_counter()
+        co.to_disk(Path(td) / "cohort_data")
+        res["write_text_files_s"] = time.perf_counter() - t
+        t = time.perf_counter()
+        back = CohortArrays.from_disk(Path(td) / "cohort_data")
+        res["parse_text_files_s"] = time.perf_counter() - t
+        assert back.n_rows == co.n_rows
+        t = time.perf_counter()
+        eng = AbdEngine(co, splits=SPLITS, device=device)
+        res["abd_create_s"] = time.perf_counter() - t
+        cache = Path(td) / "cohort.abdcache"
+        t = time.perf_counter()
+        eng.save_cache(cache)
+        res["abd_save_cache_s"] = time.perf_counter() - t
+        res["cache_file_mb"] = cache.stat().st_size / 1e6
+        eng.close()
+        t = time.perf_counter()
+        eng = AbdEngine.from_cache(cache, device=device, splits=SPLITS)
+        res["abd_create_from_cache_s"] = time.perf_counter() - t
+        eng.close()
+    res["speedup_cache_vs_text_route"] = (res["parse_text_files_s"] + res["abd_create_s"]) / res["abd_create_from_cache_s"]
+    return res
+
+
 def bench_sharded(dist, rank, world, local, dev, K, n_big=100_000, chain_counts=(4, 32), block=32):
     """BASELINE configs[3].  One evaluation = joint logp + gradient of all C chains on the 100k cohort.
     `one_gpu`: the whole cohort on rank 0's GPU (the baseline the speed-ups are quoted against; the other
@@ -291,6 +327,8 @@ def bench_sharded(dist, rank, world, local, dev, K, n_big=100_000, chain_counts=
                        f"{world} GPU(s), splits {list(SPLITS)}", "unit": "us per evaluation of all C chains", "by_chains": {}}
     side = torch.cuda.Stream(device=dev)
     n_rep = max(3, min(20, K))
+    if rank == 0:
+        out["create"] = bench_create(big, local)
     for Csh in chain_counts:
         rngb = np.random.default_rng(77)
         ib = (rngb.random((Csh, big.n_gaps, big.n_inds)) < 0.04).astype(np.int8)

@@ -107,6 +107,19 @@ int abd_version(void);
 int abd_create(abd_handle** out, const abd_cohort* cohort, int device);
 int abd_destroy(abd_handle* h);
 
+/* The preprocessed cohort as ONE binary file (the device upload format): everything abd_create derives
+ * from the cohort -- bit masks, per-antigen CSR row / cell tables sorted by (individual, gap), packed
+ * row -> cell / dilution words, the Gibbs work order, the time chunks -- so that a later process skips
+ * what TiterData.from_disk + abd.model cost on a large cohort (pd.read_csv of df.csv and np.loadtxt of
+ * vacs.txt / pcrpos.txt, abd.py:171-202, then the sorts of abd_create).  abd_create_from_cache = read +
+ * upload.  The file is tied to the splits / ignore_pcrpos the handle was built with (abd_cohort_info
+ * tells which) and to this library version.  Replaces: TiterData.to_disk / from_disk (abd.py:149-202) as
+ * the way a cohort reaches the sampler.                                                          */
+int abd_save_cache(abd_handle* h, const char* path);
+int abd_create_from_cache(abd_handle** out, const char* path, int device);
+/* What the handle was built with: number of splits (0-2), their gap indexes, whether PCR+ data is used. */
+int abd_cohort_info(const abd_handle* h, int32_t* n_splits, int32_t* splits, int32_t* has_pcrpos);
+
 /* Sizes and algorithmic-byte accounting.  Any pointer may be NULL.   */
 int abd_sizes(const abd_handle* h, int32_t* n_gaps, int32_t* n_inds, int64_t* n_rows_s,
               int64_t* n_rows_n);

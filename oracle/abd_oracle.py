@@ -479,6 +479,39 @@ def binary_gibbs_metropolis_sweep(oracle, theta13, p, p_w, i_raw, w, rng, transi
     return i_raw, w
 
 
+def binary_gibbs_metropolis_sweep_local(subs, G, N, theta13, p, p_w, i_raw, w, rng, transit_p=0.8):
+    """The same ``astep`` as ``binary_gibbs_metropolis_sweep`` (same shuffle, same uniforms, same decisions for
+    the same ``rng``), evaluating only the flipped bit's individual: ``subs[n]`` is the Oracle of individual n
+    alone.  What makes the restated reference sampler affordable on cohorts of a few hundred individuals."""
+    i_raw = np.array(i_raw).reshape(G, N).copy()
+    w = np.array(w).copy()
+    lo_i, lo_w = np.log(p) - np.log1p(-p), np.log(p_w) - np.log1p(-p_w)
+    order = rng.permutation(G * N + N)
+    cur = np.array([subs[n].loglik(theta13, i_raw[:, n:n + 1], w[n:n + 1]) for n in range(N)])
+    for idx in order:
+        if rng.random() >= transit_p:
+            continue
+        if idx < G * N:
+            t, n = divmod(idx, N)
+            old = i_raw[t, n]
+            i_raw[t, n] = 1 - old
+            prior = lo_i if old == 0 else -lo_i
+        else:
+            n = idx - G * N
+            old = w[n]
+            w[n] = 1 - old
+            prior = lo_w if old == 0 else -lo_w
+        new = subs[n].loglik(theta13, i_raw[:, n:n + 1], w[n:n + 1])
+        delta = prior + new - cur[n]
+        if np.isfinite(delta) and np.log(rng.random()) < delta:
+            cur[n] = new
+        elif idx < G * N:
+            i_raw[t, n] = old
+        else:
+            w[n] = old
+    return i_raw, w
+
+
 # ---------------------------------------------------------------------------------------
 # The device sweep, restated: same visiting order, same random numbers, same decisions as
 # abd_gibbs_sweep (include/abd_b200.h), so a CUDA sweep can be checked bit-for-bit.

@@ -403,6 +403,35 @@ def test_packed_resident_state_matches_the_int8_path(Engine, cohorts, G, N, spli
         assert np.array_equal(lp_t, lp_n) and np.array_equal(g_t, g_n)
 
 
+@pytest.mark.parametrize("name,splits,ignore", [("cohort", (14, 20), False), ("test_cohort", (), True)])
+def test_cache_file_round_trip(Engine, cohorts, tmp_path, name, splits, ignore):
+    """abd_save_cache / abd_create_from_cache: the engine read back from the file is the same engine
+    (bitwise the same logp / gradient, the same Gibbs sweep), and it knows what it was built with."""
+    co = cohorts[name]
+    rng = np.random.default_rng(2)
+    q, i_raw, w = draw_points(rng, co.n_gaps, co.n_inds, 2)
+    path = tmp_path / "c.abdcache"
+    with Engine(co, splits=splits, ignore_pcrpos=ignore) as eng:
+        eng.save_cache(path)
+        lp, g = eng.logp_dlogp(q, i_raw, w)
+        vals = [ora.backward(q[k])[0] for k in range(2)]
+        th = np.array([[v[n] for n in ora.THETA13] for v in vals])
+        p, pw = np.array([v["p"] for v in vals]), np.array([v["ab_s_p_waner"] for v in vals])
+        gi, gw, st = eng.gibbs_sweep(th, p, pw, i_raw, w, seed=4, sweep=2)
+    with Engine.from_cache(path) as e2:
+        assert (e2.G, e2.N, e2.R_s + e2.R_n) == (co.n_gaps, co.n_inds, co.n_rows)
+        assert e2.splits == tuple(splits) and e2.ignore_pcrpos == ignore
+        lp2, g2 = e2.logp_dlogp(q, i_raw, w)
+        gi2, gw2, st2 = e2.gibbs_sweep(th, p, pw, i_raw, w, seed=4, sweep=2)
+    assert np.array_equal(lp, lp2) and np.array_equal(g, g2)
+    assert np.array_equal(gi, gi2) and np.array_equal(gw, gw2) and np.array_equal(st, st2)
+    with pytest.raises(ValueError):
+        Engine.from_cache(path, splits=(3,))
+    path.write_bytes(path.read_bytes()[:200])
+    with pytest.raises(Exception, match="cache"):
+        Engine.from_cache(path)
+
+
 def test_chain_offset_keys_the_rng_streams(Engine, cohorts):
     """abd_set_chain_offset: chain c of an engine whose first chain is global chain k draws from the stream of
     global chain k + c (what processes that shard the chains of one run rely on)."""

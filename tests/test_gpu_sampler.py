@@ -83,6 +83,20 @@ def test_cli_without_pymc_writes_posterior(gpu, tmp_path):
               "--split_omicron", "--netcdf", str(out2), "--chains", "2", "--gibbs_mode", "2"])
     z2 = np.load(out2)
     assert z2["p"].shape == (2, 20) and set(np.unique(z2["last_i_raw"])) <= {0, 1}
+    # --cache: the first run writes the preprocessed cohort, the second reads it instead of the CSV files and
+    # reproduces the run exactly (same seed); a cache of other splits is refused
+    cache = tmp_path / "cohort.abdcache"
+    runs = []
+    for k in range(2):
+        outc = tmp_path / f"postc{k}.npz"
+        abd.main(["--tune", "30", "--draws", "10", "--ititers_data", str(tmp_path / "cohort_data"), "--split_delta",
+                  "--split_omicron", "--netcdf", str(outc), "--chains", "2", "--cache", str(cache), "--thinned", "0"])
+        assert cache.exists()
+        runs.append(np.load(outc))
+    assert np.array_equal(runs[0]["ab_n_perm"], runs[1]["ab_n_perm"]) and np.array_equal(runs[0]["last_i_raw"], runs[1]["last_i_raw"])
+    with pytest.raises(ValueError, match="splits"):
+        abd.main(["--tune", "5", "--draws", "5", "--ititers_data", str(tmp_path / "cohort_data"), "--netcdf",
+                  str(tmp_path / "x.npz"), "--chains", "2", "--cache", str(cache)])
 
 
 def test_hmc_transition_kernels_against_host_formulas(gpu):

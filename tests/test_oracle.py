@@ -135,6 +135,22 @@ def test_gibbs_sweep_restatement_keeps_shapes(cohorts):
     assert set(np.unique(i2)) <= {0, 1} and set(np.unique(w2)) <= {0, 1}
 
 
+def test_local_gibbs_sweep_restatement_equals_the_global_one(cohorts):
+    """binary_gibbs_metropolis_sweep_local (one individual's likelihood per proposal; what generates
+    tests/golden/posterior_goldens.npz) makes the same decisions as the whole-cohort restatement for the same rng."""
+    co = cohorts["test_cohort"]
+    o = ora.Oracle(co, splits=(14, 20), dense=False)
+    subs = [ora.Oracle(co.take(np.array([n])), splits=(14, 20), dense=False) for n in range(co.n_inds)]
+    rng = np.random.default_rng(3)
+    vals = ora.sample_prior(rng, o.G)
+    th = np.array([vals[m] for m in ora.THETA13])
+    i_raw = (rng.random((o.G, o.N)) < 0.1).astype(np.int8)
+    w = (rng.random(o.N) < 0.5).astype(np.int8)
+    a_i, a_w = ora.binary_gibbs_metropolis_sweep(o, th, 0.06, 0.5, i_raw, w, np.random.default_rng(9))
+    b_i, b_w = ora.binary_gibbs_metropolis_sweep_local(subs, o.G, o.N, th, 0.06, 0.5, i_raw, w, np.random.default_rng(9))
+    assert np.array_equal(a_i, b_i) and np.array_equal(a_w, b_w) and not np.array_equal(a_i, i_raw)
+
+
 def test_restated_blocked_sweep_leaves_exact_conditional_invariant():
     """ABD_GIBBS_BLOCKED as the oracle restates it (the checker of the CUDA kernel) is a valid Gibbs
     kernel: on a G = 5 individual with two time chunks (one of them PCR+ for the second individual)
