@@ -79,6 +79,11 @@ SIGNATURES = {
     "abd_hmc_begin_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 4 + [C.c_uint64, C.c_uint64] + [C.c_void_p] * 5),
     "abd_hmc_end_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 9 + [C.c_uint64, C.c_uint64] + [C.c_void_p] * 3
                         + [C.c_int, C.c_double, C.c_void_p]),
+    "abd_nuts_state_doubles": (C.c_int64, [C.c_int]),
+    "abd_nuts_begin_dev": (C.c_int, [H, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_uint64, C.c_uint64] + [C.c_void_p] * 7),
+    "abd_nuts_leaf_dev": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64]
+                          + [C.c_void_p] * 4),
+    "abd_nuts_end_dev": (C.c_int, [H, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_double, C.c_void_p]),
     "abd_xch_alloc": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "abd_xch_connect": (C.c_int, [H, C.c_void_p]),
     "abd_logp_dlogp_sharded_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 6),

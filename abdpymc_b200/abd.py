@@ -410,7 +410,7 @@ def _write_builtin(args, data, res, post, last):
                 for name in ("i", "ab_n_mu", "ab_s_mu"):
                     posterior[name] = res.thinned[name]
                     dims[name] = list(GAP_IND)
-            sample_stats = {"acceptance_rate": res.accept, "lp": res.logp}
+            sample_stats = {"acceptance_rate": res.accept, "lp": res.logp, **res.stats}
             idata = az.from_dict(posterior=posterior, sample_stats=sample_stats, dims=dims,
                                  coords={"gap": np.arange(data.n_gaps), "ind": np.arange(data.n_inds)})
             az.to_netcdf(idata, out)
@@ -425,6 +425,7 @@ def _write_builtin(args, data, res, post, last):
                         **{f"last_{k}": v for k, v in last.items()}, step_size=res.step_size, wall_s=res.wall_s,
                         sample_stats_acceptance_rate=res.accept, sample_stats_lp=res.logp,
                         sample_stats_step_size=np.broadcast_to(res.step_size[:, None], res.accept.shape),
+                        **{f"sample_stats_{k}": v for k, v in res.stats.items()},
                         **{("thinned_draw" if k == "draw" else k): v for k, v in res.thinned.items()})
     print(f"PyMC not installed: sampled with the built-in HMC+Gibbs driver in {res.wall_s:.1f} s; wrote {out}", file=sys.stderr)
 

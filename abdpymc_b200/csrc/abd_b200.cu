@@ -56,6 +56,7 @@ int fail(int code, const std::string& msg) {
 #include "k_gibbs.cuh"
 #include "k_gibbs_blk.cuh"
 #include "k_misc.cuh"
+#include "k_nuts.cuh"
 
 
 // ------------------------------------------------------------------------------------------
@@ -1395,6 +1396,54 @@ int abd_hmc_end_dev(abd_handle* h, int C, double* q17, double* grad17, double* l
   if (adapt && (!da || !eps)) return fail(ABD_ERR_INVALID, "adapt needs the dual-averaging state and eps");
   k_hmc_end<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, q17, grad17, logp, qw, pw, gw, lpw, inv_mass, h0, seed, iter,
                                                             accept_out, da, eps, adapt, target_accept, h->dc.chain_offset);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
+int64_t abd_nuts_state_doubles(int max_depth) {
+  if (max_depth < 1 || max_depth > kNutsMaxDepth) return 0;
+  return NutsLayout{max_depth}.size();
+}
+
+int abd_nuts_begin_dev(abd_handle* h, int C, int max_depth, const double* q17, const double* grad17, const double* logp,
+                       const double* linv_t, const double* eps, uint64_t seed, uint64_t iter, double* state, double* qw,
+                       double* pw, double* gw, double* eps_signed, int* any_active, void* stream) {
+  PROLOGUE(h, C);
+  if (!q17 || !grad17 || !logp || !linv_t || !eps || !state || !qw || !pw || !gw || !eps_signed || !any_active)
+    return fail(ABD_ERR_INVALID, "NULL argument");
+  if (max_depth < 1 || max_depth > kNutsMaxDepth) return fail(ABD_ERR_INVALID, "max_depth must be in [1, 10]");
+  k_nuts_begin<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, NutsLayout{max_depth}, q17, grad17, logp, linv_t, eps, seed, iter,
+                                                              h->dc.chain_offset, state, qw, pw, gw, eps_signed, any_active);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
+int abd_nuts_leaf_dev(abd_handle* h, int C, int max_depth, int depth, int leaf, double* qw, double* pw, double* gw,
+                      const double* lpw, const double* inv_mass, const double* eps, uint64_t seed, uint64_t iter, double* state,
+                      double* eps_signed, int* any_active, void* stream) {
+  PROLOGUE(h, C);
+  if (!qw || !pw || !gw || !lpw || !inv_mass || !eps || !state || !eps_signed || !any_active)
+    return fail(ABD_ERR_INVALID, "NULL argument");
+  if (max_depth < 1 || max_depth > kNutsMaxDepth || depth < 0 || depth >= max_depth || leaf < 0 || leaf >= (1 << depth))
+    return fail(ABD_ERR_INVALID, "bad depth / leaf");
+  k_nuts_leaf<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, NutsLayout{max_depth}, depth, leaf, max_depth, qw, pw, gw, lpw, inv_mass,
+                                                             eps, seed, iter, h->dc.chain_offset, state, eps_signed, any_active);
+  CU(cudaGetLastError());
+  h->launches++;
+  return ABD_OK;
+}
+
+int abd_nuts_end_dev(abd_handle* h, int C, int max_depth, double* q17, double* grad17, double* logp, const double* state,
+                     double* accept_out, double* depth_out, double* diverged_out, double* da, double* eps, int adapt,
+                     double target_accept, void* stream) {
+  PROLOGUE(h, C);
+  if (!q17 || !grad17 || !logp || !state || !accept_out) return fail(ABD_ERR_INVALID, "NULL argument");
+  if (max_depth < 1 || max_depth > kNutsMaxDepth) return fail(ABD_ERR_INVALID, "max_depth must be in [1, 10]");
+  if (adapt && (!da || !eps)) return fail(ABD_ERR_INVALID, "adapt needs the dual-averaging state and eps");
+  k_nuts_end<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, NutsLayout{max_depth}, q17, grad17, logp, state, accept_out, depth_out,
+                                                            diverged_out, da, eps, adapt, target_accept);
   CU(cudaGetLastError());
   h->launches++;
   return ABD_OK;

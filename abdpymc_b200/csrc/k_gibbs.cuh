@@ -44,18 +44,10 @@ __device__ __forceinline__ double gibbs_row(double x, double od, int t, bool is_
 
 // One chain's parameters into a warp's shared-memory slot (all 32 lanes call it):
 //   s_th[0..12] theta13, [13], [14] -1/(2 sigma^2) of N / S, [15], [16] logit p / p_waner,
-//   [17], [18] sigmoid of those, [19], [20], [21] log p, log(1 - p), p;
-//   [22..25] exp(+-b perm) of N / S, [26] != 0: candidate states may be evaluated incrementally;
-//   s_pw[0] = rho_n^k, s_pw[1] = rho_s^k;
-//   s_ef[0 / 1][k] = exp(+-b_n temp_n rho_n^k), s_ef[2 / 3][k] = exp(+-b_s rho_s^k): the factor by which
-//   E = exp(-b (x - m)) of an OD row changes when an infection k gaps before it appears / disappears.
-constexpr int kGibbsTh = 28;
-constexpr double kGibbsArgMax = 10.0;   // |b temp|, |b_s|, |b perm| above this: no incremental evaluation
-constexpr double kGibbsZMax = 150.0;    // |b (x - m)| above this at the current state: likewise
+//   [17], [18] sigmoid of those, [19], [20], [21] log p, log(1 - p), p; s_pw[0] = rho_n^k, s_pw[1] = rho_s^k.
 __device__ __forceinline__ void gibbs_load_chain(const double* __restrict__ theta, int theta_is_q,
                                                  const double* __restrict__ p_arr, const double* __restrict__ pw_arr,
-                                                 int c, int G, int lane, double* s_th, double (*s_pw)[kMaxGaps],
-                                                 double (*s_ef)[kMaxGaps]) {
+                                                 int c, int G, int lane, double* s_th, double (*s_pw)[kMaxGaps]) {
   __syncwarp();
   fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw[0], nullptr);
   fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw[1], nullptr);
@@ -83,91 +75,32 @@ __device__ __forceinline__ void gibbs_load_chain(const double* __restrict__ thet
     }
   }
   __syncwarp();
-  {
-    const double bn = s_th[N_B], bs = s_th[S_B];
-    const double an = bn * s_th[N_TEMP], pn = bn * s_th[N_PERM], ps = bs * s_th[S_PERM];
-    for (int k = lane; k < G; k += 32) {
-      const double zn = an * s_pw[0][k], zs = bs * s_pw[1][k];
-      s_ef[0][k] = exp(zn);
-      s_ef[1][k] = exp(-zn);
-      s_ef[2][k] = exp(zs);
-      s_ef[3][k] = exp(-zs);
-    }
-    if (lane == 0) {
-      s_th[22] = exp(pn);
-      s_th[23] = exp(-pn);
-      s_th[24] = exp(ps);
-      s_th[25] = exp(-ps);
-      const double mx = fmax(fmax(fabs(an), fabs(bs)), fmax(fabs(pn), fabs(ps)));
-      s_th[26] = (mx <= kGibbsArgMax) ? 1.0 : 0.0;  // NaN compares false
-    }
-  }
-  __syncwarp();
 }
 
-// exp(-b (x - m)) of one OD row from scratch (trajectory sum + exponential), capped at e^700; *z_out = -b (x - m).
-// Cold relative to the incremental path: kept out of line so that the sweep's loop stays small.
-template <typename M>
-__device__ __noinline__ double gibbs_scratch_E(double x, int t, bool is_s, M inf, M vac, int w, const double* s_th,
-                                               const double (*s_pw)[kMaxGaps], const double* __restrict__ s_tab, double* z_out) {
-  const M lm = low_mask<M>(t);
-  M e = inf & lm, v = is_s ? (vac & lm) : (M)0;
-  const double P = (e | v) ? s_th[is_s ? S_PERM : N_PERM] : 0.0;
-  const double* pw = is_s ? (w ? s_pw[1] : s_pw[2]) : s_pw[0];  // s_pw[2] = all ones (rho_ind = 1)
-  double T = 0.0;
-  while (e) {
-    T += pw[t - ctz(e)];
-    e &= e - 1;
-  }
-  while (v) {
-    T += pw[t - ctz(v)];
-    v &= v - 1;
-  }
-  const double m = fma(is_s ? 1.0 : s_th[N_TEMP], T, s_th[is_s ? S_INIT : N_INIT] + P);
-  double z = -s_th[is_s ? S_B : N_B] * (x - m);
-  *z_out = z;
-  z = (z > 700.0) ? 700.0 : z;
-  return fast_exp(z, s_tab);
-}
-
-// The OD rows of one individual as a warp holds them.  Lane l keeps row l (N rows first, then S rows) in
-// registers as (od, E = exp(-b (x - m)) under the CURRENT state, whether the row's individual has been exposed
-// by the row's gap); rows beyond 32 are read again in every pass.  A candidate state that differs from the
-// current one in the infections only is evaluated INCREMENTALLY: E changes by one tabulated factor per
-// infection that appears or disappears at or before the row's gap (and by exp(+-b perm) if that changes
-// "ever exposed") -- a few multiplications instead of a trajectory sum and an exponential per row.  A flip of
-// ab_s_waner changes every term of the S rows: evaluated from scratch.  Individuals with extreme |b (x - m)|
-// (or chains with extreme parameters) are evaluated from scratch throughout: the products stay <= e^700.
-// ll_*() return the individual's log-likelihood (butterfly sum: every lane gets the total).
+// The OD rows of one individual as a warp holds them: lane l keeps row l (N rows first, then S
+// rows) in registers, rows beyond 32 are read again in every pass; ll() is the individual's
+// log-likelihood under a candidate state (butterfly sum: every lane gets the total).
 template <typename M>
 struct GibbsRows {
   const DevCohort& dc;
   const double* s_th;
   const double (*s_pw)[kMaxGaps];
-  const double (*s_ef)[kMaxGaps];
   const double* s_tab;
   int lane, rn0, cnt_n, rs0, cnt_s, nrows;
-  M vac;
-  // lane-owned row
-  double E, od0, d0, nh0;
-  int t0;          // gap of the row (-1: this lane has none)
-  bool s0, P0;     // S antigen?  exposed (infection, or -- S -- vaccination) at or before t0 under the current state?
-  M lm0, vlm0;     // gaps <= t0; S rows: vaccinations among them
-  bool incr;       // incremental evaluation allowed for this individual
+  double x0, od0;
+  int t0;
+  bool s0;
+  RowPar rp0;
   int t_last, t_last_s;  // latest sampled gap of either antigen / of the S antigen (rows are sorted by gap)
 
-  __device__ __forceinline__ GibbsRows(const DevCohort& dc_, int n, M vac_, int lane_, const double* s_th_,
-                                       const double (*s_pw_)[kMaxGaps], const double (*s_ef_)[kMaxGaps], const double* s_tab_)
-      : dc(dc_), s_th(s_th_), s_pw(s_pw_), s_ef(s_ef_), s_tab(s_tab_), lane(lane_), vac(vac_) {
+  __device__ __forceinline__ GibbsRows(const DevCohort& dc_, int n, int lane_, const double* s_th_,
+                                       const double (*s_pw_)[kMaxGaps], const double* s_tab_)
+      : dc(dc_), s_th(s_th_), s_pw(s_pw_), s_tab(s_tab_), lane(lane_) {
     rn0 = dc.rp[0][n], cnt_n = dc.rp[0][n + 1] - rn0;
     rs0 = dc.rp[1][n], cnt_s = dc.rp[1][n + 1] - rs0;
     nrows = cnt_n + cnt_s;
-    double x;
-    load_row(lane, x, od0, t0, s0);
-    d0 = s_th[s0 ? S_D : N_D];
-    nh0 = s_th[s0 ? 14 : 13];
-    lm0 = (t0 >= 0) ? low_mask<M>(t0) : (M)0;
-    vlm0 = s0 ? (vac & lm0) : (M)0;
+    load_row(lane, x0, od0, t0, s0);
+    rp0 = row_par(s0);
     t_last = t0, t_last_s = s0 ? t0 : -1;
     for (int l = lane + 32; l < nrows; l += 32) {
       const bool is_s = l >= cnt_n;
@@ -178,7 +111,6 @@ struct GibbsRows {
     }
     t_last = __reduce_max_sync(0xffffffffu, t_last);
     t_last_s = __reduce_max_sync(0xffffffffu, t_last_s);
-    E = 0.0, P0 = false, incr = false;
   }
   __device__ __forceinline__ void load_row(int l, double& x, double& od, int& t, bool& is_s) const {
     is_s = l >= cnt_n;
@@ -203,109 +135,29 @@ struct GibbsRows {
     rp.nh = s_th[is_s ? 14 : 13];
     return rp;
   }
-  static __device__ __forceinline__ double warp_sum(double a) {
+  __device__ __forceinline__ double ll(M inf_, M vac, int w_) const {
+    double a = (t0 >= 0) ? gibbs_row<M>(x0, od0, t0, s0, inf_, vac, w_, rp0, s_pw, s_tab) : 0.0;
+    for (int l = lane + 32; l < nrows; l += 32) {  // individuals with more than 32 rows
+      double x, od;
+      int t;
+      bool is_s;
+      load_row(l, x, od, t, is_s);
+      a += gibbs_row<M>(x, od, t, is_s, inf_, vac, w_, row_par(is_s), s_pw, s_tab);
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
     return a;
   }
-  // rows beyond the 32 the lanes own: from scratch, every pass
-  __device__ __forceinline__ double tail(M inf_, int w_) const {
-    double a = 0.0;
-    for (int l = lane + 32; l < nrows; l += 32) {
-      double x, od, z;
-      int t;
-      bool is_s;
-      load_row(l, x, od, t, is_s);
-      const double Ev = gibbs_scratch_E<M>(x, t, is_s, inf_, vac, w_, s_th, s_pw, s_tab, &z);
-      const double sg = fast_rcp(1.0 + Ev);
-      const double r = fma(-s_th[is_s ? S_D : N_D], sg, od);
-      a += s_th[is_s ? 14 : 13] * (r * r);
-    }
-    return a;
-  }
-  // E of the lane's own row under (inf_, w_), from scratch; *z = -b (x - m)
-  __device__ __forceinline__ double own_E(M inf_, int w_, double* z) const {
-    const int r = s0 ? rs0 + (lane - cnt_n) : rn0 + lane;
-    const double x = (s0 ? dc.x[1] : dc.x[0])[r];
-    return gibbs_scratch_E<M>(x, t0, s0, inf_, vac, w_, s_th, s_pw, s_tab, z);
-  }
-  __device__ __forceinline__ double own_term(double Ev) const {
-    const double sg = fast_rcp(1.0 + Ev);
-    const double r = fma(-d0, sg, od0);
-    return nh0 * (r * r);
-  }
-  // (Re)establish the lane-owned rows for the state (inf_, w_) and return the log-likelihood.
-  __device__ __forceinline__ double set_state(M inf_, int w_) {
-    double a = 0.0;
-    bool extreme = false;
-    if (t0 >= 0) {
-      double z;
-      E = own_E(inf_, w_, &z);
-      extreme = !(fabs(z) <= kGibbsZMax);
-      P0 = ((inf_ & lm0) | vlm0) != 0;
-      a = own_term(E);
-    }
-    incr = (s_th[26] != 0.0) && !__any_sync(0xffffffffu, extreme);
-    return warp_sum(a + tail(inf_, w_));
-  }
-  // E of the lane's own row if the infections were inf2 instead of cur (same waner)
-  __device__ __forceinline__ double cand_E(M cur, M inf2, int w_) const {
-    M d = (cur ^ inf2) & lm0;
-    double E2 = E;
-    const int sel = s0 ? 2 : 0;
-    const int kmul = (s0 && !w_) ? 0 : 1;   // non-waners: rho_ind = 1, the factor is exp(+-b_s) whatever the distance
-    while (d) {
-      const int sbit = ctz(d);
-      d &= d - 1;
-      const int added = (int)((inf2 >> sbit) & 1);
-      E2 *= s_ef[sel + 1 - added][(t0 - sbit) * kmul];
-    }
-    const bool P2 = ((inf2 & lm0) | vlm0) != 0;
-    if (P2 != P0) E2 *= s_th[(s0 ? 24 : 22) + (P2 ? 0 : 1)];
-    return E2;
-  }
-  // log-likelihood under a candidate that differs from the current state (cur, w_) in the infections only
-  __device__ __forceinline__ double ll_inf(M cur, M inf2, int w_) const {
-    double a = 0.0;
-    if (incr) {
-      if (t0 >= 0) a = own_term(cand_E(cur, inf2, w_));
-    } else if (t0 >= 0) {
-      double z;
-      a = own_term(own_E(inf2, w_, &z));
-    }
-    return warp_sum(a + tail(inf2, w_));
-  }
-  // ... in ab_s_waner only: the S rows from scratch, the N rows as they are
-  __device__ __forceinline__ double ll_w(M cur, int w2) const {
-    double a = 0.0;
-    if (t0 >= 0) {
-      double Ev = E, z;
-      if (s0) Ev = own_E(cur, w2, &z);
-      a = own_term(Ev);
-    }
-    return warp_sum(a + tail(cur, w2));
-  }
-  // accept: the candidate becomes the current state
-  __device__ __forceinline__ void commit_inf(M cur, M inf2, int w_) {
-    if (t0 < 0) return;
-    double z;
-    E = incr ? cand_E(cur, inf2, w_) : own_E(inf2, w_, &z);
-    P0 = ((inf2 & lm0) | vlm0) != 0;
-  }
-  __device__ __forceinline__ void commit_w(M cur, int w2) {
-    if (t0 >= 0 && s0) {
-      double z;
-      E = own_E(cur, w2, &z);
-      // (a state whose |z| leaves the safe range switches the individual to from-scratch evaluation)
-      if (!(fabs(z) <= kGibbsZMax)) incr = false;
-    }
-    incr = __all_sync(0xffffffffu, incr);
-  }
 };
 
+// (k_gibbs below keeps its own hand-inlined copy of these two: going through the helpers costs it
+// 4 % -- 274 instead of 264 us per sweep, a few more spilled registers under its 64-register cap.)
 // Persistent warps: every warp repeatedly claims the next (chain, individual) from a global
 // counter.  Items are ordered chain-major and, inside a chain, by decreasing OD-row count
 // (longest job first), so the tail at the end of the launch is one short job.
+// 4 CTAs/SM (64 registers, a few spills) is 3 % faster than 3 x 80 registers; 5 is slower.  Also
+// measured and dropped: patching each row's decaying response for a candidate instead of summing
+// it again (no gain: the extra live registers cost what the shorter loops save).
 template <typename M>
 __global__ void __launch_bounds__(kGibbsWarps * 32, ABD_GIBBS_MINB)
 k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
@@ -318,13 +170,11 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
   const int G = dc.G, N = dc.N;
 
   __shared__ double s_tab[kExpTab];
-  __shared__ double s_th_all[kGibbsWarps][kGibbsTh];      // see gibbs_load_chain
+  __shared__ double s_th_all[kGibbsWarps][20];            // theta13, -1/(2 sigma^2) x 2, logit p / p_w, p / p_w
   __shared__ double s_pw_all[kGibbsWarps][3][kMaxGaps];   // rho_n^k, rho_s^k, ones
-  __shared__ double s_ef_all[kGibbsWarps][4][kMaxGaps];   // exp(+-b temp rho^k) tables
   __shared__ unsigned char s_ord[kGibbsWarps][kMaxGaps];
   double* s_th = s_th_all[warp];
   const double (*s_pw)[kMaxGaps] = s_pw_all[warp];
-  const double (*s_ef)[kMaxGaps] = s_ef_all[warp];
 
   fill_exp_table(s_tab, tid, kGibbsWarps * 32);
   for (int k = lane; k < kMaxGaps; k += 32) s_pw_all[warp][2][k] = 1.0;
@@ -350,7 +200,27 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
       }
       n_prop = n_acc = 0;
       cur_c = c;
-      gibbs_load_chain(theta, theta_is_q, p_arr, pw_arr, c, G, lane, s_th, s_pw_all[warp], s_ef_all[warp]);
+      __syncwarp();
+      fill_pow_warp(load_param(theta, theta_is_q, c, N_RHO), G, lane, s_pw_all[warp][0], nullptr);
+      fill_pow_warp(load_param(theta, theta_is_q, c, S_RHO), G, lane, s_pw_all[warp][1], nullptr);
+      if (lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);
+      if (lane == 13 || lane == 14) {
+        const double sg = load_param(theta, theta_is_q, c, lane == 13 ? N_SIGMA : S_SIGMA);
+        s_th[lane] = -0.5 / (sg * sg);
+      }
+      if (lane == 15 || lane == 16) {
+        const int which = lane - 15;
+        double lo;
+        if (theta_is_q) {  // logit of a logodds-transformed value is the value itself
+          lo = theta[(size_t)c * 17 + (which ? kQ_PW : kQ_P)];
+        } else {
+          const double p = which ? pw_arr[c] : p_arr[c];
+          lo = log(p) - log1p(-p);
+        }
+        s_th[lane] = lo;
+        s_th[lane + 2] = 1.0 / (1.0 + exp(-lo));
+      }
+      __syncwarp();
     }
 
     // ---- this individual's column of i_raw (lane t reads gap t), waner, masks, rows ----
@@ -376,9 +246,66 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
     const M raw_in = raw;
     const int w_in = w;
     const M vac = reinterpret_cast<const M*>(dc.vac)[n];
-    GibbsRows<M> rows(dc, n, vac, lane, s_th, s_pw, s_ef, s_tab);
-    const int t_last = rows.t_last, t_last_s = rows.t_last_s;
-    double ll = rows.set_state(inf, w);
+    const int rn0 = dc.rp[0][n], cnt_n = dc.rp[0][n + 1] - rn0;
+    const int rs0 = dc.rp[1][n], cnt_s = dc.rp[1][n + 1] - rs0;
+    const int nrows = cnt_n + cnt_s;
+
+    // rows of this individual, one per lane (N rows first, then S rows); kept in registers
+    auto load_row = [&](int l, double& x, double& od, int& t, bool& is_s) {
+      is_s = l >= cnt_n;
+      const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
+      if (l < nrows) {
+        x = (is_s ? dc.x[1] : dc.x[0])[r];
+        od = (is_s ? dc.od[1] : dc.od[0])[r];
+        t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
+      } else {
+        x = 0.0;
+        od = 0.0;
+        t = -1;
+      }
+    };
+    auto row_par = [&](bool is_s) {
+      RowPar rp;
+      rp.init = s_th[is_s ? S_INIT : N_INIT];
+      rp.perm = s_th[is_s ? S_PERM : N_PERM];
+      rp.tfac = is_s ? 1.0 : s_th[N_TEMP];
+      rp.b = s_th[is_s ? S_B : N_B];
+      rp.d = s_th[is_s ? S_D : N_D];
+      rp.nh = s_th[is_s ? 14 : 13];
+      return rp;
+    };
+    double x0, od0;
+    int t0;
+    bool s0;
+    load_row(lane, x0, od0, t0, s0);
+    const RowPar rp0 = row_par(s0);
+    // latest sampled gap of either antigen / of the S antigen (rows are sorted by gap)
+    int t_last = t0, t_last_s = s0 ? t0 : -1;
+    for (int l = lane + 32; l < nrows; l += 32) {
+      const bool is_s = l >= cnt_n;
+      const int r = is_s ? rs0 + (l - cnt_n) : rn0 + l;
+      const int t = (int)((is_s ? dc.meta[1] : dc.meta[0])[r] & 63u);
+      t_last = max(t_last, t);
+      if (is_s) t_last_s = max(t_last_s, t);
+    }
+    t_last = __reduce_max_sync(0xffffffffu, t_last);
+    t_last_s = __reduce_max_sync(0xffffffffu, t_last_s);
+
+    auto indiv_ll = [&](M inf_, int w_) {
+      double a = (t0 >= 0) ? gibbs_row<M>(x0, od0, t0, s0, inf_, vac, w_, rp0, s_pw, s_tab) : 0.0;
+      for (int l = lane + 32; l < nrows; l += 32) {  // individuals with more than 32 rows
+        double x, od;
+        int t;
+        bool is_s;
+        load_row(l, x, od, t, is_s);
+        a += gibbs_row<M>(x, od, t, is_s, inf_, vac, w_, row_par(is_s), s_pw, s_tab);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      return a;
+    };
+
+    double ll = indiv_ll(inf, w);
 
     // ---- lane-owned proposals: Philox key (visiting order), transit / accept uniforms ----
     M act = 0;              // steps that are not skipped
@@ -493,7 +420,7 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
       bool flip = true;
       if (code == 2 || cfg.mode < 0) {
         const int cur_bit = is_w ? w : (int)((raw >> jp) & 1);
-        if (code == 2) ll2 = is_w ? rows.ll_w(inf, w2) : rows.ll_inf(inf, inf2, w);
+        if (code == 2) ll2 = indiv_ll(inf2, w2);
         const double lo = s_th[is_w ? 16 : 15];
         const double d10 = cur_bit ? (ll - ll2 + lo) : (ll2 - ll + lo);  // log-odds of 1 versus 0
         if (cfg.mode < 0) {
@@ -516,10 +443,8 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
         ++n_acc;
         ll = ll2;
         if (is_w) {
-          rows.commit_w(inf, w2);
           w = w2;
         } else {
-          rows.commit_inf(inf, inf2, w);
           raw ^= (M)1 << jp;
           inf = inf2;
           refresh();

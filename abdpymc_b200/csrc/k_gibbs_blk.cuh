@@ -36,12 +36,10 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
   const int G = dc.G, N = dc.N;
 
   __shared__ double s_tab[kExpTab];
-  __shared__ double s_th_all[kGibbsWarps][kGibbsTh];      // see gibbs_load_chain
+  __shared__ double s_th_all[kGibbsWarps][24];            // see gibbs_load_chain
   __shared__ double s_pw_all[kGibbsWarps][3][kMaxGaps];   // rho_n^k, rho_s^k, ones
-  __shared__ double s_ef_all[kGibbsWarps][4][kMaxGaps];   // exp(+-b temp rho^k) tables
   double* s_th = s_th_all[warp];
   const double (*s_pw)[kMaxGaps] = s_pw_all[warp];
-  const double (*s_ef)[kMaxGaps] = s_ef_all[warp];
 
   fill_exp_table(s_tab, tid, kGibbsWarps * 32);
   for (int k = lane; k < kMaxGaps; k += 32) s_pw_all[warp][2][k] = 1.0;
@@ -66,7 +64,7 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
       }
       n_prop = n_acc = 0;
       cur_c = c;
-      gibbs_load_chain(theta, theta_is_q, p_arr, pw_arr, c, G, lane, s_th, s_pw_all[warp], s_ef_all[warp]);
+      gibbs_load_chain(theta, theta_is_q, p_arr, pw_arr, c, G, lane, s_th, s_pw_all[warp]);
     }
 
     // ---- this individual's column of i_raw (lane t reads gap t), waner, masks, rows ----
@@ -88,9 +86,11 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
     const M raw_in = raw;
     const int w_in = w;
     const M vac = reinterpret_cast<const M*>(dc.vac)[n];
-    GibbsRows<M> rows(dc, n, vac, lane, s_th, s_pw, s_ef, s_tab);
+    const GibbsRows<M> rows(dc, n, lane, s_th, s_pw, s_tab);
     const int t_last = rows.t_last, t_last_s = rows.t_last_s;
-    double ll = rows.set_state(inf, w);
+    auto indiv_ll = [&](M inf_, int w_) { return rows.ll(inf_, vac, w_); };
+
+    double ll = indiv_ll(inf, w);
 
     // ---- random numbers: lane t: fresh Bernoulli(p) draw for gap t (x), categorical uniform of
     //      chunk t (y), waner uniform (lane 0, z) ----
@@ -113,13 +113,13 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
       const M base = raw & ~cm;
       const M inf_own = constrain<M>(base | ((lane < len) ? ((M)1 << (c0 + lane)) : (M)0), pcr, dc.ch);
       const M inf_none = __shfl_sync(FULL, inf_own, len);
-      const double ll_none = (inf_none == inf) ? ll : rows.ll_inf(inf, inf_none, w);
+      const double ll_none = (inf_none == inf) ? ll : indiv_ll(inf_none, w);
       double llv = ll_none;  // lane o: log-likelihood under option o
       for (int o = 0; o < len; ++o) {
         const M io = __shfl_sync(FULL, inf_own, o);
         const M diff = io ^ inf_none;
         if (diff != 0 && ctz(diff) <= t_last) {  // otherwise the data cannot tell it from "none"
-          const double v = (io == inf) ? ll : rows.ll_inf(inf, io, w);
+          const double v = (io == inf) ? ll : indiv_ll(io, w);
           if (lane == o) llv = v;
         }
       }
@@ -147,9 +147,7 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
       const M new_first = newbits & (~newbits + 1);
       if (new_first != old_first) ++n_acc;
       raw = base | newbits;
-      const M inf_new = __shfl_sync(FULL, inf_own, pick);
-      if (inf_new != inf) rows.commit_inf(inf, inf_new, w);
-      inf = inf_new;
+      inf = __shfl_sync(FULL, inf_own, pick);
       ll = __shfl_sync(FULL, llv, pick);
     }
 
@@ -160,13 +158,12 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
       const bool affected = ex != 0 && ctz(ex | top_bit<M>()) < t_last_s;
       double d10 = s_th[16], ll2 = ll;
       if (affected) {
-        ll2 = rows.ll_w(inf, w ^ 1);
+        ll2 = indiv_ll(inf, w ^ 1);
         d10 += w ? (ll - ll2) : (ll2 - ll);  // log-odds of 1 versus 0
       }
       const double p1 = 1.0 / (1.0 + exp(-d10));
       const int w_new = (__shfl_sync(FULL, u01(rnd.z), 0) <= p1) ? 1 : 0;
       if (w_new != w) {
-        rows.commit_w(inf, w_new);
         w = w_new;
         ll = ll2;
         ++n_acc;

@@ -340,6 +340,25 @@ class AbdEngine:
         check(self._lib.abd_hmc_end_dev(self._h, C_, q17, grad17, logp, qw, pw, gw, lpw, inv_mass, h0, int(seed), int(it),
                                         accept_out, da, eps, int(adapt), float(target_accept), stream))
 
+    # the No-U-Turn tree on the device, see include/abd_b200.h
+    def nuts_state_doubles(self, max_depth):
+        return int(self._lib.abd_nuts_state_doubles(int(max_depth)))
+
+    def nuts_begin_dev(self, C_, max_depth, q17, grad17, logp, linv_t, eps, seed, it, state, qw, pw, gw, eps_signed, any_active,
+                       stream=0):
+        check(self._lib.abd_nuts_begin_dev(self._h, C_, int(max_depth), q17, grad17, logp, linv_t, eps, int(seed), int(it), state,
+                                           qw, pw, gw, eps_signed, any_active, stream))
+
+    def nuts_leaf_dev(self, C_, max_depth, depth, leaf, qw, pw, gw, lpw, inv_mass, eps, seed, it, state, eps_signed, any_active,
+                      stream=0):
+        check(self._lib.abd_nuts_leaf_dev(self._h, C_, int(max_depth), int(depth), int(leaf), qw, pw, gw, lpw, inv_mass, eps,
+                                          int(seed), int(it), state, eps_signed, any_active, stream))
+
+    def nuts_end_dev(self, C_, max_depth, q17, grad17, logp, state, accept_out, depth_out, diverged_out, da, eps, adapt,
+                     target_accept, stream=0):
+        check(self._lib.abd_nuts_end_dev(self._h, C_, int(max_depth), q17, grad17, logp, state, accept_out, depth_out, diverged_out,
+                                         da, eps, int(adapt), float(target_accept), stream))
+
     # peer exchange (fused all-reduce over NVLink), see include/abd_b200.h
     def xch_alloc(self, world, rank, max_chains) -> bytes:
         buf = C.create_string_buffer(64)

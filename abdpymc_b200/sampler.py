@@ -90,6 +90,27 @@ class AbdTarget:
                                 gw.data_ptr(), lpw.data_ptr(), inv_mass.data_ptr(), h0.data_ptr(), self.seed, it,
                                 acc.data_ptr(), da.data_ptr(), eps.data_ptr(), adapt, target_accept, self._stream())
 
+    # ---- No-U-Turn tree on the device (abd_nuts_*_dev): one launch per leaf besides the leapfrog ----
+    def nuts_scratch(self, max_depth):
+        f64 = dict(dtype=torch.float64, device=self.device)
+        return (torch.zeros(self.C, self.engine.nuts_state_doubles(max_depth), **f64), torch.zeros(self.C, **f64),
+                torch.zeros(max_depth + 1, dtype=torch.int32, device=self.device))
+
+    def nuts_begin(self, D, q, grad, logp, linv_t, eps, it, state, qw, pw, gw, eps_signed, any_active):
+        self.engine.nuts_begin_dev(self.C, D, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), linv_t.data_ptr(), eps.data_ptr(),
+                                   self.seed, it, state.data_ptr(), qw.data_ptr(), pw.data_ptr(), gw.data_ptr(),
+                                   eps_signed.data_ptr(), any_active.data_ptr(), self._stream())
+
+    def nuts_leaf(self, D, j, n, qw, pw, gw, lpw, inv_mass, eps, it, state, eps_signed, any_active):
+        self.engine.nuts_leaf_dev(self.C, D, j, n, qw.data_ptr(), pw.data_ptr(), gw.data_ptr(), lpw.data_ptr(), inv_mass.data_ptr(),
+                                  eps.data_ptr(), self.seed, it, state.data_ptr(), eps_signed.data_ptr(), any_active.data_ptr(),
+                                  self._stream())
+
+    def nuts_end(self, D, q, grad, logp, state, acc, depth, div, da, eps, adapt, target_accept):
+        self.engine.nuts_end_dev(self.C, D, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), state.data_ptr(), acc.data_ptr(),
+                                 depth.data_ptr(), div.data_ptr(), da.data_ptr(), eps.data_ptr(), adapt, target_accept,
+                                 self._stream())
+
     def gibbs(self, q, sweep):
         q = q.contiguous()
         self.engine.gibbs_sweep_dev(self.C, q.data_ptr(), 1, None, None, self.d_i, self.d_w, self.seed, sweep,
@@ -161,8 +182,11 @@ class SamplerConfig:
     seed: int = 0
     kernel: str = "hmc"                    # "hmc": jittered fixed-length trajectories (the fused device loop when it fits);
                                            # "nuts": batched multinomial No-U-Turn trajectories (what pm.sample runs for
-                                           # the 17 scalars, abd.py:922), chains doubling in lockstep, host-driven
+                                           # the 17 scalars, abd.py:922), chains doubling in lockstep; tree bookkeeping on
+                                           # the device when the target offers it (abd_nuts_*_dev), else torch ops
     max_treedepth: int = 8
+    nuts_check_from_depth: int = 1         # device NUTS: depths below this are always built (no read-back of the "any chain
+                                           # still doubling?" word before them)
 
 
 @dataclass
@@ -176,6 +200,7 @@ class SamplerResult:
     n_grad_evals: int
     means: dict = field(default_factory=dict)   # posterior means of i, ab_n_mu, ab_s_mu (G, N)
     thinned: dict = field(default_factory=dict)  # i (int8), ab_n_mu, ab_s_mu (float32): (chains, kept draws, G, N); "draw" = their indexes
+    stats: dict = field(default_factory=dict)   # NUTS: tree_depth, diverging (chains, draws); what PyMC puts in sample_stats
 
     def posterior(self):
         """{RV name: (chains, draws)} on the constrained scale, named as abd.model names them."""
@@ -253,7 +278,7 @@ class _Thinned:
                 "ab_n_mu": self.mn.permute(1, 0, 2, 3).cpu().numpy(), "ab_s_mu": self.ms.permute(1, 0, 2, 3).cpu().numpy()}
 
 
-def _sample_fused(target, q0, cfg, progress):
+def _sample_fused(target, q0, cfg, progress, nuts=False):
     """The same iteration as ``sample`` with the whole transition on the device: abd_hmc_begin_dev,
     abd_leapfrog_dev (one launch per step, or one persistent launch), abd_hmc_end_dev,
     abd_gibbs_sweep_dev, abd_logp_dlogp_dev, no host synchronisation; the host only picks the trajectory length and,
@@ -280,16 +305,35 @@ def _sample_fused(target, q0, cfg, progress):
     out_lp, out_acc = torch.empty(cfg.draws, C, **f64), torch.empty(cfg.draws, C, **f64)
     means, n_means, n_grad = {}, 0, 0
     thin = _Thinned(target, cfg)
+    if nuts:
+        D = int(min(max(cfg.max_treedepth, 1), 10))
+        nstate, eps_signed, any_active = target.nuts_scratch(D)
+        depth_d, div_d = torch.zeros(C, **f64), torch.zeros(C, **f64)
+        out_depth, out_div = torch.zeros(cfg.draws, C, **f64), torch.zeros(cfg.draws, C, **f64)
     t0 = time.perf_counter()
     for it in range(total):
-        L = max(1, int(round(cfg.n_leapfrog * (cfg.jitter[0] + (cfg.jitter[1] - cfg.jitter[0]) * rng.random()))))
-        target.hmc_begin(q, grad, logp, linv_t, it, qw, pw, gw, h0)
-        if cfg.single_step_launches:   # L overlapped launches: 14.7 us per step (one persistent launch: 16.8)
-            for _ in range(L):
-                target.leapfrog_inplace(qw, pw, gw, lpw, eps, inv_mass, 1)
+        if nuts:
+            # the chains double in lockstep: depth j adds 2^j leaves (one leapfrog launch + one tree launch each);
+            # one word is read back per depth: does any chain still want to double?
+            target.nuts_begin(D, q, grad, logp, linv_t, eps, it, nstate, qw, pw, gw, eps_signed, any_active)
+            for j in range(D):
+                for n in range(1 << j):
+                    target.leapfrog_inplace(qw, pw, gw, lpw, eps_signed, inv_mass, 1)
+                    target.nuts_leaf(D, j, n, qw, pw, gw, lpw, inv_mass, eps, it, nstate, eps_signed, any_active)
+                n_grad += 1 << j
+                if j + 1 < D and j + 1 >= cfg.nuts_check_from_depth and int(any_active[j + 1].item()) == 0:
+                    break
+            target.nuts_end(D, q, grad, logp, nstate, acc, depth_d, div_d, da, eps, it < cfg.tune, cfg.target_accept)
+            L = 0
         else:
-            target.leapfrog_inplace(qw, pw, gw, lpw, eps, inv_mass, L)
-        target.hmc_end(q, grad, logp, qw, pw, gw, lpw, inv_mass, h0, it, acc, da, eps, it < cfg.tune, cfg.target_accept)
+            L = max(1, int(round(cfg.n_leapfrog * (cfg.jitter[0] + (cfg.jitter[1] - cfg.jitter[0]) * rng.random()))))
+            target.hmc_begin(q, grad, logp, linv_t, it, qw, pw, gw, h0)
+            if cfg.single_step_launches:   # L overlapped launches: 14.7 us per step (one persistent launch: 16.8)
+                for _ in range(L):
+                    target.leapfrog_inplace(qw, pw, gw, lpw, eps, inv_mass, 1)
+            else:
+                target.leapfrog_inplace(qw, pw, gw, lpw, eps, inv_mass, L)
+            target.hmc_end(q, grad, logp, qw, pw, gw, lpw, inv_mass, h0, it, acc, da, eps, it < cfg.tune, cfg.target_accept)
         target.gibbs(q, it)
         target.logp_dlogp_into(q, logp, grad)
         n_grad += L + 1
@@ -318,6 +362,9 @@ def _sample_fused(target, q0, cfg, progress):
             out_q[k].copy_(q)
             out_lp[k].copy_(logp)
             out_acc[k].copy_(acc)
+            if nuts:
+                out_depth[k].copy_(depth_d)
+                out_div[k].copy_(div_d)
             thin.record(target, k, q)
             every = cfg.record_deterministics_every
             if every and k % every == 0:
@@ -334,10 +381,11 @@ def _sample_fused(target, q0, cfg, progress):
     torch.cuda.synchronize(dev)
     target.check_status()
     wall = time.perf_counter() - t0
+    stats = {"tree_depth": out_depth.T.cpu().numpy().astype(np.int64), "diverging": out_div.T.cpu().numpy() != 0} if nuts else {}
     return SamplerResult(
         q=out_q.permute(1, 0, 2).cpu().numpy(), logp=out_lp.T.cpu().numpy(), accept=out_acc.T.cpu().numpy(),
         step_size=eps.cpu().numpy(), inv_mass=inv_mass.cpu().numpy(), wall_s=wall, n_grad_evals=n_grad,
-        means={k: (v / n_means).cpu().numpy() for k, v in means.items()}, thinned=thin.result(),
+        means={k: (v / n_means).cpu().numpy() for k, v in means.items()}, thinned=thin.result(), stats=stats,
     )
 
 
@@ -394,7 +442,7 @@ def _nuts_transition(target, q, logp, grad, eps, inv_mass, chol, gen, max_depth)
             pn = ph + 0.5 * v * e * gn
             dh = h0 - (-lpn + 0.5 * ((pn @ inv_mass) * pn).sum(dim=1))
             dh = torch.where(torch.isfinite(dh), dh, neg_inf)
-            div = run & (dh < -1000.0)
+            div = run & (dh.abs() > 1000.0)          # PyMC's divergence threshold on the energy error
             ok = run & ~div
             r2 = run[:, None]
             q_e, p_e, g_e = torch.where(r2, qn, q_e), torch.where(r2, pn, p_e), torch.where(r2, gn, g_e)
@@ -440,6 +488,8 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     """Run tune + draws iterations of [HMC on q | binaries] then [Gibbs on binaries | q]."""
     if cfg.kernel == "hmc" and cfg.persistent_trajectories and hasattr(target, "hmc_begin") and target.fits_persistent():
         return _sample_fused(target, q0, cfg, progress)
+    if cfg.kernel == "nuts" and cfg.persistent_trajectories and hasattr(target, "nuts_begin") and target.fits_persistent():
+        return _sample_fused(target, q0, cfg, progress, nuts=True)
     dev = q0.device
     C, D = q0.shape
     gen = torch.Generator(device=dev)
@@ -457,6 +507,8 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     out_q = torch.empty(cfg.draws, C, D, dtype=torch.float64, device=dev)
     out_lp = torch.empty(cfg.draws, C, dtype=torch.float64, device=dev)
     out_acc = torch.empty(cfg.draws, C, dtype=torch.float64, device=dev)
+    out_depth = torch.zeros(cfg.draws, C, dtype=torch.long, device=dev)
+    out_div = torch.zeros(cfg.draws, C, dtype=torch.bool, device=dev)
     means, n_means, n_grad = {}, 0, 0
     thin = _Thinned(target, cfg)
     has_gibbs = hasattr(target, "gibbs")
@@ -465,8 +517,8 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     for it in range(total):
         if cfg.kernel == "nuts":
             # ---- NUTS over q given the binaries (abd.py:922 runs PyMC's) ------------------------
-            q, logp, grad, acc_p, _, _, n_leaf = _nuts_transition(target, q, logp, grad, eps, inv_mass, chol, gen,
-                                                                  cfg.max_treedepth)
+            q, logp, grad, acc_p, tree_depth, tree_div, n_leaf = _nuts_transition(target, q, logp, grad, eps, inv_mass, chol, gen,
+                                                                                  cfg.max_treedepth)
             n_grad += n_leaf
         else:
             # ---- HMC over q given the binaries ---------------------------------------------
@@ -522,6 +574,8 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
         else:
             k = it - cfg.tune
             out_q[k], out_lp[k], out_acc[k] = q, logp, acc_p
+            if cfg.kernel == "nuts":
+                out_depth[k], out_div[k] = tree_depth, tree_div
             thin.record(target, k, q)
             every = cfg.record_deterministics_every
             if every and k % every == 0:
@@ -538,8 +592,9 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     if dev.type == "cuda":
         torch.cuda.synchronize(dev)
     wall = time.perf_counter() - t0
+    stats = {"tree_depth": out_depth.T.cpu().numpy(), "diverging": out_div.T.cpu().numpy()} if cfg.kernel == "nuts" else {}
     return SamplerResult(
         q=out_q.permute(1, 0, 2).cpu().numpy(), logp=out_lp.T.cpu().numpy(), accept=out_acc.T.cpu().numpy(),
         step_size=eps.cpu().numpy(), inv_mass=inv_mass.cpu().numpy(), wall_s=wall, n_grad_evals=n_grad,
-        means={k: (v / n_means).cpu().numpy() for k, v in means.items()}, thinned=thin.result(),
+        means={k: (v / n_means).cpu().numpy() for k, v in means.items()}, thinned=thin.result(), stats=stats,
     )

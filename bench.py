@@ -136,6 +136,22 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+ISSUE_PEAK_GINST = 148 * 4 * 1.965   # warp instructions / ns: 148 SMs x 4 schedulers x 1 per clock at clocks.max.sm
+
+
+def ncu_issue(kernel, t_launch_s):
+    """The second roof: instruction issue.  Warp instructions per launch from the committed ncu capture
+    (smsp__inst_executed.sum, static) / this run's launch duration, against 148 SMs x 4 schedulers x 1.965 GHz."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        n = float(json.loads(p.read_text())[kernel]["warp_inst"])
+    except Exception:
+        return None
+    ach = n / t_launch_s / 1e9
+    return {"warp_inst_per_launch": n, "achieved_ginst_per_s": ach, "peak_ginst_per_s": ISSUE_PEAK_GINST,
+            "frac": ach / ISSUE_PEAK_GINST, "source": "static: smsp__inst_executed.sum of the committed ncu capture (profiles/ncu_traffic.json)"}
+
+
 TRAFFIC_SOURCE = ("static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture "
                   "of this kernel on this workload (profiles/ncu_traffic.json, profiles/README.md); not re-measured in this run")
 
@@ -401,6 +417,95 @@ def bench_sharded(dist, rank, world, local, dev, K, n_big=100_000, chain_counts=
     return out
 
 
+def bench_ess(eng, co, C, dev, rank, world, dist, tune_n, draws_n, cpu):
+    """A bounded run of the built-in sampler with C chains per GPU; every rank samples its own chains (chain
+    sharding: no collective; Philox streams keyed by global chain), diagnostics over all world x C chains."""
+    import torch
+
+    G, N = co.n_gaps, co.n_inds
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from abdpymc_b200 import diagnostics as dg
+    from abdpymc_b200.sampler import AbdTarget, SamplerConfig, sample
+
+    from abdpymc_b200.engine import forward
+
+    # every rank samples its own C chains (chain sharding: no collective), seeds differ by rank
+    eng.set_chain_offset(rank * C)
+    tgt = AbdTarget(eng, C, np.zeros((C, G, N), np.int8), np.zeros((C, N), np.int8), seed=1)
+    cfg = SamplerConfig(tune=tune_n, draws=draws_n, seed=1 + rank)
+    # PyMC-like initial point: prior means on the constrained scale, jittered in q space (abd.infer_builtin)
+    x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
+    q0 = forward(x0)[None, :] + np.random.default_rng(1 + rank).uniform(-1, 1, size=(C, 17))
+    barrier()
+    res = sample(tgt, torch.from_numpy(q0).to(dev), cfg)
+    draws_q, wall = res.q, res.wall_s
+    if dist:  # gather every rank's draws on all ranks: diagnostics over world x C chains, slowest rank's wall time
+        tdraw = torch.from_numpy(np.ascontiguousarray(res.q)).to(dev)
+        parts = [torch.empty_like(tdraw) for _ in range(world)]
+        dist.all_gather(parts, tdraw)
+        draws_q = torch.cat(parts, dim=0).cpu().numpy()
+        tw = torch.tensor([res.wall_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall = float(tw.item())
+    from abdpymc_b200.engine import Q17_RV, backward as _bw
+
+    xq = _bw(draws_q)
+    summ = dg.summary({name: xq[:, :, k] for k, (name, _) in enumerate(Q17_RV)})
+    res.wall_s = wall
+    vals_ess = sorted(v["ess_bulk"] for v in summ.values())
+    # R-hat gate: an ESS/s is only quoted for quantities whose chains agree (rank-normalised split R-hat <= 1.05);
+    # if any of the 17 scalars fails it the run as a whole is reported as not converged and min ESS/s is null
+    RHAT_MAX = 1.05
+    bad = sorted(name for name, v in summ.items() if not (v["rhat"] <= RHAT_MAX))
+    ok_ess = sorted(v["ess_bulk"] for v in summ.values() if v["rhat"] <= RHAT_MAX)
+    converged = not bad
+    # Gibbs sweeps on the chains' states at the end of the run (the stationary regime: few accepted flips)
+    tq_end = torch.from_numpy(res.q[:, -1, :].copy()).to(dev)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(50):
+        tgt.gibbs(tq_end, 10_000 + k)
+    e1.record()
+    torch.cuda.synchronize()
+    # wall time of the whole run (tune + draws) is charged to the draws kept
+    ess = {"sampler": f"built-in batched HMC (dense metric) + GPU Metropolised-Gibbs sweep, device-resident transitions, "
+                      f"{world * C} chains x ({tune_n} tune + {draws_n} draws)" + (f" on {world} GPUs" if world > 1 else ""),
+           "chains": world * C, "wall_s": res.wall_s, "iterations_per_s": (tune_n + draws_n) / res.wall_s,
+           "converged": converged, "rhat_gate": RHAT_MAX, "not_converged": bad,
+           "min_bulk_ess_per_s": (vals_ess[0] / res.wall_s) if converged else None,
+           "median_bulk_ess_per_s": (vals_ess[len(vals_ess) // 2] / res.wall_s) if converged else None,
+           "min_bulk_ess_per_s_over_converged_quantities": (ok_ess[0] / res.wall_s) if ok_ess else None,
+           "n_converged_quantities": len(ok_ess),
+           "max_rhat": max(v["rhat"] for v in summ.values()), "grad_evals": res.n_grad_evals,
+           "gibbs_sweeps_per_s_stationary": world * C * 50 / (e0.elapsed_time(e1) / 1e3),
+           "posterior": {name: {"mean": float(np.mean(xq[:, :, k])), "sd": float(np.std(xq[:, :, k])),
+                                "ess_bulk": float(summ[name]["ess_bulk"]), "rhat": float(summ[name]["rhat"]),
+                                "simulated_with": SIM_TRUTH.get(name)}
+                         for k, (name, _) in enumerate(Q17_RV)},
+           "note": "PyMC is not installable offline, so there is no measured PyMC-CPU ESS/s beside it (cpu_extrapolation "
+                   "scales this run's ESS per iteration by the CPU cost of one iteration); the slowest-mixing "
+                   "parameters are those coupled to the latent infection indicators (data-augmentation Gibbs); "
+                   "quantities that fail the R-hat gate get no ESS/s"}
+    if cpu and cpu.get("gibbs"):
+        # one iteration of the reference's compound step = one NUTS draw (>= the 5 leapfrogs used here) + one
+        # BinaryGibbsMetropolis sweep; its chains run one per core.  Same ESS per iteration assumed.
+        t_iter = 1.0 / (cpu["gibbs"]["value"] / cpu["cores"]) + cfg.n_leapfrog / (cpu["value"] / cpu["cores"])
+        ess_per_iter = (vals_ess[0] if converged else (ok_ess[0] if ok_ess else float("nan"))) / (tune_n + draws_n)
+        ess["cpu_extrapolation"] = {
+            "seconds_per_iteration_per_chain": t_iter, "min_bulk_ess_per_s": ess_per_iter / t_iter,
+            "how": f"this run's min bulk ESS per iteration ({world * C} chains) / CPU seconds per iteration of one chain on "
+                   f"one core (1 Gibbs sweep + {cfg.n_leapfrog} logp+grad evaluations of the restated reference, "
+                   "cpu_baseline), chains in parallel on separate cores"}
+
+    return ess
+
+
 # ------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
@@ -458,6 +563,17 @@ def run_gpu(args):
             j = k % n_rep
             engines[j].gibbs_sweep_dev(C, tth.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), states[j][0], states[j][1], 1,
                                        100 + k, mode=2)
+        # the throughput regime: 128 chains per launch (BASELINE configs[4], one GPU's share)
+        CB = 128
+        _, qb, _, ib, wb = workload(n_chains=CB)
+        eng_b = AbdEngine(co, splits=SPLITS, device=local)
+        eng_b.upload_state(ib, wb)
+        sb = eng_b.state_dev(CB)
+        tqb = torch.from_numpy(qb).to(dev)
+        ob1 = torch.zeros(CB, dtype=torch.float64, device=dev)
+        ob2 = torch.zeros(CB, 17, dtype=torch.float64, device=dev)
+        for k in range(max(K, 1)):
+            eng_b.logp_dlogp_dev(CB, tqb.data_ptr(), sb[0], sb[1], ob1.data_ptr(), ob2.data_ptr(), 0)
         torch.cuda.synchronize()
         print("profile run done:", o1.cpu().numpy())
         return
@@ -626,8 +742,11 @@ def run_gpu(args):
     ms_b = sorted(reps_b)[1]
     a_b = eng_b.algorithmic_bytes_logp(CB)
     batched = {"chains": CB, "value": world * CB * n_b / (ms_b / 1e3), "unit": "evals/s", "avg_launch_us": ms_b / n_b * 1e3,
+               "issue": ncu_issue("k_sums_128", ms_b / n_b / 1e3),
+               "algorithmic_bytes_packed_state": int(CB * (8 * N + 216) + 2 * G * N + 20 * co.n_rows + 8 * (N + 1)),
                "algorithmic_bytes_per_launch": a_b, "hbm_frac": a_b / (ms_b / n_b / 1e3) / 1e9 / measured_peak_gbs()[0],
-               "note": "one launch evaluates 128 chains (40 MB of chain state streams from HBM every launch)"}
+               "note": "one launch evaluates 128 chains; algorithmic_bytes_per_launch is SURVEY 8d's formula (int8 boundary "
+                       "state, 40 MB); the kernel reads the packed resident copy instead (8 bytes per individual and chain)"}
     eng_b.close()
     del tqb, outb, outgb
 
@@ -736,6 +855,52 @@ def run_gpu(args):
     for e in engines[1:]:
         e.close()
 
+    # ---- the PyMC-facing path (Op.perform / step protocol) driven through the protocol stand-in (tests/fake_pymc.py;
+    #      PyMC is not installable offline): host cost per NUTS leapfrog and per Gibbs step at 10k individuals ----
+    op_path = None
+    try:
+        sys.path.insert(0, str(ROOT / "tests"))
+        import fake_pymc
+
+        fabd = fake_pymc.load_abd_with_fake_pymc()
+        from abdpymc_b200.engine import Q17 as _Q17, THETA13 as _TH13
+
+        m = fabd.model(co, splits=SPLITS, device=local)
+        node = m["loglik"].owner
+        val_op, grad_op = node.op, fabd.AbdLogLikGrad(m.abd_engine, m.abd_cache)
+        i64, w64 = i_raw[0].astype(np.int64), w[0].astype(np.int64)     # PyMC holds Bernoulli values as int64
+        st_val, st_grad = [[None]], [[None] for _ in range(13)]
+
+        def leapfrog_eval(theta13):
+            inputs = [np.float64(v) for v in theta13] + [i64, w64]
+            val_op.perform(node, inputs, st_val)
+            grad_op.perform(None, inputs, st_grad)
+
+        n_op = max(200, min(2000, K * 20))
+        for k in range(20):
+            leapfrog_eval(th13[0] * (1 + 1e-6 * k))
+        t0 = time.perf_counter()
+        for k in range(n_op):
+            leapfrog_eval(th13[0] * (1 + 1e-6 * (k + 20)))
+        dt_op = time.perf_counter() - t0
+        step = fabd.GpuBinaryGibbs(model=m, seed=3)
+        point = {**{name: np.float64(q[0][k]) for k, name in enumerate(_Q17)}, "i_raw": i64, "ab_s_waner": w64}
+        point, _ = step.step(point)
+        n_st = max(5, min(30, K))
+        t0 = time.perf_counter()
+        for _ in range(n_st):
+            point, _ = step.step(point)
+        dt_step = time.perf_counter() - t0
+        op_path = {"us_per_leapfrog": dt_op / n_op * 1e6, "us_per_gibbs_step": dt_step / n_st * 1e6, "chains": 1,
+                   "uploads_of_the_binaries": int(m.abd_cache.uploads),
+                   "what": "AbdLogLik.perform + AbdLogLikGrad.perform at a new parameter point with unchanged binaries (one kernel "
+                           "launch, 13 scalars in / 14 out; i_raw stays on the GPU between Gibbs steps), and "
+                           "GpuBinaryGibbs.step (sweep on the resident state + download of the new int8 state + int64 conversion for "
+                           "PyMC's point); driven through tests/fake_pymc.py, the stand-in for the PyMC 5 protocol"}
+        m.abd_engine.close()
+    except Exception as ex:  # never let the optional leg take the headline down
+        op_path = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+
     # ---- individual sharding (BASELINE configs[3]): the 100k-individual cohort on ONE GPU (baseline, rank 0)
     #      and split over the ranks, C = 4 and C = 32 chains; NCCL all-reduce against the all-reduce fused into
     #      the kernel over NVLink peer memory, host-driven and as a CUDA graph ----
@@ -743,81 +908,14 @@ def run_gpu(args):
     if not args.no_sharded:
         sharded = bench_sharded(dist, rank, world, local, dev, K)
 
-    # ---- ESS/s of the built-in HMC + GPU-Gibbs sampler on the same cohort (bounded run) ----
-    ess = None
+    # ---- ESS/s of the built-in HMC + GPU-Gibbs sampler on the same cohort (bounded runs): the headline's 4 chains,
+    #      and 128 chains per GPU (BASELINE configs[4]: 1024 chains over 8 GPUs, chain-parallel ESS/s) ----
+    ess = ess128 = None
     if not args.no_ess:
-        from abdpymc_b200 import diagnostics as dg
-        from abdpymc_b200.sampler import AbdTarget, SamplerConfig, sample
-
-        from abdpymc_b200.engine import forward
-
-        tune_n, draws_n = args.ess_tune, args.ess_draws
-        # every rank samples its own C chains (chain sharding: no collective), seeds differ by rank
-        tgt = AbdTarget(eng0, C, np.zeros_like(i_raw), np.zeros_like(w), seed=1 + rank)
-        cfg = SamplerConfig(tune=tune_n, draws=draws_n, seed=1 + rank)
-        # PyMC-like initial point: prior means on the constrained scale, jittered in q space (abd.infer_builtin)
-        x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
-        q0 = forward(x0)[None, :] + np.random.default_rng(1 + rank).uniform(-1, 1, size=(C, 17))
-        barrier()
-        res = sample(tgt, torch.from_numpy(q0).to(dev), cfg)
-        draws_q, wall = res.q, res.wall_s
-        if dist:  # gather every rank's draws on all ranks: diagnostics over world x C chains, slowest rank's wall time
-            tdraw = torch.from_numpy(np.ascontiguousarray(res.q)).to(dev)
-            parts = [torch.empty_like(tdraw) for _ in range(world)]
-            dist.all_gather(parts, tdraw)
-            draws_q = torch.cat(parts, dim=0).cpu().numpy()
-            tw = torch.tensor([res.wall_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-            wall = float(tw.item())
-        from abdpymc_b200.engine import Q17_RV, backward as _bw
-
-        xq = _bw(draws_q)
-        summ = dg.summary({name: xq[:, :, k] for k, (name, _) in enumerate(Q17_RV)})
-        res.wall_s = wall
-        vals_ess = sorted(v["ess_bulk"] for v in summ.values())
-        # R-hat gate: an ESS/s is only quoted for quantities whose chains agree (rank-normalised split R-hat <= 1.05);
-        # if any of the 17 scalars fails it the run as a whole is reported as not converged and min ESS/s is null
-        RHAT_MAX = 1.05
-        bad = sorted(name for name, v in summ.items() if not (v["rhat"] <= RHAT_MAX))
-        ok_ess = sorted(v["ess_bulk"] for v in summ.values() if v["rhat"] <= RHAT_MAX)
-        converged = not bad
-        # Gibbs sweeps on the chains' states at the end of the run (the stationary regime: few accepted flips)
-        tq_end = torch.from_numpy(res.q[:, -1, :].copy()).to(dev)
-        torch.cuda.synchronize()
-        e0.record()
-        for k in range(50):
-            tgt.gibbs(tq_end, 10_000 + k)
-        e1.record()
-        torch.cuda.synchronize()
-        # wall time of the whole run (tune + draws) is charged to the draws kept
-        ess = {"sampler": f"built-in batched HMC (dense metric) + GPU Metropolised-Gibbs sweep, device-resident transitions, "
-                          f"{world * C} chains x ({tune_n} tune + {draws_n} draws)" + (f" on {world} GPUs" if world > 1 else ""),
-               "chains": world * C, "wall_s": res.wall_s, "iterations_per_s": (tune_n + draws_n) / res.wall_s,
-               "converged": converged, "rhat_gate": RHAT_MAX, "not_converged": bad,
-               "min_bulk_ess_per_s": (vals_ess[0] / res.wall_s) if converged else None,
-               "median_bulk_ess_per_s": (vals_ess[len(vals_ess) // 2] / res.wall_s) if converged else None,
-               "min_bulk_ess_per_s_over_converged_quantities": (ok_ess[0] / res.wall_s) if ok_ess else None,
-               "n_converged_quantities": len(ok_ess),
-               "max_rhat": max(v["rhat"] for v in summ.values()), "grad_evals": res.n_grad_evals,
-               "gibbs_sweeps_per_s_stationary": world * C * 50 / (e0.elapsed_time(e1) / 1e3),
-               "posterior": {name: {"mean": float(np.mean(xq[:, :, k])), "sd": float(np.std(xq[:, :, k])),
-                                    "ess_bulk": float(summ[name]["ess_bulk"]), "rhat": float(summ[name]["rhat"]),
-                                    "simulated_with": SIM_TRUTH.get(name)}
-                             for k, (name, _) in enumerate(Q17_RV)},
-               "note": "PyMC is not installable offline, so there is no measured PyMC-CPU ESS/s beside it (cpu_extrapolation "
-                       "scales this run's ESS per iteration by the CPU cost of one iteration); the slowest-mixing "
-                       "parameters are those coupled to the latent infection indicators (data-augmentation Gibbs); "
-                       "quantities that fail the R-hat gate get no ESS/s"}
-        if cpu and cpu.get("gibbs"):
-            # one iteration of the reference's compound step = one NUTS draw (>= the 5 leapfrogs used here) + one
-            # BinaryGibbsMetropolis sweep; its chains run one per core.  Same ESS per iteration assumed.
-            t_iter = 1.0 / (cpu["gibbs"]["value"] / cpu["cores"]) + cfg.n_leapfrog / (cpu["value"] / cpu["cores"])
-            ess_per_iter = (vals_ess[0] if converged else (ok_ess[0] if ok_ess else float("nan"))) / (tune_n + draws_n)
-            ess["cpu_extrapolation"] = {
-                "seconds_per_iteration_per_chain": t_iter, "min_bulk_ess_per_s": ess_per_iter / t_iter,
-                "how": f"this run's min bulk ESS per iteration ({world * C} chains) / CPU seconds per iteration of one chain on "
-                       f"one core (1 Gibbs sweep + {cfg.n_leapfrog} logp+grad evaluations of the restated reference, "
-                       "cpu_baseline), chains in parallel on separate cores"}
+        ess = bench_ess(eng0, co, C, dev, rank, world, dist, args.ess_tune, args.ess_draws, cpu)
+        eng128 = AbdEngine(co, splits=SPLITS, device=local)
+        ess128 = bench_ess(eng128, co, 128, dev, rank, world, dist, args.ess128_tune, args.ess128_draws, None)
+        eng128.close()
 
     if rank != 0:
         if dist:
@@ -843,6 +941,7 @@ def run_gpu(args):
                      "traffic": ncu_traffic("k_sums"), "traffic_source": TRAFFIC_SOURCE, "kernel": "k_sums",
                      "algorithmic_bytes_per_launch": a_logp,
                      "avg_launch_us": t_kernel * 1e6, "peak_source": peak_src,
+                     "issue": ncu_issue("k_sums", t_kernel),
                      # the second, honest bound: fp64 work, 60 R + 12 G N flop-equivalents per chain evaluation
                      "fp64": {"flops_per_launch": flops, "achieved_tflops": flops / t_kernel / 1e12,
                               "nominal_peak_tflops": 37.0, "frac_of_nominal": flops / t_kernel / 1e12 / 37.0,
@@ -869,10 +968,15 @@ def run_gpu(args):
                   "other_update_rules": {name: {"value": world * C * n_sw / (v / 1e3), "unit": "sweeps/s"} for name, v in ms_modes.items()},
                   "roofline": {"bound": "hbm", "achieved": ach_g, "peak": peak, "unit": "GB/s", "frac": ach_g / peak,
                                "traffic": ncu_traffic("k_gibbs"), "traffic_source": TRAFFIC_SOURCE, "kernel": "k_gibbs",
-                               "algorithmic_bytes_per_launch": a_gibbs},
+                               "algorithmic_bytes_per_launch": a_gibbs, "issue": ncu_issue("k_gibbs", t_sweep),
+                               "fp64": {"flops_per_launch": C * N * G * (4.0 * G + 60.0 * co.n_rows / N),
+                                        "achieved_tflops": C * N * G * (4.0 * G + 60.0 * co.n_rows / N) / t_sweep / 1e12,
+                                        "nominal_peak_tflops": 37.0,
+                                        "note": "SURVEY 8d: N G (4 G + 60 R / N) fp64 flop-equivalents per chain sweep; the sweep is "
+                                                "bound by instruction issue (sequential per-individual decisions), not HBM"}},
                   "e2e": {"value": world * C * n_sw_e2e / dt_gibbs_e2e, "unit": "sweeps/s",
                           "h2d_bytes_per_step": int(C * (G * N + N + 15 * 8)), "d2h_bytes_per_step": int(C * (G * N + N + 16))}},
-        "sharded_100k": sharded, "ess": ess,
+        "pymc_op_path": op_path, "sharded_100k": sharded, "ess": ess, "ess_128_chains": ess128,
         "gpu_launches": int(n_launch), "gpu_launches_host_api": int(launches), "clocks": clocks,
     }
     emit(line)
@@ -891,6 +995,8 @@ def main():
     ap.add_argument("--no-sharded", action="store_true", help="skip the 100k-individual (individual-sharded) leg")
     ap.add_argument("--ess-tune", type=int, default=2000)
     ap.add_argument("--ess-draws", type=int, default=6000)
+    ap.add_argument("--ess128-tune", type=int, default=400)
+    ap.add_argument("--ess128-draws", type=int, default=400)
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: a few un-captured logp+grad launches and Gibbs sweeps, no JSON line")
     args = ap.parse_args()

@@ -248,6 +248,33 @@ int abd_hmc_end_dev(abd_handle* h, int n_chains, double* q17, double* grad17, do
                     double* accept_out, double* da, double* eps, int adapt, double target_accept,
                     void* stream);
 
+/* The No-U-Turn sampler's tree bookkeeping on the device (what PyMC's NUTS step does on the host around
+ * its leapfrogs in pm.sample, abd.py:922): multinomial sampling inside sub-trees, biased progressive
+ * sampling between them, the generalised U-turn criterion on every balanced sub-tree, divergence when the
+ * energy error exceeds 1000.  The C chains of a batch double in lockstep; per transition the host enqueues
+ *   abd_nuts_begin_dev                                   momentum refresh, empty tree, first direction
+ *   for depth j = 0 .. max_depth - 1, leaf n = 0 .. 2^j - 1:
+ *       abd_leapfrog_dev(n_steps = 1, qw, pw, gw, lpw, eps_signed, ...)      one leaf for all chains
+ *       abd_nuts_leaf_dev(j, n)                          fold the leaf into every chain's tree
+ *     after the last leaf of a depth: any_active[j + 1] != 0 iff some chain still wants to double
+ *     (ONE word read back per depth; stop when it is 0)
+ *   abd_nuts_end_dev                                     move to the proposal, sample stats, step-size adaptation
+ * state: C x abd_nuts_state_doubles(max_depth) doubles (device scratch owned by the caller); qw / pw / gw
+ * (C x 17), lpw (C), eps_signed (C): work vectors the leapfrog integrates in place; any_active: max_depth + 1
+ * ints.  Philox streams keyed by (seed; iter, global chain, purpose).  accept_out = mean acceptance statistic
+ * of the tree, depth_out = tree depth, diverged_out = 0 / 1 (any may be NULL except accept_out).        */
+int64_t abd_nuts_state_doubles(int max_depth);
+int abd_nuts_begin_dev(abd_handle* h, int n_chains, int max_depth, const double* q17, const double* grad17,
+                       const double* logp, const double* linv_t, const double* eps, uint64_t seed, uint64_t iter,
+                       double* state, double* qw, double* pw, double* gw, double* eps_signed, int* any_active,
+                       void* stream);
+int abd_nuts_leaf_dev(abd_handle* h, int n_chains, int max_depth, int depth, int leaf, double* qw, double* pw,
+                      double* gw, const double* lpw, const double* inv_mass, const double* eps, uint64_t seed,
+                      uint64_t iter, double* state, double* eps_signed, int* any_active, void* stream);
+int abd_nuts_end_dev(abd_handle* h, int n_chains, int max_depth, double* q17, double* grad17, double* logp,
+                     const double* state, double* accept_out, double* depth_out, double* diverged_out, double* da,
+                     double* eps, int adapt, double target_accept, void* stream);
+
 /* Individual sharding over the GPUs of one node WITHOUT a separate collective: the all-reduce of
  * the C x 16 raw sums is fused into the kernel through NVLink peer memory (each rank's finishing
  * CTA stores its sums into every peer's buffer, waits for the peers' flags, adds in rank order,

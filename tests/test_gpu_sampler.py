@@ -168,7 +168,7 @@ def kin_of(p, inv_mass):
     return 0.5 * ((p @ inv_mass) * p).sum(dim=1)
 
 
-@pytest.mark.parametrize("gibbs_mode,kernel", [(0, "hmc"), (2, "hmc"), (0, "nuts")])
+@pytest.mark.parametrize("gibbs_mode,kernel", [(0, "hmc"), (2, "hmc"), (0, "nuts"), (0, "nuts_host")])
 def test_sampler_recovers_the_priors_on_a_cohort_without_data(gpu, gibbs_mode, kernel):
     """Statistical check of the whole transition (priors, transforms + Jacobians, HMC on the device,
     Gibbs over the indicators) against distributions known in closed form: without OD rows the
@@ -200,9 +200,18 @@ def test_sampler_recovers_the_priors_on_a_cohort_without_data(gpu, gibbs_mode, k
         tgt = AbdTarget(eng, C, np.zeros((C, G, N), np.int8), np.zeros((C, N), np.int8), seed=3, gibbs_mode=gibbs_mode)
         x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
         q0 = forward(x0)[None, :] + rng.uniform(-1, 1, size=(C, 17))
-        n_tune, n_draws = (1000, 6000) if kernel == "hmc" else (300, 1000)   # NUTS is host-driven: ~10 ms per draw
-        res = sample(tgt, torch.from_numpy(q0).to(gpu), SamplerConfig(tune=n_tune, draws=n_draws, seed=3, kernel=kernel))
+        # "nuts": the tree bookkeeping on the device (abd_nuts_*_dev); "nuts_host": the same algorithm as torch ops
+        # driven from the host (~10 ms per draw)
+        n_tune, n_draws = (300, 1000) if kernel == "nuts_host" else (1000, 6000)
+        cfg = SamplerConfig(tune=n_tune, draws=n_draws, seed=3, kernel=kernel.split("_")[0],
+                            persistent_trajectories=kernel != "nuts_host")
+        res = sample(tgt, torch.from_numpy(q0).to(gpu), cfg)
         i_raw, waner = tgt.state()
+    if kernel.startswith("nuts"):
+        depth, div = res.stats["tree_depth"], res.stats["diverging"]
+        assert depth.shape == (C, n_draws) and depth.min() >= 1 and depth.max() <= cfg.max_treedepth
+        assert 1.5 < depth.mean() < 6 and div.mean() < 0.02
+        assert 0.6 < res.accept.mean() < 0.97
     x = backward(res.q)
     summ = dg.summary({name: x[:, :, k] for k, (name, _) in enumerate(Q17_RV)})
     for name, dist in prior.items():
