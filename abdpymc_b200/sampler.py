@@ -306,8 +306,8 @@ def _sample_fused(target, q0, cfg, progress, nuts=False):
     means, n_means, n_grad = {}, 0, 0
     thin = _Thinned(target, cfg)
     if nuts:
-        D = int(min(max(cfg.max_treedepth, 1), 10))
-        nstate, eps_signed, any_active = target.nuts_scratch(D)
+        TD = int(min(max(cfg.max_treedepth, 1), 10))   # maximum tree depth
+        nstate, eps_signed, any_active = target.nuts_scratch(TD)
         depth_d, div_d = torch.zeros(C, **f64), torch.zeros(C, **f64)
         out_depth, out_div = torch.zeros(cfg.draws, C, **f64), torch.zeros(cfg.draws, C, **f64)
     t0 = time.perf_counter()
@@ -315,15 +315,15 @@ def _sample_fused(target, q0, cfg, progress, nuts=False):
         if nuts:
             # the chains double in lockstep: depth j adds 2^j leaves (one leapfrog launch + one tree launch each);
             # one word is read back per depth: does any chain still want to double?
-            target.nuts_begin(D, q, grad, logp, linv_t, eps, it, nstate, qw, pw, gw, eps_signed, any_active)
-            for j in range(D):
+            target.nuts_begin(TD, q, grad, logp, linv_t, eps, it, nstate, qw, pw, gw, eps_signed, any_active)
+            for j in range(TD):
                 for n in range(1 << j):
                     target.leapfrog_inplace(qw, pw, gw, lpw, eps_signed, inv_mass, 1)
-                    target.nuts_leaf(D, j, n, qw, pw, gw, lpw, inv_mass, eps, it, nstate, eps_signed, any_active)
+                    target.nuts_leaf(TD, j, n, qw, pw, gw, lpw, inv_mass, eps, it, nstate, eps_signed, any_active)
                 n_grad += 1 << j
-                if j + 1 < D and j + 1 >= cfg.nuts_check_from_depth and int(any_active[j + 1].item()) == 0:
+                if j + 1 < TD and j + 1 >= cfg.nuts_check_from_depth and int(any_active[j + 1].item()) == 0:
                     break
-            target.nuts_end(D, q, grad, logp, nstate, acc, depth_d, div_d, da, eps, it < cfg.tune, cfg.target_accept)
+            target.nuts_end(TD, q, grad, logp, nstate, acc, depth_d, div_d, da, eps, it < cfg.tune, cfg.target_accept)
             L = 0
         else:
             L = max(1, int(round(cfg.n_leapfrog * (cfg.jitter[0] + (cfg.jitter[1] - cfg.jitter[0]) * rng.random()))))
