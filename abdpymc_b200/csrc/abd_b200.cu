@@ -376,7 +376,7 @@ void plan_grid(const abd_handle* h, int C, int ctas_per_sm, int* want_tiles, int
   const int target = h->tile_rows_override > 0 ? h->tile_rows_override : 2200;
   int cpc = h->chains_per_cta_override > 0 ? h->chains_per_cta_override : (C >= 32 ? 4 : 1);
   cpc = std::min(cpc, C);
-  if (h->xch_active) cpc = std::min(cpc, 16);  // a CTA remembers at most 16 chains it finished last (k_sums: s_pend)
+  cpc = std::min(cpc, kMaxChainsPerCta);  // a CTA remembers at most this many chains it finished last (k_sums: s_pend)
   const int groups = (C + cpc - 1) / cpc;
   const int min_tiles = (h->N + kTileMaxInds - 1) / kTileMaxInds;
   const int resident = h->n_sms * ctas_per_sm;

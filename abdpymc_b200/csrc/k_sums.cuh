@@ -13,6 +13,7 @@ using namespace abd;
 // bank): the host-pointer calls (abd_logp_dlogp, abd_loglik_grad) then need no host -> device copy
 // of q17 / theta13 before the launch.  n = 0: read the `theta` pointer instead.
 constexpr int kInlineChains = 8;
+constexpr int kMaxChainsPerCta = 32;  // a CTA remembers at most this many chains it finished last
 struct ThetaInline {
   int n;
   double v[kInlineChains * 17];
@@ -248,8 +249,8 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
   }
   PHASE(1);
 
-  __shared__ int s_pend[16], s_npend;          // sharded: chains this CTA finished last (posted, not yet collected)
-  __shared__ unsigned s_pend_seq[16];
+  __shared__ int s_pend[kMaxChainsPerCta], s_npend;   // chains this CTA finished last (queued for the reduction + finaliser)
+  __shared__ unsigned s_pend_seq[kMaxChainsPerCta];
   __shared__ unsigned s_xw[kMaxPeers][32];     // sharded: the peers' 16 sums as 32-bit halves
   if (tid == 0) s_npend = 0;
   // the parameter-only part of the finaliser, parked in `aux` by the chain's first tile
@@ -260,6 +261,38 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
       else if (tid < 17 * 7 + 6) reinterpret_cast<double*>(&s_lik)[tid - 17 * 7] = v;
     }
   };
+  // all threads: the chain's totals over the tiles' partials, in a fixed order, into s_red[0] (and `sums`)
+  auto sum_partials = [&](int c, bool sharded_) {
+    const int k = tid & 15, g = tid >> 4;  // 16 groups of 16 values
+    double v = 0.0;
+    const double* src = partial + (size_t)c * ntiles * kNSums + k;
+    for (int tl = g; tl < ntiles; tl += 8 * (kSumsBlock / 16)) {  // 8 loads in flight, fixed order
+      double ld[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {  // unpredicated (clamped) loads, masked afterwards: all in flight
+        const int tt = tl + u * (kSumsBlock / 16);
+        ld[u] = __ldcg(src + (size_t)min(tt, ntiles - 1) * kNSums);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += (tl + u * (kSumsBlock / 16) < ntiles) ? ld[u] : 0.0;
+    }
+    s_fin[g][k] = v;
+    PHASE(9);
+    __syncthreads();
+    if (tid < kNSums) {
+      double tot = 0.0;
+#pragma unroll
+      for (int gg = 0; gg < kSumsBlock / 16; ++gg) tot += s_fin[gg][tid];
+      s_red[0][tid] = tot;
+      if (sums && !sharded_) sums[(size_t)c * kNSums + tid] = tot;
+    }
+    if (tid == 0) ticket[c] = 0;  // re-arm for the next launch
+    __syncthreads();
+  };
+  // thread 0: the ticket drawn for the previous chain (looked at one chain later, see below)
+  unsigned tk_prev = 0;
+  int tk_c = 0;
+  bool tk_valid = false;
   // warp 0: totals in s_red[0] -> loglik / joint logp and gradient (or, trajectory mode, the end of the step)
   auto finalize_chain = [&](int c, int step, int nsteps) {
     if (fin.mode == 1) {
@@ -595,11 +628,25 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     }
 
     PHASE(6);
-    // ---- last CTA of this chain: ordered reduction over tiles, then finalise.  One thread
-    //      releases the CTA's partials (barrier, then fence + ticket) and acquires the others'
-    //      (then barrier): the grid-sync idiom with ONE acq_rel atomic per CTA instead of a pair of
-    //      sequentially consistent fences around a relaxed one ----
+    // ---- which CTA finishes this chain last?  One thread releases the CTA's partials (barrier, then an
+    //      acq_rel ticket) and, if it drew the last ticket, has acquired everybody else's: the grid-sync idiom
+    //      with ONE atomic per CTA.  The ticket's answer is not waited for: the CTA goes straight on to its
+    //      next chain and thread 0 looks at the answer one chain later (a global atomic round trip is ~1400
+    //      cycles during which the whole CTA would sit at a barrier), queueing the chain for the ordered
+    //      cross-tile reduction + finalisation after the chain loop.  The persistent multi-step trajectory
+    //      mode must finalise in place (the chain's other CTAs wait for the next position). ----
     __syncthreads();
+    // (one chain per CTA and no exchange: nothing to overlap the answer with, finalise in place as well)
+    if (!((TRAJ && nsteps > 1) || (cfg.chains_per_cta == 1 && xch.world <= 1))) {
+      if (tid == 0) {
+        if (tk_valid && tk_prev == (unsigned)(ntiles - 1)) s_pend[s_npend++] = tk_c;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(tk_prev) : "l"(ticket + c) : "memory");
+        tk_c = c;
+        tk_valid = true;
+      }
+      PHASE(8);
+      continue;  // (the barrier above already separates this chain's shared-memory reads from the next chain's writes)
+    }
     if (tid == 0) {
       unsigned prev;
       asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ticket + c) : "memory");
@@ -608,62 +655,10 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     __syncthreads();
     PHASE(7);
     if (s_last) {
-      const bool sharded = xch.world > 1;
-      // the parameter-only part of the finaliser was parked in `aux` by the chain's first tile
-      if (!sharded) load_aux(c);
-      const int k = tid & 15, g = tid >> 4;  // 16 groups of 16 values
-      double v = 0.0;
-      const double* src = partial + (size_t)c * ntiles * kNSums + k;
-      for (int tl = g; tl < ntiles; tl += 8 * (kSumsBlock / 16)) {  // 8 loads in flight, fixed order
-        double ld[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {  // unpredicated (clamped) loads, masked afterwards: all in flight
-          const int tt = tl + u * (kSumsBlock / 16);
-          ld[u] = __ldcg(src + (size_t)min(tt, ntiles - 1) * kNSums);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v += (tl + u * (kSumsBlock / 16) < ntiles) ? ld[u] : 0.0;
-      }
-      s_fin[g][k] = v;
-      PHASE(9);
-      __syncthreads();
-      if (tid < kNSums) {
-        double tot = 0.0;
-#pragma unroll
-        for (int gg = 0; gg < kSumsBlock / 16; ++gg) tot += s_fin[gg][tid];
-        s_red[0][tid] = tot;
-        if (sums && !sharded) sums[(size_t)c * kNSums + tid] = tot;
-      }
-      if (tid == 0) ticket[c] = 0;  // re-arm for the next launch
-      __syncthreads();
+      load_aux(c);
+      sum_partials(c, false);
       PHASE(10);
-      if (sharded) {
-        // ---- post this rank's 16 sums into every peer's buffer and move on: the wait for the peers'
-        //      sums and the finalisation happen after the CTA's last chain (a CTA that finished a chain
-        //      last would otherwise sit in the exchange while its remaining chains wait, and so become
-        //      the last CTA of the next chain as well: the exchanges of a chain group would serialise).
-        //      Low-latency protocol: every 8-byte word carries 4 bytes of payload and the 4-byte sequence
-        //      number of this exchange, so the words may arrive in any order and no fence / separate flag
-        //      (a second NVLink round trip) is needed. ----
-        const unsigned seq = xch.seq[c] + 1u;  // every thread reads it before thread 0 writes it back (barrier below)
-        if (tid < 32 * xch.world) {
-          const int r = tid >> 5, j = tid & 31;
-          const double val = s_red[0][j >> 1];
-          const unsigned half = (j & 1) ? (unsigned)__double2hiint(val) : (unsigned)__double2loint(val);
-          const unsigned long long word = ((unsigned long long)seq << 32) | half;
-          unsigned long long* dst = xch.buf[r] + ((((size_t)(seq & 1u) * xch.world + xch.rank) * xch.cmax + c) << 5) + j;
-          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
-        }
-        __syncthreads();
-        if (tid == 0) {
-          xch.seq[c] = seq;
-          s_pend[s_npend] = c;
-          s_pend_seq[s_npend] = seq;
-          ++s_npend;
-        }
-      } else if (warp == 0) {
-        finalize_chain(c, step, nsteps);
-      }
+      if (warp == 0) finalize_chain(c, step, nsteps);
     }
     if (s_last) PHASE(11);
     PHASE(8);
@@ -671,10 +666,51 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
     }  // step
   }
 
-  // ---- sharded: collect the peers' sums of the chains this CTA finished last, add the `world`
-  //      contributions in rank order (bitwise the same total on every rank) and finalise ----
-  if (xch.world > 1) {
-    const int npend = s_npend;
+  // ---- the chains this CTA finished last: ordered reduction over the tiles' partials, then either the
+  //      finaliser, or (individuals sharded over GPUs) the exchange with the peers first ----
+  if (tid == 0 && tk_valid && tk_prev == (unsigned)(ntiles - 1)) s_pend[s_npend++] = tk_c;
+  __syncthreads();
+  const int npend = s_npend;
+  const bool sharded = xch.world > 1;
+  PHASE(7);
+  for (int pi = 0; pi < npend; ++pi) {
+    const int c = s_pend[pi];
+    if (!sharded) {
+      load_aux(c);
+      if (!TRAJ && warp == 1 && lane < 13) s_th[lane] = load_param(theta, theta_is_q, c, lane);  // as warp 6 computed it
+    }
+    sum_partials(c, sharded);
+    PHASE(10);
+    if (!sharded) {
+      if (warp == 0) finalize_chain(c, 0, 1);
+      __syncthreads();
+      continue;
+    }
+    // ---- post this rank's 16 sums into every peer's buffer and move on to the next pending chain; the peers'
+    //      sums are collected below.  Low-latency protocol: every 8-byte word carries 4 bytes of payload and
+    //      the 4-byte sequence number of this exchange, so the words may arrive in any order and no fence /
+    //      separate flag (a second NVLink round trip) is needed. ----
+    const unsigned seq = xch.seq[c] + 1u;  // every thread reads it before thread 0 writes it back (barrier below)
+    if (tid < 32 * xch.world) {
+      const int r = tid >> 5, j = tid & 31;
+      const double val = s_red[0][j >> 1];
+      const unsigned half = (j & 1) ? (unsigned)__double2hiint(val) : (unsigned)__double2loint(val);
+      const unsigned long long word = ((unsigned long long)seq << 32) | half;
+      unsigned long long* dst = xch.buf[r] + ((((size_t)(seq & 1u) * xch.world + xch.rank) * xch.cmax + c) << 5) + j;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      xch.seq[c] = seq;
+      s_pend_seq[pi] = seq;
+    }
+  }
+  if (npend) PHASE(11);
+
+  // ---- sharded: collect the peers' sums, add the `world` contributions in rank order (bitwise the same
+  //      total on every rank) and finalise ----
+  if (sharded) {
+    __syncthreads();
     for (int pi = 0; pi < npend; ++pi) {
       const int c = s_pend[pi];
       const unsigned seq = s_pend_seq[pi];
