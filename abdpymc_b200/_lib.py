@@ -65,6 +65,8 @@ SIGNATURES = {
     "abd_cond_logodds": (C.c_int, [H, C.c_int] + [C.c_void_p] * 7),
     "abd_gibbs_sweep": (C.c_int, [H, C.c_int] + [C.c_void_p] * 5 + [C.c_uint64, C.c_uint64, C.c_int, C.c_double, C.c_void_p]),
     "abd_deterministics": (C.c_int, [H, C.c_int] + [C.c_void_p] * 6),
+    "abd_loglik_rows": (C.c_int, [H, C.c_int] + [C.c_void_p] * 5),
+    "abd_loglik_rows_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 6),
     "abd_sums_dev": (C.c_int, [H, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "abd_finalize_loglik_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 5),
     "abd_finalize_logp_dev": (C.c_int, [H, C.c_int] + [C.c_void_p] * 5),

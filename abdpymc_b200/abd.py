@@ -319,6 +319,25 @@ if HAVE_PYMC:  # pragma: no cover
             return Competence.COMPATIBLE if var.name in ("i_raw", "ab_s_waner") else Competence.INCOMPATIBLE
 
 
+def pointwise_log_likelihood(engine, posterior, batch=64):
+    """The InferenceData's ``log_likelihood`` group for the two observed nodes of the reference model
+    (``it_s_lik`` / ``it_n_lik``, abd.py:459-469), which the GPU model replaces by one ``pm.Potential``:
+    {"it_s_lik": (chain, draw, R_s), "it_n_lik": (chain, draw, R_n)} from posterior draws of the 13 likelihood
+    scalars, ``i_raw`` (chain, draw, gap, ind) and ``ab_s_waner`` (chain, draw, ind) -- what ``az.loo`` / ``az.waic``
+    read.  ``posterior``: mapping name -> array (an InferenceData's posterior group works)."""
+    th = np.stack([np.asarray(posterior[n], dtype=np.float64) for n in THETA13], axis=-1)      # (chain, draw, 13)
+    i_raw, w = np.asarray(posterior["i_raw"]), np.asarray(posterior["ab_s_waner"])
+    n_c, n_d = th.shape[:2]
+    flat_th = th.reshape(-1, 13)
+    flat_i = i_raw.reshape((-1,) + i_raw.shape[2:])
+    flat_w = w.reshape((-1,) + w.shape[2:])
+    ls, ln = np.empty((n_c * n_d, engine.R_s)), np.empty((n_c * n_d, engine.R_n))
+    for k in range(0, n_c * n_d, batch):
+        a, b = engine.loglik_rows(flat_th[k:k + batch], flat_i[k:k + batch] != 0, flat_w[k:k + batch] != 0)
+        ls[k:k + batch], ln[k:k + batch] = np.atleast_2d(a), np.atleast_2d(b)
+    return {"it_s_lik": ls.reshape(n_c, n_d, -1), "it_n_lik": ln.reshape(n_c, n_d, -1)}
+
+
 # ------------------------------------------------------------------------------------------
 # abdpymc-infer
 # ------------------------------------------------------------------------------------------
@@ -403,16 +422,21 @@ def _write_builtin(args, data, res, post, last):
             import arviz as az
 
             posterior = dict(post)
-            dims = {}
+            dims, extra = {}, {}
+            sample_stats = {"acceptance_rate": res.accept, "lp": res.logp, **res.stats}
             if res.thinned:  # the Deterministics only exist for the kept draws: thin everything alike
                 keep = res.thinned["draw"]
                 posterior = {k: v[:, keep] for k, v in posterior.items()}
+                sample_stats = {k: v[:, keep] for k, v in sample_stats.items()}
                 for name in ("i", "ab_n_mu", "ab_s_mu"):
                     posterior[name] = res.thinned[name]
                     dims[name] = list(GAP_IND)
-            sample_stats = {"acceptance_rate": res.accept, "lp": res.logp, **res.stats}
+                if "it_s_lik" in res.thinned:   # the reference's observed nodes (abd.py:459-469)
+                    extra["log_likelihood"] = {k: res.thinned[k] for k in ("it_s_lik", "it_n_lik")}
+                    if hasattr(data, "rows"):
+                        extra["observed_data"] = {"it_s_lik": data.rows(1)[1], "it_n_lik": data.rows(0)[1]}
             idata = az.from_dict(posterior=posterior, sample_stats=sample_stats, dims=dims,
-                                 coords={"gap": np.arange(data.n_gaps), "ind": np.arange(data.n_inds)})
+                                 coords={"gap": np.arange(data.n_gaps), "ind": np.arange(data.n_inds)}, **extra)
             az.to_netcdf(idata, out)
             print(f"PyMC not installed: sampled with the built-in HMC+Gibbs driver in {res.wall_s:.1f} s; wrote {out}",
                   file=sys.stderr)
@@ -426,7 +450,10 @@ def _write_builtin(args, data, res, post, last):
                         sample_stats_acceptance_rate=res.accept, sample_stats_lp=res.logp,
                         sample_stats_step_size=np.broadcast_to(res.step_size[:, None], res.accept.shape),
                         **{f"sample_stats_{k}": v for k, v in res.stats.items()},
-                        **{("thinned_draw" if k == "draw" else k): v for k, v in res.thinned.items()})
+                        **({"observed_data_it_s_lik": data.rows(1)[1], "observed_data_it_n_lik": data.rows(0)[1]}
+                           if hasattr(data, "rows") else {}),
+                        **{("thinned_draw" if k == "draw" else ("log_likelihood_" + k if k.endswith("_lik") else k)): v
+                           for k, v in res.thinned.items()})
     print(f"PyMC not installed: sampled with the built-in HMC+Gibbs driver in {res.wall_s:.1f} s; wrote {out}", file=sys.stderr)
 
 

@@ -209,8 +209,10 @@ int build_rows(abd_handle* h, int a, int64_t R, const double* x, const double* o
   std::vector<uint32_t> rowcell((size_t)R + 4, 0u), cmeta;
   std::vector<int>& cp = h->h_cp[a];
   cp.assign((size_t)N + 1, 0);
+  std::vector<int> perm((size_t)R);
   for (int64_t k = 0; k < R; ++k) {
     const int64_t r = order[(size_t)k];
+    perm[(size_t)k] = (int)r;
     xs[(size_t)k] = x[r];
     ods[(size_t)k] = od[r];
     const uint32_t m = ((uint32_t)ind[r] << 6) | (uint32_t)gap[r];
@@ -233,6 +235,11 @@ int build_rows(abd_handle* h, int a, int64_t R, const double* x, const double* o
   if ((rc = upload(h, &d_meta, meta))) return rc;
   if ((rc = upload(h, &d_rowcell, rowcell))) return rc;
   if ((rc = upload(h, &d_cmeta, cmeta))) return rc;
+  {
+    int* d_perm;
+    if ((rc = upload(h, &d_perm, perm))) return rc;
+    h->dc.rowperm[a] = d_perm;
+  }
   h->dc.rcx[a] = nullptr;
   if (h->fx) {
     std::vector<uint32_t> rcx((size_t)R + 4, 0u);
@@ -374,7 +381,10 @@ int ensure_chains(abd_handle* h, int C) {
 void plan_grid(const abd_handle* h, int C, int ctas_per_sm, int* want_tiles, int* chains_per_cta) {
   const double rows = (double)(h->R[0] + h->R[1]);
   const int target = h->tile_rows_override > 0 ? h->tile_rows_override : 2200;
-  int cpc = h->chains_per_cta_override > 0 ? h->chains_per_cta_override : (C >= 32 ? 4 : 1);
+  // chains looped over inside one CTA (the staged tile is reused): measured at 10k / 12.5k individuals, 32 chains run
+  // 4 - 11 % faster with 2 per CTA than with 4 (twice the waves: shorter start-up and drain), 128 chains 5 % faster
+  // with 4 than with 2 (tools/tune.py sums)
+  int cpc = h->chains_per_cta_override > 0 ? h->chains_per_cta_override : (C >= 64 ? 4 : (C >= 32 ? 2 : 1));
   cpc = std::min(cpc, C);
   cpc = std::min(cpc, kMaxChainsPerCta);  // a CTA remembers at most this many chains it finished last (k_sums: s_pend)
   const int groups = (C + cpc - 1) / cpc;
@@ -710,7 +720,7 @@ struct CacheHeader {
   uint32_t ind_offset, pad;
   double xlev[kMaxXLevels];
 };
-constexpr int kCacheVersion = 1;
+constexpr int kCacheVersion = 2;
 
 struct CacheIo {
   FILE* f = nullptr;
@@ -763,6 +773,9 @@ int cache_body(abd_handle* h, CacheIo& io, const CacheHeader& hd) {
     double *x = (double*)h->dc.x[a], *od = (double*)h->dc.od[a];
     uint32_t *meta = (uint32_t*)h->dc.meta[a], *rowcell = (uint32_t*)h->dc.rowcell[a], *cmeta = (uint32_t*)h->dc.cmeta[a];
     uint32_t* rcx = (uint32_t*)h->dc.rcx[a];
+    int* perm = (int*)h->dc.rowperm[a];
+    if ((rc = cache_array(h, io, &perm, R))) return rc;
+    h->dc.rowperm[a] = perm;
     if ((rc = cache_array(h, io, &rp, N + 1, &h->h_rp[a]))) return rc;
     if ((rc = cache_array(h, io, &x, R + 2)) || (rc = cache_array(h, io, &od, R + 2))) return rc;
     if ((rc = cache_array(h, io, &meta, R + 4)) || (rc = cache_array(h, io, &rowcell, R + 4))) return rc;
@@ -1257,7 +1270,52 @@ int abd_deterministics(abd_handle* h, int C, const double* theta13, const int8_t
   return ABD_OK;
 }
 
+int abd_loglik_rows(abd_handle* h, int C, const double* theta13, const int8_t* i_raw, const int8_t* waner, double* out_s,
+                    double* out_n) {
+  PROLOGUE(h, C);
+  if (!theta13) return fail(ABD_ERR_INVALID, "NULL argument");
+  int rc = stage_state(h, C, i_raw, waner);
+  if (rc) return rc;
+  std::memcpy(h->h_pin, theta13, (size_t)C * 13 * sizeof(double));
+  CU(cudaMemcpyAsync(h->d_theta, h->h_pin, (size_t)C * 13 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  double *d_s = nullptr, *d_n = nullptr;
+  if (out_s && (rc = dev_alloc(h, &d_s, (size_t)C * h->R[1], false))) return rc;
+  if (out_n && (rc = dev_alloc(h, &d_n, (size_t)C * h->R[0], false))) {
+    if (d_s) cudaFree(d_s);
+    return rc;
+  }
+  rc = abd_loglik_rows_dev(h, C, h->d_theta, h->d_iraw, h->d_waner, d_s, d_n, h->stream);
+  cudaError_t e = cudaSuccess;
+  if (!rc && out_s) e = cudaMemcpyAsync(out_s, d_s, (size_t)C * h->R[1] * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (!rc && e == cudaSuccess && out_n)
+    e = cudaMemcpyAsync(out_n, d_n, (size_t)C * h->R[0] * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e2 = cudaStreamSynchronize(h->stream);
+  if (d_s) cudaFree(d_s);
+  if (d_n) cudaFree(d_n);
+  if (rc) return rc;
+  CU(e);
+  CU(e2);
+  return ABD_OK;
+}
+
 // ---- device-pointer variants ----------------------------------------------------------------
+int abd_loglik_rows_dev(abd_handle* h, int C, const double* theta13, const int8_t* i_raw, const int8_t* waner, double* out_s,
+                        double* out_n, void* stream) {
+  PROLOGUE(h, C);
+  if (!theta13 || !i_raw || !waner) return fail(ABD_ERR_INVALID, "NULL argument");
+  const cudaStream_t st = (cudaStream_t)stream;
+  for (int a = 0; a < 2; ++a) {
+    double* out = a ? out_s : out_n;
+    if (!out || h->R[a] == 0) continue;
+    dim3 grid((unsigned)((h->R[a] + 255) / 256), C);
+    if (h->wide) k_loglik_rows<uint64_t><<<grid, 256, 0, st>>>(h->dc, a, (int)h->R[a], theta13, i_raw, waner, out);
+    else k_loglik_rows<uint32_t><<<grid, 256, 0, st>>>(h->dc, a, (int)h->R[a], theta13, i_raw, waner, out);
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  return ABD_OK;
+}
+
 int abd_sums_dev(abd_handle* h, int C, const double* theta, int theta_is_q17, const int8_t* i_raw,
                  const int8_t* waner, double* sums, void* stream) {
   PROLOGUE(h, C);

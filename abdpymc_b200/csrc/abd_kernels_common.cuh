@@ -25,6 +25,7 @@ struct DevCohort {
   const uint32_t* meta[2];     // per row: individual << 6 | gap
   const uint32_t* rowcell[2];  // per row: index of its (individual, gap) cell
   const uint32_t* cmeta[2];    // per cell: individual << 6 | gap
+  const int* rowperm[2];       // per (sorted) row: its index among the antigen's rows as the caller passed them
   Chunks ch;
 };
 

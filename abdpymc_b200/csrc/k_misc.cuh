@@ -202,6 +202,38 @@ k_determ_accum(const DevCohort dc, const int C, const double* __restrict__ theta
   }
 }
 
+// Pointwise log-likelihood of every OD row of one antigen (what PyMC records in the InferenceData's log_likelihood
+// group for the observed nodes it_n_lik / it_s_lik, abd.py:459-469), written in the caller's row order.  One thread per
+// (row, chain); a post-processing kernel (recorded draws only), not part of the sampling loop.
+template <typename M>
+__global__ void __launch_bounds__(256)
+k_loglik_rows(const DevCohort dc, const int a, const int R, const double* __restrict__ theta13,
+              const int8_t* __restrict__ i_raw, const int8_t* __restrict__ waner, double* __restrict__ out) {
+  const int c = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = dc.G, N = dc.N;
+  __shared__ double s_th[16];
+  if (threadIdx.x < 13) s_th[threadIdx.x] = theta13[(size_t)c * 13 + threadIdx.x];
+  __syncthreads();
+  if (r >= R) return;
+  const uint32_t mt = dc.meta[a][r];
+  const int n = (int)(mt >> 6), t = (int)(mt & 63u);
+  M raw = 0;
+  const int8_t* col = i_raw + (size_t)c * G * N + n;
+  for (int g = 0; g < G; ++g) raw |= (M)(col[(size_t)g * N] != 0) << g;   // (the whole column: the constraints are per chunk)
+  const M inf = constrain<M>(raw, reinterpret_cast<const M*>(dc.pcr)[n], dc.ch) & low_mask<M>(t);
+  const M vac = a ? (reinterpret_cast<const M*>(dc.vac)[n] & low_mask<M>(t)) : (M)0;
+  const int w = waner[(size_t)c * N + n] != 0;
+  const double rho = a ? (w ? s_th[S_RHO] : 1.0) : s_th[N_RHO];
+  double T = 0.0;
+  for (int g = 0; g <= t; ++g) T = T * rho + (double)(((inf >> g) & 1) + ((vac >> g) & 1));   // abd.py:277-293
+  const double P = (inf | vac) ? 1.0 : 0.0;
+  const double m = a ? s_th[S_INIT] + s_th[S_PERM] * P + T : s_th[N_INIT] + s_th[N_PERM] * P + s_th[N_TEMP] * T;
+  const double b = s_th[a ? S_B : N_B], d = s_th[a ? S_D : N_D], sg = s_th[a ? S_SIGMA : N_SIGMA];
+  const double pred = d / (1.0 + exp(-b * (dc.x[a][r] - m)));
+  const double z = (dc.od[a][r] - pred) / sg;
+  out[(size_t)c * R + dc.rowperm[a][r]] = -0.5 * z * z - kHalfLog2Pi - log(sg);
+}
+
 // int8 boundary state -> packed resident state (see PackedState): one thread per (individual, chain)
 template <typename M>
 __global__ void __launch_bounds__(128)

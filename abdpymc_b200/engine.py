@@ -299,6 +299,16 @@ class AbdEngine:
         check(self._lib.abd_deterministics(self._h, C_, _ptr(th), _ptr(i8), _ptr(w8), _ptr(oi), _ptr(mn), _ptr(ms)))
         return (oi[0], mn[0], ms[0]) if single else (oi, mn, ms)
 
+    def loglik_rows(self, theta13, i_raw=None, waner=None):
+        """Pointwise log-likelihood of every OD row, (it_s_lik (C, R_s), it_n_lik (C, R_n)), rows in the cohort's order
+        per antigen: the InferenceData's log_likelihood group (abd.py:459-469)."""
+        C_, single = self._chains(theta13, 13)
+        th = _f64(theta13, (C_, 13))
+        i8, w8 = self._state(C_, i_raw, waner)
+        ls, ln = np.empty((C_, self.R_s)), np.empty((C_, self.R_n))
+        check(self._lib.abd_loglik_rows(self._h, C_, _ptr(th), _ptr(i8), _ptr(w8), _ptr(ls), _ptr(ln)))
+        return (ls[0], ln[0]) if single else (ls, ln)
+
     # ------------------------------------------------------------------------------ device API
     # Arguments are raw device addresses (ints, e.g. torch.Tensor.data_ptr()) and a stream handle.
     def state_dev(self, n_chains):
@@ -383,6 +393,9 @@ class AbdEngine:
         out = np.zeros(9, np.uint64)
         check(self._lib.abd_xch_stats(self._h, out.ctypes.data, int(reset)))
         return out[:8].copy(), int(out[8])
+
+    def loglik_rows_dev(self, C_, theta13, i_raw, waner, out_s, out_n, stream=0):
+        check(self._lib.abd_loglik_rows_dev(self._h, C_, theta13, i_raw, waner, out_s, out_n, stream))
 
     def deterministics_dev(self, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream=0):
         check(self._lib.abd_deterministics_dev(self._h, C_, theta13, i_raw, waner, out_i, out_mu_n, out_mu_s, stream))

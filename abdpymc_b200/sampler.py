@@ -148,6 +148,19 @@ class AbdTarget:
                                        self._stream())
         return oi, mn, ms
 
+    def loglik_rows(self, q):
+        """Pointwise log-likelihood of the current state: (it_s_lik (C, R_s), it_n_lik (C, R_n)) device tensors."""
+        C, e = self.C, self.engine
+        if not hasattr(self, "_llr"):
+            self._llr = (torch.empty(C, e.R_s, dtype=torch.float64, device=self.device),
+                         torch.empty(C, e.R_n, dtype=torch.float64, device=self.device))
+        kinds = torch.tensor([{None: 0, "log": 1, "logodds": 2}[Q17_RV[j][1]] for j in Q_OF_THETA], device=self.device)
+        y = q.index_select(1, torch.tensor(Q_OF_THETA, device=self.device))
+        th = torch.where(kinds == 1, torch.exp(y), torch.where(kinds == 2, torch.sigmoid(y), y)).contiguous()
+        ls, ln = self._llr
+        e.loglik_rows_dev(C, th.data_ptr(), self.d_i, self.d_w, ls.data_ptr(), ln.data_ptr(), self._stream())
+        return ls, ln
+
     def accumulate_deterministics(self, q, sums):
         """Streaming posterior summaries: adds this state's i, ab_n_mu, ab_s_mu, summed over the chains,
         to ``sums`` (a dict of (G, N) float64 device tensors, created on first use) in ONE launch --
@@ -252,8 +265,11 @@ class _Thinned:
 
     def __init__(self, target, cfg):
         n_keep = 0
+        self.with_ll = hasattr(target, "loglik_rows")
         if cfg.thinned_deterministics and hasattr(target, "deterministics"):
             per_draw = 9 * target.C * target.engine.G * target.engine.N           # bytes per kept draw
+            if self.with_ll:
+                per_draw += 4 * target.C * (target.engine.R_s + target.engine.R_n)
             n_keep = int(min(cfg.thinned_deterministics, cfg.draws, max(1, (4 << 30) // per_draw)))  # at most 4 GiB
         self.keep = sorted(set(np.linspace(0, cfg.draws - 1, n_keep).round().astype(int).tolist())) if n_keep else []
         self.pos = {k: j for j, k in enumerate(self.keep)}
@@ -262,6 +278,9 @@ class _Thinned:
             self.i = torch.empty(len(self.keep), C, G, N, dtype=torch.int8, device=dev)
             self.mn = torch.empty(len(self.keep), C, G, N, dtype=torch.float32, device=dev)
             self.ms = torch.empty(len(self.keep), C, G, N, dtype=torch.float32, device=dev)
+            if self.with_ll:   # the log_likelihood group of the kept draws (observed nodes it_s_lik / it_n_lik, abd.py:459-469)
+                self.ls = torch.empty(len(self.keep), C, target.engine.R_s, dtype=torch.float32, device=dev)
+                self.ln = torch.empty(len(self.keep), C, target.engine.R_n, dtype=torch.float32, device=dev)
 
     def record(self, target, k, q):
         j = self.pos.get(k)
@@ -270,12 +289,19 @@ class _Thinned:
             self.i[j].copy_(oi)
             self.mn[j].copy_(mn)
             self.ms[j].copy_(ms)
+            if self.with_ll:
+                ls, ln = target.loglik_rows(q)
+                self.ls[j].copy_(ls)
+                self.ln[j].copy_(ln)
 
     def result(self):
         if not self.keep:
             return {}
-        return {"draw": np.array(self.keep), "i": self.i.permute(1, 0, 2, 3).cpu().numpy(),
-                "ab_n_mu": self.mn.permute(1, 0, 2, 3).cpu().numpy(), "ab_s_mu": self.ms.permute(1, 0, 2, 3).cpu().numpy()}
+        out = {"draw": np.array(self.keep), "i": self.i.permute(1, 0, 2, 3).cpu().numpy(),
+               "ab_n_mu": self.mn.permute(1, 0, 2, 3).cpu().numpy(), "ab_s_mu": self.ms.permute(1, 0, 2, 3).cpu().numpy()}
+        if self.with_ll:
+            out["it_s_lik"], out["it_n_lik"] = self.ls.permute(1, 0, 2).cpu().numpy(), self.ln.permute(1, 0, 2).cpu().numpy()
+        return out
 
 
 def _sample_fused(target, q0, cfg, progress, nuts=False):

@@ -175,6 +175,15 @@ int abd_gibbs_sweep(abd_handle* h, int n_chains, const double* theta13, const do
 int abd_deterministics(abd_handle* h, int n_chains, const double* theta13, const int8_t* i_raw,
                        const int8_t* waner, int8_t* out_i, double* out_mu_n, double* out_mu_s);
 
+/* Pointwise log-likelihood of every OD row: out_s[c][r] / out_n[c][r] = the Normal log-density of row r of the
+ * S / N antigen, in the order the rows were passed to abd_create -- what PyMC stores in the InferenceData's
+ * log_likelihood group for the observed nodes it_s_lik / it_n_lik (abd.py:459-469; az.loo / az.waic read it).
+ * Either output may be NULL.  abd_loglik_rows_dev: device pointers.                                      */
+int abd_loglik_rows(abd_handle* h, int n_chains, const double* theta13, const int8_t* i_raw,
+                    const int8_t* waner, double* out_s, double* out_n);
+int abd_loglik_rows_dev(abd_handle* h, int n_chains, const double* theta13, const int8_t* i_raw,
+                        const int8_t* waner, double* out_s, double* out_n, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Device-pointer variants: every pointer is a device pointer, `stream` is a cudaStream_t.
  * Work is enqueued on `stream`; nothing is synchronised.

@@ -109,6 +109,35 @@ def test_cond_logodds_vs_reference_goldens(Engine, goldens, cohorts):
     assert n >= 8
 
 
+@pytest.mark.parametrize("name,splits", [("test_cohort", (14, 20)), ("cohort", ())])
+def test_pointwise_log_likelihood_vs_oracle(Engine, cohorts, name, splits):
+    """abd_loglik_rows: the log-density of every OD row (the InferenceData's log_likelihood group for the reference's
+    observed nodes it_s_lik / it_n_lik, abd.py:459-469), in the cohort's own row order, and its sum = the loglik."""
+    from abdpymc_b200 import abd
+
+    co = cohorts[name]
+    rng = np.random.default_rng(6)
+    C = 3
+    q, i_raw, w = draw_points(rng, co.n_gaps, co.n_inds, C)
+    vals = [ora.backward(q[k])[0] for k in range(C)]
+    th = np.array([[v[n] for n in ora.THETA13] for v in vals])
+    o = ora.Oracle(co, splits=splits, dense=False)
+    with Engine(co, splits=splits) as eng:
+        ls, ln = eng.loglik_rows(th, i_raw, w)
+        ll, _, _ = eng.loglik_grad(th, i_raw, w)
+        # the post-hoc helper for an InferenceData-like posterior (chain, draw, ...)
+        post = {n: th[None, :, k] for k, n in enumerate(ora.THETA13)}
+        post.update(i_raw=i_raw[None].astype(np.int64), ab_s_waner=w[None].astype(np.int64))
+        pw = abd.pointwise_log_likelihood(eng, post)
+    for c in range(C):
+        ref = o.loglik_rows(th[c], i_raw[c], w[c])
+        np.testing.assert_allclose(ls[c], ref["s"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(ln[c], ref["n"], rtol=1e-10, atol=1e-10)
+        assert abs(ls[c].sum() + ln[c].sum() - ll[c]) <= 1e-10 * abs(ll[c])
+    assert pw["it_s_lik"].shape == (1, C, o.rows["s"]["x"].size) and np.array_equal(pw["it_s_lik"][0], ls)
+    assert np.array_equal(pw["it_n_lik"][0], ln)
+
+
 def test_constrained_infections_vs_reference_kats(Engine, kats):
     """K1 -> K2 -> K3 through the deterministics kernel on the reference-generated cases."""
     from abdpymc_b200.cohort import CohortArrays

@@ -99,7 +99,12 @@ graph = torch.cuda.CUDAGraph()
 with torch.cuda.graph(graph, stream=side):
     for _ in range(64):
         se_fused.logp_dlogp(q)
+se_fused.engine.xch_stats(reset=True)
 us_graph = timed(graph.replay, 20) / 64
+ns_wait, n_x = se_fused.engine.xch_stats(reset=True)
+wait_vec = torch.tensor(ns_wait[:world].astype(np.float64) / max(n_x, 1) / 1e3, device=dev)   # us waited for each peer
+all_wait = [torch.empty_like(wait_vec) for _ in range(world)]
+dist.all_gather(all_wait, wait_vec)
 se_fused.engine.xch_status()
 lp_g = se_fused.logp_dlogp(q)[0]
 torch.cuda.synchronize()
@@ -110,7 +115,8 @@ dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(json.dumps({"ok": bool(flag.item()), "world": world, "n_inds": n_inds, "chains": C, "rel_err_logp_fused_vs_nccl": e_lp,
                       "rel_err_grad_fused_vs_nccl": e_g, "rel_err_vs_unsharded": e_full, "us_per_eval_nccl": us_nccl,
-                      "us_per_eval_fused": us_fused, "us_per_eval_fused_graph": us_graph}))
+                      "us_per_eval_fused": us_fused, "us_per_eval_fused_graph": us_graph,
+                      "wait_us_rank_by_peer": [[round(float(v), 2) for v in w_] for w_ in all_wait]}))
 for se in (se_nccl, se_fused):
     se.close()
 dist.destroy_process_group()
