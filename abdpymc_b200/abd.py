@@ -376,7 +376,6 @@ def infer_builtin(cohort, splits, ignore_pcrpos, tune, draws, chains=4, device=0
         target = ShardedTarget(sh, chains, np.zeros((chains, G, N), np.int8), np.zeros((chains, N), np.int8), seed=seed,
                                gibbs_mode=gibbs_mode)
         cfg.thinned_deterministics = 0      # (G, N) draws of a sharded cohort are not gathered; the means are
-        cfg.kernel = "hmc"
         res = sample(target, torch.from_numpy(q0).to(target.device), cfg, progress=progress if rank == 0 else None)
         li, lw = target.state()
         post_last = dict(i_raw=target.gather_individuals(li), ab_s_waner=target.gather_individuals(lw))

@@ -76,6 +76,12 @@ def allreduce_sums(sums, group=None):
     return sums
 
 
+def _nuts_mixin():
+    from .sampler import DeviceNutsMixin
+
+    return DeviceNutsMixin
+
+
 class ShardedEngine:
     """Individual-sharded evaluation of the joint logp + gradient on this rank's GPU.
 
@@ -180,7 +186,7 @@ class ShardedEngine:
         self.engine.close()
 
 
-class ShardedTarget:
+class ShardedTarget(_nuts_mixin()):
     """The posterior of an INDIVIDUAL-SHARDED cohort as a sampler target (same interface as
     ``sampler.AbdTarget``): every rank holds a contiguous block of individuals and the matching slice of
     every chain's binary state; the 17 scalars, their momenta, step sizes and the metric are replicated.
@@ -205,8 +211,10 @@ class ShardedTarget:
         self.dim = 17
         self.out = torch.zeros(n_chains, dtype=torch.float64, device=self.device)
         self.outg = torch.zeros(n_chains, 17, dtype=torch.float64, device=self.device)
-        if sharded.fused:  # the device-resident transition of sampler._sample_fused
+        if sharded.fused:  # the device-resident transitions of sampler._sample_fused (HMC and No-U-Turn)
             self.hmc_begin, self.hmc_end = self._hmc_begin, self._hmc_end
+        else:              # host-driven loop: hide the device tree methods
+            self.nuts_begin = None
 
     def _stream(self):
         import torch

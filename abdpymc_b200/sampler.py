@@ -31,7 +31,33 @@ import torch
 from .engine import Q17_RV, Q_OF_THETA, backward
 
 
-class AbdTarget:
+class DeviceNutsMixin:
+    """The No-U-Turn tree on the device (abd_nuts_*_dev) for a target with ``engine``, ``C``, ``seed``, ``device``
+    and ``_stream()``: one tree launch per leaf besides the leapfrog launch."""
+
+    def nuts_scratch(self, max_depth):
+        f64 = dict(dtype=torch.float64, device=self.device)
+        return (torch.zeros(self.C, self.engine.nuts_state_doubles(max_depth), **f64), torch.zeros(self.C, **f64),
+                torch.zeros(max_depth + 1, dtype=torch.int32, device=self.device))
+
+    def nuts_begin(self, D, q, grad, logp, linv_t, eps, it, state, qw, pw, gw, eps_signed, any_active):
+        self.engine.nuts_begin_dev(self.C, D, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), linv_t.data_ptr(), eps.data_ptr(),
+                                   self.seed, it, state.data_ptr(), qw.data_ptr(), pw.data_ptr(), gw.data_ptr(),
+                                   eps_signed.data_ptr(), any_active.data_ptr(), self._stream())
+
+    def nuts_leaf(self, D, j, n, qw, pw, gw, lpw, inv_mass, eps, it, state, eps_signed, any_active):
+        self.engine.nuts_leaf_dev(self.C, D, j, n, qw.data_ptr(), pw.data_ptr(), gw.data_ptr(), lpw.data_ptr(), inv_mass.data_ptr(),
+                                  eps.data_ptr(), self.seed, it, state.data_ptr(), eps_signed.data_ptr(), any_active.data_ptr(),
+                                  self._stream())
+
+    def nuts_end(self, D, q, grad, logp, state, acc, depth, div, da, eps, adapt, target_accept):
+        self.engine.nuts_end_dev(self.C, D, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), state.data_ptr(), acc.data_ptr(),
+                                 depth.data_ptr(), div.data_ptr(), da.data_ptr(), eps.data_ptr(), adapt, target_accept,
+                                 self._stream())
+
+
+
+class AbdTarget(DeviceNutsMixin):
     """The antibody-dynamics posterior on one GPU: joint logp + gradient over q17 for C chains
     with the chain state (i_raw, waner) resident on the device, and the Gibbs sweep over it."""
 
@@ -89,27 +115,6 @@ class AbdTarget:
         self.engine.hmc_end_dev(self.C, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), qw.data_ptr(), pw.data_ptr(),
                                 gw.data_ptr(), lpw.data_ptr(), inv_mass.data_ptr(), h0.data_ptr(), self.seed, it,
                                 acc.data_ptr(), da.data_ptr(), eps.data_ptr(), adapt, target_accept, self._stream())
-
-    # ---- No-U-Turn tree on the device (abd_nuts_*_dev): one launch per leaf besides the leapfrog ----
-    def nuts_scratch(self, max_depth):
-        f64 = dict(dtype=torch.float64, device=self.device)
-        return (torch.zeros(self.C, self.engine.nuts_state_doubles(max_depth), **f64), torch.zeros(self.C, **f64),
-                torch.zeros(max_depth + 1, dtype=torch.int32, device=self.device))
-
-    def nuts_begin(self, D, q, grad, logp, linv_t, eps, it, state, qw, pw, gw, eps_signed, any_active):
-        self.engine.nuts_begin_dev(self.C, D, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), linv_t.data_ptr(), eps.data_ptr(),
-                                   self.seed, it, state.data_ptr(), qw.data_ptr(), pw.data_ptr(), gw.data_ptr(),
-                                   eps_signed.data_ptr(), any_active.data_ptr(), self._stream())
-
-    def nuts_leaf(self, D, j, n, qw, pw, gw, lpw, inv_mass, eps, it, state, eps_signed, any_active):
-        self.engine.nuts_leaf_dev(self.C, D, j, n, qw.data_ptr(), pw.data_ptr(), gw.data_ptr(), lpw.data_ptr(), inv_mass.data_ptr(),
-                                  eps.data_ptr(), self.seed, it, state.data_ptr(), eps_signed.data_ptr(), any_active.data_ptr(),
-                                  self._stream())
-
-    def nuts_end(self, D, q, grad, logp, state, acc, depth, div, da, eps, adapt, target_accept):
-        self.engine.nuts_end_dev(self.C, D, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), state.data_ptr(), acc.data_ptr(),
-                                 depth.data_ptr(), div.data_ptr(), da.data_ptr(), eps.data_ptr(), adapt, target_accept,
-                                 self._stream())
 
     def gibbs(self, q, sweep):
         q = q.contiguous()
@@ -514,7 +519,8 @@ def sample(target, q0, cfg: SamplerConfig = SamplerConfig(), progress=None) -> S
     """Run tune + draws iterations of [HMC on q | binaries] then [Gibbs on binaries | q]."""
     if cfg.kernel == "hmc" and cfg.persistent_trajectories and hasattr(target, "hmc_begin") and target.fits_persistent():
         return _sample_fused(target, q0, cfg, progress)
-    if cfg.kernel == "nuts" and cfg.persistent_trajectories and hasattr(target, "nuts_begin") and target.fits_persistent():
+    if (cfg.kernel == "nuts" and cfg.persistent_trajectories and getattr(target, "nuts_begin", None) is not None
+            and target.fits_persistent()):
         return _sample_fused(target, q0, cfg, progress, nuts=True)
     dev = q0.device
     C, D = q0.shape

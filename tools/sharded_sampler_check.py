@@ -47,6 +47,7 @@ cfg = SamplerConfig(tune=tune, draws=draws, seed=5, record_deterministics_every=
 # a short run from a small fixed step for the step-by-step comparison with the unsharded sampler (rounding
 # differences of the tile sums grow along a long adapted run; both remain valid chains)
 cfg_short = SamplerConfig(tune=3, draws=8, seed=5, init_step=0.002, record_deterministics_every=1)
+cfg_nuts = SamplerConfig(tune=2, draws=6, seed=5, init_step=0.002, kernel="nuts", max_treedepth=4)
 ok, info = True, {}
 
 runs = {}
@@ -58,7 +59,8 @@ for name, fused in (("fused", True), ("nccl", False)):
     state = (tgt.gather_individuals(li), tgt.gather_individuals(lw))
     means = {k: tgt.gather_individuals(v) for k, v in short.means.items()}
     res = sample(tgt, torch.from_numpy(q0).to(dev), cfg)
-    runs[name] = (res, state, means, short)
+    nuts = sample(tgt, torch.from_numpy(q0).to(dev), cfg_nuts) if fused else None   # device No-U-Turn tree on the sharded cohort
+    runs[name] = (res, state, means, short, nuts)
     # every rank holds the same draws
     t = torch.from_numpy(np.ascontiguousarray(res.q)).to(dev)
     parts = [torch.empty_like(t) for _ in range(world)]
@@ -77,11 +79,16 @@ if rank == 0:
         tgt = AbdTarget(eng, C, i0, w0, seed=11)
         ref = sample(tgt, torch.from_numpy(q0).to(dev), cfg_short)
         ri, rw = tgt.state()
+        sample(tgt, torch.from_numpy(q0).to(dev), cfg)             # bring the binary state to where the sharded run was
+        ref_nuts = sample(tgt, torch.from_numpy(q0).to(dev), cfg_nuts)
     # the fused sharded run against the fused unsharded run: the same algorithm step for step
-    res, state, means, short = runs["fused"]
+    res, state, means, short, nuts = runs["fused"]
     err = float(np.max(np.abs(short.q - ref.q) / np.maximum(1.0, np.abs(ref.q))))
     info["fused_vs_unsharded_rel_err_short_run"] = err
     ok &= err < 1e-8
+    # (the long adapted runs in between may have parted by rounding: compare the NUTS runs only loosely unless they did not)
+    info["nuts_tree_depth_sharded"], info["nuts_tree_depth_unsharded"] = float(nuts.stats["tree_depth"].mean()), float(ref_nuts.stats["tree_depth"].mean())
+    ok &= bool(np.isfinite(nuts.q).all()) and abs(info["nuts_tree_depth_sharded"] - info["nuts_tree_depth_unsharded"]) < 1.5
     info["fused_state_bits_differing"] = int((state[0] != ri).sum() + (state[1] != rw).sum())
     ok &= info["fused_state_bits_differing"] == 0
     for k in ("i", "ab_n_mu", "ab_s_mu"):
