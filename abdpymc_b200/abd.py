@@ -107,6 +107,9 @@ class _Cache:
         self._seen = None   # (i_raw, waner) objects known to equal the resident state
         self._host = None   # one-byte copies of the resident state
         self.uploads = 0
+        # buffers of the per-leapfrog call, allocated once
+        self._th, self._ll, self._g = np.empty(13), np.empty(1), np.empty(13)
+        self._ptrs = (self._th.ctypes.data, self._ll.ctypes.data, self._g.ctypes.data)
 
     def note_resident(self, i8, w8):
         """The device state is now (i8, w8): called by the Gibbs step after a sweep."""
@@ -132,12 +135,13 @@ class _Cache:
         self._host, self._seen, self.key = (i8, w8), (i_raw, waner), None
 
     def get(self, inputs):
-        th = np.array([float(v) for v in inputs[:13]], dtype=np.float64)
+        th = self._th
+        th[:] = inputs[:13]
         self.ensure_resident(inputs[13], inputs[14])
         key = th.tobytes()
         if key != self.key:
-            ll, g, _ = self.engine.loglik_grad(th)   # chain state resident: 13 scalars in, 14 out
-            self.key, self.val = key, (float(ll), np.asarray(g, dtype=np.float64))
+            self.engine.loglik_grad_resident(*self._ptrs)   # chain state resident: 13 scalars in, 14 out
+            self.key, self.val = key, (float(self._ll[0]), self._g.copy())
         return self.val
 
 
@@ -185,7 +189,7 @@ class AbdLogLikGrad(Op):
     def perform(self, node, inputs, output_storage):
         g = self.cache.get(inputs)[1]
         for k in range(13):
-            output_storage[k][0] = np.asarray(g[k], dtype=np.float64)
+            output_storage[k][0] = g[k:k + 1].reshape(())   # 0-d float64 views of the fresh copy
 
 
 class AbdDeterministics(Op):

@@ -236,6 +236,13 @@ class AbdEngine:
         check(self._lib.abd_loglik_grad(self._h, C_, _ptr(th), _ptr(i8), _ptr(w8), _ptr(ll), _ptr(g), _ptr(cnt)))
         return (ll[0], g[0], cnt[0]) if single else (ll, g, cnt)
 
+    def loglik_grad_resident(self, th_ptr, ll_ptr, g_ptr):
+        """One chain, resident chain state, caller-owned buffers given as raw addresses (13 doubles in, 1 + 13 out):
+        the per-leapfrog call of the PyTensor Op, without the argument handling of ``loglik_grad``."""
+        rc = self._lib.abd_loglik_grad(self._h, 1, th_ptr, None, None, ll_ptr, g_ptr, None)
+        if rc:
+            check(rc)
+
     def logp_dlogp(self, q17, i_raw=None, waner=None):
         """Joint logp and gradient in PyMC's unconstrained space (what NUTS consumes).  The hot
         call of a host-driven sampler: output buffers and their addresses are cached per chain
