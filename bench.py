@@ -995,7 +995,7 @@ def main():
     ap.add_argument("--no-sharded", action="store_true", help="skip the 100k-individual (individual-sharded) leg")
     ap.add_argument("--ess-tune", type=int, default=2000)
     ap.add_argument("--ess-draws", type=int, default=6000)
-    ap.add_argument("--ess128-tune", type=int, default=1000)
+    ap.add_argument("--ess128-tune", type=int, default=2000)
     ap.add_argument("--ess128-draws", type=int, default=2000)
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: a few un-captured logp+grad launches and Gibbs sweeps, no JSON line")
