@@ -509,8 +509,17 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
   int want, cpc, rc;
   abd_handle::Tiling* tl = nullptr;
   for (int occ = ABD_SUMS_MINB; occ >= 1; --occ) {
-    plan_grid(h, C, occ, &want, &cpc);
-    if (traj.n_steps > 0 && cpc != 1) {  // re-plan with one chain per CTA, exactly one wave
+    if (traj.n_steps == 1) {
+      // a single leapfrog step waits on nothing inside the grid: the ordinary plan with one chain per CTA (the
+      // trajectory variant keeps a chain's position in shared memory), any number of waves
+      const int keep = h->chains_per_cta_override;
+      h->chains_per_cta_override = 1;
+      plan_grid(h, C, occ, &want, &cpc);
+      h->chains_per_cta_override = keep;
+    } else {
+      plan_grid(h, C, occ, &want, &cpc);
+    }
+    if (traj.n_steps > 1 && cpc != 1) {  // persistent trajectory: re-plan with one chain per CTA, exactly one wave
       cpc = 1;
       want = std::max((h->N + kTileMaxInds - 1) / kTileMaxInds, (h->n_sms * occ) / C);
       want = std::max(1, std::min(want, h->N));
@@ -528,7 +537,7 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
     }
     if (tl->occ >= occ) break;
   }
-  if (traj.n_steps > 0) {
+  if (traj.n_steps > 1) {
     // persistent mode: one chain per CTA and every CTA resident at once
     if (cpc != 1 || (long)tl->ntiles * C > (long)h->n_sms * tl->occ)
       return fail(ABD_ERR_INVALID, "abd_leapfrog_dev: too many chains for one resident grid on this cohort; "

@@ -732,7 +732,7 @@ def test_fast_math(Engine):
     assert np.max(np.abs(r[np.isfinite(z)] * x - 1.0)) < 4.5e-16
 
 
-@pytest.mark.parametrize("n_inds,C,L", [(10_000, 4, 7), (1000, 2, 1), (1000, 3, 12)])
+@pytest.mark.parametrize("n_inds,C,L", [(10_000, 4, 7), (1000, 2, 1), (1000, 3, 12), (60_000, 3, 1)])  # (the last: several waves, single step)
 def test_persistent_leapfrog_matches_stepwise(Engine, n_inds, C, L):
     """abd_leapfrog_dev (one persistent launch, CTAs hand the position over through a generation
     counter) against the same L leapfrog steps done with one abd_logp_dlogp call per step."""
