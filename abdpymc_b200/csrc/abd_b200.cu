@@ -89,7 +89,7 @@ struct abd_handle {
   int n_sms = 148;
   size_t smem_optin = 0;
   int* d_order = nullptr;       // individuals by decreasing OD-row count (Gibbs work queue)
-  unsigned* d_queue = nullptr;  // Gibbs work-queue counter
+  unsigned* d_queue = nullptr;  // Gibbs work queues: one counter per chain (per-handle scratch, allocated with the chains)
   int gibbs_ctas = 0;
   int gibbs_blk_ctas = 0;
   ThetaInline thin{};           // parameters passed by value with the next k_sums launch (n = 0: none)
@@ -340,7 +340,8 @@ int ensure_chains(abd_handle* h, int C) {
     CU(cudaMemcpy(nw, old_w, (size_t)oldC * h->N, cudaMemcpyDeviceToDevice));
   }
   for (void* p : {(void*)old_i, (void*)old_w, h->d_pack, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
-                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_aux, (void*)h->d_traj, (void*)h->d_gen})
+                  (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_aux, (void*)h->d_traj, (void*)h->d_gen,
+                  (void*)h->d_queue})
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   h->d_iraw = ni;
@@ -361,6 +362,7 @@ int ensure_chains(abd_handle* h, int C) {
   if ((rc = dev_alloc(h, &h->d_traj, (size_t)C * 34, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_gen, (size_t)C + 1, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_stats, (size_t)C * 2, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_queue, (size_t)C, false))) return rc;
   CU(cudaMemset(h->d_ticket, 0, (size_t)C * sizeof(unsigned)));
   CU(cudaMemset(h->d_gen, 0, ((size_t)C + 1) * sizeof(unsigned)));
   CU(cudaMallocHost((void**)&h->h_pin, (size_t)C * 40 * sizeof(double)));
@@ -585,7 +587,7 @@ int launch_gibbs(abd_handle* h, int C, const double* theta, int theta_is_q, cons
     }
     const long items = (long)C * h->N;
     const int grid = (int)std::min<long>(h->gibbs_blk_ctas, (items + kGibbsWarps - 1) / kGibbsWarps);
-    CU(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
+    CU(cudaMemsetAsync(h->d_queue, 0, (size_t)C * sizeof(unsigned), st));
     void* pack = nullptr;
     int rcp = resident_pack(h, C, i_raw, waner, st, &pack);
     if (rcp) return rcp;
@@ -605,7 +607,7 @@ int launch_gibbs(abd_handle* h, int C, const double* theta, int theta_is_q, cons
   }
   const long items = (long)C * h->N;
   const int grid = (int)std::min<long>(h->gibbs_ctas, (items + kGibbsWarps - 1) / kGibbsWarps);
-  CU(cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned), st));
+  CU(cudaMemsetAsync(h->d_queue, 0, (size_t)C * sizeof(unsigned), st));
   void* pack = nullptr;
   int rcp = resident_pack(h, C, i_raw, waner, st, &pack);
   if (rcp) return rcp;
@@ -708,7 +710,6 @@ int new_handle(abd_handle** out, int device, int G, int N) {
 // what every handle needs after its cohort arrays are on the device
 int finish_handle(abd_handle* h) {
   int rc;
-  if ((rc = dev_alloc(h, &h->d_queue, 1))) return rc;
   Priors pr = default_priors(h->G);
   if ((rc = dev_alloc(h, &h->d_priors, 1))) return rc;
   CU(cudaMemcpy(h->d_priors, &pr, sizeof(pr), cudaMemcpyHostToDevice));
@@ -1026,7 +1027,7 @@ int abd_destroy(abd_handle* h) {
   for (void* p : h->owned) cudaFree(p);
   for (void* p : {(void*)h->d_iraw, (void*)h->d_waner, h->d_pack, (void*)h->d_theta, (void*)h->d_p, (void*)h->d_sums,
                   (void*)h->d_out, (void*)h->d_ticket, (void*)h->d_stats, (void*)h->d_partial, (void*)h->d_aux, (void*)h->d_traj,
-                  (void*)h->d_gen})
+                  (void*)h->d_gen, (void*)h->d_queue})
     if (p) cudaFree(p);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->stream) cudaStreamDestroy(h->stream);
