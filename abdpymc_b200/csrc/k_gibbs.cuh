@@ -42,6 +42,35 @@ __device__ __forceinline__ double gibbs_row(double x, double od, int t, bool is_
   return rp.nh * row_resid2(x, od, fma(rp.tfac, T, rp.init + P), rp.b, rp.d, s_tab);
 }
 
+// The vaccinations' share of an S row's decaying response, sum_{s in vac, s <= t} rho_ind^(t - s): it only changes with
+// ab_s_waner, so a lane keeps it for its row instead of re-summing it in every candidate evaluation.
+template <typename M>
+__device__ __forceinline__ double gibbs_vac_sum(int t, M vac, int w, const double (*s_pw)[kMaxGaps]) {
+  M v = vac & low_mask<M>(t);
+  const double* pw = w ? s_pw[1] : s_pw[2];
+  double T = 0.0;
+  while (v) {
+    T += pw[t - ctz(v)];
+    v &= v - 1;
+  }
+  return T;
+}
+// gibbs_row with the vaccinations' share handed in (tv; any_v: a vaccination at or before t)
+template <typename M>
+__device__ __forceinline__ double gibbs_row_tv(double x, double od, int t, bool is_s, M inf, double tv, bool any_v, int w,
+                                               const RowPar& rp, const double (*s_pw)[kMaxGaps],
+                                               const double* __restrict__ s_tab) {
+  M e = inf & low_mask<M>(t);
+  const double P = (e != 0 || any_v) ? rp.perm : 0.0;
+  const double* pw = is_s ? (w ? s_pw[1] : s_pw[2]) : s_pw[0];  // s_pw[2] = all ones (rho_ind = 1)
+  double T = tv;
+  while (e) {
+    T += pw[t - ctz(e)];
+    e &= e - 1;
+  }
+  return rp.nh * row_resid2(x, od, fma(rp.tfac, T, rp.init + P), rp.b, rp.d, s_tab);
+}
+
 // One chain's parameters into a warp's shared-memory slot (all 32 lanes call it):
 //   s_th[0..12] theta13, [13], [14] -1/(2 sigma^2) of N / S, [15], [16] logit p / p_waner,
 //   [17], [18] sigmoid of those, [19], [20], [21] log p, log(1 - p), p; s_pw[0] = rho_n^k, s_pw[1] = rho_s^k.
@@ -91,6 +120,10 @@ struct GibbsRows {
   int t0;
   bool s0;
   RowPar rp0;
+  int w_cur;       // the waner state tv0 was summed for
+  double tv0;      // the vaccinations' share of the lane's own row (S rows; 0 for N rows)
+  bool anyv0;
+  M vac_own;
   int t_last, t_last_s;  // latest sampled gap of either antigen / of the S antigen (rows are sorted by gap)
 
   __device__ __forceinline__ GibbsRows(const DevCohort& dc_, int n, int lane_, const double* s_th_,
@@ -111,6 +144,14 @@ struct GibbsRows {
     }
     t_last = __reduce_max_sync(0xffffffffu, t_last);
     t_last_s = __reduce_max_sync(0xffffffffu, t_last_s);
+    w_cur = -1, tv0 = 0.0, anyv0 = false, vac_own = 0;
+  }
+  // (re)sum the vaccinations' share of the lane's own row for waner state w
+  __device__ __forceinline__ void set_w(M vac, int w) {
+    vac_own = (t0 >= 0 && s0) ? (vac & low_mask<M>(t0)) : (M)0;
+    anyv0 = vac_own != 0;
+    tv0 = anyv0 ? gibbs_vac_sum<M>(t0, vac_own, w, s_pw) : 0.0;
+    w_cur = w;
   }
   __device__ __forceinline__ void load_row(int l, double& x, double& od, int& t, bool& is_s) const {
     is_s = l >= cnt_n;
@@ -136,7 +177,11 @@ struct GibbsRows {
     return rp;
   }
   __device__ __forceinline__ double ll(M inf_, M vac, int w_) const {
-    double a = (t0 >= 0) ? gibbs_row<M>(x0, od0, t0, s0, inf_, vac, w_, rp0, s_pw, s_tab) : 0.0;
+    double a = 0.0;
+    if (t0 >= 0) {
+      const double tv = (w_ == w_cur || !anyv0) ? tv0 : gibbs_vac_sum<M>(t0, vac_own, w_, s_pw);
+      a = gibbs_row_tv<M>(x0, od0, t0, s0, inf_, tv, anyv0, w_, rp0, s_pw, s_tab);
+    }
     for (int l = lane + 32; l < nrows; l += 32) {  // individuals with more than 32 rows
       double x, od;
       int t;
@@ -299,6 +344,8 @@ k_gibbs(const DevCohort dc, const int* __restrict__ order, const int C,
     t_last = __reduce_max_sync(0xffffffffu, t_last);
     t_last_s = __reduce_max_sync(0xffffffffu, t_last_s);
 
+    // (keeping the vaccinations' share of the row in a register, as k_gibbs_blk does through GibbsRows, was measured
+    // here too: 245 -> 255 us per sweep -- two more live registers under the 64-register cap cost more than the loop saves)
     auto indiv_ll = [&](M inf_, int w_) {
       double a = (t0 >= 0) ? gibbs_row<M>(x0, od0, t0, s0, inf_, vac, w_, rp0, s_pw, s_tab) : 0.0;
       for (int l = lane + 32; l < nrows; l += 32) {  // individuals with more than 32 rows

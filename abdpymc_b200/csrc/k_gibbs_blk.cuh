@@ -94,8 +94,9 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
     const M raw_in = raw;
     const int w_in = w;
     const M vac = reinterpret_cast<const M*>(dc.vac)[n];
-    const GibbsRows<M> rows(dc, n, lane, s_th, s_pw, s_tab);
+    GibbsRows<M> rows(dc, n, lane, s_th, s_pw, s_tab);
     const int t_last = rows.t_last, t_last_s = rows.t_last_s;
+    rows.set_w(vac, w);
     auto indiv_ll = [&](M inf_, int w_) { return rows.ll(inf_, vac, w_); };
 
     double ll = indiv_ll(inf, w);
@@ -173,6 +174,7 @@ k_gibbs_blk(const DevCohort dc, const int* __restrict__ order, const int C,
       const int w_new = (__shfl_sync(FULL, u01(rnd.z), 0) <= p1) ? 1 : 0;
       if (w_new != w) {
         w = w_new;
+        rows.set_w(vac, w);
         ll = ll2;
         ++n_acc;
       }
