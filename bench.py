@@ -939,12 +939,26 @@ def run_gpu(args):
 
     # ---- ESS/s of the built-in HMC + GPU-Gibbs sampler on the same cohort (bounded runs): the headline's 4 chains,
     #      and 128 chains per GPU (BASELINE configs[4]: 1024 chains over 8 GPUs, chain-parallel ESS/s) ----
-    ess = ess128 = None
+    ess = ess128 = nuts = None
     if not args.no_ess:
         ess = bench_ess(eng0, co, C, dev, rank, world, dist, args.ess_tune, args.ess_draws, cpu)
         eng128 = AbdEngine(co, splits=SPLITS, device=local)
         ess128 = bench_ess(eng128, co, 128, dev, rank, world, dist, args.ess128_tune, args.ess128_draws, None)
         eng128.close()
+        # what pm.sample runs for the 17 scalars is NUTS (abd.py:922): the device-resident No-U-Turn tree + the same sweep
+        from abdpymc_b200.engine import forward as _fw
+        from abdpymc_b200.sampler import AbdTarget as _T, SamplerConfig as _SC, sample as _sample
+
+        x0 = np.array([1.0 / G, 2, 1, 10 / 11, -2, 2, 10 / 11, 0.5, 1, 1, -2, -1, 2, 1, -1, 2, 1], dtype=np.float64)
+        q0n = _fw(x0)[None, :] + np.random.default_rng(11 + rank).uniform(-1, 1, size=(C, 17))
+        eng0.set_chain_offset(rank * C)
+        rn = _sample(_T(eng0, C, np.zeros((C, G, N), np.int8), np.zeros((C, N), np.int8), seed=2), torch.from_numpy(q0n).to(dev),
+                     _SC(tune=600, draws=400, seed=2 + rank, kernel="nuts"))
+        nuts = {"iterations_per_s": 1000 / rn.wall_s, "chains": C, "mean_tree_depth": float(rn.stats["tree_depth"].mean()),
+                "mean_leapfrogs_per_iteration": rn.n_grad_evals / 1000 - 1, "diverging_fraction": float(rn.stats["diverging"].mean()),
+                "mean_accept": float(rn.accept.mean()),
+                "what": "device No-U-Turn tree (abd_nuts_*_dev: one leapfrog launch + one tree launch per leaf for all chains, one word "
+                        "read back per tree depth) + Gibbs sweep, 600 tune + 400 draws"}
 
     if rank != 0:
         if dist:
@@ -1005,7 +1019,7 @@ def run_gpu(args):
                                                 "bound by instruction issue (sequential per-individual decisions), not HBM"}},
                   "e2e": {"value": world * C * n_sw_e2e / dt_gibbs_e2e, "unit": "sweeps/s",
                           "h2d_bytes_per_step": int(C * (G * N + N + 15 * 8)), "d2h_bytes_per_step": int(C * (G * N + N + 16))}},
-        "pymc_op_path": op_path, "sharded_100k": sharded, "ess": ess, "ess_128_chains": ess128,
+        "pymc_op_path": op_path, "sharded_100k": sharded, "ess": ess, "ess_128_chains": ess128, "nuts": nuts,
         "gpu_launches": int(n_launch), "gpu_launches_host_api": int(launches), "clocks": clocks,
     }
     emit(line)
