@@ -85,6 +85,8 @@ SIGNATURES = {
     "abd_nuts_begin_dev": (C.c_int, [H, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_uint64, C.c_uint64] + [C.c_void_p] * 7),
     "abd_nuts_leaf_dev": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64]
                           + [C.c_void_p] * 4),
+    "abd_nuts_extend_dev": (C.c_int, [H, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64]
+                            + [C.c_void_p] * 6),
     "abd_nuts_end_dev": (C.c_int, [H, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_double, C.c_void_p]),
     "abd_xch_alloc": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "abd_xch_connect": (C.c_int, [H, C.c_void_p]),

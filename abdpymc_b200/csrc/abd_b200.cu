@@ -56,7 +56,6 @@ int fail(int code, const std::string& msg) {
 #include "k_gibbs.cuh"
 #include "k_gibbs_blk.cuh"
 #include "k_misc.cuh"
-#include "k_nuts.cuh"
 
 
 // ------------------------------------------------------------------------------------------
@@ -1430,7 +1429,7 @@ int abd_leapfrog_dev(abd_handle* h, int C, int n_steps, double* q17, double* p17
   if (n_steps < 1 || n_steps > 4096) return fail(ABD_ERR_INVALID, "n_steps must be in [1, 4096]");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_steps > 1) CU(cudaMemsetAsync(h->d_gen, 0, ((size_t)C + 1) * sizeof(unsigned), st));
-  TrajCfg traj{n_steps, q17, p17, grad17, logp, eps, inv_mass, h->d_traj, h->d_gen, h->d_gen + C};
+  TrajCfg traj{n_steps, q17, p17, grad17, logp, eps, inv_mass, h->d_traj, h->d_gen, h->d_gen + C, NutsLeafArgs{}};
   FinalizeCfg fin{2, h->tot, nullptr, nullptr};
   return launch_sums(h, C, q17, 1, i_raw, waner, nullptr, fin, st, &traj);
 }
@@ -1496,10 +1495,51 @@ int abd_nuts_leaf_dev(abd_handle* h, int C, int max_depth, int depth, int leaf, 
     return fail(ABD_ERR_INVALID, "NULL argument");
   if (max_depth < 1 || max_depth > kNutsMaxDepth || depth < 0 || depth >= max_depth || leaf < 0 || leaf >= (1 << depth))
     return fail(ABD_ERR_INVALID, "bad depth / leaf");
-  k_nuts_leaf<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(C, NutsLayout{max_depth}, depth, leaf, max_depth, qw, pw, gw, lpw, inv_mass,
-                                                             eps, seed, iter, h->dc.chain_offset, state, eps_signed, any_active);
+  {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((C + 3) / 4);
+    lc.blockDim = dim3(128);
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = h->use_pdl ? 1 : 0;
+    const NutsLeafArgs a{state, NutsLayout{max_depth}, depth, leaf, max_depth, eps, seed, iter, h->dc.chain_offset, eps_signed,
+                         any_active};
+    const double* lpw_c = lpw;
+    const double* im_c = inv_mass;
+    CU(cudaLaunchKernelEx(&lc, k_nuts_leaf, C, a, qw, pw, gw, lpw_c, im_c));
+  }
   CU(cudaGetLastError());
   h->launches++;
+  return ABD_OK;
+}
+
+// all 2^depth leaves of one doubling in ONE call: per leaf a single-step leapfrog launch and the tree launch
+int abd_nuts_extend_dev(abd_handle* h, int C, int max_depth, int depth, double* qw, double* pw, double* gw, double* lpw,
+                        const double* inv_mass, const double* eps, uint64_t seed, uint64_t iter, double* state,
+                        double* eps_signed, int* any_active, const int8_t* i_raw, const int8_t* waner, void* stream) {
+  if (depth < 0 || depth >= max_depth) return fail(ABD_ERR_INVALID, "bad depth");
+  PROLOGUE(h, C);
+  h->lazy_pack = true;
+  if (!qw || !pw || !gw || !lpw || !inv_mass || !eps || !state || !eps_signed || !any_active || !i_raw || !waner)
+    return fail(ABD_ERR_INVALID, "NULL argument");
+  if (max_depth < 1 || max_depth > kNutsMaxDepth) return fail(ABD_ERR_INVALID, "max_depth must be in [1, 10]");
+  const bool sharded = h->xch_local != nullptr;
+  if (sharded && (!h->xch.buf[h->xch.world - 1] || !h->xch.buf[0] || C > h->xch.cmax))
+    return fail(ABD_ERR_INVALID, "abd_nuts_extend_dev on a sharded handle: connect the exchange first (and reserve enough chains)");
+  for (int n = 0; n < (1 << depth); ++n) {
+    // the leaf's leapfrog step and its tree bookkeeping in ONE launch (the finishing warp of each chain does both)
+    TrajCfg traj{1, qw, pw, gw, lpw, eps_signed, inv_mass, h->d_traj, h->d_gen, h->d_gen + C,
+                 NutsLeafArgs{state, NutsLayout{max_depth}, depth, n, max_depth, eps, seed, iter, h->dc.chain_offset, eps_signed,
+                              any_active}};
+    FinalizeCfg fin{2, h->tot, nullptr, nullptr};
+    h->xch_active = sharded;
+    const int rc = launch_sums(h, C, qw, 1, i_raw, waner, nullptr, fin, (cudaStream_t)stream, &traj);
+    h->xch_active = false;
+    if (rc) return rc;
+  }
   return ABD_OK;
 }
 
@@ -1590,7 +1630,7 @@ int abd_leapfrog_sharded_dev(abd_handle* h, int C, double* q17, double* p17, dou
   if (!h->xch_local || !h->xch.buf[h->xch.world - 1] || !h->xch.buf[0])
     return fail(ABD_ERR_INVALID, "abd_leapfrog_sharded_dev: call abd_xch_alloc and abd_xch_connect first");
   if (C > h->xch.cmax) return fail(ABD_ERR_INVALID, "more chains than abd_xch_alloc reserved");
-  TrajCfg traj{1, q17, p17, grad17, logp, eps, inv_mass, h->d_traj, h->d_gen, h->d_gen + C};
+  TrajCfg traj{1, q17, p17, grad17, logp, eps, inv_mass, h->d_traj, h->d_gen, h->d_gen + C, NutsLeafArgs{}};
   FinalizeCfg fin{2, h->tot, nullptr, nullptr};
   h->xch_active = true;
   const int rc = launch_sums(h, C, q17, 1, i_raw, waner, nullptr, fin, (cudaStream_t)stream, &traj);

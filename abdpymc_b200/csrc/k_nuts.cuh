@@ -124,21 +124,30 @@ k_nuts_begin(const int C, const NutsLayout L, const double* __restrict__ q, cons
   if (lane == 0) atomicOr(&any_active[0], 1);
 }
 
-// Leaf n of the depth-j sub-tree has just been integrated into (qw, pw, gw, lpw).
-__global__ void __launch_bounds__(128)
-k_nuts_leaf(const int C, const NutsLayout L, const int j, const int n, const int max_depth, double* __restrict__ qw,
-            double* __restrict__ pw, double* __restrict__ gw, const double* __restrict__ lpw,
-            const double* __restrict__ inv_mass, const double* __restrict__ eps, const uint64_t seed, const uint64_t iter,
-            const unsigned chain_offset, double* __restrict__ state, double* __restrict__ eps_signed,
-            int* __restrict__ any_active) {
-  __shared__ double s_im[17 * 17];
-  for (int k = threadIdx.x; k < 17 * 17; k += blockDim.x) s_im[k] = inv_mass[k];
-  __syncthreads();
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= C) return;
-  double* st = state + (size_t)c * L.size();
+// What one warp does for its chain once leaf n of the depth-j sub-tree has been integrated into (qw, pw, gw, lpw).
+// Called by k_nuts_leaf (its own launch) and by the finishing warp of a single-step leapfrog launch of k_sums (the
+// leaf and its bookkeeping are then ONE launch).  s_im: the 17 x 17 metric in shared memory.
+struct NutsLeafArgs {
+  double* state;            // nullptr: no tree bookkeeping
+  NutsLayout L;
+  int j, n, max_depth;
+  const double* eps;        // unsigned per-chain step sizes
+  uint64_t seed, iter;
+  unsigned chain_offset;
+  double* eps_signed;
+  int* any_active;
+};
+__device__ __noinline__ void nuts_leaf_chain(const NutsLeafArgs a, const int c, const int lane, double* qw, double* pw,
+                                             double* gw, const double* lpw, const double* s_im) {
+  const NutsLayout L = a.L;
+  const int j = a.j, n = a.n, max_depth = a.max_depth;
+  const uint64_t seed = a.seed, iter = a.iter;
+  const double* eps = a.eps;
+  double* eps_signed = a.eps_signed;
+  int* any_active = a.any_active;
+  double* st = a.state + (size_t)c * L.size();
   double* sc = st + L.scal();
-  const unsigned cg = (unsigned)c + chain_offset;
+  const unsigned cg = (unsigned)c + a.chain_offset;
   const bool active = sc[NutsLayout::ACTIVE] != 0.0;
   bool s_stop = sc[NutsLayout::SSTOP] != 0.0;
   const bool run = active && !s_stop;
@@ -225,6 +234,23 @@ k_nuts_leaf(const int C, const NutsLayout L, const int j, const int n, const int
     nuts_open_subtree(st, L, j + 1, c, lane, seed, iter, cg, eps, qw, pw, gw, eps_signed);
     if (lane == 0) atomicOr(&any_active[j + 1], 1);
   }
+}
+
+// Leaf n of the depth-j sub-tree has just been integrated into (qw, pw, gw, lpw): the bookkeeping as its own launch.
+__global__ void __launch_bounds__(128)
+k_nuts_leaf(const int C, const NutsLeafArgs a, double* qw, double* pw, double* gw, const double* lpw,
+            const double* __restrict__ inv_mass) {
+  __shared__ double s_im[17 * 17];
+  // launched with programmatic stream serialisation: the metric (written by the host only) is staged while the leapfrog
+  // launch this leaf belongs to is still finishing; everything else waits for it; the next leapfrog launch may start its
+  // own prologue (immutable cohort data) right away
+  griddep_launch_dependents();
+  for (int k = threadIdx.x; k < 17 * 17; k += blockDim.x) s_im[k] = inv_mass[k];
+  __syncthreads();
+  griddep_wait();
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  nuts_leaf_chain(a, c, lane, qw, pw, gw, lpw, s_im);
 }
 
 // The transition's end: the chain moves to the tree's proposal; sample stats; dual averaging of the step size.

@@ -2,6 +2,7 @@
 // See DESIGN.md section 4 for the phases, the measured timeline and what was tried.
 #pragma once
 #include "abd_kernels_common.cuh"
+#include "k_nuts.cuh"
 
 namespace {
 using namespace abd;
@@ -70,6 +71,7 @@ struct TrajCfg {
   double* state;           // [C][34] scratch: position and half-step momentum of the current step
   unsigned* gen;           // [C] generation counters (zeroed before the launch)
   unsigned* err;           // set to 1 if a wait timed out
+  NutsLeafArgs nuts;       // single-step launches: fold the new state into the chain's No-U-Turn tree (state == nullptr: no)
 };
 
 // tile descriptor (48 bytes, three 16-byte loads): individuals [i0, i1); per antigen the OD rows
@@ -317,6 +319,10 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
           traj.grad[(size_t)c * 17 + lane] = g;
         }
         if (lane == 0) traj.logp[c] = s_out[0];
+        if (traj.nuts.state) {  // the leaf's tree bookkeeping in the same launch (this warp is the chain's only writer)
+          __syncwarp();
+          nuts_leaf_chain(traj.nuts, c, lane, traj.q, traj.p, traj.grad, traj.logp, s_im);
+        }
       } else {
         const double ph2 = fma(e, g, ph);  // two half steps: end of this step + start of the next
         double dot = 0.0;

@@ -213,6 +213,7 @@ class ShardedTarget(_nuts_mixin()):
         self.outg = torch.zeros(n_chains, 17, dtype=torch.float64, device=self.device)
         if sharded.fused:  # the device-resident transitions of sampler._sample_fused (HMC and No-U-Turn)
             self.hmc_begin, self.hmc_end = self._hmc_begin, self._hmc_end
+            self.nuts_extend_in_library = True   # abd_nuts_extend_dev exchanges inside its leapfrog launches
         else:              # host-driven loop: hide the device tree methods
             self.nuts_begin = None
 
@@ -220,6 +221,14 @@ class ShardedTarget(_nuts_mixin()):
         import torch
 
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def d_i(self):
+        return self.engine.state_dev(self.C)[0]
+
+    @property
+    def d_w(self):
+        return self.engine.state_dev(self.C)[1]
 
     def logp_dlogp(self, q):
         lp, g = self.sh.logp_dlogp(q.contiguous(), self.C)

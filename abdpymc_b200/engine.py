@@ -371,6 +371,11 @@ class AbdEngine:
         check(self._lib.abd_nuts_leaf_dev(self._h, C_, int(max_depth), int(depth), int(leaf), qw, pw, gw, lpw, inv_mass, eps,
                                           int(seed), int(it), state, eps_signed, any_active, stream))
 
+    def nuts_extend_dev(self, C_, max_depth, depth, qw, pw, gw, lpw, inv_mass, eps, seed, it, state, eps_signed, any_active,
+                        i_raw, waner, stream=0):
+        check(self._lib.abd_nuts_extend_dev(self._h, C_, int(max_depth), int(depth), qw, pw, gw, lpw, inv_mass, eps, int(seed),
+                                            int(it), state, eps_signed, any_active, i_raw, waner, stream))
+
     def nuts_end_dev(self, C_, max_depth, q17, grad17, logp, state, accept_out, depth_out, diverged_out, da, eps, adapt,
                      target_accept, stream=0):
         check(self._lib.abd_nuts_end_dev(self._h, C_, int(max_depth), q17, grad17, logp, state, accept_out, depth_out, diverged_out,

@@ -50,6 +50,18 @@ class DeviceNutsMixin:
                                   eps.data_ptr(), self.seed, it, state.data_ptr(), eps_signed.data_ptr(), any_active.data_ptr(),
                                   self._stream())
 
+    def nuts_extend(self, D, j, qw, pw, gw, lpw, inv_mass, eps, it, state, eps_signed, any_active):
+        """All 2^j leaves of one doubling (leapfrog + tree launch each) in one library call; targets whose leapfrog is
+        not ``abd_leapfrog_dev`` on their own engine (sharded cohorts) loop over ``leapfrog_inplace`` / ``nuts_leaf``."""
+        if getattr(self, "nuts_extend_in_library", False):
+            self.engine.nuts_extend_dev(self.C, D, j, qw.data_ptr(), pw.data_ptr(), gw.data_ptr(), lpw.data_ptr(), inv_mass.data_ptr(),
+                                        eps.data_ptr(), self.seed, it, state.data_ptr(), eps_signed.data_ptr(), any_active.data_ptr(),
+                                        self.d_i, self.d_w, self._stream())
+            return
+        for n in range(1 << j):
+            self.leapfrog_inplace(qw, pw, gw, lpw, eps_signed, inv_mass, 1)
+            self.nuts_leaf(D, j, n, qw, pw, gw, lpw, inv_mass, eps, it, state, eps_signed, any_active)
+
     def nuts_end(self, D, q, grad, logp, state, acc, depth, div, da, eps, adapt, target_accept):
         self.engine.nuts_end_dev(self.C, D, q.data_ptr(), grad.data_ptr(), logp.data_ptr(), state.data_ptr(), acc.data_ptr(),
                                  depth.data_ptr(), div.data_ptr(), da.data_ptr(), eps.data_ptr(), adapt, target_accept,
@@ -60,6 +72,8 @@ class DeviceNutsMixin:
 class AbdTarget(DeviceNutsMixin):
     """The antibody-dynamics posterior on one GPU: joint logp + gradient over q17 for C chains
     with the chain state (i_raw, waner) resident on the device, and the Gibbs sweep over it."""
+
+    nuts_extend_in_library = True
 
     def __init__(self, engine, n_chains, i_raw, waner, seed=0, gibbs_mode=0, transit_p=0.8):
         self.engine, self.C = engine, n_chains
@@ -348,9 +362,7 @@ def _sample_fused(target, q0, cfg, progress, nuts=False):
             # one word is read back per depth: does any chain still want to double?
             target.nuts_begin(TD, q, grad, logp, linv_t, eps, it, nstate, qw, pw, gw, eps_signed, any_active)
             for j in range(TD):
-                for n in range(1 << j):
-                    target.leapfrog_inplace(qw, pw, gw, lpw, eps_signed, inv_mass, 1)
-                    target.nuts_leaf(TD, j, n, qw, pw, gw, lpw, inv_mass, eps, it, nstate, eps_signed, any_active)
+                target.nuts_extend(TD, j, qw, pw, gw, lpw, inv_mass, eps, it, nstate, eps_signed, any_active)
                 n_grad += 1 << j
                 if j + 1 < TD and j + 1 >= cfg.nuts_check_from_depth and int(any_active[j + 1].item()) == 0:
                     break

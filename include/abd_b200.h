@@ -280,6 +280,12 @@ int abd_nuts_begin_dev(abd_handle* h, int n_chains, int max_depth, const double*
 int abd_nuts_leaf_dev(abd_handle* h, int n_chains, int max_depth, int depth, int leaf, double* qw, double* pw,
                       double* gw, const double* lpw, const double* inv_mass, const double* eps, uint64_t seed,
                       uint64_t iter, double* state, double* eps_signed, int* any_active, void* stream);
+/* One doubling in one call: for leaf n = 0 .. 2^depth - 1, abd_leapfrog_dev(n_steps = 1) + abd_nuts_leaf_dev (a host
+ * that pays microseconds per foreign call -- Python -- would otherwise be the bottleneck of deep trees).   */
+int abd_nuts_extend_dev(abd_handle* h, int n_chains, int max_depth, int depth, double* qw, double* pw, double* gw,
+                        double* lpw, const double* inv_mass, const double* eps, uint64_t seed, uint64_t iter,
+                        double* state, double* eps_signed, int* any_active, const int8_t* i_raw,
+                        const int8_t* waner, void* stream);
 int abd_nuts_end_dev(abd_handle* h, int n_chains, int max_depth, double* q17, double* grad17, double* logp,
                      const double* state, double* accept_out, double* depth_out, double* diverged_out, double* da,
                      double* eps, int adapt, double target_accept, void* stream);
