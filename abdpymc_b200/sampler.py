@@ -217,8 +217,8 @@ class SamplerConfig:
                                            # the 17 scalars, abd.py:922), chains doubling in lockstep; tree bookkeeping on
                                            # the device when the target offers it (abd_nuts_*_dev), else torch ops
     max_treedepth: int = 8
-    nuts_check_from_depth: int = 1         # device NUTS: depths below this are always built (no read-back of the "any chain
-                                           # still doubling?" word before them)
+    nuts_check_from_depth: int = 2         # device NUTS: depths below this are always built (no read-back of the "any chain
+                                           # still doubling?" word before them: a read-back costs as much as two leaves)
 
 
 @dataclass
