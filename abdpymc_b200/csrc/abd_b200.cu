@@ -5,7 +5,8 @@
 //   per antigen a in {N, S}:    CSR by individual -- rp_a[N+1] (int32), and row arrays sorted by
 //                               (individual, gap): od_a[R_a] f64, x_a[R_a] f64,
 //                               meta_a[R_a] u32 = individual << 6 | gap
-//   per chain (resident state): i_raw[C][G][N] int8, waner[C][N] int8  (the reference layout)
+//   per chain (resident state): i_raw[C][G][N] int8, waner[C][N] int8  (the reference layout), and beside it
+//                               PackedState[C][N] (raw bit mask | waner, constrained infections): what the kernels read
 //
 // Files
 //   abd_device.cuh          per-individual building blocks (constraints, trajectories, row likelihood,
@@ -13,9 +14,11 @@
 //   abd_kernels_common.cuh  device view of the cohort, launch configurations
 //   k_sums.cuh              k_sums (joint logp + gradient sums, fused finaliser, persistent trajectory
 //                           mode, fused peer all-reduce), k_finalize
-//   k_gibbs.cuh             k_gibbs (Gibbs sweep, conditional log-odds)
-//   k_misc.cuh              k_hmc_begin / k_hmc_end, k_determ, k_pull, k_debug_fast_math
-//   abd_b200.cu (this file) host side: cohort preprocessing, tilings and grid plans, the C ABI
+//   k_gibbs.cuh             k_gibbs (Gibbs sweep, conditional log-odds); k_gibbs_blk.cuh: the per-chunk block draw
+//   k_nuts.cuh              the No-U-Turn tree (k_nuts_begin / k_nuts_leaf / k_nuts_end; nuts_leaf_chain is also called by
+//                           the finishing warp of k_sums' single-step leapfrog launches)
+//   k_misc.cuh              k_hmc_begin / k_hmc_end, k_determ, k_determ_accum, k_loglik_rows, k_pack, k_pull, k_debug_fast_math
+//   abd_b200.cu (this file) host side: cohort preprocessing, cache file, tilings and grid plans, the C ABI
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
