@@ -45,6 +45,13 @@ for case in range(n_cases):
     try:
         with AbdEngine(co, splits=splits, ignore_pcrpos=ignore) as eng:
             lp, g = eng.logp_dlogp(q, i_raw, w)
+            eng.upload_state(i_raw, w)                    # the resident (packed) route: bitwise the same numbers
+            lp_r, g_r = eng.logp_dlogp(q)
+            assert np.array_equal(lp, lp_r) and np.array_equal(g, g_r), "packed resident state vs int8 route"
+            ls, ln = eng.loglik_rows(th, i_raw, w)         # pointwise log-likelihood, the cohort's row order
+            for c in range(C):
+                ref = o.loglik_rows(th[c], i_raw[c], w[c])
+                assert np.allclose(ls[c], ref["s"], rtol=1e-10, atol=1e-10) and np.allclose(ln[c], ref["n"], rtol=1e-10, atol=1e-10), "loglik rows"
             for c in range(C):
                 rl, rg = o.logp_dlogp(q[c], i_raw[c], w[c])
                 scale = np.maximum(np.abs(rg), 1e-3 * np.abs(rg).max())
@@ -61,11 +68,16 @@ for case in range(n_cases):
                 assert np.all(np.abs(lo - rlo) <= 1e-9 * np.maximum(1, np.abs(rlo))), "cond logodds i"
                 assert np.all(np.abs(low - rlow) <= 1e-9 * np.maximum(1, np.abs(rlow))), "cond logodds w"
                 mode = int(rng.integers(0, 3))
-                gi, gw, st = eng.gibbs_sweep(th[:1], [p0], [pw0], i_raw[:1], w[:1], seed=case, sweep=3, mode=mode)
+                pa, pwa = np.array([v["p"] for v in vals]), np.array([v["ab_s_p_waner"] for v in vals])
+                off = int(rng.integers(0, 5))
+                eng.set_chain_offset(off)
+                gi, gw, st = eng.gibbs_sweep(th, pa, pwa, i_raw, w, seed=case, sweep=3, mode=mode)   # all chains, one launch
                 # the block draw needs time chunks and 32-bit masks; the library runs it as heat bath otherwise
                 omode = 1 if (mode == 2 and (G > 31 or not splits)) else mode
-                ri2, rw2, rst = ora.device_gibbs_sweep(co, splits, ignore, th[0], p0, pw0, i_raw[0], w[0], case, 3, 0, mode=omode)
-                assert np.array_equal(gi[0], ri2) and np.array_equal(gw[0], rw2) and list(st[0]) == rst, "gibbs sweep"
+                for c in range(C):
+                    ri2, rw2, rst = ora.device_gibbs_sweep(co, splits, ignore, th[c], pa[c], pwa[c], i_raw[c], w[c], case, 3, off + c,
+                                                           mode=omode)
+                    assert np.array_equal(gi[c], ri2) and np.array_equal(gw[c], rw2) and list(st[c]) == rst, "gibbs sweep"
     except AssertionError as ex:
         bad += 1
         print(f"case {case}: G={G} N={N} splits={splits} ignore_pcrpos={ignore} rows={r} C={C} dens={dens}: MISMATCH {ex}", flush=True)
