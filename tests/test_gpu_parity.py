@@ -432,12 +432,17 @@ def test_packed_resident_state_matches_the_int8_path(Engine, cohorts, G, N, spli
         assert np.array_equal(lp_t, lp_n) and np.array_equal(g_t, g_n)
 
 
-@pytest.mark.parametrize("name,splits,ignore", [("cohort", (14, 20), False), ("test_cohort", (), True)])
+@pytest.mark.parametrize("name,splits,ignore", [("cohort", (14, 20), False), ("test_cohort", (), True), ("wide_random", (20,), False)])
 def test_cache_file_round_trip(Engine, cohorts, tmp_path, name, splits, ignore):
     """abd_save_cache / abd_create_from_cache: the engine read back from the file is the same engine
-    (bitwise the same logp / gradient, the same Gibbs sweep), and it knows what it was built with."""
-    co = cohorts[name]
+    (bitwise the same logp / gradient, the same Gibbs sweep), and it knows what it was built with.
+    ("wide_random": 64-bit masks and continuous dilutions, i.e. the kernel variant without the factored exponential.)"""
     rng = np.random.default_rng(2)
+    if name == "wide_random":
+        co = random_cohort(rng, 45, 70, rows_per_ind=9)
+        co.x[:] = co.x + rng.random(co.x.size)
+    else:
+        co = cohorts[name]
     q, i_raw, w = draw_points(rng, co.n_gaps, co.n_inds, 2)
     path = tmp_path / "c.abdcache"
     with Engine(co, splits=splits, ignore_pcrpos=ignore) as eng:
