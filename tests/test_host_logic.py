@@ -344,3 +344,68 @@ def test_reference_interface_mirror_errors(cohorts):
             abd.model(t)
     q = np.arange(17, dtype=float)
     assert np.array_equal(abd.point_to_q17(dict(zip(abd.Q17, q))), q)
+
+
+def test_cohort_rejects_non_binary_exposures(cohorts):
+    """vacs / pcrpos enter the reference numerically (exposure = i + v, abd.py:368,384); the device layout is one bit
+    per (individual, gap), so anything but 0 / 1 must be refused, not silently binarised."""
+    t = cohorts["test_cohort"]
+    bad = t.vacs.copy().astype(np.int64)
+    bad[0, 0] = 2
+    with pytest.raises(ValueError, match="vacs"):
+        CohortArrays(vacs=bad, pcrpos=t.pcrpos, ind=t.ind, gap=t.gap, antigen=t.antigen, x=t.x, od=t.od)
+    with pytest.raises(ValueError, match="pcrpos"):
+        CohortArrays(vacs=t.vacs, pcrpos=-t.pcrpos.astype(np.int64), ind=t.ind, gap=t.gap, antigen=t.antigen, x=t.x, od=t.od)
+    from abdpymc_b200.cohort import splits_from_t0
+
+    assert splits_from_t0("2020-05", True, True) == (14, 20) and splits_from_t0("2020-05", False, False) == ()
+
+
+def test_op_cache_sends_the_binaries_only_when_they_changed():
+    """abd._Cache (shared by the PyTensor Ops and the Gibbs step): object identity decides on the hot path, one content
+    comparison when the objects are new, an upload only for a real difference; value + gradient from one call."""
+    from abdpymc_b200 import abd
+
+    class StubEngine:
+        def __init__(self):
+            self.uploads, self.evals, self.state = 0, 0, None
+
+        def upload_state(self, i8, w8):
+            self.uploads += 1
+            self.state = (i8.copy(), w8.copy())
+
+        def loglik_grad_resident(self, th_ptr, ll_ptr, g_ptr):
+            import ctypes
+
+            self.evals += 1
+            th = np.ctypeslib.as_array(ctypes.cast(th_ptr, ctypes.POINTER(ctypes.c_double)), (13,))
+            np.ctypeslib.as_array(ctypes.cast(ll_ptr, ctypes.POINTER(ctypes.c_double)), (1,))[0] = th.sum() + self.state[0].sum()
+            np.ctypeslib.as_array(ctypes.cast(g_ptr, ctypes.POINTER(ctypes.c_double)), (13,))[:] = 2 * th
+
+    eng = StubEngine()
+    cache = abd._Cache(eng)
+    rng = np.random.default_rng(0)
+    i_raw, w = (rng.random((5, 4)) < 0.3).astype(np.int64), (rng.random(4) < 0.5).astype(np.int64)
+    th = [np.float64(k) for k in range(13)]
+    v1, g1 = cache.get(th + [i_raw, w])
+    assert (eng.uploads, eng.evals) == (1, 1) and v1 == sum(range(13)) + i_raw.sum() and np.array_equal(g1, 2 * np.arange(13.0))
+    cache.get(th + [i_raw, w])                                   # same point: neither an upload nor a launch
+    assert (eng.uploads, eng.evals) == (1, 1)
+    th2 = [np.float64(k + 0.5) for k in range(13)]
+    cache.get(th2 + [i_raw, w])                                  # a leapfrog: new scalars, the same binary objects
+    assert (eng.uploads, eng.evals) == (1, 2)
+    cache.get(th2 + [i_raw.copy(), w.copy()])                    # new objects, equal contents (PyMC re-set the values)
+    assert (eng.uploads, eng.evals) == (1, 2)
+    other = 1 - i_raw
+    v3, _ = cache.get(th2 + [other, w])                          # a real change: uploaded, evaluated
+    assert (eng.uploads, eng.evals) == (2, 3) and v3 == sum(k + 0.5 for k in range(13)) + other.sum()
+    new_i, new_w = (other != 0).astype(np.int8), (w != 0).astype(np.int8)
+    cache.note_resident(new_i, new_w)                            # what the Gibbs step does after a sweep
+    cache.get(th2 + [new_i.astype(np.int64), new_w.astype(np.int64)])
+    assert eng.uploads == 2 and eng.evals == 4                   # no upload; evaluated again (the state may have changed)
+    strict = abd._Cache(eng, strict=True)
+    strict.get(th + [i_raw, w])
+    i_raw[0, 0] ^= 1                                             # mutated in place: only the strict cache notices
+    n = eng.uploads
+    strict.get(th + [i_raw, w])
+    assert eng.uploads == n + 1
