@@ -106,19 +106,25 @@ class _Cache:
         self.key, self.val = None, None
         self._seen = None   # (i_raw, waner) objects known to equal the resident state
         self._host = None   # one-byte copies of the resident state
+        self._returned = None
         self.uploads = 0
         # buffers of the per-leapfrog call, allocated once
         self._th, self._ll, self._g = np.empty(13), np.empty(1), np.empty(13)
         self._ptrs = (self._th.ctypes.data, self._ll.ctypes.data, self._g.ctypes.data)
 
-    def note_resident(self, i8, w8):
-        """The device state is now (i8, w8): called by the Gibbs step after a sweep."""
+    def note_resident(self, i8, w8, as_returned=None):
+        """The device state is now (i8, w8): called by the Gibbs step after a sweep.  ``as_returned``: the same state in
+        the dtype handed back to PyMC (int64), so that the one comparison per step is between arrays of one dtype."""
         self._host, self._seen, self.key = (i8, w8), None, None
+        self._returned = as_returned
 
     def binaries_resident(self, i_raw, waner) -> bool:
         if not self.strict and self._seen is not None and self._seen[0] is i_raw and self._seen[1] is waner:
             return True
         h = self._host
+        r = self._returned
+        if r is not None and r[0].dtype == getattr(i_raw, "dtype", None) and r[0].shape == np.shape(i_raw):
+            h = r   # same dtype: a plain memory comparison
         if h is not None and h[0].shape == np.shape(i_raw) and np.array_equal(h[0], i_raw) and np.array_equal(h[1], waner):
             self._seen = (i_raw, waner)
             return True
@@ -304,7 +310,6 @@ if HAVE_PYMC:  # pragma: no cover
                 self.cache.ensure_resident(point["i_raw"], point["ab_s_waner"])
                 i_raw, waner, st = self.engine.gibbs_sweep(x[Q_OF_THETA], x[Q_P], x[Q_PW], seed=self.seed, sweep=self.sweep,
                                                            mode=self.mode, transit_p=self.transit_p)
-                self.cache.note_resident(i_raw, waner)
             else:
                 i_raw, waner, st = self.engine.gibbs_sweep(x[Q_OF_THETA], x[Q_P], x[Q_PW], point["i_raw"],
                                                            point["ab_s_waner"], seed=self.seed, sweep=self.sweep,
@@ -313,6 +318,8 @@ if HAVE_PYMC:  # pragma: no cover
             new = dict(point)
             new["i_raw"] = i_raw.astype(np.asarray(point["i_raw"]).dtype)
             new["ab_s_waner"] = waner.astype(np.asarray(point["ab_s_waner"]).dtype)
+            if self.cache is not None:
+                self.cache.note_resident(i_raw, waner, (new["i_raw"], new["ab_s_waner"]))
             return new, [{"p_jump": float(st[1]) / max(float(st[0]), 1.0), "tune": self.tune}]
 
         def stop_tuning(self):
