@@ -233,6 +233,8 @@ class SamplerResult:
     means: dict = field(default_factory=dict)   # posterior means of i, ab_n_mu, ab_s_mu (G, N)
     thinned: dict = field(default_factory=dict)  # i (int8), ab_n_mu, ab_s_mu (float32): (chains, kept draws, G, N); "draw" = their indexes
     stats: dict = field(default_factory=dict)   # NUTS: tree_depth, diverging (chains, draws); what PyMC puts in sample_stats
+    wall_tune_s: float = 0.0           # device-resident drivers: the part of wall_s spent in the tuning iterations ...
+    n_grad_evals_tune: int = 0         # ... and the gradient evaluations they took
 
     def posterior(self):
         """{RV name: (chains, draws)} on the constrained scale, named as abd.model names them."""
@@ -356,6 +358,7 @@ def _sample_fused(target, q0, cfg, progress, nuts=False):
         depth_d, div_d = torch.zeros(C, **f64), torch.zeros(C, **f64)
         out_depth, out_div = torch.zeros(cfg.draws, C, **f64), torch.zeros(cfg.draws, C, **f64)
     t0 = time.perf_counter()
+    wall_tune, n_grad_tune = 0.0, 0
     for it in range(total):
         if nuts:
             # the chains double in lockstep: depth j adds 2^j leaves (one leapfrog launch + one tree launch each);
@@ -400,6 +403,8 @@ def _sample_fused(target, q0, cfg, progress, nuts=False):
                 da[:, 0] = torch.log(10.0 * eps)
             if it + 1 == cfg.tune:
                 eps = torch.where(da[:, 3] > 0, torch.exp(da[:, 2]), eps).contiguous()
+                torch.cuda.synchronize(dev)     # once per run: the draws are timed on their own as well
+                wall_tune, n_grad_tune = time.perf_counter() - t0, n_grad
         else:
             k = it - cfg.tune
             out_q[k].copy_(q)
@@ -429,6 +434,7 @@ def _sample_fused(target, q0, cfg, progress, nuts=False):
         q=out_q.permute(1, 0, 2).cpu().numpy(), logp=out_lp.T.cpu().numpy(), accept=out_acc.T.cpu().numpy(),
         step_size=eps.cpu().numpy(), inv_mass=inv_mass.cpu().numpy(), wall_s=wall, n_grad_evals=n_grad,
         means={k: (v / n_means).cpu().numpy() for k, v in means.items()}, thinned=thin.result(), stats=stats,
+        wall_tune_s=wall_tune, n_grad_evals_tune=n_grad_tune,
     )
 
 

@@ -957,7 +957,9 @@ def run_gpu(args):
         nuts = {"iterations_per_s": 1000 / rn.wall_s, "chains": C, "mean_tree_depth": float(rn.stats["tree_depth"].mean()),
                 "mean_leapfrogs_per_iteration": rn.n_grad_evals / 1000 - 1, "diverging_fraction": float(rn.stats["diverging"].mean()),
                 "mean_accept": float(rn.accept.mean()),
-                "mean_tree_depth_draws": float(rn.stats["tree_depth"].mean()),
+                # the 400 draws on their own (adapted step size and metric; the trees of early tuning are several times deeper)
+                "draws_per_s_after_tuning": 400 / (rn.wall_s - rn.wall_tune_s),
+                "mean_leapfrogs_per_draw": (rn.n_grad_evals - rn.n_grad_evals_tune) / 400 - 1,
                 "what": "device No-U-Turn tree (abd_nuts_extend_dev: ONE launch per leaf for all chains -- the leapfrog step, and its "
                         "finishing warp folds the new state into the chain's tree --, one word read back per tree depth) + Gibbs "
                         "sweep; 600 tune (deep trees early on) + 400 draws, rate over all 1000 iterations"}
