@@ -94,7 +94,7 @@ k_nuts_begin(const int C, const NutsLayout L, const double* __restrict__ q, cons
              double* __restrict__ qw, double* __restrict__ pw, double* __restrict__ gw, double* __restrict__ eps_signed,
              int* __restrict__ any_active) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c == 0 && lane <= kNutsMaxDepth) any_active[lane] = 0;
+  if (c == 0 && lane <= L.D) any_active[lane] = (lane == 0);  // max_depth + 1 words; [j]: does any chain want depth j?
   if (c >= C) return;
   double* st = state + (size_t)c * L.size();
   double* sc = st + L.scal();
@@ -121,7 +121,6 @@ k_nuts_begin(const int C, const NutsLayout L, const double* __restrict__ q, cons
   }
   __syncwarp();
   nuts_open_subtree(st, L, 0, c, lane, seed, iter, (unsigned)c + chain_offset, eps, qw, pw, gw, eps_signed);
-  if (lane == 0) atomicOr(&any_active[0], 1);
 }
 
 // What one warp does for its chain once leaf n of the depth-j sub-tree has been integrated into (qw, pw, gw, lpw).

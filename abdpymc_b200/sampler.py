@@ -23,6 +23,7 @@ CPU against a Gaussian with known moments (tests/test_sampler.py).
 from __future__ import annotations
 
 import time
+from collections import deque
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -219,6 +220,7 @@ class SamplerConfig:
     max_treedepth: int = 8
     nuts_check_from_depth: int = 2         # device NUTS: depths below this are always built (no read-back of the "any chain
                                            # still doubling?" word before them: a read-back costs as much as two leaves)
+    nuts_adaptive_checks: bool = True      # ... and so are the depths every tree of the last 32 iterations reached
 
 
 @dataclass
@@ -357,6 +359,7 @@ def _sample_fused(target, q0, cfg, progress, nuts=False):
         nstate, eps_signed, any_active = target.nuts_scratch(TD)
         depth_d, div_d = torch.zeros(C, **f64), torch.zeros(C, **f64)
         out_depth, out_div = torch.zeros(cfg.draws, C, **f64), torch.zeros(cfg.draws, C, **f64)
+        recent_depths = deque(maxlen=32)
     t0 = time.perf_counter()
     wall_tune, n_grad_tune = 0.0, 0
     for it in range(total):
@@ -364,11 +367,21 @@ def _sample_fused(target, q0, cfg, progress, nuts=False):
             # the chains double in lockstep: depth j adds 2^j leaves (one leapfrog launch + one tree launch each);
             # one word is read back per depth: does any chain still want to double?
             target.nuts_begin(TD, q, grad, logp, linv_t, eps, it, nstate, qw, pw, gw, eps_signed, any_active)
+            # Depths below `check_from` are built without asking (a read-back costs as much as two leaves): the shallowest
+            # tree of the last 32 iterations, never below cfg.nuts_check_from_depth.  Building a depth no chain wanted
+            # changes nothing (its leaves are masked on the device), it only costs their launches.
+            check_from = max(cfg.nuts_check_from_depth, min(recent_depths)) if cfg.nuts_adaptive_checks and recent_depths \
+                else cfg.nuts_check_from_depth
+            flags = None
             for j in range(TD):
                 target.nuts_extend(TD, j, qw, pw, gw, lpw, inv_mass, eps, it, nstate, eps_signed, any_active)
                 n_grad += 1 << j
-                if j + 1 < TD and j + 1 >= cfg.nuts_check_from_depth and int(any_active[j + 1].item()) == 0:
-                    break
+                if j + 1 < TD and j + 1 >= check_from:
+                    flags = any_active.tolist()       # [k]: did any chain want depth k?  (one read-back, all depths)
+                    if flags[j + 1] == 0:
+                        break
+            # lockstep depth of this tree: the first depth nobody wanted
+            recent_depths.append(TD if flags is None else next((k for k in range(1, TD + 1) if flags[k] == 0), TD))
             target.nuts_end(TD, q, grad, logp, nstate, acc, depth_d, div_d, da, eps, it < cfg.tune, cfg.target_accept)
             L = 0
         else:

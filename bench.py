@@ -961,7 +961,7 @@ def run_gpu(args):
                 "draws_per_s_after_tuning": 400 / (rn.wall_s - rn.wall_tune_s),
                 "mean_leapfrogs_per_draw": (rn.n_grad_evals - rn.n_grad_evals_tune) / 400 - 1,
                 "what": "device No-U-Turn tree (abd_nuts_extend_dev: ONE launch per leaf for all chains -- the leapfrog step, and its "
-                        "finishing warp folds the new state into the chain's tree --, one word read back per tree depth) + Gibbs "
+                        "finishing warp folds the new state into the chain's tree --, one read-back per tree depth, none for the depths every recent tree reached) + Gibbs "
                         "sweep; 600 tune (deep trees early on) + 400 draws, rate over all 1000 iterations"}
 
     if rank != 0:
