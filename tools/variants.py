@@ -81,6 +81,18 @@ def probe():
                     e1.record()
                 side.synchronize()
                 out[name] = e0.elapsed_time(e1) / 20 * 1e3
+                # the same sweep once the states have settled under these parameters (few accepted flips: what a sampler sees)
+                with torch.cuda.stream(side):
+                    for k in range(60):
+                        eng.gibbs_sweep_dev(C, th.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), di, dw, 1, 23 + k, mode=mode,
+                                            stream=side.cuda_stream)
+                    e0.record()
+                    for k in range(20):
+                        eng.gibbs_sweep_dev(C, th.data_ptr(), 0, tp.data_ptr(), tpw.data_ptr(), di, dw, 1, 83 + k, mode=mode,
+                                            stream=side.cuda_stream)
+                    e1.record()
+                side.synchronize()
+                out[name.replace("_us_", "_settled_us_")] = e0.elapsed_time(e1) / 20 * 1e3
                 si, sw = eng.download_state(C)
                 out[name.replace("_us_", "_state_")] = int(si.sum()) * 1000003 + int(sw.sum())
         eng.close()
