@@ -37,6 +37,24 @@ def run(co, splits, C):
         eng.leapfrog_dev(C, 3, tq.data_ptr(), tp.data_ptr(), tg.data_ptr(), tl.data_ptr(), te.data_ptr(), tm.data_ptr(), di, dw, 0)
         torch.cuda.synchronize()
         eng.leapfrog_status(C)
+        # round 2: block draw, pointwise log-likelihood, the cache file, the device-resident samplers (packed resident
+        # state, single-step leapfrog launches with the tree bookkeeping fused, streaming Deterministic sums)
+        eng.gibbs_sweep(x[:, Q_OF_THETA], x[:, 0], x[:, 7], i_raw, w, seed=1, sweep=2, mode=2)
+        eng.loglik_rows(x[:, Q_OF_THETA], i_raw != 0, w != 0)
+        import tempfile
+
+        with tempfile.TemporaryDirectory() as tmp:
+            eng.save_cache(tmp + "/c.bin")
+            with AbdEngine.from_cache(tmp + "/c.bin", splits=splits or ()) as e2:
+                lp2, _ = e2.logp_dlogp(q, i_raw, w)
+                assert np.array_equal(lp, lp2)
+    from abdpymc_b200.sampler import AbdTarget, SamplerConfig, sample
+
+    for kernel in ("hmc", "nuts"):
+        with AbdEngine(co, splits=splits) as eng:
+            tgt = AbdTarget(eng, C, i_raw, w, seed=3)
+            sample(tgt, torch.from_numpy(q).to(dev), SamplerConfig(tune=4, draws=4, seed=1, kernel=kernel, max_treedepth=3,
+                                                                   thinned_deterministics=2, record_deterministics_every=1))
     print("ok", co.n_inds, co.n_gaps, lp[:2])
 
 
