@@ -98,6 +98,7 @@ SIGNATURES = {
     "abd_state_touch": (C.c_int, [H]),
     "abd_set_chain_offset": (C.c_int, [H, C.c_int64]),
     "abd_set_tuning": (C.c_int, [H, C.c_int, C.c_int]),
+    "abd_last_plan": (C.c_int, [H, C.c_void_p]),
     "abd_debug_fast_math": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }  # fmt: skip
 

@@ -82,10 +82,14 @@ struct abd_handle {
     int ntiles = 0;
     void* d_tiles = nullptr;   // TileDesc[ntiles]
     int cap_n = 0, cap_s = 0, capr_n = 0, capr_s = 0, capk_n = 0, capk_s = 0;  // staging capacities (elements)
-    size_t smem = 0;                                     // dynamic shared memory per CTA
+    size_t smem = 0;                                     // dynamic shared memory per CTA (0 = does not fit at all)
     int occ = 0;                                         // resident CTAs per SM (0 = not queried yet)
+    size_t smem_cp = 0;                                  // the same with the compact cell layout (factored mode; 0 = none)
+    int occ_cp = 0;
   };
   std::map<int, Tiling> tilings;  // keyed by number of tiles requested
+  int last_plan[6] = {0, 0, 0, 0, 0, 0};  // abd_last_plan
+  bool force_compact = false;
   int tile_rows_override = 0;     // 0 = automatic
   int chains_per_cta_override = 0;
   int n_sms = 148;
@@ -303,10 +307,13 @@ int get_tiling(abd_handle* h, int want, abd_handle::Tiling** out) {
     t.capr_s = std::max(t.capr_s, 4);
     t.capk_n = std::max(t.capk_n, 4);
     t.capk_s = std::max(t.capk_s, 4);
-    t.smem = (size_t)(t.cap_n + t.cap_s) * 8 + (size_t)(t.capr_n + t.capr_s) * 4 +
-             (h->fx ? (size_t)(t.capk_n + t.capk_s) * (sizeof(CellValT<true>) + 4)
-                    : (size_t)(t.capk_n + t.capk_s) * (sizeof(CellValT<false>) + 4) + (size_t)(t.cap_n + t.cap_s) * 8);
-    if (t.smem + 12 * 1024 > h->smem_optin)
+    const size_t rows_b = (size_t)(t.cap_n + t.cap_s) * 8 + (size_t)(t.capr_n + t.capr_s) * 4, cells = (size_t)(t.capk_n + t.capk_s);
+    t.smem = rows_b + (h->fx ? cells * (sizeof(CellValT<true, false>) + 4)
+                             : cells * (sizeof(CellValT<false, false>) + 4) + (size_t)(t.cap_n + t.cap_s) * 8);
+    t.smem_cp = h->fx ? rows_b + cells * (sizeof(CellValT<true, true>) + 8 + 4) : 0;
+    if (t.smem_cp && t.smem_cp + 12 * 1024 > h->smem_optin) t.smem_cp = 0;
+    if (t.smem + 12 * 1024 > h->smem_optin) t.smem = 0;
+    if (!t.smem && !t.smem_cp)
       return fail(ABD_ERR_INVALID, "an individual tile does not fit in shared memory (too many OD rows per 128 individuals)");
     std::vector<TileDesc> desc((size_t)t.ntiles);
     for (int k = 0; k < t.ntiles; ++k) {
@@ -382,53 +389,89 @@ int ensure_chains(abd_handle* h, int C) {
 // to exactly `waves` full waves of resident CTAs (n_sms x CTAs-per-SM), so every SM gets the
 // same number of equally sized tiles and there is no partial last wave; beyond that the tail is
 // negligible and tiles simply hold ~`target` OD rows (a handful per thread).
-void plan_grid(const abd_handle* h, int C, int ctas_per_sm, int* want_tiles, int* chains_per_cta) {
+// `one_wave_rows`: tiles may grow to this many OD rows if that lets the whole grid run as ONE wave (12 500 individuals x
+// 4 chains -- an eighth of the 100k cohort -- is 1.25 waves of 2 200-row tiles: two waves, 18.4 us, against one wave of
+// 2 650-row tiles); 0 = the ordinary limit.  The caller falls back to 0 when such tiles do not fit in shared memory.
+constexpr int kTileRowsOneWave = 2750;
+void plan_grid(const abd_handle* h, int C, int ctas_per_sm, int* want_tiles, int* chains_per_cta, int one_wave_rows = 0) {
   const double rows = (double)(h->R[0] + h->R[1]);
   const int target = h->tile_rows_override > 0 ? h->tile_rows_override : 2200;
+  const int min_tiles = (h->N + kTileMaxInds - 1) / kTileMaxInds;
+  const int resident = h->n_sms * ctas_per_sm;
+  // tiles for `cpc` chains per CTA; returns the number of waves the grid then takes
+  auto tiles_for = [&](int cpc, int* tiles_out) -> double {
+    const int groups = (C + cpc - 1) / cpc;
+    int tiles = std::max(min_tiles, (int)std::ceil(rows / target));
+    double waves = std::ceil((double)tiles * groups / resident);
+    if ((long)tiles * groups <= 6L * resident) {
+      for (int w = 1; w <= 6; ++w) {
+        const int t = (resident * w) / groups;
+        const double limit = (w == 1 && one_wave_rows > target && h->tile_rows_override == 0) ? (double)one_wave_rows : target * 1.02;
+        if (t >= min_tiles && t >= 1 && rows / t <= limit) {
+          tiles = t;
+          waves = w;
+          break;
+        }
+      }
+    }
+    *tiles_out = std::max(1, std::min(tiles, h->N));
+    return waves;
+  };
   // chains looped over inside one CTA (the staged tile is reused): measured at 10k / 12.5k individuals, 32 chains run
   // 4 - 11 % faster with 2 per CTA than with 4 (twice the waves: shorter start-up and drain), 128 chains 5 % faster
-  // with 4 than with 2 (tools/tune.py sums)
+  // with 4 than with 2, and 8 / 16 per CTA are 10 / 25 % slower than 4 (tools/tune.py sums)
   int cpc = h->chains_per_cta_override > 0 ? h->chains_per_cta_override : (C >= 64 ? 4 : (C >= 32 ? 2 : 1));
   cpc = std::min(cpc, C);
   cpc = std::min(cpc, kMaxChainsPerCta);  // a CTA remembers at most this many chains it finished last (k_sums: s_pend)
-  const int groups = (C + cpc - 1) / cpc;
-  const int min_tiles = (h->N + kTileMaxInds - 1) / kTileMaxInds;
-  const int resident = h->n_sms * ctas_per_sm;
-  int tiles = std::max(min_tiles, (int)std::ceil(rows / target));
-  if ((long)tiles * groups <= 6L * resident) {
-    for (int waves = 1; waves <= 6; ++waves) {
-      const int t = (resident * waves) / groups;
-      if (t >= min_tiles && t >= 1 && rows / t <= target * 1.02) {
-        tiles = t;
-        break;
-      }
+  int tiles;
+  const double waves1 = tiles_for(cpc, &tiles);
+  if (h->chains_per_cta_override == 0 && cpc == 1 && waves1 >= 3.0) {
+    // Few chains on a cohort of several waves: a wave of one-chain CTAs costs ~9.3 us whatever its tile size, a CTA
+    // that loops over k chains ~1 + 8.3 k us per wave (measured, 4 chains: 25 000 individuals 28.3 us as 3 waves
+    // against 21.2 as ONE wave of two-chain CTAs; 50 000 individuals 47.1 as 5 waves against 35.8 as one wave of
+    // four-chain CTAs).  Taken only when the estimate wins by 15 %: e.g. not at 100 000 individuals (82.7 against 85.7).
+    double best = 9.3 * waves1;
+    for (int k = 2; k <= 4 && k <= C; k *= 2) {
+      if (C % k) continue;
+      int tk;
+      const double cost = tiles_for(k, &tk) * (1.0 + 8.3 * k);
+      if (cost < 0.85 * 9.3 * waves1 && cost < best) best = cost, cpc = k, tiles = tk;
     }
   }
-  *want_tiles = std::max(1, std::min(tiles, h->N));
+  *want_tiles = tiles;
   *chains_per_cta = cpc;
 }
 
 // The dynamic shared-memory limit of a kernel is a per-device function attribute shared by every
 // handle of the process: only ever raise it (a small cohort must not lower it under a large one).
-template <typename M, typename XT, bool TRAJ>
+template <typename M, typename XT, bool TRAJ, bool CP>
 cudaError_t sums_smem_attr(int device, size_t smem) {
   static size_t configured[64] = {};
   const int d = (device >= 0 && device < 64) ? device : 0;
   const size_t want = std::max<size_t>(smem, 48 * 1024);
   if (want <= configured[d]) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(k_sums<M, XT, TRAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+  cudaError_t e = cudaFuncSetAttribute(k_sums<M, XT, TRAJ, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_sums<M, XT, TRAJ>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(k_sums<M, XT, TRAJ, CP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   configured[d] = want;
   return cudaSuccess;
 }
 
-template <typename M, typename XT>
+template <typename M, typename XT, bool CP>
 cudaError_t sums_occupancy(int device, size_t smem, int* occ) {
-  cudaError_t e = sums_smem_attr<M, XT, false>(device, smem);
+  cudaError_t e = sums_smem_attr<M, XT, false, CP>(device, smem);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sums<M, XT, false>, kSumsBlock, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sums<M, XT, false, CP>, kSumsBlock, smem);
+}
+// resident CTAs per SM of the plain-evaluation kernel for this handle's mask width / dilution mode
+cudaError_t sums_occupancy_h(const abd_handle* h, bool compact, size_t smem, int* occ) {
+  if (compact) return h->wide ? sums_occupancy<uint64_t, uint8_t, true>(h->device, smem, occ)
+                              : sums_occupancy<uint32_t, uint8_t, true>(h->device, smem, occ);
+  if (h->wide) return h->fx ? sums_occupancy<uint64_t, uint8_t, false>(h->device, smem, occ)
+                            : sums_occupancy<uint64_t, double, false>(h->device, smem, occ);
+  return h->fx ? sums_occupancy<uint32_t, uint8_t, false>(h->device, smem, occ)
+               : sums_occupancy<uint32_t, double, false>(h->device, smem, occ);
 }
 
 // The packed copy of the resident chain state for a launch that reads (i_raw, waner): non-null only
@@ -450,23 +493,24 @@ int resident_pack(abd_handle* h, int C, const int8_t* i_raw, const int8_t* waner
   return ABD_OK;
 }
 
-template <typename M, typename XT>
+template <typename M, typename XT, bool CP>
 int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cfg, dim3 grid, const double* theta,
                   int theta_is_q, const int8_t* i_raw, const int8_t* waner, const void* pack_v, double* sums,
                   const FinalizeCfg& fin, const TrajCfg& traj, cudaStream_t st, const ThetaInline& thin) {
   const PackedState<M>* pack = reinterpret_cast<const PackedState<M>*>(pack_v);
+  const size_t smem = CP ? tl.smem_cp : tl.smem;
   if (std::getenv("ABD_B200_VERBOSE")) {
-    const int occ = tl.occ;
-    std::fprintf(stderr, "[abd_b200] k_sums grid (%u, %u) dyn smem %zu B, occupancy %d CTAs/SM, caps rows %d/%d cells %d/%d\n",
-                 grid.x, grid.y, tl.smem, occ, tl.cap_n, tl.cap_s, tl.capk_n, tl.capk_s);
+    const int occ = CP ? tl.occ_cp : tl.occ;
+    std::fprintf(stderr, "[abd_b200] k_sums grid (%u, %u) dyn smem %zu B%s, occupancy %d CTAs/SM, caps rows %d/%d cells %d/%d\n",
+                 grid.x, grid.y, smem, CP ? " (compact cells)" : "", occ, tl.cap_n, tl.cap_s, tl.capk_n, tl.capk_s);
   }
   const int tj = traj.n_steps > 0 ? 1 : 0;
-  if (tj) CU((sums_smem_attr<M, XT, true>(h->device, tl.smem)));
-  else CU((sums_smem_attr<M, XT, false>(h->device, tl.smem)));
+  if (tj) CU((sums_smem_attr<M, XT, true, CP>(h->device, smem)));
+  else CU((sums_smem_attr<M, XT, false, CP>(h->device, smem)));
   cudaLaunchConfig_t lc{};
   lc.gridDim = grid;
   lc.blockDim = dim3(kSumsBlock);
-  lc.dynamicSmemBytes = tl.smem;
+  lc.dynamicSmemBytes = smem;
   lc.stream = st;
   cudaLaunchAttribute attr[1];
   const TileDesc* tiles = reinterpret_cast<const TileDesc*>(tl.d_tiles);
@@ -476,7 +520,7 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
       return fail(ABD_ERR_INVALID, "sharded leapfrog: one step per launch");
     if (traj.n_steps > 1) {  // CTAs wait on one another: they must all be resident
       int occ = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sums<M, XT, true>, kSumsBlock, tl.smem));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sums<M, XT, true, CP>, kSumsBlock, smem));
       if ((long)grid.x * grid.y > (long)occ * h->n_sms)
         return fail(ABD_ERR_INVALID, "abd_leapfrog_dev: the grid does not fit on the device at once");
       attr[0].id = cudaLaunchAttributeCooperative;
@@ -488,14 +532,14 @@ int launch_sums_t(abd_handle* h, const abd_handle::Tiling& tl, const SumsCfg& cf
       lc.numAttrs = h->use_pdl ? 1 : 0;
     }
     lc.attrs = attr;
-    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, true>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, pack, h->d_partial,
+    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, true, CP>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, pack, h->d_partial,
                           h->d_ticket, sums, fin, pri, h->d_aux, traj, h->xch_active ? h->xch : XchCfg{}, ThetaInline{}));
   } else {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = h->use_pdl ? 1 : 0;
-    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, false>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, pack, h->d_partial,
+    CU(cudaLaunchKernelEx(&lc, k_sums<M, XT, false, CP>, h->dc, tiles, cfg, theta, theta_is_q, i_raw, waner, pack, h->d_partial,
                           h->d_ticket, sums, fin, pri, h->d_aux, traj, h->xch_active ? h->xch : XchCfg{}, thin));
   }
   return ABD_OK;
@@ -511,17 +555,20 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
   // plan for the kernel's register-limited occupancy first; if the tiles that plan needs do not
   // fit that many CTAs per SM (shared memory), plan again for what actually fits
   int want, cpc, rc;
+  bool compact = false;
   abd_handle::Tiling* tl = nullptr;
-  for (int occ = ABD_SUMS_MINB; occ >= 1; --occ) {
+  for (int attempt = 0; attempt < 2 * ABD_SUMS_MINB; ++attempt) {
+    const int occ = ABD_SUMS_MINB - attempt / 2;
+    const int one_wave_rows = (attempt & 1) ? 0 : kTileRowsOneWave;  // first with the larger one-wave tiles, then without
     if (traj.n_steps == 1) {
       // a single leapfrog step waits on nothing inside the grid: the ordinary plan with one chain per CTA (the
       // trajectory variant keeps a chain's position in shared memory), any number of waves
       const int keep = h->chains_per_cta_override;
       h->chains_per_cta_override = 1;
-      plan_grid(h, C, occ, &want, &cpc);
+      plan_grid(h, C, occ, &want, &cpc, one_wave_rows);
       h->chains_per_cta_override = keep;
     } else {
-      plan_grid(h, C, occ, &want, &cpc);
+      plan_grid(h, C, occ, &want, &cpc, one_wave_rows);
     }
     if (traj.n_steps > 1 && cpc != 1) {  // persistent trajectory: re-plan with one chain per CTA, exactly one wave
       cpc = 1;
@@ -529,21 +576,29 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
       want = std::max(1, std::min(want, h->N));
     }
     if ((rc = get_tiling(h, want, &tl))) return rc;
-    if (!tl->occ) {
+    // the 32-byte cells if the tile fits `occ` CTAs per SM with them (two shared-memory loads per row), else the
+    // compact cells (three narrower loads per row: 2 % slower at equal tiles, but 12 500 individuals x 4 chains -- an
+    // eighth of the 100k cohort -- then run as one wave: 18.5 -> 11.6 us per launch)
+    if (tl->smem && !tl->occ) {
       int o = 0;
-      cudaError_t e;
-      if (h->wide)
-        e = h->fx ? sums_occupancy<uint64_t, uint8_t>(h->device, tl->smem, &o) : sums_occupancy<uint64_t, double>(h->device, tl->smem, &o);
-      else
-        e = h->fx ? sums_occupancy<uint32_t, uint8_t>(h->device, tl->smem, &o) : sums_occupancy<uint32_t, double>(h->device, tl->smem, &o);
-      CU(e);
+      CU(sums_occupancy_h(h, false, tl->smem, &o));
       tl->occ = std::max(o, 1);
     }
-    if (tl->occ >= occ) break;
+    compact = false;
+    if (tl->smem && tl->occ >= occ && !(h->force_compact && tl->smem_cp)) break;
+    if (tl->smem_cp && !tl->occ_cp) {
+      int o = 0;
+      CU(sums_occupancy_h(h, true, tl->smem_cp, &o));
+      tl->occ_cp = std::max(o, 1);
+    }
+    compact = tl->smem_cp != 0;
+    if (compact && tl->occ_cp >= occ) break;
+    if (attempt + 1 == 2 * ABD_SUMS_MINB && !compact && !tl->smem) return fail(ABD_ERR_INVALID, "tile does not fit in shared memory");
   }
+  const int tl_occ = compact ? tl->occ_cp : tl->occ;
   if (traj.n_steps > 1) {
     // persistent mode: one chain per CTA and every CTA resident at once
-    if (cpc != 1 || (long)tl->ntiles * C > (long)h->n_sms * tl->occ)
+    if (cpc != 1 || (long)tl->ntiles * C > (long)h->n_sms * tl_occ)
       return fail(ABD_ERR_INVALID, "abd_leapfrog_dev: too many chains for one resident grid on this cohort; "
                                    "use abd_logp_dlogp_dev per step");
   }
@@ -558,14 +613,16 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
   }
   SumsCfg cfg{tl->ntiles, tl->cap_n, tl->cap_s, tl->capr_n, tl->capr_s, tl->capk_n, tl->capk_s, cpc, C};
   dim3 grid(tl->ntiles, (C + cpc - 1) / cpc);
+  h->last_plan[0] = tl->ntiles, h->last_plan[1] = (int)grid.y, h->last_plan[2] = cpc;
+  h->last_plan[3] = (int)(compact ? tl->smem_cp : tl->smem), h->last_plan[4] = compact ? 1 : 0, h->last_plan[5] = tl_occ;
   void* pack = nullptr;
   if ((rc = resident_pack(h, C, i_raw, waner, st, &pack))) return rc;
-  if (h->wide)
-    rc = h->fx ? launch_sums_t<uint64_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, pack, sums, fin, traj, st, thin)
-               : launch_sums_t<uint64_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, pack, sums, fin, traj, st, thin);
-  else
-    rc = h->fx ? launch_sums_t<uint32_t, uint8_t>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, pack, sums, fin, traj, st, thin)
-               : launch_sums_t<uint32_t, double>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, pack, sums, fin, traj, st, thin);
+#define ABD_LAUNCH_SUMS(M_, XT_, CP_) \
+  launch_sums_t<M_, XT_, CP_>(h, *tl, cfg, grid, theta, theta_is_q, i_raw, waner, pack, sums, fin, traj, st, thin)
+  if (compact) rc = h->wide ? ABD_LAUNCH_SUMS(uint64_t, uint8_t, true) : ABD_LAUNCH_SUMS(uint32_t, uint8_t, true);
+  else if (h->wide) rc = h->fx ? ABD_LAUNCH_SUMS(uint64_t, uint8_t, false) : ABD_LAUNCH_SUMS(uint64_t, double, false);
+  else rc = h->fx ? ABD_LAUNCH_SUMS(uint32_t, uint8_t, false) : ABD_LAUNCH_SUMS(uint32_t, double, false);
+#undef ABD_LAUNCH_SUMS
   if (rc) return rc;
   CU(cudaGetLastError());
   h->launches++;
@@ -693,6 +750,7 @@ int new_handle(abd_handle** out, int device, int G, int N) {
   if (const char* e = std::getenv("ABD_B200_NO_PULL")) h->use_pull = !(e[0] == '1');
   if (const char* e = std::getenv("ABD_B200_NO_INLINE")) h->use_inline = !(e[0] == '1');
   if (const char* e = std::getenv("ABD_B200_NO_PACK")) h->use_pack = !(e[0] == '1');
+  if (const char* e = std::getenv("ABD_B200_COMPACT_CELLS")) h->force_compact = (e[0] == '1');  // tests: compact cells wherever they exist
   {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->n_sms = v;
@@ -1058,6 +1116,12 @@ int64_t abd_algorithmic_bytes_gibbs(const abd_handle* h, int C) {
   return (int64_t)C * (2 * (G * N + N) + 120) + 2 * G * N + 20 * R + 8 * (N + 1);
 }
 int64_t abd_launch_count(const abd_handle* h) { return h ? h->launches : 0; }
+
+int abd_last_plan(const abd_handle* h, int32_t* out6) {
+  if (!h || !out6) return fail(ABD_ERR_INVALID, "NULL argument");
+  for (int k = 0; k < 6; ++k) out6[k] = h->last_plan[k];
+  return ABD_OK;
+}
 
 int abd_set_tuning(abd_handle* h, int rows_per_tile, int chains_per_cta) {
   if (!h) return fail(ABD_ERR_INVALID, "NULL handle");

@@ -84,13 +84,21 @@ struct __align__(16) TileDesc {
 
 // trajectory of one cell: titer m, decaying part T (or U) and its rho-derivative; in factored mode
 // also Em = exp(b m) (capped so that exp(-b x) * Em <= e^700)
-template <bool FX>
+template <bool FX, bool CP>
 struct CellValT {
   double m, T, dT;
 };
 template <>
-struct __align__(16) CellValT<true> {
+struct __align__(16) CellValT<true, false> {
   double m, T, dT, Em;
+};
+// Compact layout (factored mode, tiles too large for the 32-byte cells at full occupancy): 16 bytes per cell plus
+// Em = exp(b m) in an array of its own (24 bytes per cell, not 32).  N antigen: m is not kept, sum q (x - m) is formed
+// as  sum q x - (init sum q + perm sum q P + temp sum q T)  from sums the rows accumulate anyway; S antigen: the T
+// slot holds m (the S rows never need U itself).
+template <>
+struct __align__(16) CellValT<true, true> {
+  double T, dT;
 };
 constexpr int kMaxXLevels = 32;
 
@@ -155,7 +163,7 @@ constexpr int kRowUnroll = ABD_ROW_UNROLL, kCellUnroll = ABD_CELL_UNROLL;
 // its dilution (packed with its cell index), exp(-b (x - m)) = exp(-b x) * exp(b m) costs one exp
 // per CELL plus a per-chain table over the distinct dilutions; double = general fallback, the
 // dilutions themselves are staged and every row evaluates its own exp.
-template <typename M, typename XT, bool TRAJ>
+template <typename M, typename XT, bool TRAJ, bool CP>
 __global__ void __launch_bounds__(kSumsBlock, ABD_SUMS_MINB)
 k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg,
        const double* __restrict__ theta_ptr, const int theta_is_q,
@@ -171,12 +179,15 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
   // dynamic shared memory: staged rows (od, x, row->cell), staged cell meta, per-cell values
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   constexpr bool kFX = sizeof(XT) == 1;
-  using CellVal = CellValT<kFX>;
+  constexpr bool kCP = kFX && CP;  // compact cells (see CellValT)
+  using CellVal = CellValT<kFX, kCP>;
   double* s_od_n = reinterpret_cast<double*>(dyn_smem);
   double* s_od_s = s_od_n + cfg.cap_n;
   CellVal* s_cv_n = reinterpret_cast<CellVal*>(s_od_s + cfg.cap_s);
   CellVal* s_cv_s = s_cv_n + cfg.capk_n;
-  double* s_x_n = reinterpret_cast<double*>(s_cv_s + cfg.capk_s);   // cap_n doubles (not in factored mode)
+  double* s_em_n = reinterpret_cast<double*>(s_cv_s + cfg.capk_s);  // capk_n + capk_s doubles (compact cells only)
+  double* s_em_s = s_em_n + (kCP ? cfg.capk_n : 0);
+  double* s_x_n = s_em_s + (kCP ? cfg.capk_s : 0);                  // cap_n doubles (not in factored mode)
   double* s_x_s = s_x_n + (kFX ? 0 : cfg.cap_n);
   uint32_t* s_rc_n = reinterpret_cast<uint32_t*>(s_x_s + (kFX ? 0 : cfg.cap_s));
   uint32_t* s_rc_s = s_rc_n + cfg.capr_n;
@@ -522,12 +533,15 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         double P, T, dT;
         traj_n<M>(s_ind[li].inf, t, s_pw[0], P, T, dT);
         CellVal cv;
-        cv.m = init + perm * P + temp * T;
+        const double m = init + perm * P + temp * T;
         cv.T = T;
         cv.dT = (P != 0.0) ? dT : -0.0;  // sign bit of dT carries "never exposed" (P = 0)
+        if constexpr (!kCP) cv.m = m;
         if constexpr (kFX) {
-          const double z = bn_fx * cv.m;
-          cv.Em = fast_exp((z > zmax_n) ? zmax_n : z, s_tab);  // NaN stays NaN
+          const double z = bn_fx * m;
+          const double em = fast_exp((z > zmax_n) ? zmax_n : z, s_tab);  // NaN stays NaN
+          if constexpr (kCP) s_em_n[k - cn0] = em;
+          else cv.Em = em;
         }
         s_cv_n[k - cn0] = cv;
       }
@@ -543,12 +557,15 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         double P, U, dU;
         traj_s<M>(st.inf, st.vacw & ~top_bit<M>(), (st.vacw & top_bit<M>()) != 0, t, s_pw[1], P, U, dU);
         CellVal cv;
-        cv.m = init + perm * P + U;
-        cv.T = U;
+        const double m = init + perm * P + U;
+        cv.T = kCP ? m : U;
         cv.dT = (P != 0.0) ? dU : -0.0;
+        if constexpr (!kCP) cv.m = m;
         if constexpr (kFX) {
-          const double z = bs_fx * cv.m;
-          cv.Em = fast_exp((z > zmax_s) ? zmax_s : z, s_tab);
+          const double z = bs_fx * m;
+          const double em = fast_exp((z > zmax_s) ? zmax_s : z, s_tab);
+          if constexpr (kCP) s_em_s[k - cs0] = em;
+          else cv.Em = em;
         }
         s_cv_s[k - cs0] = cv;
       }
@@ -567,12 +584,22 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         const uint32_t* rcp = s_rc_n - qn0;
         const double* odp = s_od_n - an0;
         const CellVal* cvp = s_cv_n - cn0;
+        [[maybe_unused]] const double* emp = s_em_n - cn0;
 #pragma unroll kRowUnroll
         for (int r = rn0 + tid; r < rn1 && tid < nwork; r += nwork) {
           double sg, res, q, xm;
           const uint32_t rc = rcp[r];
           const CellVal cv = cvp[kFX ? (rc >> 5) : rc];
-          if constexpr (kFX) {
+          if constexpr (kCP) {
+            const double2 xe = s_xe[0][rc & 31];
+            if constexpr (kDirect) {  // (the cell's response again: init + perm P + temp T)
+              const double m = s_th[N_INIT] + ((__double2hiint(cv.dT) < 0) ? 0.0 : s_th[N_PERM]) + s_th[N_TEMP] * cv.T;
+              row_eval(xe.x, odp[r], m, b, d, s_tab, sg, res, q, xm);
+            } else {
+              row_eval_E(xe.y * emp[rc >> 5], odp[r], d, sg, res, q);
+              xm = xe.x;  // sum q x here; the cells' share  sum q m  is taken off the block's total (below)
+            }
+          } else if constexpr (kFX) {
             const double2 xe = s_xe[0][rc & 31];
             xm = xe.x - cv.m;
             if constexpr (kDirect) row_eval(xe.x, odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
@@ -594,12 +621,18 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
         const uint32_t* rcp = s_rc_s - qs0;
         const double* odp = s_od_s - as0;
         const CellVal* cvp = s_cv_s - cs0;
+        [[maybe_unused]] const double* emp = s_em_s - cs0;
 #pragma unroll kRowUnroll
         for (int r = rs0 + tid; r < rs1 && tid < nwork; r += nwork) {
           double sg, res, q, xm;
           const uint32_t rc = rcp[r];
           const CellVal cv = cvp[kFX ? (rc >> 5) : rc];
-          if constexpr (kFX) {
+          if constexpr (kCP) {  // (the T slot holds m)
+            const double2 xe = s_xe[1][rc & 31];
+            xm = xe.x - cv.T;
+            if constexpr (kDirect) row_eval(xe.x, odp[r], cv.T, b, d, s_tab, sg, res, q, xm);
+            else row_eval_E(xe.y * emp[rc >> 5], odp[r], d, sg, res, q);
+          } else if constexpr (kFX) {
             const double2 xe = s_xe[1][rc & 31];
             xm = xe.x - cv.m;
             if constexpr (kDirect) row_eval(xe.x, odp[r], cv.m, b, d, s_tab, sg, res, q, xm);
@@ -626,11 +659,22 @@ k_sums(const DevCohort dc, const TileDesc* __restrict__ tiles, const SumsCfg cfg
       if ((lane & 1) == 0) s_red[warp][warp_reduce16_index(lane)] = tot;
     }
     __syncthreads();
-    if (tid < kNSums) {
+    if (warp == 0) {
       double v = 0.0;
+      if (lane < kNSums) {
 #pragma unroll
-      for (int wv = 0; wv < kSumsWarps; ++wv) v += s_red[wv][tid];
-      partial[((size_t)c * ntiles + tile) * kNSums + tid] = v;
+        for (int wv = 0; wv < kSumsWarps; ++wv) v += s_red[wv][lane];
+      }
+      if constexpr (kCP) {
+        if (!s_direct) {
+          // the factored N rows accumulated  sum q x;  sum q (x - m) = sum q x - sum q m  with
+          // m = init + perm P + temp T, linear in sums this warp holds
+          const double qi = __shfl_sync(0xffffffffu, v, SN_QINIT), qp = __shfl_sync(0xffffffffu, v, SN_QPERM);
+          const double qt = __shfl_sync(0xffffffffu, v, SN_QTEMP);
+          if (lane == SN_2) v -= s_th[N_INIT] * qi + s_th[N_PERM] * qp + s_th[N_TEMP] * qt;
+        }
+      }
+      if (lane < kNSums) partial[((size_t)c * ntiles + tile) * kNSums + lane] = v;
     }
 
     PHASE(6);

@@ -211,6 +211,14 @@ class AbdEngine:
     def set_tuning(self, rows_per_tile=0, chains_per_cta=0):
         check(self._lib.abd_set_tuning(self._h, int(rows_per_tile), int(chains_per_cta)))
 
+    def last_plan(self) -> dict:
+        """Grid plan of the most recent log-likelihood launch (tiles, chain groups, chains per CTA, shared memory,
+        compact cell layout or not, resident CTAs per SM)."""
+        out = np.zeros(6, dtype=np.int32)
+        check(self._lib.abd_last_plan(self._h, _ptr(out)))
+        keys = ("tiles", "chain_groups", "chains_per_cta", "smem_bytes", "compact_cells", "ctas_per_sm")
+        return dict(zip(keys, (int(v) for v in out)))
+
     # ------------------------------------------------------------------------------ state
     def upload_state(self, i_raw, waner):
         i_raw = np.asarray(i_raw)

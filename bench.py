@@ -369,12 +369,15 @@ def bench_sharded(dist, rank, world, local, dev, K, n_big=100_000, chain_counts=
                         e1g.logp_dlogp_dev(Csh, tqs.data_ptr(), di, dw, o1.data_ptr(), o2.data_ptr(), side.cuda_stream)
                 t1[0] = _timed_us(g1.replay, n_rep, None, dev, warm=2) / block
                 lp1.copy_(o1)
+                plan1 = e1g.last_plan()
                 del g1
         if dist:
             dist.broadcast(t1, 0)
             dist.broadcast(lp1, 0)
         us1 = float(t1.item())
         res["one_gpu"] = {"us_per_eval": us1, "evals_per_s": Csh / us1 * 1e6}
+        if rank == 0:
+            res["one_gpu"]["plan"] = plan1
         if dist:
             se = ShardedEngine(big, splits=SPLITS, device_index=local, rank=rank, world=world)
             se.upload_state(ib, wb)
@@ -400,6 +403,7 @@ def bench_sharded(dist, rank, world, local, dev, K, n_big=100_000, chain_counts=
             tw = torch.tensor([wait_us], dtype=torch.float64, device=dev)
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
             sf.engine.xch_status()
+            plan_f = sf.engine.last_plan()
             del gf
             sf.close()
             rel = float(((lp_f - lp1).abs() / lp1.abs()).max())
@@ -410,7 +414,7 @@ def bench_sharded(dist, rank, world, local, dev, K, n_big=100_000, chain_counts=
                 "bitwise_equal_to_nccl_path": bool(torch.equal(lp_f, lp_n)), "rel_err_vs_one_gpu": rel}
             res["fused_peer_allreduce_graph"] = {
                 "us_per_eval": us_graph, "speedup_vs_1gpu": us1 / us_graph, "evals_per_s": Csh / us_graph * 1e6,
-                "exchange_wait_us_per_eval_max_over_ranks": float(tw.item()),
+                "exchange_wait_us_per_eval_max_over_ranks": float(tw.item()), "plan_rank0": plan_f,
                 "note": f"CUDA graph of {block} evaluations per rank; exchange_wait = mean time the finishing CTA spent waiting "
                         "for its slowest peer's sums (launch skew + NVLink latency), measured in the kernel with %globaltimer"}
         out["by_chains"][str(Csh)] = res

@@ -342,6 +342,10 @@ int abd_set_chain_offset(abd_handle* h, int64_t chain_offset);
 /* Tuning knobs of the log-likelihood kernel (0 = automatic): target OD rows per CTA tile and
  * chains looped over inside one CTA (reusing the rows staged in shared memory).             */
 int abd_set_tuning(abd_handle* h, int rows_per_tile, int chains_per_cta);
+/* The grid plan of the handle's most recent log-likelihood launch: out6 = {tiles of individuals, chain groups,
+ * chains per CTA, dynamic shared memory per CTA (bytes), 1 if the compact cell layout was used, resident CTAs per
+ * SM}.  (Introspection for tests and measurements; nothing in the reference corresponds to it.)              */
+int abd_last_plan(const abd_handle* h, int32_t* out6);
 
 /* Test hook: out_exp[i] = the kernels' fast exp(z[i]), out_rcp[i] = their fast 1/(1 + |z[i]|)
  * (host pointers; checked against libm in tests/test_gpu_parity.py).                        */

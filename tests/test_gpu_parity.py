@@ -235,6 +235,81 @@ def test_factored_exponential_vs_fallback_and_direct_rows(Engine, monkeypatch):
         assert grad_ok(b, ref_g), np.abs(b - ref_g).max()
 
 
+def test_compact_cell_layout_against_the_oracle(Engine, monkeypatch):
+    """Tiles too large for the 32-byte (m, T, dT, exp(b m)) cells at full occupancy take the compact layout
+    (16-byte cells + an exp(b m) array; the N antigen's  sum q (x - m)  is rebuilt from sums the rows accumulate
+    anyway).  (1) Forced on the 1k cohort (ABD_B200_COMPACT_CELLS=1): logp + gradient against the oracle at ordinary
+    and extreme points (direct rows, capped b m), host state and resident packed state, one single-step leapfrog
+    launch (the trajectory variant of the kernel), beside the ordinary layout on the same points.  (2) Chosen by the
+    planner itself: 12 500 individuals x 4 chains (an eighth of the 100k cohort) run as ONE wave of larger tiles."""
+    import torch
+
+    from abdpymc_b200.cohort import synthetic_cohort
+
+    co = synthetic_cohort(1000)
+    rng = np.random.default_rng(78)
+    q, i_raw, w = draw_points(rng, co.n_gaps, co.n_inds, 16)
+    q[6, 11], q[6, 14] = -80.0, 55.0      # |b| x_max > 300: direct rows
+    q[7, 11], q[7, 14] = -42.0, -42.8     # just below the switch
+    q[8, 4], q[8, 10] = 90.0, -120.0      # b m far outside exp's range
+    q[9, 11], q[9, 4] = -40.0, 30.0       # b m beyond the cap
+    o = ora.Oracle(co, splits=(14, 20), dense=False)
+    ref = [o.logp_dlogp(q[k], i_raw[k], w[k]) for k in range(len(q))]
+    ref_lp, ref_g = np.array([r[0] for r in ref]), np.stack([r[1] for r in ref])
+    with Engine(co, splits=(14, 20)) as eng:
+        lp0, g0 = eng.logp_dlogp(q, i_raw, w)
+        assert eng.last_plan()["compact_cells"] == 0
+    monkeypatch.setenv("ABD_B200_COMPACT_CELLS", "1")
+    with Engine(co, splits=(14, 20)) as eng:
+        lp, g = eng.logp_dlogp(q, i_raw, w)
+        plan = eng.last_plan()
+        assert plan["compact_cells"] == 1, plan
+        eng.upload_state(i_raw, w)
+        lp_r, g_r = eng.logp_dlogp(q)
+        assert np.array_equal(lp_r, lp) and np.array_equal(g_r, g)
+        for a, b in ((lp0, g0), (lp, g)):
+            assert np.all(np.abs(a - ref_lp) <= RTOL * np.abs(ref_lp)), np.abs((a - ref_lp) / ref_lp).max()
+            assert grad_ok(b, ref_g), np.abs(b - ref_g).max()
+        # one leapfrog step in one launch = half step, drift, evaluation, half step
+        C = 4
+        dev = torch.device("cuda:0")
+        eng.upload_state(i_raw[:C], w[:C])
+        a = rng.normal(size=(17, 17))
+        inv_mass = 1e-4 * (a @ a.T / 17 + np.eye(17))
+        eps, p = rng.uniform(0.05, 0.2, size=C), rng.normal(size=(C, 17)) * 30
+        ph = p + 0.5 * eps[:, None] * g[:C]
+        qn = q[:C] + eps[:, None] * (ph @ inv_mass)
+        lpn, gn = eng.logp_dlogp(qn)
+        pn = ph + 0.5 * eps[:, None] * gn
+        tq, tp, tg = (torch.from_numpy(v.copy()).to(dev) for v in (q[:C], p, g[:C]))
+        te, tm = torch.from_numpy(eps).to(dev), torch.from_numpy(inv_mass).to(dev)
+        tl = torch.zeros(C, dtype=torch.float64, device=dev)
+        di, dw = eng.state_dev(C)
+        eng.leapfrog_dev(C, 1, tq.data_ptr(), tp.data_ptr(), tg.data_ptr(), tl.data_ptr(), te.data_ptr(), tm.data_ptr(),
+                         di, dw, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        eng.leapfrog_status(C)
+        assert eng.last_plan()["compact_cells"] == 1
+        fin = np.isfinite(lpn)
+        assert fin.sum() >= 2
+        np.testing.assert_allclose(tq.cpu().numpy(), qn, rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(tl.cpu().numpy()[fin], lpn[fin], rtol=1e-11)
+        np.testing.assert_allclose(tp.cpu().numpy()[fin], pn[fin], rtol=1e-9, atol=1e-7)
+    monkeypatch.delenv("ABD_B200_COMPACT_CELLS")
+    # (2) the planner's own choice
+    co = synthetic_cohort(12_500)
+    q, i_raw, w = draw_points(np.random.default_rng(79), co.n_gaps, co.n_inds, 4)
+    o = ora.Oracle(co, splits=(14, 20), dense=False)
+    with Engine(co, splits=(14, 20)) as eng:
+        lp, g = eng.logp_dlogp(q, i_raw, w)
+        plan = eng.last_plan()
+        assert plan["compact_cells"] == 1 and plan["tiles"] * plan["chain_groups"] <= 148 * plan["ctas_per_sm"], plan
+        for k in range(4):
+            rl, rg = o.logp_dlogp(q[k], i_raw[k], w[k])
+            assert abs(lp[k] - rl) <= RTOL * abs(rl)
+            assert grad_ok(g[k], rg)
+
+
 def random_cohort(rng, G, N, rows_per_ind=6, p_empty=0.2):
     from abdpymc_b200.cohort import CohortArrays
 
