@@ -25,6 +25,19 @@ def test_fused_peer_allreduce_matches_nccl_and_unsharded():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_peer_allreduce_with_multi_chain_ctas_and_compact_cells():
+    """Shards of 25 000 individuals x 4 chains: the planner runs them as one wave of two-chain CTAs with the compact
+    cell layout, i.e. the exchange is posted from the deferred (after the chain loop) finaliser."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29595", str(ROOT / "tools" / "xch_check.py"), "50000", "4"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["ok"] and line["rel_err_vs_unsharded"] < 1e-11
+    assert line["plan_rank0"]["compact_cells"] == 1 and line["plan_rank0"]["chains_per_cta"] == 2, line
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_compound_sampler_on_an_individual_sharded_cohort():
     """HMC + Gibbs with the individuals split over 2 GPUs (distributed.ShardedTarget: fused NVLink all-reduce
     inside every leapfrog launch, local Gibbs sweeps) against the same sampler on one GPU."""

@@ -115,7 +115,7 @@ dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(json.dumps({"ok": bool(flag.item()), "world": world, "n_inds": n_inds, "chains": C, "rel_err_logp_fused_vs_nccl": e_lp,
                       "rel_err_grad_fused_vs_nccl": e_g, "rel_err_vs_unsharded": e_full, "us_per_eval_nccl": us_nccl,
-                      "us_per_eval_fused": us_fused, "us_per_eval_fused_graph": us_graph,
+                      "us_per_eval_fused": us_fused, "us_per_eval_fused_graph": us_graph, "plan_rank0": se_fused.engine.last_plan(),
                       "wait_us_rank_by_peer": [[round(float(v), 2) for v in w_] for w_ in all_wait]}))
 for se in (se_nccl, se_fused):
     se.close()
