@@ -593,8 +593,7 @@ int launch_sums(abd_handle* h, int C, const double* theta, int theta_is_q, const
     }
     compact = tl->smem_cp != 0;
     if (compact && tl->occ_cp >= occ) break;
-    if (attempt + 1 == 2 * ABD_SUMS_MINB && !compact && !tl->smem) return fail(ABD_ERR_INVALID, "tile does not fit in shared memory");
-  }
+  }  // (the last attempts ask for one CTA per SM, which any tiling get_tiling accepted provides: the loop always breaks)
   const int tl_occ = compact ? tl->occ_cp : tl->occ;
   if (traj.n_steps > 1) {
     // persistent mode: one chain per CTA and every CTA resident at once
