@@ -150,6 +150,11 @@ int abd_loglik_grad(abd_handle* h, int n_chains, const double* theta13, const in
  * transforms with their Jacobians, and the Bernoulli terms of i_raw and ab_s_waner.          */
 int abd_logp_dlogp(abd_handle* h, int n_chains, const double* q17, const int8_t* i_raw,
                    const int8_t* waner, double* out_logp, double* out_dlogp);
+/* (Both host-pointer calls above return as soon as their results have arrived: the kernel writes them
+ * straight into pinned host memory and the library watches them arrive instead of waiting for the end
+ * of the stream -- for <= 64 chains, falling back to cudaStreamSynchronize after 150 us; the handle's
+ * stream may still be draining the launch's last CTAs, which later calls on the handle are ordered
+ * behind.  ABD_B200_NO_POLL=1 restores the stream synchronisation.)                                   */
 
 /* Conditional log-odds of every binary variable given all others (test hook; what "Gibbs
  * parity" means):  out_i[c][t][n] = logp(i_raw[t,n]=1 | rest) -
