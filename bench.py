@@ -215,6 +215,31 @@ def cpu_throughput(n_sub, dense, cores, steps, warmup, fn=None):
     return evals / dt, dt / steps
 
 
+def cpu_c_port(seconds=3.0):
+    """The compiled CPU port (oracle/abd_oracle_c.c: plain C, OpenMP over individuals and OD rows, recurrence
+    form) on all host threads, whole 10k cohort: joint logp + gradient evaluations per second.  Never fatal."""
+    try:
+        from oracle import c_oracle
+
+        co, q, _, i_raw, w = workload()
+        threads = min(os.cpu_count() or 1, 64)
+        o = c_oracle.COracle(co, splits=SPLITS, threads=threads)
+        for c in range(N_CHAINS):
+            o.logp_dlogp(q[c], i_raw[c], w[c])
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds or n < 8:
+            o.logp_dlogp(q[n % N_CHAINS], i_raw[n % N_CHAINS], w[n % N_CHAINS])
+            n += 1
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "evals/s", "threads": threads, "kind": "port",
+                "sample": f"{n} joint logp+grad evaluations of the whole {co.n_inds}-individual cohort in {dt:.1f} s, one process, "
+                          f"{threads} OpenMP threads",
+                "what": "oracle/abd_oracle_c.c: the O(G N) recurrence form in plain C (gcc -O2 -fopenmp), checked against the "
+                        "reference-generated goldens; the algorithmically fair compiled CPU implementation of this path"}
+    except Exception as exc:  # a missing compiler on some box must not cost the bench line
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
+
 def cpu_baseline():
     """The bounded CPU sample reported next to the GPU number (rank 0, N = 1 only).  Runs
     before CUDA is initialised in this process (the pool forks)."""
@@ -237,7 +262,8 @@ def cpu_baseline():
             "sample": (f"{steps} steps x {cores} processes x 1 dense-formulation logp+grad evaluation on the first {n_sub} of "
                        f"{N_INDS} individuals, scaled by {n_sub}/{N_INDS}; PyMC is not installable offline, so this is "
                        "the NumPy restatement of the reference graph (oracle/abd_oracle.py)"),
-            "recurrence_port_evals_per_s": v_scan}
+            "recurrence_port_evals_per_s": v_scan,
+            "c_port": cpu_c_port()}  # (last: its OpenMP threads must not exist when the pools above fork)
 
 
 def run_reference(args):

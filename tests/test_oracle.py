@@ -70,6 +70,39 @@ def test_joint_logp_and_grad_match_reference(goldens, cohorts, dense):
         assert np.all(np.abs(grad - gref) <= tol), (k, grad - gref)
 
 
+def test_c_oracle_matches_reference_goldens_and_the_numpy_oracle(goldens, cohorts):
+    """oracle/abd_oracle_c.c (plain C, OpenMP; the compiled CPU port bench.py times beside the GPU) against the
+    goldens produced by executing the reference's own code -- every case: all split configurations, PCR+ ignored
+    or not, both bundled cohorts -- and against the NumPy oracle on a simulated 1k-individual cohort, with 1 and
+    with several threads."""
+    from abdpymc_b200.cohort import synthetic_cohort
+    from oracle import c_oracle
+
+    z, cases = goldens
+    for c in cases:
+        o = c_oracle.COracle(cohorts[c["cohort"]], splits=c["splits"], ignore_pcrpos=c["ignore_pcrpos"])
+        k = c["key"]
+        logp, grad = o.logp_dlogp(z[f"{k}/q"], z[f"{k}/i_raw"], z[f"{k}/w"])
+        ref, gref = float(z[f"{k}/logp"]), z[f"{k}/grad"]
+        assert abs(logp - ref) <= 1e-11 * abs(ref), (k, logp, ref)
+        tol = 1e-10 * np.maximum(np.abs(gref), 1e-3 * np.abs(gref).max())
+        assert np.all(np.abs(grad - gref) <= tol), (k, grad - gref)
+    co = synthetic_cohort(1000)
+    rng = np.random.default_rng(5)
+    for splits in ((), (14,), (14, 20)):
+        o_np = ora.Oracle(co, splits=splits, dense=False)
+        for threads in (1, 3):
+            o_c = c_oracle.COracle(co, splits=splits, threads=threads)
+            for _ in range(3):
+                q = ora.forward(ora.sample_prior(rng, co.n_gaps))
+                i_raw = (rng.random((co.n_gaps, co.n_inds)) < 0.06).astype(np.int8)
+                w = (rng.random(co.n_inds) < 0.5).astype(np.int8)
+                a, ga = o_np.logp_dlogp(q, i_raw, w)
+                b, gb = o_c.logp_dlogp(q, i_raw, w)
+                assert abs(a - b) <= 1e-12 * abs(a)
+                assert np.all(np.abs(ga - gb) <= 1e-10 * np.maximum(np.abs(ga), 1e-3 * np.abs(ga).max()))
+
+
 def test_deterministics_match_reference(goldens, cohorts):
     z, cases = goldens
     for c in cases:
