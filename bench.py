@@ -240,6 +240,32 @@ def cpu_c_port(seconds=3.0):
         return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 
 
+def cpu_c_gibbs(seconds=3.0):
+    """One Gibbs sweep of one chain over the whole 10k cohort by the compiled CPU port (abd_c_gibbs_sweep: the
+    sweep exactly as the CUDA kernel schedules it -- same Philox streams, same decisions --, OpenMP over
+    individuals, the flipped bit's individual re-evaluated per proposal), all host threads.  Never fatal."""
+    try:
+        from oracle import c_oracle
+
+        co, _, vals, i_raw, w = workload()
+        th = vals[:, [1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14, 15, 16]]
+        threads = min(os.cpu_count() or 1, 64)
+        o = c_oracle.COracle(co, splits=SPLITS, threads=threads)
+        o.gibbs_sweep(th[0], vals[0, 0], vals[0, 7], i_raw[0], w[0], 1, 0, 0)
+        n, t0, props = 0, time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds or n < 2:
+            c = n % N_CHAINS
+            props += o.gibbs_sweep(th[c], vals[c, 0], vals[c, 7], i_raw[c], w[c], 1, n, c)[2][0]
+            n += 1
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "sweeps/s", "threads": threads, "kind": "port", "proposals_per_sweep": props / n,
+                "sample": f"{n} sweeps of one chain over all {co.n_inds} individuals in {dt:.1f} s, one process, {threads} OpenMP threads",
+                "what": "oracle/abd_oracle_c.c abd_c_gibbs_sweep: the kernel's sweep restated in plain C (bit-identical decisions to "
+                        "the NumPy restatement the GPU sweep is tested against); measured, not extrapolated"}
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+
+
 def cpu_baseline():
     """The bounded CPU sample reported next to the GPU number (rank 0, N = 1 only).  Runs
     before CUDA is initialised in this process (the pool forks)."""
@@ -253,9 +279,11 @@ def cpu_baseline():
     v_val, _ = cpu_throughput(n_sub, True, cores, 8, 1, fn=_cpu_eval_value)
     co = workload()[0]
     proposals = 0.8 * (co.n_gaps * co.n_inds + co.n_inds)
+    c_port = cpu_c_port()  # (after the pools above: its OpenMP threads must not exist when they fork)
+    c_gibbs = cpu_c_gibbs()
     return {"value": v_dense, "unit": "evals/s", "cores": cores, "kind": "port",
             "gibbs": {"value": v_val / proposals, "unit": "sweeps/s", "logp_value_evals_per_s": v_val,
-                      "proposals_per_sweep": proposals,
+                      "proposals_per_sweep": proposals, "c_port": c_gibbs,
                       "sample": f"extrapolated: {cores} processes x 8 value-only dense-formulation logp evaluations on the "
                                 f"first {n_sub} individuals (scaled to {N_INDS}), one evaluation per proposed flip, "
                                 f"0.8 (G N + N) proposals per sweep (BinaryGibbsMetropolis, transit_p = 0.8)"},
@@ -263,7 +291,7 @@ def cpu_baseline():
                        f"{N_INDS} individuals, scaled by {n_sub}/{N_INDS}; PyMC is not installable offline, so this is "
                        "the NumPy restatement of the reference graph (oracle/abd_oracle.py)"),
             "recurrence_port_evals_per_s": v_scan,
-            "c_port": cpu_c_port()}  # (last: its OpenMP threads must not exist when the pools above fork)
+            "c_port": c_port}
 
 
 def run_reference(args):

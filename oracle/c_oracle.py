@@ -43,6 +43,9 @@ def load() -> C.CDLL:
         lib.abd_c_loglik_grad.restype = C.c_int
         lib.abd_c_loglik_grad.argtypes = [i32, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp,
                                           vp, i32]
+        lib.abd_c_gibbs_sweep.restype = C.c_int
+        lib.abd_c_gibbs_sweep.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double,
+                                          vp, vp, C.c_uint64, C.c_uint64, C.c_uint32, i32, C.c_double, i64, vp, i32]
         lib.abd_c_max_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -81,3 +84,32 @@ class COracle(ora.Oracle):
         if rc:
             raise ValueError("abd_c_loglik_grad: invalid sizes")
         return float(self._out[0]), self._out[1:].copy()
+
+    def _csr(self):
+        """OD rows sorted by individual + row pointers per antigen (built on first use)."""
+        if not hasattr(self, "_csr_rows"):
+            self._csr_rows = {}
+            for a in "ns":
+                x, od, gap, ind = self._rows[a]
+                order = np.argsort(ind, kind="stable")
+                ptr = np.concatenate(([0], np.cumsum(np.bincount(ind, minlength=self.N)))).astype(np.int64)
+                self._csr_rows[a] = (ptr, np.ascontiguousarray(x[order]), np.ascontiguousarray(od[order]),
+                                     np.ascontiguousarray(gap[order]))
+        return self._csr_rows
+
+    def gibbs_sweep(self, theta13, p, p_w, i_raw, w, seed, sweep, chain, mode=0, transit_p=0.8, ind_offset=0):
+        """One sweep of one chain as the CUDA kernel schedules it (same visiting order, random numbers and
+        decisions as ``abd_oracle.device_gibbs_sweep`` and ``abd_gibbs_sweep``); modes 0 (Metropolis) and 1 (heat
+        bath).  Returns (i_raw, w, [proposals, flips])."""
+        th = np.ascontiguousarray(theta13, dtype=np.float64)
+        i8 = np.ascontiguousarray(np.asarray(i_raw).reshape(self.G, self.N) != 0, dtype=np.int8).copy()
+        w8 = np.ascontiguousarray(np.asarray(w) != 0, dtype=np.int8).copy()
+        (pn, xn, odn, gn), (ps, xs, ods, gs) = self._csr()["n"], self._csr()["s"]
+        stats = np.zeros(2, dtype=np.int64)
+        rc = self._lib.abd_c_gibbs_sweep(self.G, self.N, len(self._splits), _p(self._splits), _p(self._pcr8), _p(self._vac8),
+                                         _p(pn), _p(xn), _p(odn), _p(gn), _p(ps), _p(xs), _p(ods), _p(gs), _p(th), float(p),
+                                         float(p_w), _p(i8), _p(w8), int(seed), int(sweep), int(chain), int(mode),
+                                         float(transit_p), int(ind_offset), _p(stats), self.threads)
+        if rc:
+            raise ValueError("abd_c_gibbs_sweep: invalid sizes or mode")
+        return i8, w8, [int(stats[0]), int(stats[1])]

@@ -103,6 +103,31 @@ def test_c_oracle_matches_reference_goldens_and_the_numpy_oracle(goldens, cohort
                 assert np.all(np.abs(ga - gb) <= 1e-10 * np.maximum(np.abs(ga), 1e-3 * np.abs(ga).max()))
 
 
+def test_c_gibbs_sweep_makes_the_numpy_restatements_decisions(cohorts):
+    """oracle/abd_oracle_c.c abd_c_gibbs_sweep (the compiled CPU sweep bench.py times) against
+    abd_oracle.device_gibbs_sweep: same Philox streams, visiting order and accept decisions, bit for bit, for the
+    Metropolis and heat-bath rules, with and without splits / PCR+, a chain index, a 64-bit seed and sweep counter
+    and an individual offset; and the result does not depend on the number of threads."""
+    from oracle import c_oracle
+
+    co = cohorts["test_cohort"]
+    rng = np.random.default_rng(11)
+    seed, sweep = 7 + (1 << 35), 3 + (1 << 33)
+    for splits, ignore in (((), False), ((14,), True), ((14, 20), False)):
+        for mode in (0, 1):
+            v = ora.sample_prior(rng, co.n_gaps)
+            th = np.array([v[n] for n in ora.THETA13])
+            i_raw = (rng.random((co.n_gaps, co.n_inds)) < 0.1).astype(np.int8)
+            w = (rng.random(co.n_inds) < 0.5).astype(np.int8)
+            want = ora.device_gibbs_sweep(co, splits, ignore, th, v["p"], v["ab_s_p_waner"], i_raw, w, seed, sweep, 2,
+                                          mode=mode, ind_offset=1000)
+            for threads in (1, 3):
+                o = c_oracle.COracle(co, splits=splits, ignore_pcrpos=ignore, threads=threads)
+                got = o.gibbs_sweep(th, v["p"], v["ab_s_p_waner"], i_raw, w, seed, sweep, 2, mode=mode, ind_offset=1000)
+                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2] == want[2]
+            assert want[2][1] > 0
+
+
 def test_deterministics_match_reference(goldens, cohorts):
     z, cases = goldens
     for c in cases:
