@@ -316,6 +316,8 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # beside the reference's own (dense) formulation: the compiled O(G N) port of the same path on the same cores
+        "fair_port": cpu_c_port(),
     }
     emit(line)
 
