@@ -3,9 +3,9 @@
 (oracle/abd_oracle_c.c abd_c_gibbs_sweep) at BASELINE's full size -- 10 000 individuals x 4 chains, both
 single-site rules -- bit for bit, and the CPU / GPU sweep times side by side.
 
-    python tools/gibbs_fullsize_check.py [n_inds] [n_chains]
+    python tests/gibbs_fullsize_check.py [n_inds] [n_chains]
 
-Not part of the test suite yet: written after the round's GPU budget was spent, so it has not run on a GPU."""
+Kept under tests/ (it calls the oracle) but not collected by pytest yet: written after the round's GPU budget was spent, so it has not run on a GPU."""
 import sys
 import time
 from pathlib import Path
